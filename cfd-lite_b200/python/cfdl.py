@@ -1,0 +1,257 @@
+"""ctypes binding of libcfdl.so (include/cfdl.h) — the host-side mirror of the reference's
+Fortran call sites for the SIMPLE hot path (src/equations/mod_uvwp.f90:95-134,
+src/main.f90:50-63).  Thin by design: every method is one C-ABI call with host (numpy)
+buffers.  There is no CPU fallback: compute entry points raise CfdlError when the CUDA
+library or a GPU is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libcfdl.so")
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+MESH_HEX, MESH_TET = 0, 1
+BC_WALL, BC_LID, BC_SYMMETRY = 0, 1, 2
+SOLVER_PARITY, SOLVER_MCSGS, SOLVER_PCG = 0, 1, 2
+EQ_U, EQ_V, EQ_W, EQ_PC = 0, 1, 2, 3
+FIELDS = ("u v w p u0 v0 w0 pc gu gv gw gp gpc mip mip0 bu bv bw d dc ap b anb").split()
+FIELD_ID = {n: i for i, n in enumerate(FIELDS)}
+
+
+class CfdlError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CfdlError("libcfdl.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`): " + LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.cfdl_last_error.restype = C.c_char_p
+    return _lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise CfdlError("cfdl error %d: %s" % (rc, lib().cfdl_last_error().decode()))
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp) if a is not None else None
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def device_count():
+    return int(lib().cfdl_device_count())
+
+
+# ---- host mesh tooling -----------------------------------------------------------------------
+def meshgen(kind, n, jitter=0.0, shuffle=False, seed=12345):
+    """Synthetic unit-cube mesh in CGNS conventions (what cell_input.f90:36-99 reads)."""
+    L = lib()
+    nvx, ne, nbf = C.c_int64(), C.c_int64(), C.c_int64()
+    nsec, w = C.c_int(), C.c_int()
+    _chk(L.cfdl_meshgen_sizes(C.c_int(kind), C.c_int(n), C.byref(nvx), C.byref(ne), C.byref(nbf), C.byref(nsec), C.byref(w)))
+    x, y, z = (np.zeros(nvx.value) for _ in range(3))
+    e2vx = np.zeros(w.value * (ne.value + nbf.value), np.int32)
+    etype = np.zeros(nsec.value, np.int32)
+    esec = np.zeros(2 * nsec.value, np.int32)
+    names = C.create_string_buffer(32 * nsec.value)
+    _chk(L.cfdl_meshgen_fill(C.c_int(kind), C.c_int(n), C.c_double(jitter), C.c_int(int(shuffle)), C.c_uint64(seed),
+                             _d(x), _d(y), _d(z), _i(e2vx), _i(etype), _i(esec), names))
+    return dict(kind=kind, n=n, nvx=nvx.value, ne=ne.value, nbf=nbf.value, nsec=nsec.value, ne2vx_max=w.value,
+                x=x, y=y, z=z, e2vx=e2vx, etype=etype, esec=esec, names=names.raw)
+
+
+def mesh_build(raw):
+    """Connectivity + geometry (find_element_nb, calc_aip_xyzip_uns, calc_vol_cv_centers_uns)."""
+    L = lib()
+    ne, nbf = int(raw["ne"]), int(raw["nbf"])
+    nface_per = {17: 6, 10: 4, 12: 5, 14: 5}
+    tot = 0
+    for s in range(raw["nsec"]):
+        t = int(raw["etype"][s])
+        cnt = int(raw["esec"][2 * s + 1] - raw["esec"][2 * s] + 1)
+        if t >= 10:
+            tot += nface_per[t] * cnt
+    nf = (tot + nbf) // 2
+    Z = 2 * nf - nbf
+    H = ne + nbf
+    g = dict(ne=ne, nf=nf, nbf=nbf,
+             ef2nb_idx=np.zeros(ne + 1, np.int32), ef2nb_nb=np.zeros(Z, np.int32), ef2nb_fg=np.zeros(Z, np.int32),
+             s2g=np.zeros(nf, np.int32), bs=np.zeros(nbf, np.int32),
+             xc=np.zeros(H), yc=np.zeros(H), zc=np.zeros(H), aip=np.zeros(3 * nf), rip=np.zeros(3 * nf), vol=np.zeros(ne))
+    x, y, z = _f64(raw["x"]), _f64(raw["y"]), _f64(raw["z"])
+    et, es, e2vx = _i32(raw["etype"]), _i32(raw["esec"]), _i32(raw["e2vx"])
+    _chk(L.cfdl_mesh_build(C.c_int64(len(x)), _d(x), _d(y), _d(z), C.c_int(len(et)), _i(et), _i(es),
+                           C.c_int(int(raw["ne2vx_max"])), _i(e2vx), C.c_int32(ne), C.c_int32(nf), C.c_int32(nbf),
+                           _i(g["ef2nb_idx"]), _i(g["ef2nb_nb"]), _i(g["ef2nb_fg"]), _i(g["s2g"]), _i(g["bs"]),
+                           _d(g["xc"]), _d(g["yc"]), _d(g["zc"]), _d(g["aip"]), _d(g["rip"]), _d(g["vol"])))
+    return g
+
+
+def default_bcs(raw):
+    """The reference's hard-wired BCs (mod_uvwp.f90:73-78): 'top' = lid u=1, others no-slip;
+    one BC per 2-D section in section order (mod_eqn_setup.f90:46-68)."""
+    esec, kind, uvw = [], [], []
+    for s in range(raw["nsec"]):
+        if int(raw["etype"][s]) >= 10:
+            continue
+        name = raw["names"][32 * s:32 * s + 32].decode().strip()
+        esec += [int(raw["esec"][2 * s]), int(raw["esec"][2 * s + 1])]
+        if name and name in "top":
+            kind.append(BC_LID)
+            uvw += [1.0, 0.0, 0.0]
+        else:
+            kind.append(BC_WALL)
+            uvw += [0.0, 0.0, 0.0]
+    return np.array(esec, np.int32), np.array(kind, np.int32), np.array(uvw, np.float64)
+
+
+class Solver:
+    """Device-resident SIMPLE hot path for one mesh (one GPU).  Mirrors phys_t + uvwp_t."""
+
+    def __init__(self, geom, bcs, rho=5.0, mu=0.01, n_subdomains=1, g2gf_p=None, g2gf_idx=None, device=0):
+        L = lib()
+        self.ne, self.nf, self.nbf = int(geom["ne"]), int(geom["nf"]), int(geom["nbf"])
+        self.H = self.ne + self.nbf
+        self.Z = 2 * self.nf - self.nbf
+        a = {k: _i32(geom[k]) for k in ("ef2nb_idx", "ef2nb_nb", "ef2nb_fg", "s2g", "bs")}
+        r = {k: _f64(geom[k]) for k in ("xc", "yc", "zc", "aip", "rip", "vol")}
+        rho = _f64(np.broadcast_to(rho, (self.ne,)))
+        mu = _f64(np.broadcast_to(mu, (self.ne,)))
+        esec, kind, uvw = (_i32(bcs[0]), _i32(bcs[1]), _f64(bcs[2]))
+        p = _i32(g2gf_p) if n_subdomains > 1 else None
+        pi = _i32(g2gf_idx) if n_subdomains > 1 else None
+        h = C.c_void_p()
+        _chk(L.cfdl_create(C.byref(h), C.c_int32(self.ne), C.c_int32(self.nf), C.c_int32(self.nbf),
+                           _i(a["ef2nb_idx"]), _i(a["ef2nb_nb"]), _i(a["ef2nb_fg"]), _i(a["s2g"]), _i(a["bs"]),
+                           _d(r["xc"]), _d(r["yc"]), _d(r["zc"]), _d(r["aip"]), _d(r["rip"]), _d(r["vol"]),
+                           _d(rho), _d(mu), C.c_int32(len(kind)), _i(esec), _i(kind), _d(uvw),
+                           C.c_int32(n_subdomains), _i(p), _i(pi), C.c_int32(device)))
+        self.h = h
+        self.n_subdomains = n_subdomains
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().cfdl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def field_size(self, name):
+        if name in ("u", "v", "w", "p", "u0", "v0", "w0", "pc"):
+            return self.H
+        if name in ("gu", "gv", "gw", "gp", "gpc"):
+            return 3 * self.H
+        if name in ("mip", "mip0"):
+            return self.nf
+        if name == "anb":
+            return self.Z
+        return self.ne
+
+    def set_option(self, key, value):
+        _chk(lib().cfdl_set_option(self.h, key.encode(), C.c_double(value)))
+
+    def get_info(self, key):
+        v = C.c_double()
+        _chk(lib().cfdl_get_info(self.h, key.encode(), C.byref(v)))
+        return v.value
+
+    def upload(self, name, arr):
+        arr = _f64(arr)
+        assert arr.size == self.field_size(name), (name, arr.size, self.field_size(name))
+        _chk(lib().cfdl_upload_field(self.h, C.c_int(FIELD_ID[name]), _d(arr)))
+
+    def download(self, name):
+        out = np.zeros(self.field_size(name))
+        _chk(lib().cfdl_download_field(self.h, C.c_int(FIELD_ID[name]), _d(out)))
+        return out
+
+    def update_boundaries(self):
+        _chk(lib().cfdl_update_boundaries(self.h))
+
+    def update_time(self):
+        _chk(lib().cfdl_update_time(self.h))
+
+    def solve_uvwp(self, dt=0.01, nit=100):
+        hist = np.zeros(16)
+        _chk(lib().cfdl_solve_uvwp(self.h, C.c_double(dt), C.c_int32(nit), _d(hist)))
+        return hist.reshape(4, 4)
+
+    def run(self, dt=0.01, nit=100, ntstep=10, ncoef=3, want_hist=True):
+        hist = np.zeros(ntstep * ncoef * 16) if want_hist else None
+        _chk(lib().cfdl_run(self.h, C.c_double(dt), C.c_int32(nit), C.c_int32(ntstep), C.c_int32(ncoef), _d(hist)))
+        return hist.reshape(ntstep * ncoef, 4, 4) if want_hist else None
+
+    def calc_coef_uvw(self, dt=0.01):
+        _chk(lib().cfdl_calc_coef_uvw(self.h, C.c_double(dt)))
+
+    def calc_mip(self, rhie_chow=True, dt=0.01):
+        _chk(lib().cfdl_calc_mip(self.h, C.c_int32(1 if rhie_chow else 0), C.c_double(dt)))
+
+    def calc_coef_p(self):
+        _chk(lib().cfdl_calc_coef_p(self.h))
+
+    def adjust_pc(self):
+        _chk(lib().cfdl_adjust_pc(self.h))
+
+    def update_uvwp(self):
+        _chk(lib().cfdl_update_uvwp(self.h))
+
+    def calc_grad(self, phi_name, grad_name):
+        _chk(lib().cfdl_calc_grad(self.h, C.c_int(FIELD_ID[phi_name]), C.c_int(FIELD_ID[grad_name])))
+
+    def solve_eq(self, eq, nit=100):
+        out = np.zeros(4)
+        _chk(lib().cfdl_solve_eq(self.h, C.c_int(eq), C.c_int32(nit), _d(out)))
+        return out
+
+    # stand-alone drop-ins (host arrays in, host arrays out)
+    def host_calc_grad(self, phi):
+        phi = _f64(phi)
+        grad = np.zeros(3 * self.H)
+        _chk(lib().cfdl_host_calc_grad(self.h, _d(phi), _d(grad)))
+        return grad
+
+    def host_solve_gs(self, eq, phi, ap, anb, b, nit=100):
+        phi = _f64(phi).copy()
+        ap, anb, b = _f64(ap), _f64(anb), _f64(b)
+        out = np.zeros(4)
+        _chk(lib().cfdl_host_solve_gs(self.h, C.c_int(eq), _d(phi), _d(ap), _d(anb), _d(b), C.c_int32(nit), _d(out)))
+        return phi, out
+
+    def host_solve(self, eq, phi, ap, anb, b, nit=100):
+        phi = _f64(phi).copy()
+        ap, anb, b = _f64(ap), _f64(anb), _f64(b)
+        out = np.zeros(4)
+        _chk(lib().cfdl_host_solve(self.h, C.c_int(eq), _d(phi), _d(ap), _d(anb), _d(b), C.c_int32(nit), _d(out)))
+        return phi, out
+
+    def host_calc_residual(self, phi, ap, anb, b):
+        phi, ap, anb, b = _f64(phi), _f64(ap), _f64(anb), _f64(b)
+        res, res_max = C.c_double(), C.c_double()
+        _chk(lib().cfdl_host_calc_residual(self.h, _d(phi), _d(ap), _d(anb), _d(b), C.byref(res), C.byref(res_max)))
+        return res.value, res_max.value

@@ -1,0 +1,183 @@
+/* cfdl.h — C ABI of the B200-native SIMPLE hot path of CFD-Lite.
+ *
+ * The reference has no FFI registry for this path: the boundary is the set of Fortran call
+ * sites inside solve_uvwp (src/equations/mod_uvwp.f90:95-134) and the two per-iteration
+ * calls in src/main.f90:52,63.  Every entry point below names the reference routine it
+ * replaces.  Conventions follow the reference's own bind(C) precedent
+ * (src/VTK/mod_vtk.f90:3-29): plain `double*` / `int32_t*`, arrays passed as their first
+ * element, nothing retained beyond the call except what cfdl_create copies to the device.
+ *
+ * Index conventions at this boundary are the reference's:
+ *   - cells 1..ne, halo (boundary-face) cells ne+1..ne+nbf, faces 1..nf, all 1-based;
+ *   - ef2nb(:,1) packs (neighbour<<5)|neighbour_local_face, local_face==0 <=> halo
+ *     (src/modules/mod_util.f90:1428-1448); ef2nb(:,2) is the signed global face id;
+ *   - vectors (aip, rip, gu, gv, gw, gp, gpc) are AoS xyz.
+ * All functions return 0 on success, a CFDL_ERR_* code otherwise; cfdl_last_error() gives
+ * the message.  The library never calls abort()/exit().  There is NO CPU fallback: every
+ * compute entry point fails with CFDL_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef CFDL_H
+#define CFDL_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  CFDL_OK = 0,
+  CFDL_ERR_ARG = 1,      /* bad argument */
+  CFDL_ERR_RANGE = 2,    /* size exceeds an index limit */
+  CFDL_ERR_CUDA = 3,     /* CUDA runtime error / no device */
+  CFDL_ERR_NCCL = 4,     /* NCCL error / library not loadable */
+  CFDL_ERR_MESH = 5,     /* inconsistent connectivity (reference: `stop` in find_element_nb) */
+  CFDL_ERR_INTERNAL = 6,
+  CFDL_ERR_UNSUPPORTED = 7
+};
+
+/* boundary-condition kinds == the reference's BC callbacks (mod_uvwp.f90:493-570) */
+enum {
+  CFDL_BC_WALL = 0,     /* dirichlet0: u=v=w=0, bc_type 'dirichlet' */
+  CFDL_BC_LID = 1,      /* lid: (u,v,w)=bc_uvw (reference: 1,0,0), 'dirichlet' */
+  CFDL_BC_SYMMETRY = 2  /* symmetry: mirrored velocity, 'zero_flux' */
+};
+
+/* linear-solver modes */
+enum {
+  CFDL_SOLVER_PARITY = 0, /* exact reference order: natural-order SGS (solve_gs) for u,v,w and,
+                             for pc, solve_gs (n_subdomains==1) or the block-SGS of
+                             multi_subdomain_solver (n_subdomains>1); level-scheduled on the GPU */
+  CFDL_SOLVER_MCSGS = 1,  /* multicolour symmetric Gauss-Seidel: same update formula, same
+                             stopping rule, colour order instead of natural order */
+  CFDL_SOLVER_PCG = 2     /* pc only: Jacobi-preconditioned CG with the reference's 10x / nit
+                             stopping rule; u,v,w use MCSGS */
+};
+
+/* field selectors for upload/download and the per-routine entry points */
+enum {
+  CFDL_F_U = 0, CFDL_F_V, CFDL_F_W, CFDL_F_P,         /* (ne+nbf) */
+  CFDL_F_U0, CFDL_F_V0, CFDL_F_W0, CFDL_F_PC,         /* (ne+nbf) */
+  CFDL_F_GU, CFDL_F_GV, CFDL_F_GW, CFDL_F_GP, CFDL_F_GPC, /* 3*(ne+nbf), AoS */
+  CFDL_F_MIP, CFDL_F_MIP0,                            /* (nf) */
+  CFDL_F_BU, CFDL_F_BV, CFDL_F_BW, CFDL_F_D, CFDL_F_DC, /* (ne) */
+  CFDL_F_AP, CFDL_F_B,                                /* (ne)  shared ap / b of phys_t */
+  CFDL_F_ANB,                                         /* (2nf-nbf) CSR order of ef2nb */
+  CFDL_F_COUNT
+};
+
+/* equation selector replacing the Fortran `cname` string (mod_solver.f90:268-269) */
+enum { CFDL_EQ_U = 0, CFDL_EQ_V = 1, CFDL_EQ_W = 2, CFDL_EQ_PC = 3 };
+
+typedef struct cfdl_handle_s* cfdl_handle;
+
+const char* cfdl_last_error(void);
+int cfdl_version(void);
+/* number of usable CUDA devices (0 on a CPU-only box; never an error) */
+int cfdl_device_count(void);
+
+/* ---- lifecycle: replaces construct_physics / construct_uvwp / construct_subdomains
+ *      (mod_physics.f90:52-75, mod_uvwp.f90:20-84, mod_subdomains.f90:18-160).
+ *  Mesh arrays are geometry_t + meshds_t as built by cell_input:
+ *    ef2nb_idx(ne+1), ef2nb_nb(Z) = ef2nb(:,1), ef2nb_fg(Z) = ef2nb(:,2), Z = 2nf-nbf,
+ *    s2g(nf), bs(nbf) (halo ne+1.. first), xc,yc,zc(ne+nbf), aip(3nf), rip(3nf), vol(ne),
+ *    rho,mu(ne).
+ *  BCs: bc_esec(2,nbc) halo ranges in 2-D section order (mod_eqn_setup.f90:60), bc_kind(nbc),
+ *    bc_uvw(3,nbc).
+ *  Subdomains (pc block solver): n_subdomains, and when >1 g2gf_p(ne) = cells sorted by block
+ *    in the reference's own (unstable-sort) order and g2gf_idx(n_subdomains+1)
+ *    (mod_mg_lvl_uns.f90:883-902); both 1-based.  The library never recomputes the RCB.
+ *  device: CUDA device ordinal.  Fields start at the reference's initial state (all zero,
+ *  mod_uvwp.f90:57-69) including mip from calc_mip(.false.) (:81-82). */
+int cfdl_create(cfdl_handle* out, int32_t ne, int32_t nf, int32_t nbf,
+                const int32_t* ef2nb_idx, const int32_t* ef2nb_nb, const int32_t* ef2nb_fg,
+                const int32_t* s2g, const int32_t* bs,
+                const double* xc, const double* yc, const double* zc,
+                const double* aip, const double* rip, const double* vol,
+                const double* rho, const double* mu,
+                int32_t nbc, const int32_t* bc_esec, const int32_t* bc_kind, const double* bc_uvw,
+                int32_t n_subdomains, const int32_t* g2gf_p, const int32_t* g2gf_idx,
+                int32_t device);
+int cfdl_destroy(cfdl_handle h);
+
+/* options: "solver" (CFDL_SOLVER_*), "reorder" (0/1, set before first use) ... */
+int cfdl_set_option(cfdl_handle h, const char* key, double value);
+int cfdl_get_info(cfdl_handle h, const char* key, double* value);
+
+/* ---- host <-> device field sync (for write_vtubin, main.f90:79,89) */
+int cfdl_upload_field(cfdl_handle h, int field, const double* host);
+int cfdl_download_field(cfdl_handle h, int field, double* host);
+
+/* ---- whole-step path (device-resident; no host transfers besides the 16-double history) */
+/* update_boundaries, mod_physics.f90:38-50 -> BC callbacks mod_uvwp.f90:493-570 */
+int cfdl_update_boundaries(cfdl_handle h);
+/* solve_uvwp, mod_uvwp.f90:95-134.  hist[4][4] (row = u,v,w,pc; col = it,res_i,res_f,res_max)
+ * is what the reference prints per solve (mod_solver.f90:184,325); may be NULL. */
+int cfdl_solve_uvwp(cfdl_handle h, double dt, int32_t nit, double* hist);
+/* update_time, mod_physics.f90:101-112 */
+int cfdl_update_time(cfdl_handle h);
+/* the main.f90:50-63 loop: ntstep x (ncoef x (update_boundaries; solve_uvwp); update_time).
+ * hist (ntstep*ncoef*16 doubles) may be NULL. */
+int cfdl_run(cfdl_handle h, double dt, int32_t nit, int32_t ntstep, int32_t ncoef, double* hist);
+
+/* ---- per-routine path on the handle's device-resident state (one reference routine each) */
+int cfdl_calc_coef_uvw(cfdl_handle h, double dt);                 /* mod_uvwp.f90:161-286 */
+int cfdl_calc_mip(cfdl_handle h, int32_t l_rhie_chow, double dt); /* mod_uvwp.f90:438-490 */
+int cfdl_calc_coef_p(cfdl_handle h);                              /* mod_uvwp.f90:289-368 */
+int cfdl_adjust_pc(cfdl_handle h);                                /* mod_uvwp.f90:129-130,136-158 */
+int cfdl_update_uvwp(cfdl_handle h);                              /* mod_uvwp.f90:370-436 */
+/* calc_grad, mod_solver.f90:40-81: phi in {U,V,W,P,PC} -> grad in {GU,GV,GW,GP,GPC} */
+int cfdl_calc_grad(cfdl_handle h, int phi_field, int grad_field);
+/* solve_gs / solve, mod_solver.f90:255-327,329-344 with the handle's ap/anb and the rhs of
+ * equation eq (bu,bv,bw or b); out4 = it,res_i,res_f,res_max */
+int cfdl_solve_eq(cfdl_handle h, int eq, int32_t nit, double* out4);
+
+/* ---- stand-alone drop-ins with host arrays, argument order of the flat Fortran signatures.
+ * The mesh comes from the handle (connectivity never changes between calls). */
+/* calc_grad(phi,grad,...) mod_solver.f90:40 */
+int cfdl_host_calc_grad(cfdl_handle h, const double* phi, double* grad);
+/* solve_gs(cname,phi,ap,anb,b,...,nit) mod_solver.f90:255; eq selects omega */
+int cfdl_host_solve_gs(cfdl_handle h, int eq, double* phi, const double* ap, const double* anb,
+                       const double* b, int32_t nit, double* out4);
+/* calc_residual(phi,ap,anb,b,...,res,res_max) mod_solver.f90:230 */
+int cfdl_host_calc_residual(cfdl_handle h, const double* phi, const double* ap, const double* anb,
+                            const double* b, double* res, double* res_max);
+/* solve('pc',subdomain,intf,...) mod_solver.f90:329: multi_subdomain_solver when the handle
+ * was created with n_subdomains>1, else solve_gs */
+int cfdl_host_solve(cfdl_handle h, int eq, double* phi, const double* ap, const double* anb,
+                    const double* b, int32_t nit, double* out4);
+
+/* ---- multi-GPU: one process per GPU, one partition per process.
+ * A partition is a mesh in the same format whose halo range additionally contains the cells
+ * owned by other ranks; the interface description tells which halos they are. */
+/* 128-byte NCCL unique id, created on rank 0 and broadcast by the caller (MPI / torch) */
+int cfdl_comm_unique_id(uint8_t id[128]);
+int cfdl_comm_init(cfdl_handle h, const uint8_t id[128], int32_t rank, int32_t nranks);
+/* per neighbour rank r (nnbr of them): send_cells[send_ptr[r]:send_ptr[r+1]] are local owned
+ * cells (1-based) whose values go to r; recv_halos[...] the local halo ids (ne+1..) filled
+ * from r; both sides list the shared faces in the same order. */
+int cfdl_set_interfaces(cfdl_handle h, int32_t nnbr, const int32_t* nbr_rank,
+                        const int32_t* send_ptr, const int32_t* send_cells,
+                        const int32_t* recv_ptr, const int32_t* recv_halos,
+                        int64_t ne_global, int32_t owns_ref_cell);
+
+/* ---- host-side mesh tooling (no GPU needed) ------------------------------------------- */
+enum { CFDL_MESH_HEX = 0, CFDL_MESH_TET = 1 };
+/* synthetic unit-cube meshes standing in for the CGNS file read by cell_input.f90:36-99 */
+int cfdl_meshgen_sizes(int kind, int n, int64_t* nvx, int64_t* ne, int64_t* nbf, int* nsec,
+                       int* ne2vx_max);
+int cfdl_meshgen_fill(int kind, int n, double jitter, int shuffle, uint64_t seed,
+                      double* x, double* y, double* z, int32_t* e2vx, int32_t* etype,
+                      int32_t* esec, char* names);
+/* fast connectivity + geometry build producing exactly the arrays of find_element_nb,
+ * calc_aip_xyzip_uns and calc_vol_cv_centers_uns (mod_mg_lvl_uns.f90:283-488,
+ * calc_aip_xyzip.f90, calc_vol_cv_centers.f90), including the reference's face numbering. */
+int cfdl_mesh_build(int64_t nvx, const double* x, const double* y, const double* z,
+                    int nsec, const int32_t* etype, const int32_t* esec, int ne2vx_max,
+                    const int32_t* e2vx, int32_t ne, int32_t nf, int32_t nbf,
+                    int32_t* ef2nb_idx, int32_t* ef2nb_nb, int32_t* ef2nb_fg, int32_t* s2g,
+                    int32_t* bs, double* xc, double* yc, double* zc, double* aip, double* rip,
+                    double* vol);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
