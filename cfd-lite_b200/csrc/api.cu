@@ -1,0 +1,340 @@
+// C ABI of libcfdl (include/cfdl.h): lifecycle, host<->device field sync, the whole-step path
+// (update_boundaries / solve_uvwp / update_time, src/main.f90:50-63) and the per-routine path.
+#include <cstring>
+#include <new>
+#include <algorithm>
+#include "state.h"
+
+using namespace cfdl;
+
+namespace {
+
+template <class T>
+int dev_upload(Handle* h, T*& dst, const T* src, size_t n) {
+  dst = nullptr;
+  if (n == 0) return CFDL_OK;
+  CFDL_CUDA(cudaMalloc(&dst, sizeof(T) * n));
+  h->allocs.push_back(dst);
+  CFDL_CUDA(cudaMemcpy(dst, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+  return CFDL_OK;
+}
+template <class T>
+int dev_zero(Handle* h, T*& dst, size_t n) {
+  dst = nullptr;
+  if (n == 0) n = 1;
+  CFDL_CUDA(cudaMalloc(&dst, sizeof(T) * n));
+  h->allocs.push_back(dst);
+  CFDL_CUDA(cudaMemset(dst, 0, sizeof(T) * n));
+  return CFDL_OK;
+}
+
+size_t field_len(const Handle* h, int f) {
+  if (f <= CFDL_F_PC) return (size_t)h->H;
+  if (f <= CFDL_F_GPC) return 3 * (size_t)h->H;
+  if (f <= CFDL_F_MIP0) return (size_t)h->F;
+  if (f == CFDL_F_ANB) return (size_t)h->K * h->Np;  // device ELL storage
+  return (size_t)h->N;
+}
+
+bool good(cfdl_handle h) { return h != nullptr; }
+
+int use_device(Handle* h) {
+  CFDL_CUDA(cudaSetDevice(h->device));
+  return CFDL_OK;
+}
+
+// host (reference numbering) -> device field
+int upload_field(Handle* h, int f, const double* host) {
+  if (f == CFDL_F_ANB) {
+    CFDL_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * (size_t)h->Z, cudaMemcpyHostToDevice, h->stream));
+    return k_csr_to_ell(h, h->fld[f], h->stage);
+  }
+  if (f <= CFDL_F_PC || (f >= CFDL_F_GU && f <= CFDL_F_GPC)) {
+    const int nc = (f <= CFDL_F_PC) ? 1 : 3;
+    CFDL_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * nc * (size_t)h->H, cudaMemcpyHostToDevice, h->stream));
+    int rc = k_gather(h, h->fld[f], h->stage, h->c2o, h->N, nc);  // cells permuted
+    if (rc) return rc;
+    if (h->B) CFDL_CUDA(cudaMemcpyAsync(h->fld[f] + (size_t)nc * h->N, h->stage + (size_t)nc * h->N, sizeof(double) * nc * (size_t)h->B,
+                                        cudaMemcpyDeviceToDevice, h->stream));  // halos keep their order
+    return CFDL_OK;
+  }
+  if (f == CFDL_F_MIP || f == CFDL_F_MIP0) {
+    CFDL_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * (size_t)h->F, cudaMemcpyHostToDevice, h->stream));
+    return k_gather(h, h->fld[f], h->stage, h->f2o, h->F, 1);
+  }
+  CFDL_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * (size_t)h->N, cudaMemcpyHostToDevice, h->stream));
+  return k_gather(h, h->fld[f], h->stage, h->c2o, h->N, 1);
+}
+
+int download_field(Handle* h, int f, double* host) {
+  int rc;
+  size_t n;
+  if (f == CFDL_F_ANB) {
+    if ((rc = k_ell_to_csr(h, h->stage, h->fld[f]))) return rc;
+    n = (size_t)h->Z;
+  } else if (f <= CFDL_F_PC || (f >= CFDL_F_GU && f <= CFDL_F_GPC)) {
+    const int nc = (f <= CFDL_F_PC) ? 1 : 3;
+    if ((rc = k_scatter(h, h->stage, h->fld[f], h->c2o, h->N, nc))) return rc;
+    if (h->B) CFDL_CUDA(cudaMemcpyAsync(h->stage + (size_t)nc * h->N, h->fld[f] + (size_t)nc * h->N, sizeof(double) * nc * (size_t)h->B,
+                                        cudaMemcpyDeviceToDevice, h->stream));
+    n = (size_t)nc * h->H;
+  } else if (f == CFDL_F_MIP || f == CFDL_F_MIP0) {
+    if ((rc = k_scatter(h, h->stage, h->fld[f], h->f2o, h->F, 1))) return rc;
+    n = (size_t)h->F;
+  } else {
+    if ((rc = k_scatter(h, h->stage, h->fld[f], h->c2o, h->N, 1))) return rc;
+    n = (size_t)h->N;
+  }
+  CFDL_CUDA(cudaMemcpyAsync(host, h->stage, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CFDL_CUDA(cudaStreamSynchronize(h->stream));
+  return CFDL_OK;
+}
+
+int rhs_field(int eq) { return eq == CFDL_EQ_U ? CFDL_F_BU : eq == CFDL_EQ_V ? CFDL_F_BV : eq == CFDL_EQ_W ? CFDL_F_BW : CFDL_F_B; }
+int phi_field(int eq) { return eq == CFDL_EQ_U ? CFDL_F_U : eq == CFDL_EQ_V ? CFDL_F_V : eq == CFDL_EQ_W ? CFDL_F_W : CFDL_F_PC; }
+
+// solve_uvwp, src/equations/mod_uvwp.f90:95-134
+int solve_uvwp_impl(Handle* h, double dt, int nit, double* hist) {
+  int rc;
+  double st[16] = {0};
+  if ((rc = k_calc_coef_uvw(h, dt))) return rc;                                              // :111
+  for (int eq = CFDL_EQ_U; eq <= CFDL_EQ_W; ++eq)                                            // :114-116
+    if ((rc = solve_equation(h, eq, h->fld[phi_field(eq)], h->fld[rhs_field(eq)], nit, st + 4 * eq, false))) return rc;
+  if ((rc = k_calc_grad3(h))) return rc;                                                     // :118-120
+  if ((rc = k_calc_mip(h, true, dt))) return rc;                                             // :122
+  if ((rc = k_calc_coef_p(h))) return rc;                                                    // :124
+  CFDL_CUDA(cudaMemsetAsync(h->fld[CFDL_F_PC], 0, sizeof(double) * (size_t)h->H, h->stream)); // :126 set_a_0
+  if ((rc = solve_equation(h, CFDL_EQ_PC, h->fld[CFDL_F_PC], h->fld[CFDL_F_B], nit, st + 12, true))) return rc;  // :127
+  if ((rc = k_adjust_pc(h))) return rc;                                                      // :129-130
+  if ((rc = k_calc_grad(h, h->fld[CFDL_F_PC], h->fld[CFDL_F_GPC]))) return rc;               // :131
+  if ((rc = k_update_uvwp(h))) return rc;                                                    // :132
+  if (hist) std::memcpy(hist, st, sizeof st);
+  return CFDL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cfdl_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int cfdl_create(cfdl_handle* out, int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_idx, const int32_t* ef2nb_nb,
+                const int32_t* ef2nb_fg, const int32_t* s2g, const int32_t* bs, const double* xc, const double* yc,
+                const double* zc, const double* aip, const double* rip, const double* vol, const double* rho,
+                const double* mu, int32_t nbc, const int32_t* bc_esec, const int32_t* bc_kind, const double* bc_uvw,
+                int32_t n_subdomains, const int32_t* g2gf_p, const int32_t* g2gf_idx, int32_t device) {
+  if (!out) return fail(CFDL_ERR_ARG, "cfdl_create: out is NULL");
+  *out = nullptr;
+  if (!ef2nb_idx || !ef2nb_nb || !ef2nb_fg || !s2g || (!bs && nbf) || !xc || !yc || !zc || !aip || !rip || !vol || !rho || !mu)
+    return fail(CFDL_ERR_ARG, "cfdl_create: NULL mesh array");
+  if (n_subdomains < 1) return fail(CFDL_ERR_ARG, "cfdl_create: n_subdomains must be >= 1");
+  int ndev = cfdl_device_count();
+  if (ndev < 1) return fail(CFDL_ERR_CUDA, "cfdl_create: no CUDA device is usable (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(CFDL_ERR_ARG, "cfdl_create: device %d of %d", device, ndev);
+  cfdl_handle_s* h = new (std::nothrow) cfdl_handle_s;
+  if (!h) return fail(CFDL_ERR_INTERNAL, "out of host memory");
+  h->device = device;
+  int rc = prepare(h->prep, ne, nf, nbf, ef2nb_idx, ef2nb_nb, ef2nb_fg, s2g, bs, xc, yc, zc, nbc, bc_esec, bc_kind, bc_uvw,
+                   n_subdomains, g2gf_p, g2gf_idx, /*reorder auto*/ 2);
+  if (rc) { delete h; return rc; }
+  auto bail = [&](int code) { cfdl_destroy(h); return code; };
+  if ((rc = use_device(h))) return bail(rc);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(CFDL_ERR_CUDA, "cudaGetDeviceProperties failed"));
+  if (prop.major < 10) return bail(fail(CFDL_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor));
+  h->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(CFDL_ERR_CUDA, "cudaStreamCreate failed"));
+  const Prep& p = h->prep;
+  h->N = p.N; h->F = p.F; h->B = p.B; h->H = p.H; h->Z = p.Z; h->K = p.K; h->Np = p.Np; h->Fi = p.Fi;
+  const int32_t N = p.N, F = p.F, B = p.B, H = p.H;
+#define UP(dst, vec) if ((rc = dev_upload(h, dst, (vec).data(), (vec).size()))) return bail(rc)
+  UP(h->ell_nb, p.ell_nb); UP(h->ell_fs, p.ell_fs); UP(h->nfc, p.nfc); UP(h->face_a, p.face_a); UP(h->face_b, p.face_b);
+  UP(h->halo_cell, p.halo_cell); UP(h->halo_face, p.halo_face); UP(h->halo_bc, p.halo_bc); UP(h->halo_slot, p.halo_slot);
+  UP(h->bc_kind, p.bc_kind); UP(h->bc_uvw, p.bc_uvw); UP(h->c2o, p.c2o); UP(h->o2c, p.o2c); UP(h->f2o, p.f2o); UP(h->row_ptr, p.row_ptr);
+#undef UP
+  {  // geometry in device numbering
+    std::vector<double> t((size_t)3 * std::max(H, F));
+    auto cells = [&](const double* src, double*& dst, int32_t halos) -> int {
+      for (int32_t c = 0; c < N; ++c) t[c] = src[p.c2o[c]];
+      for (int32_t j = 0; j < halos; ++j) t[N + j] = src[N + j];
+      return dev_upload(h, dst, t.data(), (size_t)N + halos);
+    };
+    if ((rc = cells(xc, h->xc, B)) || (rc = cells(yc, h->yc, B)) || (rc = cells(zc, h->zc, B))) return bail(rc);
+    if ((rc = cells(vol, h->vol, 0)) || (rc = cells(rho, h->rho, 0)) || (rc = cells(mu, h->mu, 0))) return bail(rc);
+    for (int32_t f = 0; f < F; ++f) for (int q = 0; q < 3; ++q) t[3 * (size_t)f + q] = aip[3 * (size_t)p.f2o[f] + q];
+    if ((rc = dev_upload(h, h->aip, t.data(), 3 * (size_t)F))) return bail(rc);
+    for (int32_t f = 0; f < F; ++f) for (int q = 0; q < 3; ++q) t[3 * (size_t)f + q] = rip[3 * (size_t)p.f2o[f] + q];
+    if ((rc = dev_upload(h, h->rip, t.data(), 3 * (size_t)F))) return bail(rc);
+  }
+  for (int f = 0; f < CFDL_F_COUNT; ++f)
+    if ((rc = dev_zero(h, h->fld[f], field_len(h, f) + 4))) return bail(rc);
+  h->stage_len = std::max(std::max(3 * (size_t)H, (size_t)p.Z), (size_t)F) + 4;
+  if ((rc = dev_zero(h, h->stage, h->stage_len))) return bail(rc);
+  h->partial_len = 4096 + 2 * 64 * (N / 8192 + 1);
+  if ((rc = dev_zero(h, h->partial, (size_t)h->partial_len))) return bail(rc);
+  if ((rc = dev_zero(h, h->ctl, 1)) || (rc = dev_zero(h, h->scal, 512)) || (rc = dev_zero(h, h->barrier, 4))) return bail(rc);
+  if (cudaMallocHost(&h->ctl_host, sizeof(SolveCtl)) != cudaSuccess || cudaMallocHost(&h->scal_host, sizeof(double) * 512) != cudaSuccess)
+    return bail(fail(CFDL_ERR_CUDA, "cudaMallocHost failed"));
+  if ((rc = solver_init(h))) return bail(rc);
+  // construct_uvwp: fields zero, mip from calc_mip(.false.), mip0 = mip (mod_uvwp.f90:57-82)
+  if ((rc = k_calc_mip(h, false, 0.01))) return bail(rc);
+  if (cudaMemcpyAsync(h->fld[CFDL_F_MIP0], h->fld[CFDL_F_MIP], sizeof(double) * (size_t)F, cudaMemcpyDeviceToDevice, h->stream) != cudaSuccess ||
+      cudaStreamSynchronize(h->stream) != cudaSuccess)
+    return bail(fail(CFDL_ERR_CUDA, "initial calc_mip failed: %s", cudaGetErrorString(cudaGetLastError())));
+  *out = h;
+  return CFDL_OK;
+}
+
+int cfdl_destroy(cfdl_handle h) {
+  if (!h) return CFDL_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->ctl_host) cudaFreeHost(h->ctl_host);
+  if (h->scal_host) cudaFreeHost(h->scal_host);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return CFDL_OK;
+}
+
+int cfdl_set_option(cfdl_handle h, const char* key, double value) {
+  if (!good(h) || !key) return fail(CFDL_ERR_ARG, "cfdl_set_option: bad handle/key");
+  if (!std::strcmp(key, "solver")) {
+    int m = (int)value;
+    if (m < CFDL_SOLVER_PARITY || m > CFDL_SOLVER_PCG) return fail(CFDL_ERR_ARG, "cfdl_set_option: solver mode %d", m);
+    h->solver_mode = m;
+    return CFDL_OK;
+  }
+  return fail(CFDL_ERR_ARG, "cfdl_set_option: unknown key '%s'", key);
+}
+
+int cfdl_get_info(cfdl_handle h, const char* key, double* value) {
+  if (!good(h) || !key || !value) return fail(CFDL_ERR_ARG, "cfdl_get_info: bad argument");
+  if (!std::strcmp(key, "ncolors")) *value = h->prep.ncolors;
+  else if (!std::strcmp(key, "morton")) *value = h->prep.morton ? 1 : 0;
+  else if (!std::strcmp(key, "nlevels_natural")) *value = h->prep.natural.nlevels;
+  else if (!std::strcmp(key, "nlevels_blocks")) *value = h->prep.blocks.nlevels;
+  else if (!std::strcmp(key, "ell_width")) *value = h->K;
+  else if (!std::strcmp(key, "num_sms")) *value = h->num_sms;
+  else if (!std::strcmp(key, "solver")) *value = h->solver_mode;
+  else return fail(CFDL_ERR_ARG, "cfdl_get_info: unknown key '%s'", key);
+  return CFDL_OK;
+}
+
+int cfdl_get_cell_order(cfdl_handle h, int32_t* c2o, int32_t* color_ptr) {
+  if (!good(h)) return fail(CFDL_ERR_ARG, "cfdl_get_cell_order: NULL handle");
+  if (c2o) for (int32_t i = 0; i < h->N; ++i) c2o[i] = h->prep.c2o[i] + 1;
+  if (color_ptr) for (int c = 0; c <= h->prep.ncolors; ++c) color_ptr[c] = h->prep.color_ptr[c];
+  return CFDL_OK;
+}
+
+#define ENTER(h)                                                       \
+  if (!good(h)) return fail(CFDL_ERR_ARG, "%s: NULL handle", __func__); \
+  { int rc__ = use_device(h); if (rc__) return rc__; }
+#define FINISH(h)                                                      \
+  do {                                                                 \
+    CFDL_CUDA(cudaStreamSynchronize((h)->stream));                     \
+    CFDL_CUDA(cudaGetLastError());                                     \
+    return CFDL_OK;                                                    \
+  } while (0)
+
+int cfdl_upload_field(cfdl_handle h, int field, const double* host) {
+  ENTER(h);
+  if (field < 0 || field >= CFDL_F_COUNT || !host) return fail(CFDL_ERR_ARG, "cfdl_upload_field: bad field/pointer");
+  int rc = upload_field(h, field, host);
+  if (rc) return rc;
+  FINISH(h);
+}
+int cfdl_download_field(cfdl_handle h, int field, double* host) {
+  ENTER(h);
+  if (field < 0 || field >= CFDL_F_COUNT || !host) return fail(CFDL_ERR_ARG, "cfdl_download_field: bad field/pointer");
+  return download_field(h, field, host);
+}
+
+int cfdl_update_boundaries(cfdl_handle h) { ENTER(h); int rc = k_update_boundaries(h); if (rc) return rc; FINISH(h); }
+int cfdl_update_time(cfdl_handle h) { ENTER(h); int rc = k_update_time(h); if (rc) return rc; FINISH(h); }
+int cfdl_solve_uvwp(cfdl_handle h, double dt, int32_t nit, double* hist) {
+  ENTER(h);
+  int rc = solve_uvwp_impl(h, dt, nit, hist);
+  if (rc) return rc;
+  FINISH(h);
+}
+int cfdl_run(cfdl_handle h, double dt, int32_t nit, int32_t ntstep, int32_t ncoef, double* hist) {
+  ENTER(h);
+  int rc;
+  for (int ts = 0; ts < ntstep; ++ts) {
+    for (int ic = 0; ic < ncoef; ++ic) {
+      if ((rc = k_update_boundaries(h))) return rc;
+      if ((rc = solve_uvwp_impl(h, dt, nit, hist ? hist + 16 * ((size_t)ts * ncoef + ic) : nullptr))) return rc;
+    }
+    if ((rc = k_update_time(h))) return rc;
+  }
+  FINISH(h);
+}
+
+int cfdl_calc_coef_uvw(cfdl_handle h, double dt) { ENTER(h); int rc = k_calc_coef_uvw(h, dt); if (rc) return rc; FINISH(h); }
+int cfdl_calc_mip(cfdl_handle h, int32_t lrc, double dt) { ENTER(h); int rc = k_calc_mip(h, lrc != 0, dt); if (rc) return rc; FINISH(h); }
+int cfdl_calc_coef_p(cfdl_handle h) { ENTER(h); int rc = k_calc_coef_p(h); if (rc) return rc; FINISH(h); }
+int cfdl_adjust_pc(cfdl_handle h) { ENTER(h); int rc = k_adjust_pc(h); if (rc) return rc; FINISH(h); }
+int cfdl_update_uvwp(cfdl_handle h) { ENTER(h); int rc = k_update_uvwp(h); if (rc) return rc; FINISH(h); }
+int cfdl_calc_grad(cfdl_handle h, int phi_f, int grad_f) {
+  ENTER(h);
+  if (phi_f < CFDL_F_U || phi_f > CFDL_F_PC || grad_f < CFDL_F_GU || grad_f > CFDL_F_GPC) return fail(CFDL_ERR_ARG, "cfdl_calc_grad: bad field ids");
+  int rc = k_calc_grad(h, h->fld[phi_f], h->fld[grad_f]);
+  if (rc) return rc;
+  FINISH(h);
+}
+int cfdl_solve_eq(cfdl_handle h, int eq, int32_t nit, double* out4) {
+  ENTER(h);
+  if (eq < CFDL_EQ_U || eq > CFDL_EQ_PC) return fail(CFDL_ERR_ARG, "cfdl_solve_eq: bad equation id");
+  int rc = solve_equation(h, eq, h->fld[phi_field(eq)], h->fld[rhs_field(eq)], nit, out4, eq == CFDL_EQ_PC);
+  if (rc) return rc;
+  FINISH(h);
+}
+
+// ---- stand-alone drop-ins with host arrays ------------------------------------------------------
+int cfdl_host_calc_grad(cfdl_handle h, const double* phi, double* grad) {
+  ENTER(h);
+  if (!phi || !grad) return fail(CFDL_ERR_ARG, "cfdl_host_calc_grad: NULL array");
+  int rc;
+  if ((rc = upload_field(h, CFDL_F_PC, phi))) return rc;
+  if ((rc = k_calc_grad(h, h->fld[CFDL_F_PC], h->fld[CFDL_F_GPC]))) return rc;
+  return download_field(h, CFDL_F_GPC, grad);
+}
+
+static int host_solve_common(cfdl_handle h, int eq, double* phi, const double* ap, const double* anb, const double* b, int32_t nit,
+                             double* out4, bool dispatch) {
+  if (!phi || !ap || !anb || !b) return fail(CFDL_ERR_ARG, "host solve: NULL array");
+  if (eq < CFDL_EQ_U || eq > CFDL_EQ_PC) return fail(CFDL_ERR_ARG, "host solve: bad equation id");
+  int rc;
+  if ((rc = upload_field(h, CFDL_F_AP, ap)) || (rc = upload_field(h, CFDL_F_ANB, anb)) || (rc = upload_field(h, CFDL_F_B, b)) ||
+      (rc = upload_field(h, CFDL_F_PC, phi)))
+    return rc;
+  if ((rc = solve_equation(h, eq, h->fld[CFDL_F_PC], h->fld[CFDL_F_B], nit, out4, dispatch))) return rc;
+  return download_field(h, CFDL_F_PC, phi);
+}
+int cfdl_host_solve_gs(cfdl_handle h, int eq, double* phi, const double* ap, const double* anb, const double* b, int32_t nit, double* out4) {
+  ENTER(h);
+  return host_solve_common(h, eq, phi, ap, anb, b, nit, out4, false);
+}
+int cfdl_host_solve(cfdl_handle h, int eq, double* phi, const double* ap, const double* anb, const double* b, int32_t nit, double* out4) {
+  ENTER(h);
+  return host_solve_common(h, eq, phi, ap, anb, b, nit, out4, true);
+}
+
+int cfdl_host_calc_residual(cfdl_handle h, const double* phi, const double* ap, const double* anb, const double* b, double* res,
+                            double* res_max) {
+  ENTER(h);
+  if (!phi || !ap || !anb || !b || !res || !res_max) return fail(CFDL_ERR_ARG, "cfdl_host_calc_residual: NULL array");
+  int rc;
+  if ((rc = upload_field(h, CFDL_F_AP, ap)) || (rc = upload_field(h, CFDL_F_ANB, anb)) || (rc = upload_field(h, CFDL_F_B, b)) ||
+      (rc = upload_field(h, CFDL_F_PC, phi)))
+    return rc;
+  return residual_plain(h, h->fld[CFDL_F_PC], h->fld[CFDL_F_B], true, res, res_max);
+}
+
+}  // extern "C"

@@ -1,0 +1,252 @@
+// Host-side mesh preparation (see prep.h).  Input = geometry_t/meshds_t arrays exactly as the
+// reference's cell_input builds them (src/setup/mod_mg_lvl_uns.f90:283-433).
+#include "prep.h"
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include "cfdl_common.h"
+
+namespace cfdl {
+namespace {
+
+inline uint64_t spread21(uint64_t v) {  // interleave helper for 3-D Morton keys
+  v &= 0x1fffff;
+  v = (v | v << 32) & 0x1f00000000ffffull;
+  v = (v | v << 16) & 0x1f0000ff0000ffull;
+  v = (v | v << 8) & 0x100f00f00f00f00full;
+  v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+  v = (v | v << 2) & 0x1249249249249249ull;
+  return v;
+}
+
+void morton_order(int32_t N, const double* xc, const double* yc, const double* zc, std::vector<int32_t>& order) {
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int32_t e = 0; e < N; ++e) {
+    lo[0] = std::min(lo[0], xc[e]); hi[0] = std::max(hi[0], xc[e]);
+    lo[1] = std::min(lo[1], yc[e]); hi[1] = std::max(hi[1], yc[e]);
+    lo[2] = std::min(lo[2], zc[e]); hi[2] = std::max(hi[2], zc[e]);
+  }
+  double sc[3];
+  for (int i = 0; i < 3; ++i) sc[i] = (hi[i] > lo[i]) ? 2097151.0 / (hi[i] - lo[i]) : 0.0;
+  std::vector<std::pair<uint64_t, int32_t>> key((size_t)N);
+  for (int32_t e = 0; e < N; ++e) {
+    uint64_t a = (uint64_t)((xc[e] - lo[0]) * sc[0]), b = (uint64_t)((yc[e] - lo[1]) * sc[1]), c = (uint64_t)((zc[e] - lo[2]) * sc[2]);
+    key[e] = {spread21(a) | (spread21(b) << 1) | (spread21(c) << 2), e};
+  }
+  std::sort(key.begin(), key.end());
+  order.resize(N);
+  for (int32_t i = 0; i < N; ++i) order[i] = key[i].second;
+}
+
+// Level schedule of a sequential sweep: `seq` lists original cells in sweep order (blocks
+// concatenated), blk_ptr delimits the blocks.  A cell depends on the same-block neighbours
+// that precede it; reversed levels serve the backward sweep.
+void build_schedule(const Prep& p, const std::vector<int32_t>& o_nb, const std::vector<int32_t>& seq,
+                    const std::vector<int32_t>& blk_ptr, Schedule& S) {
+  const int32_t N = p.N, K = p.K, Np = p.Np;
+  const int nb_blocks = (int)blk_ptr.size() - 1;
+  S.nblocks = nb_blocks;
+  S.blk_ptr = blk_ptr;
+  std::vector<int32_t> rank((size_t)N), blockof((size_t)N), level((size_t)N, 0);
+  for (int b = 0; b < nb_blocks; ++b)
+    for (int32_t i = blk_ptr[b]; i < blk_ptr[b + 1]; ++i) { rank[seq[i]] = i; blockof[seq[i]] = b; }
+  int32_t maxl = 0;
+  for (int32_t i = 0; i < N; ++i) {
+    int32_t e = seq[i], l = 0;
+    for (int32_t idx = p.row_ptr[e]; idx < p.row_ptr[e + 1]; ++idx) {
+      int32_t nb = o_nb[idx];
+      if (nb < N && blockof[nb] == blockof[e] && rank[nb] < i) l = std::max(l, level[nb] + 1);
+    }
+    level[e] = l;
+    maxl = std::max(maxl, l);
+  }
+  S.nlevels = maxl + 1;
+  S.lvl_ptr.assign(S.nlevels + 1, 0);
+  for (int32_t e = 0; e < N; ++e) S.lvl_ptr[level[e] + 1]++;
+  for (int l = 0; l < S.nlevels; ++l) S.lvl_ptr[l + 1] += S.lvl_ptr[l];
+  std::vector<int32_t> cur(S.lvl_ptr.begin(), S.lvl_ptr.end() - 1), c2s((size_t)N);
+  S.s2c.resize(N);
+  for (int32_t c = 0; c < N; ++c) {  // device order inside a level keeps gathers local
+    int32_t s = cur[level[p.c2o[c]]]++;
+    S.s2c[s] = c;
+    c2s[c] = s;
+  }
+  S.nbs.assign((size_t)K * Np, 0);
+  S.bpos.resize(N);
+  std::vector<uint8_t> need_lag((size_t)N, 0);
+  for (int32_t s = 0; s < N; ++s) {
+    int32_t c = S.s2c[s], e = p.c2o[c];
+    S.bpos[s] = rank[e];
+    for (int k = 0; k < K; ++k) {
+      int32_t nb = p.ell_nb[(size_t)k * Np + c], v;
+      if (p.ell_fs[(size_t)k * Np + c] == 0) v = s;                 // padding slot, anb == 0
+      else if (nb >= N) v = nb;                                      // physical-boundary halo
+      else if (blockof[p.c2o[nb]] == blockof[e]) v = c2s[nb];
+      else { v = p.H + c2s[nb]; need_lag[c2s[nb]] = 1; }             // other block: lagged copy
+      S.nbs[(size_t)k * Np + s] = v;
+    }
+  }
+  S.lag_src.clear();
+  for (int32_t s = 0; s < N; ++s) if (need_lag[s]) S.lag_src.push_back(s);
+}
+
+}  // namespace
+
+int prepare(Prep& p, int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_idx,
+            const int32_t* ef2nb_nb, const int32_t* ef2nb_fg, const int32_t* s2g, const int32_t* bs,
+            const double* xc, const double* yc, const double* zc, int32_t nbc, const int32_t* bc_esec,
+            const int32_t* bc_kind, const double* bc_uvw, int32_t n_subdomains,
+            const int32_t* g2gf_p, const int32_t* g2gf_idx, int reorder_mode) {
+  if (ne < 1 || nf < 1 || nbf < 0) return fail(CFDL_ERR_ARG, "cfdl_create: bad sizes ne=%d nf=%d nbf=%d", ne, nf, nbf);
+  const int32_t N = ne, F = nf, B = nbf, H = ne + nbf;
+  const int64_t Z64 = 2 * (int64_t)nf - nbf;
+  if (Z64 > 0x7fffffff) return fail(CFDL_ERR_RANGE, "cfdl_create: 2nf-nbf exceeds int32");
+  const int32_t Z = (int32_t)Z64;
+  p.N = N; p.F = F; p.B = B; p.H = H; p.Z = Z;
+  p.n_subdomains = n_subdomains;
+  if (ef2nb_idx[0] != 1 || ef2nb_idx[N] - 1 != Z) return fail(CFDL_ERR_MESH, "cfdl_create: ef2nb_idx does not span 2nf-nbf slots");
+  p.row_ptr.resize((size_t)N + 1);
+  int K = 0;
+  for (int32_t e = 0; e <= N; ++e) p.row_ptr[e] = ef2nb_idx[e] - 1;
+  for (int32_t e = 0; e < N; ++e) {
+    int len = p.row_ptr[e + 1] - p.row_ptr[e];
+    if (len < 1 || len > 31) return fail(CFDL_ERR_MESH, "cfdl_create: cell %d has %d faces", e + 1, len);
+    K = std::max(K, len);
+  }
+  p.K = K;
+  p.Np = (N + 31) / 32 * 32;
+  const int32_t Np = p.Np;
+  // unpack (mod_util.f90:1428-1448)
+  std::vector<int32_t> o_nb((size_t)Z), o_fg((size_t)Z);
+  for (int32_t idx = 0; idx < Z; ++idx) {
+    uint32_t pk = (uint32_t)ef2nb_nb[idx];
+    int32_t id = (int32_t)(pk >> 5), lf = (int32_t)(pk & 31u), fg = ef2nb_fg[idx];
+    if (fg == 0 || std::abs(fg) > F) return fail(CFDL_ERR_MESH, "cfdl_create: slot %d has face id %d", idx + 1, fg);
+    if (lf > 0) { if (id < 1 || id > N) return fail(CFDL_ERR_MESH, "cfdl_create: slot %d neighbour %d out of range", idx + 1, id); }
+    else { if (id <= N || id > H || fg < 0) return fail(CFDL_ERR_MESH, "cfdl_create: slot %d halo %d out of range", idx + 1, id); }
+    o_nb[idx] = id - 1;
+    o_fg[idx] = fg;
+  }
+  // ---- device cell numbering: base order (natural | Morton), then multicolour-major --------
+  std::vector<int32_t> base((size_t)N);
+  std::iota(base.begin(), base.end(), 0);
+  p.morton = false;
+  if (reorder_mode != 0) {
+    std::vector<int32_t> mo;
+    morton_order(N, xc, yc, zc, mo);
+    bool use = (reorder_mode == 1);
+    if (reorder_mode == 2) {  // auto: adopt Morton only when the given numbering has poor locality
+      std::vector<int32_t> mrank((size_t)N);
+      for (int32_t i = 0; i < N; ++i) mrank[mo[i]] = i;
+      double dn = 0, dm = 0;
+      for (int32_t e = 0; e < N; ++e)
+        for (int32_t idx = p.row_ptr[e]; idx < p.row_ptr[e + 1]; ++idx)
+          if (o_nb[idx] < N) { dn += std::abs((double)o_nb[idx] - e); dm += std::abs((double)mrank[o_nb[idx]] - mrank[e]); }
+      use = dn > 4.0 * dm;
+    }
+    if (use) { base.swap(mo); p.morton = true; }
+  }
+  std::vector<int8_t> color((size_t)N, -1);
+  int ncol = 0;
+  for (int32_t i = 0; i < N; ++i) {  // greedy colouring in base order
+    int32_t e = base[i];
+    uint32_t used = 0;
+    for (int32_t idx = p.row_ptr[e]; idx < p.row_ptr[e + 1]; ++idx)
+      if (o_nb[idx] < N && color[o_nb[idx]] >= 0) used |= 1u << color[o_nb[idx]];
+    int c = 0;
+    while (used & (1u << c)) ++c;
+    color[e] = (int8_t)c;
+    ncol = std::max(ncol, c + 1);
+  }
+  p.ncolors = ncol;
+  p.color_ptr.assign(ncol + 1, 0);
+  for (int32_t e = 0; e < N; ++e) p.color_ptr[color[e] + 1]++;
+  for (int c = 0; c < ncol; ++c) p.color_ptr[c + 1] += p.color_ptr[c];
+  p.c2o.resize(N); p.o2c.resize(N);
+  {
+    std::vector<int32_t> cur(p.color_ptr.begin(), p.color_ptr.end() - 1);
+    for (int32_t i = 0; i < N; ++i) { int32_t e = base[i]; int32_t c = cur[color[e]]++; p.c2o[c] = e; p.o2c[e] = c; }
+  }
+  // ---- faces: interior faces in owner order, then boundary faces in halo order ------------
+  p.o2f.assign(F, -1); p.f2o.assign(F, -1);
+  int32_t nfi = 0;
+  for (int32_t c = 0; c < N; ++c) {
+    int32_t e = p.c2o[c];
+    for (int32_t idx = p.row_ptr[e]; idx < p.row_ptr[e + 1]; ++idx)
+      if (o_nb[idx] < N && o_fg[idx] > 0) {
+        int32_t f = o_fg[idx] - 1;
+        if (p.o2f[f] != -1) return fail(CFDL_ERR_MESH, "cfdl_create: face %d owned twice", f + 1);
+        p.o2f[f] = nfi; p.f2o[nfi] = f; ++nfi;
+      }
+  }
+  p.Fi = nfi;
+  if (nfi != F - B) return fail(CFDL_ERR_MESH, "cfdl_create: %d interior faces found, expected %d", nfi, F - B);
+  p.halo_cell.assign(B, -1); p.halo_face.assign(B, -1); p.halo_bc.assign(B, -1); p.halo_slot.assign(B, 0);
+  for (int32_t j = 0; j < B; ++j) {
+    uint32_t pk = (uint32_t)std::abs(bs[j]);  // sign bit is a flag, every consumer takes abs (mod_mg_lvl_uns.f90:421-433)
+    int32_t e = (int32_t)(pk >> 5) - 1, lf = (int32_t)(pk & 31u);
+    if (e < 0 || e >= N || lf < 1 || lf > p.row_ptr[e + 1] - p.row_ptr[e]) return fail(CFDL_ERR_MESH, "cfdl_create: bs(%d) invalid", N + 1 + j);
+    int32_t idx = p.row_ptr[e] + lf - 1;
+    if (o_nb[idx] != N + j) return fail(CFDL_ERR_MESH, "cfdl_create: bs(%d) does not point back to its halo", N + 1 + j);
+    int32_t f = o_fg[idx] - 1;
+    if (p.o2f[f] != -1) return fail(CFDL_ERR_MESH, "cfdl_create: boundary face %d used twice", f + 1);
+    p.o2f[f] = nfi + j; p.f2o[nfi + j] = f;
+    p.halo_cell[j] = p.o2c[e]; p.halo_slot[j] = (uint8_t)(lf - 1); p.halo_face[j] = nfi + j;
+  }
+  for (int32_t f = 0; f < F; ++f) if (p.o2f[f] < 0) return fail(CFDL_ERR_MESH, "cfdl_create: face %d is referenced by no cell", f + 1);
+  // s2g consistency (owner side carries +fg; calc_mip/update_uvwp start from it)
+  for (int32_t f = 0; f < F; ++f) {
+    uint32_t pk = (uint32_t)s2g[f];
+    int32_t e = (int32_t)(pk >> 5) - 1, lf = (int32_t)(pk & 31u);
+    if (e < 0 || e >= N || lf < 1 || p.row_ptr[e] + lf - 1 >= p.row_ptr[e + 1] || o_fg[p.row_ptr[e] + lf - 1] != f + 1)
+      return fail(CFDL_ERR_MESH, "cfdl_create: s2g(%d) is not the owner slot of the face", f + 1);
+  }
+  // ---- ELL slot arrays ---------------------------------------------------------------------
+  p.ell_nb.assign((size_t)K * Np, 0); p.ell_fs.assign((size_t)K * Np, 0); p.nfc.assign(N, 0);
+  p.face_a.assign(F, -1); p.face_b.assign(F, -1);
+  for (int32_t c = 0; c < Np; ++c)
+    for (int k = 0; k < K; ++k) p.ell_nb[(size_t)k * Np + c] = std::min(c, N - 1);
+  for (int32_t c = 0; c < N; ++c) {
+    int32_t e = p.c2o[c];
+    p.nfc[c] = (uint8_t)(p.row_ptr[e + 1] - p.row_ptr[e]);
+    for (int32_t idx = p.row_ptr[e]; idx < p.row_ptr[e + 1]; ++idx) {
+      int k = idx - p.row_ptr[e];
+      int32_t nb = o_nb[idx], fdev = p.o2f[std::abs(o_fg[idx]) - 1];
+      int32_t nbd = (nb < N) ? p.o2c[nb] : nb;
+      p.ell_nb[(size_t)k * Np + c] = nbd;
+      p.ell_fs[(size_t)k * Np + c] = (o_fg[idx] > 0) ? (fdev + 1) : -(fdev + 1);
+      if (o_fg[idx] > 0) { p.face_a[fdev] = c; p.face_b[fdev] = nbd; }
+    }
+  }
+  // ---- boundary conditions -------------------------------------------------------------------
+  p.bc_kind.assign(bc_kind, bc_kind + nbc);
+  p.bc_uvw.assign(bc_uvw, bc_uvw + 3 * (size_t)nbc);
+  for (int32_t i = 0; i < nbc; ++i) {
+    if (bc_kind[i] < CFDL_BC_WALL || bc_kind[i] > CFDL_BC_SYMMETRY) return fail(CFDL_ERR_UNSUPPORTED, "cfdl_create: bc kind %d", bc_kind[i]);
+    int32_t a = bc_esec[2 * i], b = bc_esec[2 * i + 1];
+    if (a < N + 1 || b > H || a > b + 1) return fail(CFDL_ERR_ARG, "cfdl_create: bc %d halo range [%d,%d] invalid", i, a, b);
+    for (int32_t h = a; h <= b; ++h) p.halo_bc[h - N - 1] = i;
+  }
+  // ---- level schedules reproducing the reference's sequential sweeps -------------------------
+  {
+    std::vector<int32_t> seq((size_t)N), bp = {0, N};
+    std::iota(seq.begin(), seq.end(), 0);
+    build_schedule(p, o_nb, seq, bp, p.natural);
+  }
+  if (n_subdomains > 1) {
+    if (!g2gf_p || !g2gf_idx) return fail(CFDL_ERR_ARG, "cfdl_create: n_subdomains>1 needs g2gf_p and g2gf_idx");
+    std::vector<int32_t> seq((size_t)N), bp((size_t)n_subdomains + 1);
+    std::vector<uint8_t> seen((size_t)N, 0);
+    for (int b = 0; b <= n_subdomains; ++b) bp[b] = g2gf_idx[b] - 1;
+    if (bp[0] != 0 || bp[n_subdomains] != N) return fail(CFDL_ERR_ARG, "cfdl_create: g2gf_idx must span 1..ne+1");
+    for (int32_t i = 0; i < N; ++i) {
+      int32_t e = g2gf_p[i] - 1;
+      if (e < 0 || e >= N || seen[e]) return fail(CFDL_ERR_ARG, "cfdl_create: g2gf_p is not a permutation of the cells");
+      seen[e] = 1; seq[i] = e;
+    }
+    build_schedule(p, o_nb, seq, bp, p.blocks);
+  }
+  return CFDL_OK;
+}
+
+}  // namespace cfdl

@@ -1,0 +1,100 @@
+// Device-resident state of one mesh (one GPU): SoA cell/face arrays in the device numbering
+// chosen by prep.cpp, fields of uvwp_t/phys_t (src/equations/mod_uvwp.f90:6-16,
+// src/modules/mod_physics.f90:30), and solver work space.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <vector>
+#include "cfdl_common.h"
+#include "prep.h"
+
+namespace cfdl {
+
+#define CFDL_CUDA(call)                                                                          \
+  do {                                                                                           \
+    cudaError_t err__ = (call);                                                                  \
+    if (err__ != cudaSuccess)                                                                    \
+      return ::cfdl::fail(CFDL_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(err__)); \
+  } while (0)
+
+// per-solve control block, lives in device memory; kernels of an iteration return at once
+// when done != 0 so a batch of iterations can be enqueued without a host round trip
+struct SolveCtl {
+  int it, done, nit, pad;
+  double res_i, res_f, res_max, res_target;
+  unsigned int ticket, pad2;
+};
+
+struct DevSchedule {
+  int nlevels = 0, nblocks = 1, nlag = 0;
+  int32_t *lvl_ptr = nullptr, *s2c = nullptr, *nbs = nullptr, *bpos = nullptr, *lag_src = nullptr;
+  std::vector<int32_t> blk_ptr;
+  int max_level_cells = 0;
+};
+
+struct Handle {
+  Prep prep;
+  int device = 0, num_sms = 0;
+  cudaStream_t stream = nullptr;
+  int32_t N = 0, F = 0, B = 0, H = 0, Z = 0, K = 0, Np = 0, Fi = 0;
+  int solver_mode = CFDL_SOLVER_PARITY;
+  std::vector<void*> allocs;  // everything cudaMalloc'ed, freed in destroy
+  // mesh
+  int32_t *ell_nb = nullptr, *ell_fs = nullptr, *face_a = nullptr, *face_b = nullptr;
+  int32_t *halo_cell = nullptr, *halo_face = nullptr, *halo_bc = nullptr, *bc_kind = nullptr;
+  int32_t *c2o = nullptr, *o2c = nullptr, *f2o = nullptr, *row_ptr = nullptr;
+  uint8_t *nfc = nullptr, *halo_slot = nullptr;
+  double *bc_uvw = nullptr, *xc = nullptr, *yc = nullptr, *zc = nullptr, *aip = nullptr, *rip = nullptr;
+  double *vol = nullptr, *rho = nullptr, *mu = nullptr;
+  // fields, indexed by CFDL_F_*
+  double* fld[CFDL_F_COUNT] = {nullptr};
+  // staging + solver work
+  double* stage = nullptr;      // max(3H, Z, F) doubles for permuted host transfers
+  size_t stage_len = 0;
+  double* partial = nullptr;    // per-CTA reduction partials
+  int partial_len = 0;
+  SolveCtl* ctl = nullptr;      // device
+  SolveCtl* ctl_host = nullptr; // pinned
+  double* scal = nullptr;       // small device scalars (pref, ...)
+  double* scal_host = nullptr;  // pinned mirror / readback area (64 doubles)
+  unsigned int* barrier = nullptr;
+  // parity (level-scheduled) solver work: sweep-space copies
+  DevSchedule natural, blocks;
+  double *ap_s = nullptr, *b_s = nullptr, *anb_s = nullptr, *phi_s = nullptr, *rr = nullptr, *rsig = nullptr;
+  int coop_ctas = 0;
+  int32_t* color_ptr_host() { return prep.color_ptr.data(); }
+};
+
+// launch geometry helper: grids are sized as a multiple of the SM count (B200: 148)
+inline int grid_for(const Handle* h, int64_t n, int threads, int ctas_per_sm = 8) {
+  int64_t need = (n + threads - 1) / threads;
+  int64_t cap = (int64_t)h->num_sms * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// ---- kernels_assembly.cu
+int k_update_boundaries(Handle* h);
+int k_calc_coef_uvw(Handle* h, double dt);
+int k_calc_mip(Handle* h, bool rhie_chow, double dt);
+int k_calc_coef_p(Handle* h);
+int k_adjust_pc(Handle* h);
+int k_update_uvwp(Handle* h);
+int k_calc_grad(Handle* h, const double* phi, double* grad);
+int k_calc_grad3(Handle* h);  // gu,gv,gw from u,v,w in one pass
+int k_update_time(Handle* h);
+int k_gather(Handle* h, double* dst, const double* src, const int32_t* map, int64_t n, int ncomp);
+int k_scatter(Handle* h, double* dst, const double* src, const int32_t* map, int64_t n, int ncomp);
+int k_csr_to_ell(Handle* h, double* ell, const double* csr);
+int k_ell_to_csr(Handle* h, double* csr, const double* ell);
+// ---- kernels_solver.cu
+int solver_init(Handle* h);
+// dispatch=false: solve_gs (mod_solver.f90:255); dispatch=true: solve() (:329), i.e. the block
+// solver when the handle has n_subdomains>1
+int solve_equation(Handle* h, int eq, double* phi, const double* rhs, int nit, double* out4, bool dispatch);
+
+int residual_plain(Handle* h, const double* phi, const double* rhs, bool signed_max, double* res, double* res_max);
+
+}  // namespace cfdl
+
+struct cfdl_handle_s : public cfdl::Handle {};

@@ -180,6 +180,13 @@ class Solver:
         _chk(lib().cfdl_get_info(self.h, key.encode(), C.byref(v)))
         return v.value
 
+    def cell_order(self):
+        nc = int(self.get_info("ncolors"))
+        c2o = np.zeros(self.ne, np.int32)
+        cp = np.zeros(nc + 1, np.int32)
+        _chk(lib().cfdl_get_cell_order(self.h, _i(c2o), _i(cp)))
+        return c2o, cp
+
     def upload(self, name, arr):
         arr = _f64(arr)
         assert arr.size == self.field_size(name), (name, arr.size, self.field_size(name))

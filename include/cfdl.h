@@ -101,6 +101,10 @@ int cfdl_destroy(cfdl_handle h);
 /* options: "solver" (CFDL_SOLVER_*), "reorder" (0/1, set before first use) ... */
 int cfdl_set_option(cfdl_handle h, const char* key, double value);
 int cfdl_get_info(cfdl_handle h, const char* key, double* value);
+/* device cell numbering (colour-major, optionally Morton inside a colour): c2o[i] = 1-based
+ * reference cell stored at device position i; colour c occupies [color_ptr[c], color_ptr[c+1]).
+ * color_ptr has ncolors+1 entries ("ncolors" via cfdl_get_info); either pointer may be NULL. */
+int cfdl_get_cell_order(cfdl_handle h, int32_t* c2o, int32_t* color_ptr);
 
 /* ---- host <-> device field sync (for write_vtubin, main.f90:79,89) */
 int cfdl_upload_field(cfdl_handle h, int field, const double* host);

@@ -1,0 +1,51 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "cfd-lite_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def cfdl():
+    import cfdl as m
+    return m
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import oracle as m
+    m.build()
+    return m
+
+
+def make_case(cfdl, oracle, kind, n, jitter=0.0, shuffle=False, n_subdomains=1, seed=12345):
+    """Synthetic mesh -> (raw, oracle case, geometry dict in the reference's array format)."""
+    raw = cfdl.meshgen(kind, n, jitter=jitter, shuffle=shuffle, seed=seed)
+    oc = oracle.OracleCase(raw, n_subdomains=n_subdomains)
+    geom = dict(ne=oc.ne, nf=oc.nf, nbf=oc.nbf)
+    for k in ("ef2nb_idx", "ef2nb_nb", "ef2nb_fg", "s2g", "bs", "xc", "yc", "zc", "aip", "rip", "vol"):
+        geom[k] = oc[k].copy()
+    return raw, oc, geom
+
+
+def make_solver(cfdl, raw, oc, geom, **kw):
+    bcs = oc.bc_table()
+    if oc.n_subdomains > 1:
+        return cfdl.Solver(geom, bcs, n_subdomains=oc.n_subdomains, g2gf_p=oc["g2gf_p"].copy(), g2gf_idx=oc["g2gf_idx"].copy(), **kw)
+    return cfdl.Solver(geom, bcs, **kw)
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = max(np.abs(b).max(), 1e-300)
+    return np.abs(a - b).max() / scale

@@ -1,0 +1,266 @@
+"""GPU parity tests: every CUDA routine of the hot path, called through the C ABI
+(include/cfdl.h via cfd-lite_b200/python/cfdl.py), against the CPU oracle on the same inputs.
+
+Tolerances (FP64): north_star asks 1e-10 relative on residual history and final fields for
+the box case.  Per-routine checks use 1e-12; because the kernels follow the reference's
+operation order without FMA contraction most of them are in fact bit-identical, which the
+tests report through `exact` asserts where that is guaranteed by construction.
+"""
+import numpy as np
+import pytest
+
+from conftest import make_case, make_solver, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_ROUTINE = 1e-12
+TOL_RUN = 1e-10
+
+CASES = {
+    "hex8_sub4": dict(kind=0, n=8, n_subdomains=4),
+    "hex6_jitter": dict(kind=0, n=6, jitter=0.25, n_subdomains=1),
+    "tet4_shuffled": dict(kind=1, n=4, jitter=0.2, shuffle=True, n_subdomains=1),
+    "tet3_sub2": dict(kind=1, n=3, jitter=0.2, shuffle=True, n_subdomains=2),
+}
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request, cfdl, oracle):
+    raw, oc, geom = make_case(cfdl, oracle, **CASES[request.param])
+    s = make_solver(cfdl, raw, oc, geom)
+    yield request.param, raw, oc, geom, s
+    s.close()
+
+
+STATE = "u v w p u0 v0 w0 gu gv gw gp gpc mip mip0".split()
+
+
+def randomize(oc, s, seed=7):
+    """Same random state on both sides (halo entries included)."""
+    rng = np.random.default_rng(seed)
+    for name in STATE:
+        a = oc[name]
+        a[:] = rng.standard_normal(a.size) * (0.01 if name.startswith("mip") else 1.0)
+        s.upload(name, a)
+    pc = oc["phic"]
+    pc[:] = rng.standard_normal(pc.size)
+    s.upload("pc", pc)
+
+
+def check(name, got, want, tol=TOL_ROUTINE):
+    err = rel_err(got, want)
+    assert err <= tol, "%s: rel err %.3e > %.1e" % (name, err, tol)
+    return err
+
+
+def test_update_boundaries(case):
+    _, raw, oc, geom, s = case
+    randomize(oc, s)
+    oc.update_boundaries()
+    s.update_boundaries()
+    for f in ("u", "v", "w", "p", "mip"):
+        assert np.array_equal(s.download(f), oc[f]), f
+
+
+def test_calc_coef_uvw(case):
+    _, raw, oc, geom, s = case
+    randomize(oc, s, seed=11)
+    oc.update_boundaries(); s.update_boundaries()
+    oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)
+    for f in ("ap", "anb", "bu", "bv", "bw", "d", "dc"):
+        check(f, s.download(f), oc[f])
+
+
+def test_calc_grad(case):
+    _, raw, oc, geom, s = case
+    randomize(oc, s, seed=13)
+    for phi, g in (("u", "gu"), ("v", "gv"), ("w", "gw"), ("p", "gp"), ("pc", "gpc")):
+        want = oc.calc_grad(oc["phic" if phi == "pc" else phi])
+        s.calc_grad(phi, g)
+        got = s.download(g)
+        check(g, got[:3 * oc.ne], want[:3 * oc.ne])
+    # stand-alone drop-in with host arrays
+    phi = np.random.default_rng(3).standard_normal(oc.ne + oc.nbf)
+    check("host_calc_grad", s.host_calc_grad(phi)[:3 * oc.ne], oc.calc_grad(phi)[:3 * oc.ne])
+
+
+def test_lsq_gradient_is_exact_for_linear_fields(case):
+    """KAT lsq-linear (mod_solver.f90:48-79): exact gradient of a linear field on any mesh."""
+    _, raw, oc, geom, s = case
+    g = np.array([0.3, -1.7, 2.2])
+    phi = 0.5 + g[0] * oc["xc"] + g[1] * oc["yc"] + g[2] * oc["zc"]
+    got = s.host_calc_grad(phi)[:3 * oc.ne].reshape(-1, 3)
+    assert np.abs(got - g).max() < 1e-9
+
+
+@pytest.mark.parametrize("rhie_chow", [False, True])
+def test_calc_mip(case, rhie_chow):
+    _, raw, oc, geom, s = case
+    randomize(oc, s, seed=17)
+    oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)  # provides d
+    oc.calc_mip(rhie_chow); s.calc_mip(rhie_chow, dt=0.01)
+    check("mip", s.download("mip"), oc["mip"])
+
+
+def test_calc_coef_p(case):
+    _, raw, oc, geom, s = case
+    randomize(oc, s, seed=19)
+    oc.update_boundaries(); s.update_boundaries()
+    oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)
+    oc.calc_coef_p(); s.calc_coef_p()
+    for f in ("ap", "anb", "b"):
+        check(f, s.download(f), oc[f])
+    # KAT pc-matrix: ap == sum anb (singular Neumann operator), anb symmetric
+    ap, anb = s.download("ap"), s.download("anb")
+    idx = geom["ef2nb_idx"] - 1
+    rows = np.add.reduceat(anb, idx[:-1])
+    assert np.abs(rows - ap).max() <= 1e-12 * np.abs(ap).max()
+
+
+def test_adjust_pc_and_update_uvwp(case):
+    _, raw, oc, geom, s = case
+    randomize(oc, s, seed=23)
+    oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)  # provides dc
+    oc.adjust_pc(); s.adjust_pc()
+    assert np.array_equal(s.download("pc"), oc["phic"])
+    oc["gpc"][:] = oc.calc_grad(oc["phic"]); s.calc_grad("pc", "gpc")
+    oc.update_uvwp(); s.update_uvwp()
+    for f in ("p", "gp", "mip"):
+        check(f, s.download(f)[:len(oc[f])], oc[f])
+
+
+def assembled_system(oc):
+    rng = np.random.default_rng(29)
+    for name in STATE:
+        a = oc[name]
+        a[:] = rng.standard_normal(a.size) * (0.01 if name.startswith("mip") else 0.1)
+    oc.update_boundaries()
+    oc.calc_coef_uvw()
+    return oc["ap"].copy(), oc["anb"].copy(), oc["bu"].copy(), oc["u"].copy()
+
+
+def test_solve_gs_parity_mode(case, oracle):
+    """Level-scheduled natural-order SGS == the sequential sweeps of solve_gs, bit for bit."""
+    _, raw, oc, geom, s = case
+    ap, anb, b, phi0 = assembled_system(oc)
+    s.set_option("solver", 0)
+    for eq, is_pc in ((0, False), (3, True)):
+        want_phi, want = oracle.flat_solve_gs(is_pc, phi0, ap, anb, b, geom["ef2nb_idx"], geom["ef2nb_nb"], nit=7)
+        got_phi, got = s.host_solve_gs(eq, phi0, ap, anb, b, nit=7)
+        assert got[0] == want[0], (got, want)
+        assert np.array_equal(got_phi[:oc.ne], want_phi[:oc.ne]), "phi differs by %.3e" % rel_err(got_phi[:oc.ne], want_phi[:oc.ne])
+        check("res_i", got[1], want[1], 1e-12)
+        check("res_f", got[2], want[2], 1e-12)
+        if want[0] > 0:
+            check("res_max", got[3], want[3], 1e-12)
+
+
+def test_calc_residual(case, oracle):
+    _, raw, oc, geom, s = case
+    ap, anb, b, phi0 = assembled_system(oc)
+    want = oracle.flat_calc_residual(phi0, ap, anb, b, geom["ef2nb_idx"], geom["ef2nb_nb"])
+    got = s.host_calc_residual(phi0, ap, anb, b)
+    check("res", got[0], want[0], 1e-12)
+    check("res_max", got[1], want[1], 1e-12)
+
+
+def test_solve_dispatcher_block_sgs(case):
+    """solve('pc',...) == multi_subdomain_solver for n_subdomains>1 (incl. its residual quirks)."""
+    name, raw, oc, geom, s = case
+    rng = np.random.default_rng(31)
+    for nm in STATE:
+        a = oc[nm]
+        a[:] = rng.standard_normal(a.size) * (0.01 if nm.startswith("mip") else 0.1)
+    oc.update_boundaries(); oc.calc_coef_uvw(); oc.calc_coef_p()
+    ap, anb, b = oc["ap"].copy(), oc["anb"].copy(), oc["b"].copy()
+    phi0 = np.zeros(oc.ne + oc.nbf)
+    s.set_option("solver", 0)
+    want_phi, want = oc.solve(True, ap, anb, b, phi0, nit=20)
+    got_phi, got = s.host_solve(3, phi0, ap, anb, b, nit=20)
+    assert got[0] == want[0], (got, want)
+    assert np.array_equal(got_phi[:oc.ne], want_phi[:oc.ne]), "phi differs by %.3e" % rel_err(got_phi[:oc.ne], want_phi[:oc.ne])
+    for k in (1, 2, 3):
+        check("stat%d" % k, got[k], want[k], 1e-12)
+
+
+def test_mcsgs_equals_solve_gs_on_colour_permuted_system(case, oracle):
+    """Fast mode = the reference's solve_gs applied to the colour-major renumbered system."""
+    _, raw, oc, geom, s = case
+    ap, anb, b, phi0 = assembled_system(oc)
+    c2o, cp = s.cell_order()
+    ne = oc.ne
+    o2c = np.zeros(ne, np.int64)
+    o2c[c2o - 1] = np.arange(ne)
+    idx = geom["ef2nb_idx"].astype(np.int64) - 1
+    nb_packed = geom["ef2nb_nb"].astype(np.int64)
+    lens = np.diff(idx)
+    p_idx = np.concatenate([[0], np.cumsum(lens[c2o - 1])])
+    p_nb = np.zeros_like(nb_packed)
+    p_anb = np.zeros_like(anb)
+    for c in range(ne):
+        e = c2o[c] - 1
+        sl = slice(idx[e], idx[e + 1])
+        nbid = nb_packed[sl] >> 5
+        lf = nb_packed[sl] & 31
+        new = np.where(lf > 0, o2c[np.minimum(nbid, ne) - 1] + 1, nbid)
+        p_nb[p_idx[c]:p_idx[c + 1]] = (new << 5) | lf
+        p_anb[p_idx[c]:p_idx[c + 1]] = anb[sl]
+    perm_phi = np.concatenate([phi0[c2o - 1], phi0[ne:]])
+    s.set_option("solver", 1)
+    try:
+        for eq, is_pc in ((0, False), (3, True)):
+            want_phi, want = oracle.flat_solve_gs(is_pc, perm_phi, ap[c2o - 1], p_anb, b[c2o - 1], (p_idx + 1).astype(np.int32),
+                                                  p_nb.astype(np.int32), nit=9)
+            got_phi, got = s.host_solve_gs(eq, phi0, ap, anb, b, nit=9)
+            assert got[0] == want[0], (got, want)
+            assert np.array_equal(got_phi[c2o - 1], want_phi[:ne]), "phi differs by %.3e" % rel_err(got_phi[c2o - 1], want_phi[:ne])
+            check("res_f", got[2], want[2], 1e-12)
+    finally:
+        s.set_option("solver", 0)
+
+
+def test_run_parity(case):
+    """main.f90:50-63 schedule (2 steps x 3 iterations): history and fields within 1e-10."""
+    name, raw, oc, geom, s0 = case
+    from conftest import make_case as mk
+    import cfdl as cf
+    import oracle as orc
+    raw, oc, geom = mk(cf, orc, **CASES[name])
+    s = make_solver(cf, raw, oc, geom)
+    try:
+        want_hist, _ = oc.run(2, 3)
+        got_hist = s.run(dt=0.01, nit=100, ntstep=2, ncoef=3)
+        assert np.array_equal(got_hist[:, :, 0], want_hist[:, :, 0]), "iteration counts differ"
+        for k, nm in ((1, "res_i"), (2, "res_f")):
+            assert rel_err(got_hist[:, :, k], want_hist[:, :, k]) <= TOL_RUN, nm
+        ran = want_hist[:, :, 0] > 0  # res_max is undefined in the reference when no iteration ran
+        assert rel_err(got_hist[:, :, 3][ran], want_hist[:, :, 3][ran]) <= TOL_RUN
+        for f in ("u", "v", "w", "p", "mip"):
+            check(f, s.download(f), oc[f], TOL_RUN)
+    finally:
+        s.close()
+
+
+def test_box_standin_full_schedule(cfdl, oracle):
+    """Config #1: box stand-in (32^3 hex), reference defaults: n_subdomains=4, dt=0.01,
+    nit=100, 10 time steps x 3 iterations.  Residual history and final u,v,w,p to 1e-10."""
+    raw, oc, geom = make_case(cfdl, oracle, kind=0, n=32, n_subdomains=4)
+    s = make_solver(cfdl, raw, oc, geom)
+    try:
+        want_hist, _ = oc.run(10, 3)
+        got_hist = s.run(dt=0.01, nit=100, ntstep=10, ncoef=3)
+        assert np.array_equal(got_hist[:, :, 0], want_hist[:, :, 0])
+        assert rel_err(got_hist[:, :, 1:3], want_hist[:, :, 1:3]) <= TOL_RUN
+        for f in ("u", "v", "w", "p"):
+            check(f, s.download(f), oc[f], TOL_RUN)
+    finally:
+        s.close()
+
+
+def test_create_rejects_bad_mesh(cfdl, oracle):
+    raw, oc, geom = make_case(cfdl, oracle, kind=0, n=3)
+    bad = dict(geom)
+    bad["ef2nb_fg"] = geom["ef2nb_fg"].copy()
+    bad["ef2nb_fg"][0] = 0
+    with pytest.raises(cfdl.CfdlError):
+        cfdl.Solver(bad, oc.bc_table())
