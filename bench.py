@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py — SIMPLE hot path of CFD-Lite on B200: cell-iterations/s.
+
+A "step" is one SIMPLE iteration of src/main.f90:50-63 on the synthetic lid-driven-cavity
+mesh: update_boundaries + solve_uvwp (assembly, three momentum solves, gradients, Rhie-Chow,
+pressure-correction assembly + solve, correction), plus update_time after every third step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--n 128] [--mesh hex|tet] [--solver mcsgs|parity|pcg]
+
+ours       the CUDA library through its C ABI (include/cfdl.h).  `value` is timed with CUDA
+           events on the library's stream with all state resident in HBM; `e2e` repeats the
+           steps with the step's input fields uploaded from pinned host memory and the results
+           downloaded inside the timed region (what a host driver that owns the arrays pays).
+reference  the reference's own CPU algorithm (the C++ oracle, one thread: the reference is
+           serial Fortran and cannot be compiled here) on the same workload.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "cfd-lite_b200", "python"))
+
+SOLVERS = {"parity": 0, "mcsgs": 1, "pcg": 2}
+DT, NIT, NCOEF = 0.01, 100, 3  # reference defaults, src/modules/mod_physics.f90:15-18
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()  # exact PID of the sampler we started
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_mesh(cfdl, kind, n):
+    raw = cfdl.meshgen(cfdl.MESH_HEX if kind == "hex" else cfdl.MESH_TET, n, jitter=0.0 if kind == "hex" else 0.2,
+                       shuffle=(kind == "tet"), seed=12345)
+    geom = cfdl.mesh_build(raw)
+    return raw, geom
+
+
+def workload_name(kind, n, ne):
+    return "lid-driven cavity, synthetic %s mesh n=%d (%d cells), rho=5 mu=0.01 dt=0.01 nit=100" % (
+        "%d^3 hex" % n if kind == "hex" else "Kuhn-tet (jitter 0.2h, shuffled ids)", n, ne)
+
+
+def algorithmic_bytes(ne, nf, nbf, K):
+    """SURVEY §8(d) / BASELINE.md §3 per-launch algorithmic bytes of the solver kernels."""
+    Z, H = 2 * nf - nbf, ne + nbf
+    return {"sgs_sweep": 28 * ne + 12 * Z + 8 * H, "residual": 20 * ne + 12 * Z + 8 * H}
+
+
+def run_reference(args, rank):
+    """Reference arm: the reference's CPU algorithm (oracle port, 1 thread) on the same workload."""
+    if rank != 0:
+        return
+    import cfdl
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    raw, geom = build_mesh(cfdl, args.mesh, args.n)
+    oc = oracle.OracleCase(raw, n_subdomains=4, geom=geom)  # reference default n_subdomains=4
+    oc.set_param("dt", DT); oc.set_param("nit", NIT)
+
+    def step(i):
+        oc.update_boundaries()
+        oc.solve_uvwp()
+        if (i + 1) % NCOEF == 0:
+            oc.update_time()
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    sec = time.perf_counter() - t0
+    value = oc.ne * args.steps / sec
+    line = {"impl": "reference", "metric": "cell-iterations/s (SIMPLE)", "value": value, "unit": "cell-iterations/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.mesh, args.n, oc.ne), "n_subdomains": 4,
+                       "solver": "reference block-SGS (multi_subdomain_solver) + natural-order SGS"},
+            "cpu_baseline": {"value": value, "unit": "cell-iterations/s", "cores": 1, "kind": "port",
+                             "sample": "%d SIMPLE iterations of the full workload after %d warm-up iterations; C++ oracle "
+                                       "(g++ -O3 -ffp-contract=off, 1 thread: the reference is serial and has no OpenMP)" % (args.steps, args.warmup)},
+            "e2e": {"value": value, "unit": "cell-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=128)
+    ap.add_argument("--mesh", default="hex", choices=["hex", "tet"])
+    ap.add_argument("--solver", default="mcsgs", choices=list(SOLVERS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if args.steps is None:
+            args.steps = 2
+        if args.warmup is None:
+            args.warmup = 1
+        run_reference(args, rank)
+        return
+    if args.steps is None:
+        args.steps = 30
+    if args.warmup is None:
+        args.warmup = 3
+    args.warmup = max(args.warmup, 3)
+
+    import cfdl
+    if cfdl.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    raw, geom = build_mesh(cfdl, args.mesh, args.n)
+    s = cfdl.Solver(geom, cfdl.default_bcs(raw), device=local_rank)
+    s.set_option("solver", SOLVERS[args.solver])
+    ne, nf, nbf, H = s.ne, s.nf, s.nbf, s.H
+
+    def step(i):
+        s.update_boundaries()
+        s.solve_uvwp(DT, NIT)
+        if (i + 1) % NCOEF == 0:
+            s.update_time()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- value: device-resident steps, CUDA events on the library's stream -------------------
+    for i in range(args.warmup):
+        step(i)
+    hist_last = None
+    sampler = ClockSampler(local_rank)
+    barrier()
+    s.set_option("reset_counters", 1)
+    sampler.start()
+    s.timer_record(0)
+    for i in range(args.steps):
+        s.update_boundaries()
+        hist_last = s.solve_uvwp(DT, NIT)
+        if (args.warmup + i + 1) % NCOEF == 0:
+            s.update_time()
+    s.timer_record(1)
+    ms = s.timer_elapsed_ms(0, 1)
+    barrier()
+    clocks = sampler.stop()
+    launches = int(s.get_info("launches"))
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * ne * args.steps / (ms * 1e-3)
+
+    # ---- roofline: per-launch CUDA-event timing of the dominant kernel over the same steps ----
+    peak, peak_src = peaks()
+    s.set_option("profile", 1)
+    s.set_option("reset_counters", 1)
+    nprof = min(args.steps, 6)
+    for i in range(nprof):
+        step(args.warmup + args.steps + i)
+    kinds = ("sgs", "residual", "levels", "coef_uvw", "coef_p", "mip", "grad", "pcg")
+    prof = {k: (s.get_info("prof_ms_" + k), int(s.get_info("prof_n_" + k))) for k in kinds}
+    s.set_option("profile", 0)
+    ab = algorithmic_bytes(ne, nf, nbf, int(s.get_info("ell_width")))
+    ncol = int(s.get_info("ncolors"))
+    roof = None
+    extra_roof = {}
+    if prof["sgs"][1] > 0:
+        # one colour launch updates 1/ncolors of the cells: a full sweep = ncolors launches
+        per_launch = ab["sgs_sweep"] / ncol
+        avg_ms = prof["sgs"][0] / prof["sgs"][1]
+        ach = per_launch / (avg_ms * 1e-3) / 1e9
+        roof = {"kernel": "sgs_range_kernel (one colour of a Gauss-Seidel sweep)", "bound": "hbm", "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": per_launch, "avg_launch_ms": avg_ms, "launches_timed": prof["sgs"][1]}
+    if prof["residual"][1] > 0:
+        avg_ms = prof["residual"][0] / prof["residual"][1]
+        ach = ab["residual"] / (avg_ms * 1e-3) / 1e9
+        extra_roof["residual_spmv"] = {"achieved": ach, "frac": ach / peak, "unit": "GB/s", "bytes_per_launch": ab["residual"],
+                                       "avg_launch_ms": avg_ms, "launches_timed": prof["residual"][1]}
+    if roof is None and prof["levels"][1] > 0:
+        # parity mode: one persistent launch = one (or two) symmetric iterations over all levels
+        it_per_launch = 2 if (args.solver == "parity" and False) else 1
+        avg_ms = prof["levels"][0] / prof["levels"][1]
+        per_launch = 2 * ab["sgs_sweep"] * it_per_launch
+        ach = per_launch / (avg_ms * 1e-3) / 1e9
+        roof = {"kernel": "level_sgs_kernel (persistent level-scheduled exact SGS, latency-bound by design)", "bound": "hbm",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": per_launch, "avg_launch_ms": avg_ms, "launches_timed": prof["levels"][1]}
+    phase_ms = {k: prof[k][0] / nprof for k in kinds if prof[k][1] > 0}
+
+    # ---- e2e: same steps through the C ABI with host buffers inside the timed region ----------
+    e2e = None
+    if not args.no_e2e:
+        ins = "u v w p u0 v0 w0 gu gv gw gp mip mip0".split()
+        outs = "u v w p gp gpc mip".split()
+        bufs = {k: cfdl.PinnedBuffer(s.field_size(k)) for k in set(ins + outs)}
+        for k in ins:
+            s.download_into(k, bufs[k].array)
+        h2d = 8 * sum(s.field_size(k) for k in ins)
+        d2h = 8 * sum(s.field_size(k) for k in outs) + 8 * 16
+        ne2e = min(args.steps, 10)
+        base = args.warmup + args.steps + nprof
+
+        def e2e_step(i):
+            for k in ins:
+                s.upload(k, bufs[k].array)
+            s.update_boundaries()
+            s.solve_uvwp(DT, NIT)
+            if (i + 1) % NCOEF == 0:
+                s.update_time()
+                s.download_into("u0", bufs["u0"].array); s.download_into("v0", bufs["v0"].array)
+                s.download_into("w0", bufs["w0"].array); s.download_into("mip0", bufs["mip0"].array)
+            for k in outs:
+                s.download_into(k, bufs[k].array)
+
+        e2e_step(base)
+        barrier()
+        t0 = time.perf_counter()
+        s.timer_record(2)
+        for i in range(ne2e):
+            e2e_step(base + 1 + i)
+        s.timer_record(3)
+        ms_e = s.timer_elapsed_ms(2, 3)
+        wall_e = (time.perf_counter() - t0) * 1e3
+        ms_e = max(ms_e, wall_e)  # the host side of the copies counts too
+        if dist is not None:
+            import torch
+            t = torch.tensor([ms_e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e = float(t.item())
+        e2e = {"value": world * ne * ne2e / (ms_e * 1e-3), "unit": "cell-iterations/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": ne2e, "ms_per_step": ms_e / ne2e,
+               "what": "per step: upload u,v,w,p,u0,v0,w0,gu,gv,gw,gp,mip,mip0 from pinned host memory, update_boundaries + "
+                       "solve_uvwp through the C ABI, download u,v,w,p,gp,gpc,mip and the residual history"}
+        for b in bufs.values():
+            b.free()
+
+    # ---- cpu_baseline: the oracle on a bounded sample of the same workload (rank 0, N=1) -------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+        oc = oracle.OracleCase(raw, n_subdomains=4, geom=geom)
+        nsamp = 2 if ne > 500000 else 6
+        _, sec = oc.run(1, nsamp)
+        cpu = {"value": ne * nsamp / sec, "unit": "cell-iterations/s", "cores": 1, "kind": "port",
+               "sample": "%d SIMPLE iterations of the same mesh from the initial state, reference defaults incl. n_subdomains=4; "
+                         "C++ oracle, 1 thread (the reference is serial Fortran, not buildable here)" % nsamp,
+               "seconds": sec}
+        del oc
+
+    if rank == 0:
+        line = {"metric": "cell-iterations/s (SIMPLE)", "value": value, "unit": "cell-iterations/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(args.mesh, args.n, ne), "solver": args.solver, "ncolors": ncol,
+                           "cells_per_gpu": ne, "l2": "working set (>1 GB) exceeds the 126 MB L2; no flush needed" if ne > 1000000 else
+                           "working set may fit L2",
+                           "parallelism": "1 GPU" if world == 1 else "%d independent replicas (partitioned multi-GPU path not built yet)" % world,
+                           "last_step_history(it,res_i,res_f,res_max)": hist_last.tolist() if hist_last is not None else None},
+                "roofline": roof, "roofline_other": extra_roof, "phase_ms_per_step": phase_ms, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": launches, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    s.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -193,6 +193,8 @@ int cfdl_destroy(cfdl_handle h) {
   if (!h) return CFDL_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (cudaEvent_t e : h->prof_ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->timer_ev) if (e) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
   if (h->ctl_host) cudaFreeHost(h->ctl_host);
   if (h->scal_host) cudaFreeHost(h->scal_host);
@@ -209,6 +211,17 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
     h->solver_mode = m;
     return CFDL_OK;
   }
+  if (!std::strcmp(key, "profile")) {
+    int rc = prof_collect(h);
+    h->profile = value != 0.0;
+    return rc;
+  }
+  if (!std::strcmp(key, "reset_counters")) {
+    int rc = prof_collect(h);
+    h->launches = 0;
+    for (int k = 0; k < 8; ++k) { h->prof_ms[k] = 0.0; h->prof_n[k] = 0; }
+    return rc;
+  }
   return fail(CFDL_ERR_ARG, "cfdl_set_option: unknown key '%s'", key);
 }
 
@@ -221,6 +234,17 @@ int cfdl_get_info(cfdl_handle h, const char* key, double* value) {
   else if (!std::strcmp(key, "ell_width")) *value = h->K;
   else if (!std::strcmp(key, "num_sms")) *value = h->num_sms;
   else if (!std::strcmp(key, "solver")) *value = h->solver_mode;
+  else if (!std::strcmp(key, "launches")) *value = (double)h->launches;
+  else if (!std::strncmp(key, "prof_ms_", 8) || !std::strncmp(key, "prof_n_", 7)) {
+    static const char* names[8] = {"sgs", "residual", "coef_uvw", "coef_p", "mip", "grad", "levels", "pcg"};
+    const bool is_ms = key[5] == 'm';
+    const char* nm = key + (is_ms ? 8 : 7);
+    int rc = prof_collect(h);
+    if (rc) return rc;
+    for (int k = 0; k < 8; ++k)
+      if (!std::strcmp(nm, names[k])) { *value = is_ms ? h->prof_ms[k] : (double)h->prof_n[k]; return CFDL_OK; }
+    return fail(CFDL_ERR_ARG, "cfdl_get_info: unknown kernel kind '%s'", nm);
+  }
   else return fail(CFDL_ERR_ARG, "cfdl_get_info: unknown key '%s'", key);
   return CFDL_OK;
 }

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(TPB) bc_kernel(int B, int N, const int32_t* __
 
 int k_update_boundaries(Handle* h) {
   if (h->B == 0) return CFDL_OK;
-  bc_kernel<<<grid_for(h, h->B, TPB), TPB, 0, h->stream>>>(h->B, h->N, h->halo_cell, h->halo_face, h->halo_bc, h->bc_kind,
+  bc_kernel<<<grid_for(h, h->B, TPB), TPB, 0, S(h)>>>(h->B, h->N, h->halo_cell, h->halo_face, h->halo_bc, h->bc_kind,
                                                             h->bc_uvw, h->aip, h->fld[CFDL_F_U], h->fld[CFDL_F_V],
                                                             h->fld[CFDL_F_W], h->fld[CFDL_F_P], h->fld[CFDL_F_MIP]);
   CFDL_CUDA(cudaGetLastError());
@@ -205,9 +205,11 @@ int k_calc_coef_uvw(Handle* h, double dt) {
   A.bw = h->fld[CFDL_F_BW]; A.d = h->fld[CFDL_F_D]; A.dc = h->fld[CFDL_F_DC];
   A.dt = dt;
   const int g = grid_for(h, h->N, TPB);
-  if (h->K <= 4) coef_uvw_kernel<4><<<g, TPB, 0, h->stream>>>(A);
-  else if (h->K <= 6) coef_uvw_kernel<6><<<g, TPB, 0, h->stream>>>(A);
+  prof_begin(h, PROF_COEF_UVW);
+  if (h->K <= 4) coef_uvw_kernel<4><<<g, TPB, 0, S(h)>>>(A);
+  else if (h->K <= 6) coef_uvw_kernel<6><<<g, TPB, 0, S(h)>>>(A);
   else return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
+  prof_end(h);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
@@ -276,9 +278,11 @@ int k_calc_coef_p(Handle* h) {
   const int g = grid_for(h, h->N, TPB);
 #define CP_ARGS h->N, h->Np, h->ell_nb, h->ell_fs, h->nfc, h->halo_bc, h->xc, h->yc, h->zc, h->aip, h->rip, h->rho, \
                 h->fld[CFDL_F_DC], h->fld[CFDL_F_MIP], h->fld[CFDL_F_AP], h->fld[CFDL_F_ANB], h->fld[CFDL_F_B]
-  if (h->K <= 4) coef_p_kernel<4><<<g, TPB, 0, h->stream>>>(CP_ARGS);
-  else if (h->K <= 6) coef_p_kernel<6><<<g, TPB, 0, h->stream>>>(CP_ARGS);
+  prof_begin(h, PROF_COEF_P);
+  if (h->K <= 4) coef_p_kernel<4><<<g, TPB, 0, S(h)>>>(CP_ARGS);
+  else if (h->K <= 6) coef_p_kernel<6><<<g, TPB, 0, S(h)>>>(CP_ARGS);
   else return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
+  prof_end(h);
 #undef CP_ARGS
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
@@ -332,7 +336,9 @@ int k_calc_mip(Handle* h, bool rhie_chow, double dt) {
   A.u0 = h->fld[CFDL_F_U0]; A.v0 = h->fld[CFDL_F_V0]; A.w0 = h->fld[CFDL_F_W0];
   A.p = h->fld[CFDL_F_P]; A.gp = h->fld[CFDL_F_GP]; A.d = h->fld[CFDL_F_D]; A.mip0 = h->fld[CFDL_F_MIP0];
   A.mip = h->fld[CFDL_F_MIP]; A.dt = dt; A.rhie_chow = rhie_chow ? 1 : 0;
-  mip_kernel<<<grid_for(h, h->Fi, TPB), TPB, 0, h->stream>>>(A);
+  prof_begin(h, PROF_MIP);
+  mip_kernel<<<grid_for(h, h->Fi, TPB), TPB, 0, S(h)>>>(A);
+  prof_end(h);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
@@ -349,9 +355,9 @@ __global__ void __launch_bounds__(TPB) halo_copy_kernel(int B, int N, const int3
 
 int k_adjust_pc(Handle* h) {
   double* pc = h->fld[CFDL_F_PC];
-  copy_scalar_kernel<<<1, 1, 0, h->stream>>>(h->scal, pc + h->prep.o2c[0]);  // pref = phic(1)
-  shift_kernel<<<grid_for(h, h->N, TPB), TPB, 0, h->stream>>>(h->N, pc, h->scal);
-  if (h->B) halo_copy_kernel<<<grid_for(h, h->B, TPB), TPB, 0, h->stream>>>(h->B, h->N, h->halo_cell, pc);
+  copy_scalar_kernel<<<1, 1, 0, S(h)>>>(h->scal, pc + h->prep.o2c[0]);  // pref = phic(1)
+  shift_kernel<<<grid_for(h, h->N, TPB), TPB, 0, S(h)>>>(h->N, pc, h->scal);
+  if (h->B) halo_copy_kernel<<<grid_for(h, h->B, TPB), TPB, 0, S(h)>>>(h->B, h->N, h->halo_cell, pc);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
@@ -389,10 +395,10 @@ __global__ void __launch_bounds__(TPB) correct_faces_kernel(int Fi, const int32_
 }
 
 int k_update_uvwp(Handle* h) {
-  correct_cells_kernel<<<grid_for(h, h->N, TPB), TPB, 0, h->stream>>>(h->N, h->fld[CFDL_F_P], h->fld[CFDL_F_PC], h->fld[CFDL_F_GP],
+  correct_cells_kernel<<<grid_for(h, h->N, TPB), TPB, 0, S(h)>>>(h->N, h->fld[CFDL_F_P], h->fld[CFDL_F_PC], h->fld[CFDL_F_GP],
                                                                        h->fld[CFDL_F_GPC]);
   if (h->Fi)
-    correct_faces_kernel<<<grid_for(h, h->Fi, TPB), TPB, 0, h->stream>>>(h->Fi, h->face_a, h->face_b, h->xc, h->yc, h->zc, h->aip,
+    correct_faces_kernel<<<grid_for(h, h->Fi, TPB), TPB, 0, S(h)>>>(h->Fi, h->face_a, h->face_b, h->xc, h->yc, h->zc, h->aip,
                                                                           h->rip, h->rho, h->fld[CFDL_F_DC], h->fld[CFDL_F_PC],
                                                                           h->fld[CFDL_F_MIP]);
   CFDL_CUDA(cudaGetLastError());
@@ -471,8 +477,8 @@ __global__ void __launch_bounds__(TPB) grad_kernel(int N, int Np, const int32_t*
 
 int k_calc_grad(Handle* h, const double* phi, double* grad) {
   const int g = grid_for(h, h->N, TPB);
-  if (h->K <= 4) grad_kernel<4, 1><<<g, TPB, 0, h->stream>>>(h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, phi, phi, phi, grad, grad, grad);
-  else if (h->K <= 6) grad_kernel<6, 1><<<g, TPB, 0, h->stream>>>(h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, phi, phi, phi, grad, grad, grad);
+  if (h->K <= 4) grad_kernel<4, 1><<<g, TPB, 0, S(h)>>>(h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, phi, phi, phi, grad, grad, grad);
+  else if (h->K <= 6) grad_kernel<6, 1><<<g, TPB, 0, S(h)>>>(h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, phi, phi, phi, grad, grad, grad);
   else return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
@@ -482,9 +488,11 @@ int k_calc_grad3(Handle* h) {  // the three calc_grad calls of mod_uvwp.f90:118-
   const int g = grid_for(h, h->N, TPB);
 #define G3 h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, h->fld[CFDL_F_U], h->fld[CFDL_F_V], h->fld[CFDL_F_W], \
            h->fld[CFDL_F_GU], h->fld[CFDL_F_GV], h->fld[CFDL_F_GW]
-  if (h->K <= 4) grad_kernel<4, 3><<<g, TPB, 0, h->stream>>>(G3);
-  else if (h->K <= 6) grad_kernel<6, 3><<<g, TPB, 0, h->stream>>>(G3);
+  prof_begin(h, PROF_GRAD);
+  if (h->K <= 4) grad_kernel<4, 3><<<g, TPB, 0, S(h)>>>(G3);
+  else if (h->K <= 6) grad_kernel<6, 3><<<g, TPB, 0, S(h)>>>(G3);
   else return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
+  prof_end(h);
 #undef G3
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
@@ -514,13 +522,13 @@ __global__ void __launch_bounds__(TPB) scatter_kernel(double* __restrict__ dst, 
 }
 int k_gather(Handle* h, double* dst, const double* src, const int32_t* map, int64_t n, int ncomp) {
   if (n == 0) return CFDL_OK;
-  gather_kernel<<<grid_for(h, n, TPB), TPB, 0, h->stream>>>(dst, src, map, n, ncomp);
+  gather_kernel<<<grid_for(h, n, TPB), TPB, 0, S(h)>>>(dst, src, map, n, ncomp);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
 int k_scatter(Handle* h, double* dst, const double* src, const int32_t* map, int64_t n, int ncomp) {
   if (n == 0) return CFDL_OK;
-  scatter_kernel<<<grid_for(h, n, TPB), TPB, 0, h->stream>>>(dst, src, map, n, ncomp);
+  scatter_kernel<<<grid_for(h, n, TPB), TPB, 0, S(h)>>>(dst, src, map, n, ncomp);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
@@ -537,12 +545,12 @@ __global__ void __launch_bounds__(TPB) csr_ell_kernel(int N, int Np, const int32
   }
 }
 int k_csr_to_ell(Handle* h, double* ell, const double* csr) {
-  csr_ell_kernel<<<grid_for(h, h->N, TPB), TPB, 0, h->stream>>>(h->N, h->Np, h->c2o, h->row_ptr, ell, const_cast<double*>(csr), 1);
+  csr_ell_kernel<<<grid_for(h, h->N, TPB), TPB, 0, S(h)>>>(h->N, h->Np, h->c2o, h->row_ptr, ell, const_cast<double*>(csr), 1);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
 int k_ell_to_csr(Handle* h, double* csr, const double* ell) {
-  csr_ell_kernel<<<grid_for(h, h->N, TPB), TPB, 0, h->stream>>>(h->N, h->Np, h->c2o, h->row_ptr, const_cast<double*>(ell), csr, 0);
+  csr_ell_kernel<<<grid_for(h, h->N, TPB), TPB, 0, S(h)>>>(h->N, h->Np, h->c2o, h->row_ptr, const_cast<double*>(ell), csr, 0);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }

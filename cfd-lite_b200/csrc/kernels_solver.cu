@@ -286,7 +286,9 @@ static int launch_levels(Handle* h, const DevSchedule& D, double sor, int niter)
   // no more CTAs than the widest level can feed
   int ctas = std::min(h->coop_ctas, std::max(1, (D.max_level_cells + TPB - 1) / TPB));
   const void* fn = (h->K <= 4) ? (const void*)level_sgs_kernel<4> : (const void*)level_sgs_kernel<6>;
-  CFDL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(ctas), dim3(TPB), args, 0, h->stream));
+  prof_begin(h, PROF_LEVELS);
+  CFDL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(ctas), dim3(TPB), args, 0, S(h)));
+  prof_end(h);
   return CFDL_OK;
 }
 
@@ -297,9 +299,9 @@ static int parity_solve_t(Handle* h, int eq, double* phi, const double* rhs, int
   const bool multi = dispatch && h->prep.n_subdomains > 1;  // solve() dispatch, mod_solver.f90:338-342
   const DevSchedule& D = multi ? h->blocks : h->natural;
   const int N = h->N, Np = h->Np, g = grid_for(h, N, TPB);
-  to_sweep_kernel<K><<<g, TPB, 0, h->stream>>>(N, Np, D.s2c, h->fld[CFDL_F_AP], h->fld[CFDL_F_ANB], rhs, phi, h->ap_s, h->anb_s,
+  to_sweep_kernel<K><<<g, TPB, 0, S(h)>>>(N, Np, D.s2c, h->fld[CFDL_F_AP], h->fld[CFDL_F_ANB], rhs, phi, h->ap_s, h->anb_s,
                                                h->b_s, h->phi_s, h->H);
-  if (h->B) halo_to_sweep_kernel<<<grid_for(h, h->B, TPB), TPB, 0, h->stream>>>(N, h->B, phi, h->phi_s);
+  if (h->B) halo_to_sweep_kernel<<<grid_for(h, h->B, TPB), TPB, 0, S(h)>>>(N, h->B, phi, h->phi_s);
   CFDL_CUDA(cudaGetLastError());
   int rc;
   int it = 0;
@@ -307,7 +309,7 @@ static int parity_solve_t(Handle* h, int eq, double* phi, const double* rhs, int
   if (!multi) {
     // solve_gs, mod_solver.f90:255-327
     CFDL_CUDA(cudaMemsetAsync(&h->ctl->ticket, 0, sizeof(unsigned int), h->stream));
-    residual_kernel<K><<<g, TPB, 0, h->stream>>>(N, Np, D.nbs, h->ap_s, h->anb_s, h->b_s, h->phi_s, h->partial, h->ctl, RES_PLAIN, 0, h->scal + 8);
+    residual_kernel<K><<<g, TPB, 0, S(h)>>>(N, Np, D.nbs, h->ap_s, h->anb_s, h->b_s, h->phi_s, h->partial, h->ctl, RES_PLAIN, 0, h->scal + 8);
     CFDL_CUDA(cudaMemcpyAsync(h->scal_host, h->scal + 8, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CFDL_CUDA(cudaStreamSynchronize(h->stream));
     res_i = h->scal_host[0];
@@ -316,7 +318,7 @@ static int parity_solve_t(Handle* h, int eq, double* phi, const double* rhs, int
     while (it < nit && res_f > res_target) {
       it += 1;
       if ((rc = launch_levels(h, D, sor, 1))) return rc;
-      residual_kernel<K><<<g, TPB, 0, h->stream>>>(N, Np, D.nbs, h->ap_s, h->anb_s, h->b_s, h->phi_s, h->partial, h->ctl, RES_PLAIN, 0, h->scal + 8);
+      residual_kernel<K><<<g, TPB, 0, S(h)>>>(N, Np, D.nbs, h->ap_s, h->anb_s, h->b_s, h->phi_s, h->partial, h->ctl, RES_PLAIN, 0, h->scal + 8);
       CFDL_CUDA(cudaMemcpyAsync(h->scal_host, h->scal + 8, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       CFDL_CUDA(cudaStreamSynchronize(h->stream));
       res_f = h->scal_host[0];
@@ -333,9 +335,9 @@ static int parity_solve_t(Handle* h, int eq, double* phi, const double* rhs, int
     int32_t* blk_ptr_dev = (int32_t*)(h->scal + 16);  // small device scratch: P+1 ints
     CFDL_CUDA(cudaMemcpyAsync(blk_ptr_dev, D.blk_ptr.data(), sizeof(int32_t) * (P + 1), cudaMemcpyHostToDevice, h->stream));
     auto block_residuals = [&](double& sum_res2, double& mx) -> int {
-      residual_cells_kernel<K><<<g, TPB, 0, h->stream>>>(N, Np, D.nbs, D.bpos, h->ap_s, h->anb_s, h->b_s, h->phi_s, h->rr);
-      seg_reduce_kernel<<<dim3(nchunks, P), TPB, 0, h->stream>>>(h->rr, blk_ptr_dev, h->partial, nchunks);
-      seg_final_kernel<<<1, 1024, 0, h->stream>>>(h->partial, nchunks, P, h->scal + 64);
+      residual_cells_kernel<K><<<g, TPB, 0, S(h)>>>(N, Np, D.nbs, D.bpos, h->ap_s, h->anb_s, h->b_s, h->phi_s, h->rr);
+      seg_reduce_kernel<<<dim3(nchunks, P), TPB, 0, S(h)>>>(h->rr, blk_ptr_dev, h->partial, nchunks);
+      seg_final_kernel<<<1, 1024, 0, S(h)>>>(h->partial, nchunks, P, h->scal + 64);
       CFDL_CUDA(cudaMemcpyAsync(h->scal_host, h->scal + 64, 2 * P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       CFDL_CUDA(cudaStreamSynchronize(h->stream));
       for (int b = 0; b < P; ++b) {
@@ -361,7 +363,7 @@ static int parity_solve_t(Handle* h, int eq, double* phi, const double* rhs, int
     }
     res_i = res_i_tot; res_f = res_f_tot; res_max = res_max_tot;
   }
-  from_sweep_kernel<<<g, TPB, 0, h->stream>>>(N, D.s2c, h->phi_s, phi);
+  from_sweep_kernel<<<g, TPB, 0, S(h)>>>(N, D.s2c, h->phi_s, phi);
   CFDL_CUDA(cudaGetLastError());
   if (out4) { out4[0] = it; out4[1] = res_i; out4[2] = res_f; out4[3] = res_max; }
   return CFDL_OK;
@@ -380,7 +382,7 @@ static int mcsgs_solve_t(Handle* h, int eq, double* phi, const double* rhs, int 
   init.nit = nit;
   *h->ctl_host = init;
   CFDL_CUDA(cudaMemcpyAsync(h->ctl, h->ctl_host, sizeof(SolveCtl), cudaMemcpyHostToDevice, h->stream));
-  residual_kernel<K><<<g, TPB, 0, h->stream>>>(N, Np, h->ell_nb, ap, anb, rhs, phi, h->partial, h->ctl, RES_INIT, 0, nullptr);
+  residual_kernel<K><<<g, TPB, 0, S(h)>>>(N, Np, h->ell_nb, ap, anb, rhs, phi, h->partial, h->ctl, RES_INIT, 0, nullptr);
   int launched = 0, batch = 1;
   for (;;) {
     CFDL_CUDA(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(SolveCtl), cudaMemcpyDeviceToHost, h->stream));
@@ -390,13 +392,15 @@ static int mcsgs_solve_t(Handle* h, int eq, double* phi, const double* rhs, int 
     for (int i = 0; i < m; ++i) {
       for (int c = 0; c < nc; ++c) {
         const int n = cp[c + 1] - cp[c];
-        if (n > 0) sgs_range_kernel<K><<<grid_for(h, n, TPB), TPB, 0, h->stream>>>(cp[c], cp[c + 1], Np, h->ell_nb, ap, anb, rhs, phi, sor, h->ctl);
+        if (n > 0) { prof_begin(h, PROF_SGS_SWEEP); sgs_range_kernel<K><<<grid_for(h, n, TPB), TPB, 0, S(h)>>>(cp[c], cp[c + 1], Np, h->ell_nb, ap, anb, rhs, phi, sor, h->ctl); prof_end(h); }
       }
       for (int c = nc - 1; c >= 0; --c) {
         const int n = cp[c + 1] - cp[c];
-        if (n > 0) sgs_range_kernel<K><<<grid_for(h, n, TPB), TPB, 0, h->stream>>>(cp[c], cp[c + 1], Np, h->ell_nb, ap, anb, rhs, phi, sor, h->ctl);
+        if (n > 0) { prof_begin(h, PROF_SGS_SWEEP); sgs_range_kernel<K><<<grid_for(h, n, TPB), TPB, 0, S(h)>>>(cp[c], cp[c + 1], Np, h->ell_nb, ap, anb, rhs, phi, sor, h->ctl); prof_end(h); }
       }
-      residual_kernel<K><<<g, TPB, 0, h->stream>>>(N, Np, h->ell_nb, ap, anb, rhs, phi, h->partial, h->ctl, RES_ITER, 0, nullptr);
+      prof_begin(h, PROF_RESIDUAL);
+      residual_kernel<K><<<g, TPB, 0, S(h)>>>(N, Np, h->ell_nb, ap, anb, rhs, phi, h->partial, h->ctl, RES_ITER, 0, nullptr);
+      prof_end(h);
     }
     CFDL_CUDA(cudaGetLastError());
     launched += m;
@@ -412,9 +416,9 @@ int residual_plain(Handle* h, const double* phi, const double* rhs, bool signed_
   const int g = grid_for(h, h->N, TPB);
   CFDL_CUDA(cudaMemsetAsync(&h->ctl->ticket, 0, sizeof(unsigned int), h->stream));
   if (h->K <= 4)
-    residual_kernel<4><<<g, TPB, 0, h->stream>>>(h->N, h->Np, h->ell_nb, h->fld[CFDL_F_AP], h->fld[CFDL_F_ANB], rhs, phi, h->partial, h->ctl, RES_PLAIN, signed_max ? 1 : 0, h->scal + 8);
+    residual_kernel<4><<<g, TPB, 0, S(h)>>>(h->N, h->Np, h->ell_nb, h->fld[CFDL_F_AP], h->fld[CFDL_F_ANB], rhs, phi, h->partial, h->ctl, RES_PLAIN, signed_max ? 1 : 0, h->scal + 8);
   else
-    residual_kernel<6><<<g, TPB, 0, h->stream>>>(h->N, h->Np, h->ell_nb, h->fld[CFDL_F_AP], h->fld[CFDL_F_ANB], rhs, phi, h->partial, h->ctl, RES_PLAIN, signed_max ? 1 : 0, h->scal + 8);
+    residual_kernel<6><<<g, TPB, 0, S(h)>>>(h->N, h->Np, h->ell_nb, h->fld[CFDL_F_AP], h->fld[CFDL_F_ANB], rhs, phi, h->partial, h->ctl, RES_PLAIN, signed_max ? 1 : 0, h->scal + 8);
   CFDL_CUDA(cudaMemcpyAsync(h->scal_host, h->scal + 8, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CFDL_CUDA(cudaStreamSynchronize(h->stream));
   *res = h->scal_host[0];

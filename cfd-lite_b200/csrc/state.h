@@ -62,8 +62,25 @@ struct Handle {
   DevSchedule natural, blocks;
   double *ap_s = nullptr, *b_s = nullptr, *anb_s = nullptr, *phi_s = nullptr, *rr = nullptr, *rsig = nullptr;
   int coop_ctas = 0;
-  int32_t* color_ptr_host() { return prep.color_ptr.data(); }
+  // instrumentation
+  int64_t launches = 0;         // kernels launched since the last reset ("gpu_launches")
+  int profile = 0;              // 1: bracket every launch of the profiled kernel kinds with CUDA events
+  std::vector<cudaEvent_t> prof_ev;  // pairs (begin, end)
+  std::vector<int> prof_kind;
+  size_t prof_used = 0;
+  double prof_ms[8] = {0};
+  int64_t prof_n[8] = {0};
+  cudaEvent_t timer_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
+
+// every launch site takes its stream from S(h), which also counts the launch
+inline cudaStream_t S(Handle* h) { h->launches++; return h->stream; }
+
+// profiled kernel kinds (per-launch CUDA-event timing when h->profile is on)
+enum { PROF_SGS_SWEEP = 0, PROF_RESIDUAL = 1, PROF_COEF_UVW = 2, PROF_COEF_P = 3, PROF_MIP = 4, PROF_GRAD = 5, PROF_LEVELS = 6, PROF_PCG = 7 };
+int prof_begin(Handle* h, int kind);
+int prof_end(Handle* h);
+int prof_collect(Handle* h);  // after a stream sync: fold finished event pairs into prof_ms / prof_n
 
 // launch geometry helper: grids are sized as a multiple of the SM count (B200: 148)
 inline int grid_for(const Handle* h, int64_t n, int threads, int ctas_per_sm = 8) {

@@ -126,6 +126,21 @@ def default_bcs(raw):
     return np.array(esec, np.int32), np.array(kind, np.int32), np.array(uvw, np.float64)
 
 
+class PinnedBuffer:
+    """Page-locked host array (cudaMallocHost) for the end-to-end path."""
+
+    def __init__(self, n):
+        self.ptr = C.c_void_p()
+        _chk(lib().cfdl_host_alloc(C.byref(self.ptr), C.c_uint64(8 * max(int(n), 1))))
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, _dp), shape=(max(int(n), 1),))[:int(n)]
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().cfdl_host_free(self.ptr)
+            self.ptr = None
+
+
 class Solver:
     """Device-resident SIMPLE hot path for one mesh (one GPU).  Mirrors phys_t + uvwp_t."""
 
@@ -187,6 +202,14 @@ class Solver:
         _chk(lib().cfdl_get_cell_order(self.h, _i(c2o), _i(cp)))
         return c2o, cp
 
+    def timer_record(self, slot):
+        _chk(lib().cfdl_timer_record(self.h, C.c_int32(slot)))
+
+    def timer_elapsed_ms(self, a, b):
+        ms = C.c_double()
+        _chk(lib().cfdl_timer_elapsed_ms(self.h, C.c_int32(a), C.c_int32(b), C.byref(ms)))
+        return ms.value
+
     def upload(self, name, arr):
         arr = _f64(arr)
         assert arr.size == self.field_size(name), (name, arr.size, self.field_size(name))
@@ -194,6 +217,11 @@ class Solver:
 
     def download(self, name):
         out = np.zeros(self.field_size(name))
+        _chk(lib().cfdl_download_field(self.h, C.c_int(FIELD_ID[name]), _d(out)))
+        return out
+
+    def download_into(self, name, out):
+        assert out.size == self.field_size(name) and out.dtype == np.float64 and out.flags.c_contiguous
         _chk(lib().cfdl_download_field(self.h, C.c_int(FIELD_ID[name]), _d(out)))
         return out
 

@@ -106,6 +106,17 @@ int cfdl_get_info(cfdl_handle h, const char* key, double* value);
  * color_ptr has ncolors+1 entries ("ncolors" via cfdl_get_info); either pointer may be NULL. */
 int cfdl_get_cell_order(cfdl_handle h, int32_t* c2o, int32_t* color_ptr);
 
+/* ---- instrumentation (bench.py): CUDA events on the library's stream, pinned host buffers.
+ * set_option keys: "solver", "profile" (0/1: time every launch of the dominant kernels),
+ *                  "reset_counters" (any value).
+ * get_info keys:   "launches" (kernels launched since reset), "prof_ms_<k>" / "prof_n_<k>" with
+ *                  k in sgs, residual, coef_uvw, coef_p, mip, grad, levels, pcg;
+ *                  "ncolors", "morton", "nlevels_natural", "nlevels_blocks", "ell_width", "num_sms". */
+int cfdl_timer_record(cfdl_handle h, int32_t slot);                 /* slot 0..3 */
+int cfdl_timer_elapsed_ms(cfdl_handle h, int32_t slot_begin, int32_t slot_end, double* ms);
+int cfdl_host_alloc(void** ptr, uint64_t bytes);                    /* page-locked host memory */
+int cfdl_host_free(void* ptr);
+
 /* ---- host <-> device field sync (for write_vtubin, main.f90:79,89) */
 int cfdl_upload_field(cfdl_handle h, int field, const double* host);
 int cfdl_download_field(cfdl_handle h, int field, double* host);

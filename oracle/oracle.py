@@ -63,16 +63,28 @@ class OracleCase:
             "u0 v0 w0 bu bv bw d dc").split()
     INT = "ef2nb_idx ef2nb_nb ef2nb_fg s2g bs gf2g g2gf_p g2gf_idx".split()
 
-    def __init__(self, raw, n_subdomains=1):
+    def __init__(self, raw, n_subdomains=1, geom=None):
+        """raw: CGNS-like mesh content.  geom (optional): prebuilt geometry_t arrays — skips the
+        oracle's own (slow, faithful) face matching; used for timing runs on large meshes."""
         L = lib()
         self.raw = raw
-        x, y, z = _f64(raw["x"]), _f64(raw["y"]), _f64(raw["z"])
-        et, es, e2vx = _i32(raw["etype"]), _i32(raw["esec"]), _i32(raw["e2vx"])
+        et, es = _i32(raw["etype"]), _i32(raw["esec"])
         names = raw["names"]
-        nelem = int(raw["ne"] + raw["nbf"])
-        self.h = L.orc_create(C.c_int(len(x)), _d(x), _d(y), _d(z), C.c_int(len(et)), _i(et), _i(es),
-                              C.c_char_p(names), C.c_int(int(raw["ne2vx_max"])), C.c_int(nelem),
-                              _i(e2vx), C.c_int(n_subdomains))
+        if geom is not None:
+            L.orc_create_from_geom.restype = C.c_void_p
+            a = {k: _i32(geom[k]) for k in ("ef2nb_idx", "ef2nb_nb", "ef2nb_fg", "s2g", "bs")}
+            r = {k: _f64(geom[k]) for k in ("xc", "yc", "zc", "aip", "rip", "vol")}
+            self.h = L.orc_create_from_geom(C.c_int(int(geom["ne"])), C.c_int(int(geom["nf"])), C.c_int(int(geom["nbf"])),
+                                            _i(a["ef2nb_idx"]), _i(a["ef2nb_nb"]), _i(a["ef2nb_fg"]), _i(a["s2g"]), _i(a["bs"]),
+                                            _d(r["xc"]), _d(r["yc"]), _d(r["zc"]), _d(r["aip"]), _d(r["rip"]), _d(r["vol"]),
+                                            C.c_int(len(et)), _i(et), _i(es), C.c_char_p(names), C.c_int(n_subdomains))
+        else:
+            x, y, z = _f64(raw["x"]), _f64(raw["y"]), _f64(raw["z"])
+            e2vx = _i32(raw["e2vx"])
+            nelem = int(raw["ne"] + raw["nbf"])
+            self.h = L.orc_create(C.c_int(len(x)), _d(x), _d(y), _d(z), C.c_int(len(et)), _i(et), _i(es),
+                                  C.c_char_p(names), C.c_int(int(raw["ne2vx_max"])), C.c_int(nelem),
+                                  _i(e2vx), C.c_int(n_subdomains))
         if not self.h:
             raise RuntimeError("oracle: " + L.orc_last_error().decode())
         self.h = C.c_void_p(self.h)

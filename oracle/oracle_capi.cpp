@@ -35,6 +35,46 @@ void* orc_create(int nvx, const double* x, const double* y, const double* z, int
   } catch (const std::exception& ex) { g_err = ex.what(); delete c; return nullptr; }
 }
 
+// Same as orc_create but starting from already-built geometry_t arrays (the outputs of
+// find_element_nb / calc_aip_xyzip_uns / calc_vol_cv_centers_uns), so that timing runs on big
+// meshes skip the reference's O(nvx k^2) face matching.  The hot path, the RCB partition and
+// construct_subdomains are still the oracle's own.
+void* orc_create_from_geom(int ne, int nf, int nbf, const int* ef2nb_idx, const int* ef2nb_nb, const int* ef2nb_fg,
+                           const int* s2g, const int* bs, const double* xc, const double* yc, const double* zc,
+                           const double* aip, const double* rip, const double* vol, int nsec, const int* etype,
+                           const int* esec, const char* names, int n_subdomains) {
+  Case* c = nullptr;
+  try {
+    c = new Case;
+    Mesh& m = c->m;
+    m.nsec = nsec; m.ne = ne; m.nf = nf; m.nbf = nbf; m.nelem = ne + nbf;
+    m.etype.assign(etype, etype + nsec);
+    m.esec.assign(esec, esec + 2 * nsec);
+    for (int s = 0; s < nsec; ++s) m.sectionName.push_back(std::string(names + 32 * s, 32));
+    m.bs_idx.alloc(nsec + 1, 0);
+    m.bs_idx(1) = 1;
+    for (int s = 1; s <= nsec; ++s) m.bs_idx(s + 1) = m.esec[2 * (s - 1) + 1] + 1;
+    for (int s = 1; s <= nsec; ++s) if (m.etype[s - 1] < 10) m.intf2sec.push_back(s);
+    m.nintf_c2b = (int)m.intf2sec.size();
+    const long Z = 2L * nf - nbf, H = ne + nbf;
+    m.ef2nb_idx.alloc(ne + 1); std::copy(ef2nb_idx, ef2nb_idx + ne + 1, m.ef2nb_idx.data());
+    m.ef2nb1.alloc(Z); std::copy(ef2nb_nb, ef2nb_nb + Z, m.ef2nb1.data());
+    m.ef2nb2.alloc(Z); std::copy(ef2nb_fg, ef2nb_fg + Z, m.ef2nb2.data());
+    m.s2g.alloc(nf + 1); std::copy(s2g, s2g + nf, m.s2g.data());
+    m.bs.alloc(nbf, 0, ne + 1); std::copy(bs, bs + nbf, m.bs.data());
+    m.xc.alloc(H); std::copy(xc, xc + H, m.xc.data());
+    m.yc.alloc(H); std::copy(yc, yc + H, m.yc.data());
+    m.zc.alloc(H); std::copy(zc, zc + H, m.zc.data());
+    m.aip.alloc(3L * nf); std::copy(aip, aip + 3L * nf, m.aip.data());
+    m.rip.alloc(3L * nf); std::copy(rip, rip + 3L * nf, m.rip.data());
+    m.vol.alloc(ne); std::copy(vol, vol + ne, m.vol.data());
+    m.n_subdomains = 1;
+    if (n_subdomains > 1) rcb_partition(m, n_subdomains);
+    construct_physics(*c, n_subdomains);
+    return c;
+  } catch (const std::exception& ex) { g_err = ex.what(); delete c; return nullptr; }
+}
+
 void orc_destroy(void* h) { delete (Case*)h; }
 
 int orc_dims(void* h, int* ne, int* nf, int* nbf, int* nbc) {
