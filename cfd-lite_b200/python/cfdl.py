@@ -108,6 +108,15 @@ def mesh_build(raw):
     return g
 
 
+def partition_rcb(geom, P):
+    """The reference's RCB blocks: (cell2sub, g2gf_p, g2gf_idx), all 1-based."""
+    ne = int(geom["ne"])
+    c2s, p, idx = np.zeros(ne, np.int32), np.zeros(ne, np.int32), np.zeros(P + 1, np.int32)
+    xc, yc, zc, vol = (_f64(geom[k]) for k in ("xc", "yc", "zc", "vol"))
+    _chk(lib().cfdl_partition_rcb(C.c_int32(ne), _d(xc), _d(yc), _d(zc), _d(vol), C.c_int32(P), _i(c2s), _i(p), _i(idx)))
+    return c2s, p, idx
+
+
 def default_bcs(raw):
     """The reference's hard-wired BCs (mod_uvwp.f90:73-78): 'top' = lid u=1, others no-slip;
     one BC per 2-D section in section order (mod_eqn_setup.f90:46-68)."""

@@ -192,6 +192,14 @@ int cfdl_mesh_build(int64_t nvx, const double* x, const double* y, const double*
                     int32_t* bs, double* xc, double* yc, double* zc, double* aip, double* rip,
                     double* vol);
 
+/* the reference's recursive-coordinate-bisection block decomposition (generate_seeds/grow/
+ * split_leaf, mod_agglomeration.f90:380-561) and its block-local cell order (the unstable
+ * quicksort of mod_mg_lvl_uns.f90:883-902): cell2sub(ne) in 1..P, g2gf_p(ne) cells sorted by
+ * block, g2gf_idx(P+1); all 1-based, any output may be NULL. */
+int cfdl_partition_rcb(int32_t ne, const double* xc, const double* yc, const double* zc,
+                       const double* vol, int32_t P, int32_t* cell2sub, int32_t* g2gf_p,
+                       int32_t* g2gf_idx);
+
 #ifdef __cplusplus
 }
 #endif
