@@ -6,7 +6,7 @@ mesh: update_boundaries + solve_uvwp (assembly, three momentum solves, gradients
 pressure-correction assembly + solve, correction), plus update_time after every third step.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--n 128] [--mesh hex|tet] [--solver mcsgs|parity|pcg]
+                    [--size 128] [--mesh hex|tet] [--solver mcsgs|parity|pcg]
 
 ours       the CUDA library through its C ABI (include/cfdl.h).  `value` is timed with CUDA
            events on the library's stream with all state resident in HBM; `e2e` repeats the
@@ -100,9 +100,9 @@ def workload_name(kind, n, ne):
         "%d^3 hex" % n if kind == "hex" else "Kuhn-tet (jitter 0.2h, shuffled ids)", n, ne)
 
 
-def algorithmic_bytes(ne, nf, nbf, K):
-    """SURVEY §8(d) / BASELINE.md §3 per-launch algorithmic bytes of the solver kernels."""
-    Z, H = 2 * nf - nbf, ne + nbf
+def algorithmic_bytes(ne, Z, H):
+    """SURVEY §8(d) / BASELINE.md §3 algorithmic bytes of one full sweep / one residual pass over
+    ne rows with Z coefficient slots gathering from H values (cells + ghosts + halos)."""
     return {"sgs_sweep": 28 * ne + 12 * Z + 8 * H, "residual": 20 * ne + 12 * Z + 8 * H}
 
 
@@ -143,13 +143,18 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def dbg(*a):
+    if os.environ.get("CFDL_BENCH_DEBUG"):
+        print("[rank %s]" % os.environ.get("RANK", "0"), *a, file=sys.stderr, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=128)
+    ap.add_argument("--size", dest="n", type=int, default=128, help="cells per edge per GPU (torchrun would swallow --n)")
     ap.add_argument("--mesh", default="hex", choices=["hex", "tet"])
     ap.add_argument("--solver", default="mcsgs", choices=list(SOLVERS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -182,10 +187,23 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    raw, geom = build_mesh(cfdl, args.mesh, args.n)
-    s = cfdl.Solver(geom, cfdl.default_bcs(raw), device=local_rank)
-    s.set_option("solver", SOLVERS[args.solver])
-    ne, nf, nbf, H = s.ne, s.nf, s.nbf, s.H
+    # weak scaling: the global cube grows with the GPU count so that every GPU keeps ~n^3 cells;
+    # the mesh is split by the reference's own RCB (x-slabs, columns, octants on a cube)
+    n_global = args.n if world == 1 else int(round(args.n * world ** (1.0 / 3.0)))
+    raw, geom = build_mesh(cfdl, args.mesh, n_global)
+    if world == 1:
+        s = cfdl.Solver(geom, cfdl.default_bcs(raw), device=local_rank)
+        s.set_option("solver", SOLVERS[args.solver])
+    else:
+        if args.solver == "parity":
+            raise SystemExit("bench.py: the exact natural-order solver is single-GPU; use --solver mcsgs with --gpus > 1")
+        c2r, _, _ = cfdl.partition_rcb(geom, world, want_order=False)
+        s = cfdl.Solver(geom, cfdl.default_bcs(raw), device=local_rank, cell2rank=c2r, rank=rank, nranks=world)
+        ids = [cfdl.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        s.comm_init(ids[0])
+        s.set_option("solver", SOLVERS[args.solver])
+    ne, nf, nbf, H = s.ne, s.nf, s.nbf, s.H  # global sizes
 
     def step(i):
         s.update_boundaries()
@@ -198,8 +216,10 @@ def main():
             dist.barrier()
 
     # ---- value: device-resident steps, CUDA events on the library's stream -------------------
+    dbg("solver ready; owned", int(s.get_info("owned_cells")), "ghost", int(s.get_info("ghost_cells")))
     for i in range(args.warmup):
         step(i)
+        dbg("warmup step", i)
     hist_last = None
     sampler = ClockSampler(local_rank)
     barrier()
@@ -213,6 +233,7 @@ def main():
             s.update_time()
     s.timer_record(1)
     ms = s.timer_elapsed_ms(0, 1)
+    dbg("timed steps done", ms)
     barrier()
     clocks = sampler.stop()
     launches = int(s.get_info("launches"))
@@ -221,7 +242,9 @@ def main():
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * ne * args.steps / (ms * 1e-3)
+    value = ne * args.steps / (ms * 1e-3)  # ne = cells of the whole (global) mesh over all ranks
+    n_owned = int(s.get_info("owned_cells"))
+    n_local_faces, n_local_halos = int(s.get_info("local_faces")), int(s.get_info("local_halos"))
 
     # ---- roofline: per-launch CUDA-event timing of the dominant kernel over the same steps ----
     peak, peak_src = peaks()
@@ -233,7 +256,8 @@ def main():
     kinds = ("sgs", "residual", "levels", "coef_uvw", "coef_p", "mip", "grad", "pcg")
     prof = {k: (s.get_info("prof_ms_" + k), int(s.get_info("prof_n_" + k))) for k in kinds}
     s.set_option("profile", 0)
-    ab = algorithmic_bytes(ne, nf, nbf, int(s.get_info("ell_width")))
+    K = int(s.get_info("ell_width"))  # faces per cell (hex 6, tet 4: no ELL padding)
+    ab = algorithmic_bytes(n_owned, K * n_owned, n_owned + int(s.get_info("ghost_cells")) + n_local_halos)  # this rank's partition
     ncol = int(s.get_info("ncolors"))
     roof = None
     extra_roof = {}
@@ -266,25 +290,36 @@ def main():
     if not args.no_e2e:
         ins = "u v w p u0 v0 w0 gu gv gw gp mip mip0".split()
         outs = "u v w p gp gpc mip".split()
-        bufs = {k: cfdl.PinnedBuffer(s.field_size(k)) for k in set(ins + outs)}
+        # one GPU: host arrays in the reference's numbering (cfdl_upload_field / cfdl_download_field);
+        # several GPUs: every rank moves its own partition (cfdl_*_field_local), bytes summed over ranks
+        if world == 1:
+            size_of, up, down = s.field_size, s.upload, s.download_into
+        else:
+            size_of, up, down = s.local_size, s.upload_local, s.download_local
+        bufs = {k: cfdl.PinnedBuffer(size_of(k)) for k in set(ins + outs)}
         for k in ins:
-            s.download_into(k, bufs[k].array)
-        h2d = 8 * sum(s.field_size(k) for k in ins)
-        d2h = 8 * sum(s.field_size(k) for k in outs) + 8 * 16
+            down(k, bufs[k].array)
+        h2d = 8 * sum(size_of(k) for k in ins)
+        d2h = 8 * sum(size_of(k) for k in outs) + 8 * 16
+        if dist is not None:
+            import torch
+            t = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t)
+            h2d, d2h = int(t[0].item()), int(t[1].item())
         ne2e = min(args.steps, 10)
         base = args.warmup + args.steps + nprof
 
         def e2e_step(i):
             for k in ins:
-                s.upload(k, bufs[k].array)
+                up(k, bufs[k].array)
             s.update_boundaries()
             s.solve_uvwp(DT, NIT)
             if (i + 1) % NCOEF == 0:
                 s.update_time()
-                s.download_into("u0", bufs["u0"].array); s.download_into("v0", bufs["v0"].array)
-                s.download_into("w0", bufs["w0"].array); s.download_into("mip0", bufs["mip0"].array)
+                for k in ("u0", "v0", "w0", "mip0"):
+                    down(k, bufs[k].array)
             for k in outs:
-                s.download_into(k, bufs[k].array)
+                down(k, bufs[k].array)
 
         e2e_step(base)
         barrier()
@@ -301,7 +336,7 @@ def main():
             t = torch.tensor([ms_e], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e = float(t.item())
-        e2e = {"value": world * ne * ne2e / (ms_e * 1e-3), "unit": "cell-iterations/s", "h2d_bytes_per_step": h2d,
+        e2e = {"value": ne * ne2e / (ms_e * 1e-3), "unit": "cell-iterations/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": ne2e, "ms_per_step": ms_e / ne2e,
                "what": "per step: upload u,v,w,p,u0,v0,w0,gu,gv,gw,gp,mip,mip0 from pinned host memory, update_boundaries + "
                        "solve_uvwp through the C ABI, download u,v,w,p,gp,gpc,mip and the residual history"}
@@ -326,10 +361,12 @@ def main():
         line = {"metric": "cell-iterations/s (SIMPLE)", "value": value, "unit": "cell-iterations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args.mesh, args.n, ne), "solver": args.solver, "ncolors": ncol,
-                           "cells_per_gpu": ne, "l2": "working set (>1 GB) exceeds the 126 MB L2; no flush needed" if ne > 1000000 else
+                "config": {"workload": workload_name(args.mesh, n_global, ne), "solver": args.solver, "ncolors": ncol,
+                           "cells_per_gpu": ne // world, "l2": "working set (>1 GB per GPU) exceeds the 126 MB L2; no flush needed" if ne // world > 1000000 else
                            "working set may fit L2",
-                           "parallelism": "1 GPU" if world == 1 else "%d independent replicas (partitioned multi-GPU path not built yet)" % world,
+                           "parallelism": "1 GPU" if world == 1 else
+                           "%d GPUs, one RCB block of the global mesh per GPU; ghost-cell exchange by NCCL send/recv after every colour sweep, "
+                           "residual norms by NCCL all-reduce" % world,
                            "last_step_history(it,res_i,res_f,res_max)": hist_last.tolist() if hist_last is not None else None},
                 "roofline": roof, "roofline_other": extra_roof, "phase_ms_per_step": phase_ms, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks}

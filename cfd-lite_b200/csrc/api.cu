@@ -1,8 +1,8 @@
 // C ABI of libcfdl (include/cfdl.h): lifecycle, host<->device field sync, the whole-step path
 // (update_boundaries / solve_uvwp / update_time, src/main.f90:50-63) and the per-routine path.
+#include <algorithm>
 #include <cstring>
 #include <new>
-#include <algorithm>
 #include "state.h"
 
 using namespace cfdl;
@@ -28,12 +28,23 @@ int dev_zero(Handle* h, T*& dst, size_t n) {
   return CFDL_OK;
 }
 
+// device-side length of a field (device numbering)
 size_t field_len(const Handle* h, int f) {
   if (f <= CFDL_F_PC) return (size_t)h->H;
   if (f <= CFDL_F_GPC) return 3 * (size_t)h->H;
   if (f <= CFDL_F_MIP0) return (size_t)h->F;
   if (f == CFDL_F_ANB) return (size_t)h->K * h->Np;  // device ELL storage
+  if (f == CFDL_F_D || f == CFDL_F_DC) return (size_t)h->Nc;  // gathered at neighbours: ghost copies needed
   return (size_t)h->N;
+}
+// host-side length (reference numbering of the global mesh)
+size_t host_len(const Handle* h, int f) {
+  const Prep& p = h->prep;
+  if (f <= CFDL_F_PC) return (size_t)p.gN + p.gB;
+  if (f <= CFDL_F_GPC) return 3 * ((size_t)p.gN + p.gB);
+  if (f <= CFDL_F_MIP0) return (size_t)p.gF;
+  if (f == CFDL_F_ANB) return (size_t)p.gZ;
+  return (size_t)p.gN;
 }
 
 bool good(cfdl_handle h) { return h != nullptr; }
@@ -43,64 +54,72 @@ int use_device(Handle* h) {
   return CFDL_OK;
 }
 
-// host (reference numbering) -> device field
+// host (reference numbering, global mesh) -> device field (owned + ghost cells, local halos/faces)
 int upload_field(Handle* h, int f, const double* host) {
-  if (f == CFDL_F_ANB) {
-    CFDL_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * (size_t)h->Z, cudaMemcpyHostToDevice, h->stream));
-    return k_csr_to_ell(h, h->fld[f], h->stage);
-  }
-  if (f <= CFDL_F_PC || (f >= CFDL_F_GU && f <= CFDL_F_GPC)) {
-    const int nc = (f <= CFDL_F_PC) ? 1 : 3;
-    CFDL_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * nc * (size_t)h->H, cudaMemcpyHostToDevice, h->stream));
-    int rc = k_gather(h, h->fld[f], h->stage, h->c2o, h->N, nc);  // cells permuted
-    if (rc) return rc;
-    if (h->B) CFDL_CUDA(cudaMemcpyAsync(h->fld[f] + (size_t)nc * h->N, h->stage + (size_t)nc * h->N, sizeof(double) * nc * (size_t)h->B,
-                                        cudaMemcpyDeviceToDevice, h->stream));  // halos keep their order
-    return CFDL_OK;
-  }
-  if (f == CFDL_F_MIP || f == CFDL_F_MIP0) {
-    CFDL_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * (size_t)h->F, cudaMemcpyHostToDevice, h->stream));
-    return k_gather(h, h->fld[f], h->stage, h->f2o, h->F, 1);
-  }
-  CFDL_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * (size_t)h->N, cudaMemcpyHostToDevice, h->stream));
+  CFDL_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * host_len(h, f), cudaMemcpyHostToDevice, h->stream));
+  if (f == CFDL_F_ANB) return k_csr_to_ell(h, h->fld[f], h->stage);
+  if (f <= CFDL_F_PC) return k_gather(h, h->fld[f], h->stage, h->cellmap, h->H, 1);
+  if (f <= CFDL_F_GPC) return k_gather(h, h->fld[f], h->stage, h->cellmap, h->H, 3);
+  if (f <= CFDL_F_MIP0) return k_gather(h, h->fld[f], h->stage, h->f2o, h->F, 1);
   return k_gather(h, h->fld[f], h->stage, h->c2o, h->N, 1);
 }
 
+// device field -> host.  One rank: the whole host array is written.  Several ranks: only the
+// entries this rank owns (cells, its boundary halos, faces whose owner cell it owns) are written.
 int download_field(Handle* h, int f, double* host) {
   int rc;
-  size_t n;
+  const Prep& p = h->prep;
+  if (p.nranks == 1) {
+    if (f == CFDL_F_ANB) rc = k_ell_to_csr(h, h->stage, h->fld[f]);
+    else if (f <= CFDL_F_PC) rc = k_scatter(h, h->stage, h->fld[f], h->cellmap, h->H, 1);
+    else if (f <= CFDL_F_GPC) rc = k_scatter(h, h->stage, h->fld[f], h->cellmap, h->H, 3);
+    else if (f <= CFDL_F_MIP0) rc = k_scatter(h, h->stage, h->fld[f], h->f2o, h->F, 1);
+    else rc = k_scatter(h, h->stage, h->fld[f], h->c2o, h->N, 1);
+    if (rc) return rc;
+    CFDL_CUDA(cudaMemcpyAsync(host, h->stage, sizeof(double) * host_len(h, f), cudaMemcpyDeviceToHost, h->stream));
+    CFDL_CUDA(cudaStreamSynchronize(h->stream));
+    return CFDL_OK;
+  }
+  std::vector<double> t;
   if (f == CFDL_F_ANB) {
     if ((rc = k_ell_to_csr(h, h->stage, h->fld[f]))) return rc;
-    n = (size_t)h->Z;
-  } else if (f <= CFDL_F_PC || (f >= CFDL_F_GU && f <= CFDL_F_GPC)) {
-    const int nc = (f <= CFDL_F_PC) ? 1 : 3;
-    if ((rc = k_scatter(h, h->stage, h->fld[f], h->c2o, h->N, nc))) return rc;
-    if (h->B) CFDL_CUDA(cudaMemcpyAsync(h->stage + (size_t)nc * h->N, h->fld[f] + (size_t)nc * h->N, sizeof(double) * nc * (size_t)h->B,
-                                        cudaMemcpyDeviceToDevice, h->stream));
-    n = (size_t)nc * h->H;
-  } else if (f == CFDL_F_MIP || f == CFDL_F_MIP0) {
-    if ((rc = k_scatter(h, h->stage, h->fld[f], h->f2o, h->F, 1))) return rc;
-    n = (size_t)h->F;
-  } else {
-    if ((rc = k_scatter(h, h->stage, h->fld[f], h->c2o, h->N, 1))) return rc;
-    n = (size_t)h->N;
+    t.resize((size_t)p.gZ);
+    CFDL_CUDA(cudaMemcpyAsync(t.data(), h->stage, sizeof(double) * t.size(), cudaMemcpyDeviceToHost, h->stream));
+    CFDL_CUDA(cudaStreamSynchronize(h->stream));
+    for (int32_t c = 0; c < p.N; ++c)
+      for (int32_t i = p.row_ptr[p.c2o[c]]; i < p.row_ptr[p.c2o[c] + 1]; ++i) host[i] = t[i];
+    return CFDL_OK;
   }
-  CFDL_CUDA(cudaMemcpyAsync(host, h->stage, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  t.resize(field_len(h, f));
+  CFDL_CUDA(cudaMemcpyAsync(t.data(), h->fld[f], sizeof(double) * t.size(), cudaMemcpyDeviceToHost, h->stream));
   CFDL_CUDA(cudaStreamSynchronize(h->stream));
+  if (f <= CFDL_F_GPC) {
+    const int nc = (f <= CFDL_F_PC) ? 1 : 3;
+    for (int32_t c = 0; c < p.N; ++c) for (int q = 0; q < nc; ++q) host[(size_t)p.c2o[c] * nc + q] = t[(size_t)c * nc + q];
+    for (int32_t j = 0; j < p.B; ++j) for (int q = 0; q < nc; ++q) host[((size_t)p.gN + p.h2o[j]) * nc + q] = t[((size_t)p.Nc + j) * nc + q];
+  } else if (f <= CFDL_F_MIP0) {
+    for (int32_t i = 0; i < p.F; ++i) if (p.fown[i]) host[p.f2o[i]] = t[i];
+  } else {
+    for (int32_t c = 0; c < p.N; ++c) host[p.c2o[c]] = t[c];
+  }
   return CFDL_OK;
 }
 
 int rhs_field(int eq) { return eq == CFDL_EQ_U ? CFDL_F_BU : eq == CFDL_EQ_V ? CFDL_F_BV : eq == CFDL_EQ_W ? CFDL_F_BW : CFDL_F_B; }
 int phi_field(int eq) { return eq == CFDL_EQ_U ? CFDL_F_U : eq == CFDL_EQ_V ? CFDL_F_V : eq == CFDL_EQ_W ? CFDL_F_W : CFDL_F_PC; }
 
-// solve_uvwp, src/equations/mod_uvwp.f90:95-134
+// solve_uvwp, src/equations/mod_uvwp.f90:95-134.  On several GPUs the ghost-cell copies of the
+// fields a later kernel gathers are refreshed right after the kernel that produces them.
 int solve_uvwp_impl(Handle* h, double dt, int nit, double* hist) {
   int rc;
   double st[16] = {0};
   if ((rc = k_calc_coef_uvw(h, dt))) return rc;                                              // :111
+  if ((rc = comm_exchange(h, h->fld[CFDL_F_D], 1, -1)) || (rc = comm_exchange(h, h->fld[CFDL_F_DC], 1, -1))) return rc;
   for (int eq = CFDL_EQ_U; eq <= CFDL_EQ_W; ++eq)                                            // :114-116
     if ((rc = solve_equation(h, eq, h->fld[phi_field(eq)], h->fld[rhs_field(eq)], nit, st + 4 * eq, false))) return rc;
   if ((rc = k_calc_grad3(h))) return rc;                                                     // :118-120
+  for (int f = CFDL_F_GU; f <= CFDL_F_GW; ++f)
+    if ((rc = comm_exchange(h, h->fld[f], 3, -1))) return rc;
   if ((rc = k_calc_mip(h, true, dt))) return rc;                                             // :122
   if ((rc = k_calc_coef_p(h))) return rc;                                                    // :124
   CFDL_CUDA(cudaMemsetAsync(h->fld[CFDL_F_PC], 0, sizeof(double) * (size_t)h->H, h->stream)); // :126 set_a_0
@@ -108,7 +127,84 @@ int solve_uvwp_impl(Handle* h, double dt, int nit, double* hist) {
   if ((rc = k_adjust_pc(h))) return rc;                                                      // :129-130
   if ((rc = k_calc_grad(h, h->fld[CFDL_F_PC], h->fld[CFDL_F_GPC]))) return rc;               // :131
   if ((rc = k_update_uvwp(h))) return rc;                                                    // :132
+  if ((rc = comm_exchange(h, h->fld[CFDL_F_GP], 3, -1))) return rc;
   if (hist) std::memcpy(hist, st, sizeof st);
+  return CFDL_OK;
+}
+
+int create_impl(cfdl_handle* out, int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_idx, const int32_t* ef2nb_nb,
+                const int32_t* ef2nb_fg, const int32_t* s2g, const int32_t* bs, const double* xc, const double* yc,
+                const double* zc, const double* aip, const double* rip, const double* vol, const double* rho,
+                const double* mu, int32_t nbc, const int32_t* bc_esec, const int32_t* bc_kind, const double* bc_uvw,
+                int32_t n_subdomains, const int32_t* g2gf_p, const int32_t* g2gf_idx, const int32_t* cell2rank, int32_t rank,
+                int32_t nranks, int32_t device) {
+  if (!out) return fail(CFDL_ERR_ARG, "cfdl_create: out is NULL");
+  *out = nullptr;
+  if (!ef2nb_idx || !ef2nb_nb || !ef2nb_fg || !s2g || (!bs && nbf) || !xc || !yc || !zc || !aip || !rip || !vol || !rho || !mu)
+    return fail(CFDL_ERR_ARG, "cfdl_create: NULL mesh array");
+  if (n_subdomains < 1) return fail(CFDL_ERR_ARG, "cfdl_create: n_subdomains must be >= 1");
+  int ndev = cfdl_device_count();
+  if (ndev < 1) return fail(CFDL_ERR_CUDA, "cfdl_create: no CUDA device is usable (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(CFDL_ERR_ARG, "cfdl_create: device %d of %d", device, ndev);
+  cfdl_handle_s* h = new (std::nothrow) cfdl_handle_s;
+  if (!h) return fail(CFDL_ERR_INTERNAL, "out of host memory");
+  h->device = device;
+  int rc = prepare(h->prep, ne, nf, nbf, ef2nb_idx, ef2nb_nb, ef2nb_fg, s2g, bs, xc, yc, zc, nbc, bc_esec, bc_kind, bc_uvw,
+                   n_subdomains, g2gf_p, g2gf_idx, /*reorder auto*/ 2, cell2rank, rank, nranks);
+  if (rc) { delete h; return rc; }
+  auto bail = [&](int code) { cfdl_destroy(h); return code; };
+  if ((rc = use_device(h))) return bail(rc);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(CFDL_ERR_CUDA, "cudaGetDeviceProperties failed"));
+  if (prop.major < 10) return bail(fail(CFDL_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor));
+  h->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(CFDL_ERR_CUDA, "cudaStreamCreate failed"));
+  const Prep& p = h->prep;
+  h->N = p.N; h->G = p.G; h->Nc = p.Nc; h->F = p.F; h->B = p.B; h->H = p.H; h->Z = p.Z; h->K = p.K; h->Np = p.Np; h->Fi = p.Fi;
+  h->ne_global = p.gN;
+  h->nnbr = (int)p.nbr_rank.size();
+  if (nranks > 1) h->solver_mode = CFDL_SOLVER_MCSGS;
+  const int32_t N = p.N, Nc = p.Nc, F = p.F, B = p.B, H = p.H;
+#define UP(dst, vec) if ((rc = dev_upload(h, dst, (vec).data(), (vec).size()))) return bail(rc)
+  UP(h->ell_nb, p.ell_nb); UP(h->ell_fs, p.ell_fs); UP(h->nfc, p.nfc); UP(h->face_a, p.face_a); UP(h->face_b, p.face_b);
+  UP(h->halo_cell, p.halo_cell); UP(h->halo_face, p.halo_face); UP(h->halo_bc, p.halo_bc); UP(h->halo_slot, p.halo_slot);
+  UP(h->bc_kind, p.bc_kind); UP(h->bc_uvw, p.bc_uvw); UP(h->c2o, p.c2o); UP(h->f2o, p.f2o); UP(h->row_ptr, p.row_ptr);
+  UP(h->send_cells, p.send_cells);
+#undef UP
+  {  // global index of every device cell | halo (host transfers), geometry in device numbering
+    std::vector<int32_t> cm((size_t)H);
+    for (int32_t c = 0; c < Nc; ++c) cm[c] = p.c2o[c];
+    for (int32_t j = 0; j < B; ++j) cm[Nc + j] = p.gN + p.h2o[j];
+    if ((rc = dev_upload(h, h->cellmap, cm.data(), cm.size()))) return bail(rc);
+    std::vector<double> t((size_t)3 * std::max(H, F));
+    auto cells = [&](const double* src, double*& dst, int32_t count) -> int {
+      for (int32_t i = 0; i < count; ++i) t[i] = src[cm[i]];
+      return dev_upload(h, dst, t.data(), (size_t)count);
+    };
+    if ((rc = cells(xc, h->xc, H)) || (rc = cells(yc, h->yc, H)) || (rc = cells(zc, h->zc, H))) return bail(rc);
+    if ((rc = cells(vol, h->vol, N)) || (rc = cells(rho, h->rho, Nc)) || (rc = cells(mu, h->mu, Nc))) return bail(rc);
+    for (int32_t f = 0; f < F; ++f) for (int q = 0; q < 3; ++q) t[3 * (size_t)f + q] = aip[3 * (size_t)p.f2o[f] + q];
+    if ((rc = dev_upload(h, h->aip, t.data(), 3 * (size_t)F))) return bail(rc);
+    for (int32_t f = 0; f < F; ++f) for (int q = 0; q < 3; ++q) t[3 * (size_t)f + q] = rip[3 * (size_t)p.f2o[f] + q];
+    if ((rc = dev_upload(h, h->rip, t.data(), 3 * (size_t)F))) return bail(rc);
+  }
+  for (int f = 0; f < CFDL_F_COUNT; ++f)
+    if ((rc = dev_zero(h, h->fld[f], field_len(h, f) + 4))) return bail(rc);
+  h->stage_len = std::max(std::max(3 * ((size_t)p.gN + p.gB), (size_t)p.gZ), (size_t)p.gF) + 4;
+  if ((rc = dev_zero(h, h->stage, h->stage_len))) return bail(rc);
+  h->partial_len = 4096 + 2 * 64 * (N / 8192 + 1);
+  if ((rc = dev_zero(h, h->partial, (size_t)h->partial_len))) return bail(rc);
+  if ((rc = dev_zero(h, h->ctl, 1)) || (rc = dev_zero(h, h->scal, 512)) || (rc = dev_zero(h, h->barrier, 4))) return bail(rc);
+  if (nranks > 1 && (rc = dev_zero(h, h->send_buf, 9 * p.send_cells.size() + 16))) return bail(rc);
+  if (cudaMallocHost(&h->ctl_host, sizeof(SolveCtl)) != cudaSuccess || cudaMallocHost(&h->scal_host, sizeof(double) * 512) != cudaSuccess)
+    return bail(fail(CFDL_ERR_CUDA, "cudaMallocHost failed"));
+  if ((rc = solver_init(h))) return bail(rc);
+  // construct_uvwp: fields zero, mip from calc_mip(.false.), mip0 = mip (mod_uvwp.f90:57-82)
+  if ((rc = k_calc_mip(h, false, 0.01))) return bail(rc);
+  if (cudaMemcpyAsync(h->fld[CFDL_F_MIP0], h->fld[CFDL_F_MIP], sizeof(double) * (size_t)F, cudaMemcpyDeviceToDevice, h->stream) != cudaSuccess ||
+      cudaStreamSynchronize(h->stream) != cudaSuccess)
+    return bail(fail(CFDL_ERR_CUDA, "initial calc_mip failed: %s", cudaGetErrorString(cudaGetLastError())));
+  *out = h;
   return CFDL_OK;
 }
 
@@ -127,72 +223,25 @@ int cfdl_create(cfdl_handle* out, int32_t ne, int32_t nf, int32_t nbf, const int
                 const double* zc, const double* aip, const double* rip, const double* vol, const double* rho,
                 const double* mu, int32_t nbc, const int32_t* bc_esec, const int32_t* bc_kind, const double* bc_uvw,
                 int32_t n_subdomains, const int32_t* g2gf_p, const int32_t* g2gf_idx, int32_t device) {
-  if (!out) return fail(CFDL_ERR_ARG, "cfdl_create: out is NULL");
-  *out = nullptr;
-  if (!ef2nb_idx || !ef2nb_nb || !ef2nb_fg || !s2g || (!bs && nbf) || !xc || !yc || !zc || !aip || !rip || !vol || !rho || !mu)
-    return fail(CFDL_ERR_ARG, "cfdl_create: NULL mesh array");
-  if (n_subdomains < 1) return fail(CFDL_ERR_ARG, "cfdl_create: n_subdomains must be >= 1");
-  int ndev = cfdl_device_count();
-  if (ndev < 1) return fail(CFDL_ERR_CUDA, "cfdl_create: no CUDA device is usable (this library has no CPU path)");
-  if (device < 0 || device >= ndev) return fail(CFDL_ERR_ARG, "cfdl_create: device %d of %d", device, ndev);
-  cfdl_handle_s* h = new (std::nothrow) cfdl_handle_s;
-  if (!h) return fail(CFDL_ERR_INTERNAL, "out of host memory");
-  h->device = device;
-  int rc = prepare(h->prep, ne, nf, nbf, ef2nb_idx, ef2nb_nb, ef2nb_fg, s2g, bs, xc, yc, zc, nbc, bc_esec, bc_kind, bc_uvw,
-                   n_subdomains, g2gf_p, g2gf_idx, /*reorder auto*/ 2);
-  if (rc) { delete h; return rc; }
-  auto bail = [&](int code) { cfdl_destroy(h); return code; };
-  if ((rc = use_device(h))) return bail(rc);
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(CFDL_ERR_CUDA, "cudaGetDeviceProperties failed"));
-  if (prop.major < 10) return bail(fail(CFDL_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor));
-  h->num_sms = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(CFDL_ERR_CUDA, "cudaStreamCreate failed"));
-  const Prep& p = h->prep;
-  h->N = p.N; h->F = p.F; h->B = p.B; h->H = p.H; h->Z = p.Z; h->K = p.K; h->Np = p.Np; h->Fi = p.Fi;
-  const int32_t N = p.N, F = p.F, B = p.B, H = p.H;
-#define UP(dst, vec) if ((rc = dev_upload(h, dst, (vec).data(), (vec).size()))) return bail(rc)
-  UP(h->ell_nb, p.ell_nb); UP(h->ell_fs, p.ell_fs); UP(h->nfc, p.nfc); UP(h->face_a, p.face_a); UP(h->face_b, p.face_b);
-  UP(h->halo_cell, p.halo_cell); UP(h->halo_face, p.halo_face); UP(h->halo_bc, p.halo_bc); UP(h->halo_slot, p.halo_slot);
-  UP(h->bc_kind, p.bc_kind); UP(h->bc_uvw, p.bc_uvw); UP(h->c2o, p.c2o); UP(h->o2c, p.o2c); UP(h->f2o, p.f2o); UP(h->row_ptr, p.row_ptr);
-#undef UP
-  {  // geometry in device numbering
-    std::vector<double> t((size_t)3 * std::max(H, F));
-    auto cells = [&](const double* src, double*& dst, int32_t halos) -> int {
-      for (int32_t c = 0; c < N; ++c) t[c] = src[p.c2o[c]];
-      for (int32_t j = 0; j < halos; ++j) t[N + j] = src[N + j];
-      return dev_upload(h, dst, t.data(), (size_t)N + halos);
-    };
-    if ((rc = cells(xc, h->xc, B)) || (rc = cells(yc, h->yc, B)) || (rc = cells(zc, h->zc, B))) return bail(rc);
-    if ((rc = cells(vol, h->vol, 0)) || (rc = cells(rho, h->rho, 0)) || (rc = cells(mu, h->mu, 0))) return bail(rc);
-    for (int32_t f = 0; f < F; ++f) for (int q = 0; q < 3; ++q) t[3 * (size_t)f + q] = aip[3 * (size_t)p.f2o[f] + q];
-    if ((rc = dev_upload(h, h->aip, t.data(), 3 * (size_t)F))) return bail(rc);
-    for (int32_t f = 0; f < F; ++f) for (int q = 0; q < 3; ++q) t[3 * (size_t)f + q] = rip[3 * (size_t)p.f2o[f] + q];
-    if ((rc = dev_upload(h, h->rip, t.data(), 3 * (size_t)F))) return bail(rc);
-  }
-  for (int f = 0; f < CFDL_F_COUNT; ++f)
-    if ((rc = dev_zero(h, h->fld[f], field_len(h, f) + 4))) return bail(rc);
-  h->stage_len = std::max(std::max(3 * (size_t)H, (size_t)p.Z), (size_t)F) + 4;
-  if ((rc = dev_zero(h, h->stage, h->stage_len))) return bail(rc);
-  h->partial_len = 4096 + 2 * 64 * (N / 8192 + 1);
-  if ((rc = dev_zero(h, h->partial, (size_t)h->partial_len))) return bail(rc);
-  if ((rc = dev_zero(h, h->ctl, 1)) || (rc = dev_zero(h, h->scal, 512)) || (rc = dev_zero(h, h->barrier, 4))) return bail(rc);
-  if (cudaMallocHost(&h->ctl_host, sizeof(SolveCtl)) != cudaSuccess || cudaMallocHost(&h->scal_host, sizeof(double) * 512) != cudaSuccess)
-    return bail(fail(CFDL_ERR_CUDA, "cudaMallocHost failed"));
-  if ((rc = solver_init(h))) return bail(rc);
-  // construct_uvwp: fields zero, mip from calc_mip(.false.), mip0 = mip (mod_uvwp.f90:57-82)
-  if ((rc = k_calc_mip(h, false, 0.01))) return bail(rc);
-  if (cudaMemcpyAsync(h->fld[CFDL_F_MIP0], h->fld[CFDL_F_MIP], sizeof(double) * (size_t)F, cudaMemcpyDeviceToDevice, h->stream) != cudaSuccess ||
-      cudaStreamSynchronize(h->stream) != cudaSuccess)
-    return bail(fail(CFDL_ERR_CUDA, "initial calc_mip failed: %s", cudaGetErrorString(cudaGetLastError())));
-  *out = h;
-  return CFDL_OK;
+  return create_impl(out, ne, nf, nbf, ef2nb_idx, ef2nb_nb, ef2nb_fg, s2g, bs, xc, yc, zc, aip, rip, vol, rho, mu, nbc, bc_esec, bc_kind,
+                     bc_uvw, n_subdomains, g2gf_p, g2gf_idx, nullptr, 0, 1, device);
+}
+
+int cfdl_create_distributed(cfdl_handle* out, int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_idx, const int32_t* ef2nb_nb,
+                            const int32_t* ef2nb_fg, const int32_t* s2g, const int32_t* bs, const double* xc, const double* yc,
+                            const double* zc, const double* aip, const double* rip, const double* vol, const double* rho,
+                            const double* mu, int32_t nbc, const int32_t* bc_esec, const int32_t* bc_kind, const double* bc_uvw,
+                            const int32_t* cell2rank, int32_t rank, int32_t nranks, int32_t device) {
+  if (nranks > 1 && !cell2rank) return fail(CFDL_ERR_ARG, "cfdl_create_distributed: cell2rank is NULL");
+  return create_impl(out, ne, nf, nbf, ef2nb_idx, ef2nb_nb, ef2nb_fg, s2g, bs, xc, yc, zc, aip, rip, vol, rho, mu, nbc, bc_esec, bc_kind,
+                     bc_uvw, 1, nullptr, nullptr, cell2rank, rank, nranks, device);
 }
 
 int cfdl_destroy(cfdl_handle h) {
   if (!h) return CFDL_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  comm_destroy(h);
   for (cudaEvent_t e : h->prof_ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->timer_ev) if (e) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
@@ -208,6 +257,8 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "solver")) {
     int m = (int)value;
     if (m < CFDL_SOLVER_PARITY || m > CFDL_SOLVER_PCG) return fail(CFDL_ERR_ARG, "cfdl_set_option: solver mode %d", m);
+    if (m == CFDL_SOLVER_PARITY && h->prep.nranks > 1)
+      return fail(CFDL_ERR_UNSUPPORTED, "cfdl_set_option: the exact natural-order solver needs the whole mesh on one GPU");
     h->solver_mode = m;
     return CFDL_OK;
   }
@@ -235,6 +286,11 @@ int cfdl_get_info(cfdl_handle h, const char* key, double* value) {
   else if (!std::strcmp(key, "num_sms")) *value = h->num_sms;
   else if (!std::strcmp(key, "solver")) *value = h->solver_mode;
   else if (!std::strcmp(key, "launches")) *value = (double)h->launches;
+  else if (!std::strcmp(key, "owned_cells")) *value = h->N;
+  else if (!std::strcmp(key, "ghost_cells")) *value = h->G;
+  else if (!std::strcmp(key, "local_halos")) *value = h->B;
+  else if (!std::strcmp(key, "local_faces")) *value = h->F;
+  else if (!std::strcmp(key, "neighbour_ranks")) *value = h->nnbr;
   else if (!std::strncmp(key, "prof_ms_", 8) || !std::strncmp(key, "prof_n_", 7)) {
     static const char* names[8] = {"sgs", "residual", "coef_uvw", "coef_p", "mip", "grad", "levels", "pcg"};
     const bool is_ms = key[5] == 'm';
@@ -278,6 +334,23 @@ int cfdl_download_field(cfdl_handle h, int field, double* host) {
   if (field < 0 || field >= CFDL_F_COUNT || !host) return fail(CFDL_ERR_ARG, "cfdl_download_field: bad field/pointer");
   return download_field(h, field, host);
 }
+int cfdl_field_local_size(cfdl_handle h, int field, int64_t* n) {
+  if (!good(h) || field < 0 || field >= CFDL_F_COUNT || !n) return fail(CFDL_ERR_ARG, "cfdl_field_local_size: bad argument");
+  *n = (int64_t)field_len(h, field);
+  return CFDL_OK;
+}
+int cfdl_upload_field_local(cfdl_handle h, int field, const double* host) {
+  ENTER(h);
+  if (field < 0 || field >= CFDL_F_COUNT || !host) return fail(CFDL_ERR_ARG, "cfdl_upload_field_local: bad field/pointer");
+  CFDL_CUDA(cudaMemcpyAsync(h->fld[field], host, sizeof(double) * field_len(h, field), cudaMemcpyHostToDevice, h->stream));
+  FINISH(h);
+}
+int cfdl_download_field_local(cfdl_handle h, int field, double* host) {
+  ENTER(h);
+  if (field < 0 || field >= CFDL_F_COUNT || !host) return fail(CFDL_ERR_ARG, "cfdl_download_field_local: bad field/pointer");
+  CFDL_CUDA(cudaMemcpyAsync(host, h->fld[field], sizeof(double) * field_len(h, field), cudaMemcpyDeviceToHost, h->stream));
+  FINISH(h);
+}
 
 int cfdl_update_boundaries(cfdl_handle h) { ENTER(h); int rc = k_update_boundaries(h); if (rc) return rc; FINISH(h); }
 int cfdl_update_time(cfdl_handle h) { ENTER(h); int rc = k_update_time(h); if (rc) return rc; FINISH(h); }
@@ -300,16 +373,26 @@ int cfdl_run(cfdl_handle h, double dt, int32_t nit, int32_t ntstep, int32_t ncoe
   FINISH(h);
 }
 
-int cfdl_calc_coef_uvw(cfdl_handle h, double dt) { ENTER(h); int rc = k_calc_coef_uvw(h, dt); if (rc) return rc; FINISH(h); }
+int cfdl_calc_coef_uvw(cfdl_handle h, double dt) {
+  ENTER(h);
+  int rc = k_calc_coef_uvw(h, dt);
+  if (rc || (rc = comm_exchange(h, h->fld[CFDL_F_D], 1, -1)) || (rc = comm_exchange(h, h->fld[CFDL_F_DC], 1, -1))) return rc;
+  FINISH(h);
+}
 int cfdl_calc_mip(cfdl_handle h, int32_t lrc, double dt) { ENTER(h); int rc = k_calc_mip(h, lrc != 0, dt); if (rc) return rc; FINISH(h); }
 int cfdl_calc_coef_p(cfdl_handle h) { ENTER(h); int rc = k_calc_coef_p(h); if (rc) return rc; FINISH(h); }
 int cfdl_adjust_pc(cfdl_handle h) { ENTER(h); int rc = k_adjust_pc(h); if (rc) return rc; FINISH(h); }
-int cfdl_update_uvwp(cfdl_handle h) { ENTER(h); int rc = k_update_uvwp(h); if (rc) return rc; FINISH(h); }
+int cfdl_update_uvwp(cfdl_handle h) {
+  ENTER(h);
+  int rc = k_update_uvwp(h);
+  if (rc || (rc = comm_exchange(h, h->fld[CFDL_F_GP], 3, -1))) return rc;
+  FINISH(h);
+}
 int cfdl_calc_grad(cfdl_handle h, int phi_f, int grad_f) {
   ENTER(h);
   if (phi_f < CFDL_F_U || phi_f > CFDL_F_PC || grad_f < CFDL_F_GU || grad_f > CFDL_F_GPC) return fail(CFDL_ERR_ARG, "cfdl_calc_grad: bad field ids");
   int rc = k_calc_grad(h, h->fld[phi_f], h->fld[grad_f]);
-  if (rc) return rc;
+  if (rc || (rc = comm_exchange(h, h->fld[grad_f], 3, -1))) return rc;
   FINISH(h);
 }
 int cfdl_solve_eq(cfdl_handle h, int eq, int32_t nit, double* out4) {
@@ -354,6 +437,7 @@ int cfdl_host_calc_residual(cfdl_handle h, const double* phi, const double* ap, 
                             double* res_max) {
   ENTER(h);
   if (!phi || !ap || !anb || !b || !res || !res_max) return fail(CFDL_ERR_ARG, "cfdl_host_calc_residual: NULL array");
+  if (h->prep.nranks > 1) return fail(CFDL_ERR_UNSUPPORTED, "cfdl_host_calc_residual: single-GPU drop-in");
   int rc;
   if ((rc = upload_field(h, CFDL_F_AP, ap)) || (rc = upload_field(h, CFDL_F_ANB, anb)) || (rc = upload_field(h, CFDL_F_B, b)) ||
       (rc = upload_field(h, CFDL_F_PC, phi)))

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(TPB) bc_kernel(int B, int N, const int32_t* __
 
 int k_update_boundaries(Handle* h) {
   if (h->B == 0) return CFDL_OK;
-  bc_kernel<<<grid_for(h, h->B, TPB), TPB, 0, S(h)>>>(h->B, h->N, h->halo_cell, h->halo_face, h->halo_bc, h->bc_kind,
+  bc_kernel<<<grid_for(h, h->B, TPB), TPB, 0, S(h)>>>(h->B, h->Nc, h->halo_cell, h->halo_face, h->halo_bc, h->bc_kind,
                                                             h->bc_uvw, h->aip, h->fld[CFDL_F_U], h->fld[CFDL_F_V],
                                                             h->fld[CFDL_F_W], h->fld[CFDL_F_P], h->fld[CFDL_F_MIP]);
   CFDL_CUDA(cudaGetLastError());
@@ -64,7 +64,7 @@ int k_update_boundaries(Handle* h) {
 
 // ---- calc_coef_uvw, mod_uvwp.f90:161-286 ------------------------------------------------------
 struct UvwArgs {
-  int N, Np;
+  int N, Nc, Np;  // owned cells, owned+ghost cells (halo indices start at Nc), ELL column stride
   const int32_t *ell_nb, *ell_fs, *halo_bc, *bc_kind;
   const uint8_t* nfc;
   const double *xc, *yc, *zc, *aip, *rip, *vol, *rho, *mu;
@@ -75,7 +75,7 @@ struct UvwArgs {
 
 template <int K>
 __global__ void __launch_bounds__(TPB) coef_uvw_kernel(const UvwArgs A) {
-  const int N = A.N, Np = A.Np;
+  const int N = A.N, Nc = A.Nc, Np = A.Np;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
     const int n = A.nfc[c];
     const double rp[3] = {A.xc[c], A.yc[c], A.zc[c]};
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(TPB) coef_uvw_kernel(const UvwArgs A) {
         const int fs = A.ell_fs[(size_t)k * Np + c];
         nbk[k] = nb;
         double d = 0.0, fnb = 0.0;
-        if (nb < N) {  // lfnb > 0
+        if (nb < Nc) {  // lfnb > 0 (owned or ghost cell)
           const int f = abs(fs) - 1;
           const double sg = fs > 0 ? 1.0 : -1.0;
           double a[3], rip[3];
@@ -152,10 +152,10 @@ __global__ void __launch_bounds__(TPB) coef_uvw_kernel(const UvwArgs A) {
       int best = 0x7fffffff, bk = -1;
 #pragma unroll
       for (int k = 0; k < K; ++k)
-        if (nbk[k] >= N && nbk[k] > last && nbk[k] < best) { best = nbk[k]; bk = k; }
+        if (nbk[k] >= Nc && nbk[k] > last && nbk[k] < best) { best = nbk[k]; bk = k; }
       if (bk < 0) break;
       last = best;
-      const int bc = A.halo_bc[best - N];
+      const int bc = A.halo_bc[best - Nc];
       if (bc < 0) continue;
       const int f = A.ell_fs[(size_t)bk * Np + c] - 1;  // always outward on boundary
       double a[3];
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(TPB) coef_uvw_kernel(const UvwArgs A) {
 
 int k_calc_coef_uvw(Handle* h, double dt) {
   UvwArgs A;
-  A.N = h->N; A.Np = h->Np;
+  A.N = h->N; A.Nc = h->Nc; A.Np = h->Np;
   A.ell_nb = h->ell_nb; A.ell_fs = h->ell_fs; A.halo_bc = h->halo_bc; A.bc_kind = h->bc_kind; A.nfc = h->nfc;
   A.xc = h->xc; A.yc = h->yc; A.zc = h->zc; A.aip = h->aip; A.rip = h->rip; A.vol = h->vol; A.rho = h->rho; A.mu = h->mu;
   A.u = h->fld[CFDL_F_U]; A.v = h->fld[CFDL_F_V]; A.w = h->fld[CFDL_F_W];
@@ -216,7 +216,7 @@ int k_calc_coef_uvw(Handle* h, double dt) {
 
 // ---- calc_coef_p, mod_uvwp.f90:289-368 --------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(TPB) coef_p_kernel(int N, int Np, const int32_t* __restrict__ ell_nb,
+__global__ void __launch_bounds__(TPB) coef_p_kernel(int N, int Nc, int Np, const int32_t* __restrict__ ell_nb,
                                                      const int32_t* __restrict__ ell_fs, const uint8_t* __restrict__ nfc,
                                                      const int32_t* __restrict__ halo_bc,
                                                      const double* __restrict__ xc, const double* __restrict__ yc,
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(TPB) coef_p_kernel(int N, int Np, const int32_
         const int fs = ell_fs[(size_t)k * Np + c];
         nbk[k] = nb;
         double d = 0.0;
-        if (nb < N) {
+        if (nb < Nc) {
           const int f = abs(fs) - 1;
           const double sg = fs > 0 ? 1.0 : -1.0;
           double a[3], r[3];
@@ -263,10 +263,10 @@ __global__ void __launch_bounds__(TPB) coef_p_kernel(int N, int Np, const int32_
       int best = 0x7fffffff, bk = -1;
 #pragma unroll
       for (int k = 0; k < K; ++k)
-        if (nbk[k] >= N && nbk[k] > last && nbk[k] < best) { best = nbk[k]; bk = k; }
+        if (nbk[k] >= Nc && nbk[k] > last && nbk[k] < best) { best = nbk[k]; bk = k; }
       if (bk < 0) break;
       last = best;
-      if (halo_bc[best - N] < 0) continue;
+      if (halo_bc[best - Nc] < 0) continue;
       b = b - mip[ell_fs[(size_t)bk * Np + c] - 1];
     }
     ap_o[c] = ap;
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(TPB) coef_p_kernel(int N, int Np, const int32_
 
 int k_calc_coef_p(Handle* h) {
   const int g = grid_for(h, h->N, TPB);
-#define CP_ARGS h->N, h->Np, h->ell_nb, h->ell_fs, h->nfc, h->halo_bc, h->xc, h->yc, h->zc, h->aip, h->rip, h->rho, \
+#define CP_ARGS h->N, h->Nc, h->Np, h->ell_nb, h->ell_fs, h->nfc, h->halo_bc, h->xc, h->yc, h->zc, h->aip, h->rip, h->rho, \
                 h->fld[CFDL_F_DC], h->fld[CFDL_F_MIP], h->fld[CFDL_F_AP], h->fld[CFDL_F_ANB], h->fld[CFDL_F_B]
   prof_begin(h, PROF_COEF_P);
   if (h->K <= 4) coef_p_kernel<4><<<g, TPB, 0, S(h)>>>(CP_ARGS);
@@ -355,18 +355,23 @@ __global__ void __launch_bounds__(TPB) halo_copy_kernel(int B, int N, const int3
 
 int k_adjust_pc(Handle* h) {
   double* pc = h->fld[CFDL_F_PC];
-  copy_scalar_kernel<<<1, 1, 0, S(h)>>>(h->scal, pc + h->prep.o2c[0]);  // pref = phic(1)
-  shift_kernel<<<grid_for(h, h->N, TPB), TPB, 0, S(h)>>>(h->N, pc, h->scal);
-  if (h->B) halo_copy_kernel<<<grid_for(h, h->B, TPB), TPB, 0, S(h)>>>(h->B, h->N, h->halo_cell, pc);
+  if (h->prep.o2c[0] >= 0 && h->prep.o2c[0] < h->N)
+    copy_scalar_kernel<<<1, 1, 0, S(h)>>>(h->scal, pc + h->prep.o2c[0]);  // pref = phic(1)
+  int rc = comm_bcast(h, h->scal, 1, h->prep.ref_cell_owner);  // several GPUs: the owner of cell 1 provides pref
+  if (rc) return rc;
+  // ghost copies are shifted by the same subtraction, so they stay equal to their owners' values
+  shift_kernel<<<grid_for(h, h->Nc, TPB), TPB, 0, S(h)>>>(h->Nc, pc, h->scal);
+  if (h->B) halo_copy_kernel<<<grid_for(h, h->B, TPB), TPB, 0, S(h)>>>(h->B, h->Nc, h->halo_cell, pc);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
 
 // ---- update_uvwp, mod_uvwp.f90:370-436 (cell-velocity correction is disabled there) ------------
-__global__ void __launch_bounds__(TPB) correct_cells_kernel(int N, double* p, const double* __restrict__ pc, double* gp,
+__global__ void __launch_bounds__(TPB) correct_cells_kernel(int N, int Nc, double* p, const double* __restrict__ pc, double* gp,
                                                             const double* __restrict__ gpc) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
-    p[c] = p[c] + pc[c];
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < Nc; c += gridDim.x * blockDim.x) {
+    p[c] = p[c] + pc[c];  // ghost cells too: their pc is current, so p stays equal to the owner's
+    if (c >= N) continue;
     const size_t i = 3 * (size_t)c;
     gp[i] = gp[i] + gpc[i]; gp[i + 1] = gp[i + 1] + gpc[i + 1]; gp[i + 2] = gp[i + 2] + gpc[i + 2];
   }
@@ -395,7 +400,7 @@ __global__ void __launch_bounds__(TPB) correct_faces_kernel(int Fi, const int32_
 }
 
 int k_update_uvwp(Handle* h) {
-  correct_cells_kernel<<<grid_for(h, h->N, TPB), TPB, 0, S(h)>>>(h->N, h->fld[CFDL_F_P], h->fld[CFDL_F_PC], h->fld[CFDL_F_GP],
+  correct_cells_kernel<<<grid_for(h, h->Nc, TPB), TPB, 0, S(h)>>>(h->N, h->Nc, h->fld[CFDL_F_P], h->fld[CFDL_F_PC], h->fld[CFDL_F_GP],
                                                                        h->fld[CFDL_F_GPC]);
   if (h->Fi)
     correct_faces_kernel<<<grid_for(h, h->Fi, TPB), TPB, 0, S(h)>>>(h->Fi, h->face_a, h->face_b, h->xc, h->yc, h->zc, h->aip,

@@ -67,13 +67,13 @@ __global__ void __launch_bounds__(TPB) sgs_range_kernel(int c0, int c1, int Np, 
 // residual r = b + sum anb*phi_nb - ap*phi (mod_solver.f90:309-321 / 230-253): per-CTA partial
 // sums of r^2 and max|r| (or max(0, r) in signed mode), combined in fixed order by the last
 // CTA to finish, which also advances the solve control block.
-enum { RES_INIT = 0, RES_ITER = 1, RES_PLAIN = 2 };
+enum { RES_INIT = 0, RES_ITER = 1, RES_PLAIN = 2, RES_LOCAL = 3, RES_LOCAL_GUARDED = 4 };
 template <int K>
 __global__ void __launch_bounds__(TPB) residual_kernel(int N, int Np, const int32_t* __restrict__ nbi,
                                                        const double* __restrict__ ap, const double* __restrict__ anb,
                                                        const double* __restrict__ b, const double* __restrict__ phi,
                                                        double* partial, SolveCtl* ctl, int mode, int signed_max, double* out2) {
-  if (mode == RES_ITER && ctl->done) return;
+  if ((mode == RES_ITER || mode == RES_LOCAL_GUARDED) && ctl->done) return;
   double s = 0.0, m = 0.0;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
     double sumnb = b[c];
@@ -114,9 +114,27 @@ __global__ void __launch_bounds__(TPB) residual_kernel(int N, int Np, const int3
       ctl->it += 1;
       ctl->res_f = res; ctl->res_max = m;
       ctl->done = !(ctl->it < ctl->nit && res > ctl->res_target);
-    } else {
+    } else if (mode == RES_PLAIN) {
       out2[0] = res; out2[1] = m;
+    } else {  // RES_LOCAL: this rank's sum of r^2 and max, combined across ranks by NCCL
+      out2[0] = s; out2[1] = m;
     }
+  }
+}
+
+// several GPUs: after the all-reduce of (sum r^2, max) advance the control block on every rank
+__global__ void finalize_residual_kernel(SolveCtl* ctl, const double* sm, double ne_global, int mode) {
+  if (mode == RES_ITER && ctl->done) return;
+  const double res = sqrt(sm[0] / ne_global);
+  if (mode == RES_INIT) {
+    ctl->it = 0;
+    ctl->res_i = res; ctl->res_f = res; ctl->res_max = 0.0;
+    ctl->res_target = res / 10.0;
+    ctl->done = !(0 < ctl->nit && res > ctl->res_target);
+  } else {
+    ctl->it += 1;
+    ctl->res_f = res; ctl->res_max = sm[1];
+    ctl->done = !(ctl->it < ctl->nit && res > ctl->res_target);
   }
 }
 
@@ -382,7 +400,36 @@ static int mcsgs_solve_t(Handle* h, int eq, double* phi, const double* rhs, int 
   init.nit = nit;
   *h->ctl_host = init;
   CFDL_CUDA(cudaMemcpyAsync(h->ctl, h->ctl_host, sizeof(SolveCtl), cudaMemcpyHostToDevice, h->stream));
-  residual_kernel<K><<<g, TPB, 0, S(h)>>>(N, Np, h->ell_nb, ap, anb, rhs, phi, h->partial, h->ctl, RES_INIT, 0, nullptr);
+  // Several GPUs: the colouring is global, and the ghost copies of a colour are refreshed right
+  // after that colour's sweep, so every update sees exactly the operands of the single-GPU
+  // sweep; the residual norm is all-reduced (sum of r^2, max) before the stopping test.
+  const bool dist = h->prep.nranks > 1;
+  int rc;
+  auto residual = [&](int mode) -> int {
+    prof_begin(h, PROF_RESIDUAL);
+    if (!dist) {
+      residual_kernel<K><<<g, TPB, 0, S(h)>>>(N, Np, h->ell_nb, ap, anb, rhs, phi, h->partial, h->ctl, mode, 0, nullptr);
+    } else {
+      residual_kernel<K><<<g, TPB, 0, S(h)>>>(N, Np, h->ell_nb, ap, anb, rhs, phi, h->partial, h->ctl,
+                                              mode == RES_ITER ? RES_LOCAL_GUARDED : RES_LOCAL, 0, h->scal + 8);
+      int r = comm_allreduce_sum_max(h, h->scal + 8);
+      if (r) return r;
+      finalize_residual_kernel<<<1, 1, 0, S(h)>>>(h->ctl, h->scal + 8, (double)h->ne_global, mode);
+    }
+    prof_end(h);
+    return CFDL_OK;
+  };
+  auto sweep = [&](int c) -> int {
+    const int n = cp[c + 1] - cp[c];
+    if (n > 0) {
+      prof_begin(h, PROF_SGS_SWEEP);
+      sgs_range_kernel<K><<<grid_for(h, n, TPB), TPB, 0, S(h)>>>(cp[c], cp[c + 1], Np, h->ell_nb, ap, anb, rhs, phi, sor, h->ctl);
+      prof_end(h);
+    }
+    return dist ? comm_exchange(h, phi, 1, c) : CFDL_OK;
+  };
+  if (dist && (rc = comm_exchange(h, phi, 1, -1))) return rc;
+  if ((rc = residual(RES_INIT))) return rc;
   int launched = 0, batch = 1;
   for (;;) {
     CFDL_CUDA(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(SolveCtl), cudaMemcpyDeviceToHost, h->stream));
@@ -390,17 +437,9 @@ static int mcsgs_solve_t(Handle* h, int eq, double* phi, const double* rhs, int 
     if (h->ctl_host->done || launched >= nit) break;
     const int m = std::min(batch, nit - launched);
     for (int i = 0; i < m; ++i) {
-      for (int c = 0; c < nc; ++c) {
-        const int n = cp[c + 1] - cp[c];
-        if (n > 0) { prof_begin(h, PROF_SGS_SWEEP); sgs_range_kernel<K><<<grid_for(h, n, TPB), TPB, 0, S(h)>>>(cp[c], cp[c + 1], Np, h->ell_nb, ap, anb, rhs, phi, sor, h->ctl); prof_end(h); }
-      }
-      for (int c = nc - 1; c >= 0; --c) {
-        const int n = cp[c + 1] - cp[c];
-        if (n > 0) { prof_begin(h, PROF_SGS_SWEEP); sgs_range_kernel<K><<<grid_for(h, n, TPB), TPB, 0, S(h)>>>(cp[c], cp[c + 1], Np, h->ell_nb, ap, anb, rhs, phi, sor, h->ctl); prof_end(h); }
-      }
-      prof_begin(h, PROF_RESIDUAL);
-      residual_kernel<K><<<g, TPB, 0, S(h)>>>(N, Np, h->ell_nb, ap, anb, rhs, phi, h->partial, h->ctl, RES_ITER, 0, nullptr);
-      prof_end(h);
+      for (int c = 0; c < nc; ++c) if ((rc = sweep(c))) return rc;
+      for (int c = nc - 1; c >= 0; --c) if ((rc = sweep(c))) return rc;
+      if ((rc = residual(RES_ITER))) return rc;
     }
     CFDL_CUDA(cudaGetLastError());
     launched += m;
@@ -429,6 +468,8 @@ int residual_plain(Handle* h, const double* phi, const double* rhs, bool signed_
 int solve_equation(Handle* h, int eq, double* phi, const double* rhs, int nit, double* out4, bool dispatch) {
   if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
   const bool k4 = h->K <= 4;
+  if (h->prep.nranks > 1 && h->solver_mode == CFDL_SOLVER_PARITY)
+    return fail(CFDL_ERR_UNSUPPORTED, "the exact natural-order solver is sequential across partitions; use solver=mcsgs on several GPUs");
   switch (h->solver_mode) {
     case CFDL_SOLVER_PARITY:
       return k4 ? parity_solve_t<4>(h, eq, phi, rhs, nit, out4, dispatch) : parity_solve_t<6>(h, eq, phi, rhs, nit, out4, dispatch);

@@ -112,3 +112,36 @@ extern "C" int cfdl_partition_rcb(int32_t ne, const double* xc, const double* yc
   }
   return CFDL_OK;
 }
+
+// ---- partition plan (host only; what cfdl_create_distributed derives internally) ---------------
+#include "prep.h"
+
+// For rank `rank` of `nranks`: owned cells and ghost cells in device order (1-based ids of the
+// global mesh), the neighbour ranks, and per neighbour the cells sent to it / the slice of the
+// ghost range received from it.  send_ptr/recv_ptr have n_nbr+1 entries; the sender's list and
+// the receiver's ghost slice enumerate the same cells in the same order on both ranks.
+extern "C" int cfdl_partition_plan(int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_idx, const int32_t* ef2nb_nb,
+                                   const int32_t* ef2nb_fg, const int32_t* s2g, const int32_t* bs, const double* xc,
+                                   const double* yc, const double* zc, const int32_t* cell2rank, int32_t nranks, int32_t rank,
+                                   int32_t* n_owned, int32_t* owned, int32_t* n_ghost, int32_t* ghost, int32_t* n_nbr,
+                                   int32_t* nbr_rank, int32_t* send_ptr, int32_t* send_cells, int32_t* recv_ptr,
+                                   int32_t* ncolors, int32_t* owned_color_ptr) {
+  using namespace cfdl;
+  Prep p;
+  int rc = prepare(p, ne, nf, nbf, ef2nb_idx, ef2nb_nb, ef2nb_fg, s2g, bs, xc, yc, zc, 0, nullptr, nullptr, nullptr, 1, nullptr, nullptr, 2,
+                   cell2rank, rank, nranks);
+  if (rc) return rc;
+  const int nnbr = (int)p.nbr_rank.size(), nc = p.ncolors;
+  if (n_owned) *n_owned = p.N;
+  if (n_ghost) *n_ghost = p.G;
+  if (n_nbr) *n_nbr = nnbr;
+  if (ncolors) *ncolors = nc;
+  if (owned) for (int32_t c = 0; c < p.N; ++c) owned[c] = p.c2o[c] + 1;
+  if (ghost) for (int32_t g = 0; g < p.G; ++g) ghost[g] = p.c2o[p.N + g] + 1;
+  if (nbr_rank) for (int r = 0; r < nnbr; ++r) nbr_rank[r] = p.nbr_rank[r];
+  if (send_ptr) for (int r = 0; r <= nnbr; ++r) send_ptr[r] = p.send_ptr[(size_t)r * nc];
+  if (recv_ptr) for (int r = 0; r <= nnbr; ++r) recv_ptr[r] = p.recv_ptr[(size_t)r * nc];
+  if (send_cells) for (size_t i = 0; i < p.send_cells.size(); ++i) send_cells[i] = p.c2o[p.send_cells[i]] + 1;
+  if (owned_color_ptr) for (int c = 0; c <= nc; ++c) owned_color_ptr[c] = p.color_ptr[c];
+  return CFDL_OK;
+}

@@ -96,114 +96,195 @@ int prepare(Prep& p, int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_i
             const int32_t* ef2nb_nb, const int32_t* ef2nb_fg, const int32_t* s2g, const int32_t* bs,
             const double* xc, const double* yc, const double* zc, int32_t nbc, const int32_t* bc_esec,
             const int32_t* bc_kind, const double* bc_uvw, int32_t n_subdomains,
-            const int32_t* g2gf_p, const int32_t* g2gf_idx, int reorder_mode) {
+            const int32_t* g2gf_p, const int32_t* g2gf_idx, int reorder_mode,
+            const int32_t* cell2rank, int32_t rank, int32_t nranks) {
   if (ne < 1 || nf < 1 || nbf < 0) return fail(CFDL_ERR_ARG, "cfdl_create: bad sizes ne=%d nf=%d nbf=%d", ne, nf, nbf);
-  const int32_t N = ne, F = nf, B = nbf, H = ne + nbf;
+  if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !cell2rank)) return fail(CFDL_ERR_ARG, "cfdl_create: bad rank %d of %d", rank, nranks);
+  if (nranks > 1 && n_subdomains > 1) return fail(CFDL_ERR_UNSUPPORTED, "cfdl_create: the pc block solver (n_subdomains>1) is single-GPU; on several GPUs the GPUs are the blocks");
+  const int32_t gN = ne, gF = nf, gB = nbf, gH = ne + nbf;
   const int64_t Z64 = 2 * (int64_t)nf - nbf;
   if (Z64 > 0x7fffffff) return fail(CFDL_ERR_RANGE, "cfdl_create: 2nf-nbf exceeds int32");
-  const int32_t Z = (int32_t)Z64;
-  p.N = N; p.F = F; p.B = B; p.H = H; p.Z = Z;
+  const int32_t gZ = (int32_t)Z64;
+  p.gN = gN; p.gF = gF; p.gB = gB; p.gZ = gZ;
+  p.rank = rank; p.nranks = nranks;
   p.n_subdomains = n_subdomains;
-  if (ef2nb_idx[0] != 1 || ef2nb_idx[N] - 1 != Z) return fail(CFDL_ERR_MESH, "cfdl_create: ef2nb_idx does not span 2nf-nbf slots");
-  p.row_ptr.resize((size_t)N + 1);
+  if (ef2nb_idx[0] != 1 || ef2nb_idx[gN] - 1 != gZ) return fail(CFDL_ERR_MESH, "cfdl_create: ef2nb_idx does not span 2nf-nbf slots");
+  p.row_ptr.resize((size_t)gN + 1);
   int K = 0;
-  for (int32_t e = 0; e <= N; ++e) p.row_ptr[e] = ef2nb_idx[e] - 1;
-  for (int32_t e = 0; e < N; ++e) {
+  for (int32_t e = 0; e <= gN; ++e) p.row_ptr[e] = ef2nb_idx[e] - 1;
+  for (int32_t e = 0; e < gN; ++e) {
     int len = p.row_ptr[e + 1] - p.row_ptr[e];
     if (len < 1 || len > 31) return fail(CFDL_ERR_MESH, "cfdl_create: cell %d has %d faces", e + 1, len);
     K = std::max(K, len);
   }
   p.K = K;
-  p.Np = (N + 31) / 32 * 32;
-  const int32_t Np = p.Np;
   // unpack (mod_util.f90:1428-1448)
-  std::vector<int32_t> o_nb((size_t)Z), o_fg((size_t)Z);
-  for (int32_t idx = 0; idx < Z; ++idx) {
+  std::vector<int32_t> o_nb((size_t)gZ), o_fg((size_t)gZ);
+  for (int32_t idx = 0; idx < gZ; ++idx) {
     uint32_t pk = (uint32_t)ef2nb_nb[idx];
     int32_t id = (int32_t)(pk >> 5), lf = (int32_t)(pk & 31u), fg = ef2nb_fg[idx];
-    if (fg == 0 || std::abs(fg) > F) return fail(CFDL_ERR_MESH, "cfdl_create: slot %d has face id %d", idx + 1, fg);
-    if (lf > 0) { if (id < 1 || id > N) return fail(CFDL_ERR_MESH, "cfdl_create: slot %d neighbour %d out of range", idx + 1, id); }
-    else { if (id <= N || id > H || fg < 0) return fail(CFDL_ERR_MESH, "cfdl_create: slot %d halo %d out of range", idx + 1, id); }
+    if (fg == 0 || std::abs(fg) > gF) return fail(CFDL_ERR_MESH, "cfdl_create: slot %d has face id %d", idx + 1, fg);
+    if (lf > 0) { if (id < 1 || id > gN) return fail(CFDL_ERR_MESH, "cfdl_create: slot %d neighbour %d out of range", idx + 1, id); }
+    else { if (id <= gN || id > gH || fg < 0) return fail(CFDL_ERR_MESH, "cfdl_create: slot %d halo %d out of range", idx + 1, id); }
     o_nb[idx] = id - 1;
     o_fg[idx] = fg;
   }
-  // ---- device cell numbering: base order (natural | Morton), then multicolour-major --------
-  std::vector<int32_t> base((size_t)N);
+  // s2g consistency (owner side carries +fg; calc_mip/update_uvwp start from it)
+  for (int32_t f = 0; f < gF; ++f) {
+    uint32_t pk = (uint32_t)s2g[f];
+    int32_t e = (int32_t)(pk >> 5) - 1, lf = (int32_t)(pk & 31u);
+    if (e < 0 || e >= gN || lf < 1 || p.row_ptr[e] + lf - 1 >= p.row_ptr[e + 1] || o_fg[p.row_ptr[e] + lf - 1] != f + 1)
+      return fail(CFDL_ERR_MESH, "cfdl_create: s2g(%d) is not the owner slot of the face", f + 1);
+  }
+  // ---- global base order (natural | Morton) and global greedy colouring --------------------
+  std::vector<int32_t> base((size_t)gN), brank((size_t)gN);
   std::iota(base.begin(), base.end(), 0);
   p.morton = false;
   if (reorder_mode != 0) {
     std::vector<int32_t> mo;
-    morton_order(N, xc, yc, zc, mo);
+    morton_order(gN, xc, yc, zc, mo);
     bool use = (reorder_mode == 1);
     if (reorder_mode == 2) {  // auto: adopt Morton only when the given numbering has poor locality
-      std::vector<int32_t> mrank((size_t)N);
-      for (int32_t i = 0; i < N; ++i) mrank[mo[i]] = i;
+      std::vector<int32_t> mrank((size_t)gN);
+      for (int32_t i = 0; i < gN; ++i) mrank[mo[i]] = i;
       double dn = 0, dm = 0;
-      for (int32_t e = 0; e < N; ++e)
+      for (int32_t e = 0; e < gN; ++e)
         for (int32_t idx = p.row_ptr[e]; idx < p.row_ptr[e + 1]; ++idx)
-          if (o_nb[idx] < N) { dn += std::abs((double)o_nb[idx] - e); dm += std::abs((double)mrank[o_nb[idx]] - mrank[e]); }
+          if (o_nb[idx] < gN) { dn += std::abs((double)o_nb[idx] - e); dm += std::abs((double)mrank[o_nb[idx]] - mrank[e]); }
       use = dn > 4.0 * dm;
     }
     if (use) { base.swap(mo); p.morton = true; }
   }
-  std::vector<int8_t> color((size_t)N, -1);
+  for (int32_t i = 0; i < gN; ++i) brank[base[i]] = i;
+  std::vector<int8_t> color((size_t)gN, -1);
   int ncol = 0;
-  for (int32_t i = 0; i < N; ++i) {  // greedy colouring in base order
+  for (int32_t i = 0; i < gN; ++i) {
     int32_t e = base[i];
     uint32_t used = 0;
     for (int32_t idx = p.row_ptr[e]; idx < p.row_ptr[e + 1]; ++idx)
-      if (o_nb[idx] < N && color[o_nb[idx]] >= 0) used |= 1u << color[o_nb[idx]];
+      if (o_nb[idx] < gN && color[o_nb[idx]] >= 0) used |= 1u << color[o_nb[idx]];
     int c = 0;
     while (used & (1u << c)) ++c;
     color[e] = (int8_t)c;
     ncol = std::max(ncol, c + 1);
   }
   p.ncolors = ncol;
+  auto owner = [&](int32_t e) -> int32_t { return nranks > 1 ? cell2rank[e] - 1 : 0; };
+  if (nranks > 1)
+    for (int32_t e = 0; e < gN; ++e)
+      if (cell2rank[e] < 1 || cell2rank[e] > nranks) return fail(CFDL_ERR_ARG, "cfdl_create: cell2rank(%d)=%d outside 1..%d", e + 1, cell2rank[e], nranks);
+  p.ref_cell_owner = owner(0);
+  // ---- owned cells: colour-major, base order inside a colour ---------------------------------
   p.color_ptr.assign(ncol + 1, 0);
-  for (int32_t e = 0; e < N; ++e) p.color_ptr[color[e] + 1]++;
+  int32_t N = 0;
+  for (int32_t e = 0; e < gN; ++e) if (owner(e) == rank) { p.color_ptr[color[e] + 1]++; ++N; }
+  if (N < 1) return fail(CFDL_ERR_ARG, "cfdl_create: rank %d owns no cell", rank);
   for (int c = 0; c < ncol; ++c) p.color_ptr[c + 1] += p.color_ptr[c];
-  p.c2o.resize(N); p.o2c.resize(N);
+  p.o2c.assign(gN, -1);
+  p.c2o.resize(N);
   {
     std::vector<int32_t> cur(p.color_ptr.begin(), p.color_ptr.end() - 1);
-    for (int32_t i = 0; i < N; ++i) { int32_t e = base[i]; int32_t c = cur[color[e]]++; p.c2o[c] = e; p.o2c[e] = c; }
+    for (int32_t i = 0; i < gN; ++i) {
+      int32_t e = base[i];
+      if (owner(e) != rank) continue;
+      int32_t c = cur[color[e]]++;
+      p.c2o[c] = e; p.o2c[e] = c;
+    }
   }
-  // ---- faces: interior faces in owner order, then boundary faces in halo order ------------
-  p.o2f.assign(F, -1); p.f2o.assign(F, -1);
-  int32_t nfi = 0;
-  for (int32_t c = 0; c < N; ++c) {
-    int32_t e = p.c2o[c];
-    for (int32_t idx = p.row_ptr[e]; idx < p.row_ptr[e + 1]; ++idx)
-      if (o_nb[idx] < N && o_fg[idx] > 0) {
-        int32_t f = o_fg[idx] - 1;
-        if (p.o2f[f] != -1) return fail(CFDL_ERR_MESH, "cfdl_create: face %d owned twice", f + 1);
-        p.o2f[f] = nfi; p.f2o[nfi] = f; ++nfi;
+  // ---- ghost cells (owned by other ranks, face-adjacent to an owned cell) and interface lists -
+  struct Key { int32_t r, c, b, e; };
+  auto key_less = [](const Key& a, const Key& b) { return a.r != b.r ? a.r < b.r : (a.c != b.c ? a.c < b.c : a.b < b.b); };
+  std::vector<Key> ghosts, sends;
+  if (nranks > 1) {
+    std::vector<uint8_t> is_ghost((size_t)gN, 0);
+    for (int32_t c = 0; c < N; ++c) {
+      int32_t e = p.c2o[c];
+      uint64_t sent_to = 0;  // neighbour ranks this cell was already listed for (nranks <= 64 checked below)
+      for (int32_t idx = p.row_ptr[e]; idx < p.row_ptr[e + 1]; ++idx) {
+        int32_t nb = o_nb[idx];
+        if (nb >= gN || owner(nb) == rank) continue;
+        if (!is_ghost[nb]) { is_ghost[nb] = 1; ghosts.push_back({owner(nb), color[nb], brank[nb], nb}); }
+        const int32_t r = owner(nb);
+        if (r < 64) { if (sent_to >> r & 1) continue; sent_to |= uint64_t(1) << r; }
+        sends.push_back({r, color[e], brank[e], e});
       }
+    }
+    if (nranks > 64) return fail(CFDL_ERR_UNSUPPORTED, "cfdl_create: more than 64 ranks");
+    std::sort(ghosts.begin(), ghosts.end(), key_less);
+    std::sort(sends.begin(), sends.end(), key_less);
   }
-  p.Fi = nfi;
-  if (nfi != F - B) return fail(CFDL_ERR_MESH, "cfdl_create: %d interior faces found, expected %d", nfi, F - B);
-  p.halo_cell.assign(B, -1); p.halo_face.assign(B, -1); p.halo_bc.assign(B, -1); p.halo_slot.assign(B, 0);
-  for (int32_t j = 0; j < B; ++j) {
+  const int32_t G = (int32_t)ghosts.size(), Nc = N + G;
+  p.N = N; p.G = G; p.Nc = Nc;
+  p.Np = (N + 31) / 32 * 32;
+  const int32_t Np = p.Np;
+  p.c2o.resize(Nc);
+  for (int32_t g = 0; g < G; ++g) { p.c2o[N + g] = ghosts[g].e; p.o2c[ghosts[g].e] = N + g; }
+  p.nbr_rank.clear();
+  for (const Key& k : ghosts) if (p.nbr_rank.empty() || p.nbr_rank.back() != k.r) p.nbr_rank.push_back(k.r);
+  {
+    std::vector<int32_t> chk;
+    for (const Key& k : sends) if (chk.empty() || chk.back() != k.r) chk.push_back(k.r);
+    if (chk != p.nbr_rank) return fail(CFDL_ERR_INTERNAL, "cfdl_create: send and receive neighbour sets differ");
+  }
+  const int nnbr = (int)p.nbr_rank.size();
+  p.recv_ptr.assign((size_t)nnbr * ncol + 1, 0);
+  p.send_ptr.assign((size_t)nnbr * ncol + 1, 0);
+  p.send_cells.resize(sends.size());
+  {
+    auto slot_of = [&](const Key& k) { return (size_t)(std::lower_bound(p.nbr_rank.begin(), p.nbr_rank.end(), k.r) - p.nbr_rank.begin()) * ncol + k.c; };
+    for (const Key& k : ghosts) p.recv_ptr[slot_of(k) + 1]++;
+    for (const Key& k : sends) p.send_ptr[slot_of(k) + 1]++;
+    for (size_t i = 0; i < (size_t)nnbr * ncol; ++i) { p.recv_ptr[i + 1] += p.recv_ptr[i]; p.send_ptr[i + 1] += p.send_ptr[i]; }
+    for (size_t i = 0; i < sends.size(); ++i) p.send_cells[i] = p.o2c[sends[i].e];
+  }
+  // ---- halos: physical boundary faces of owned cells, in original halo order ----------------
+  p.h2o.clear();
+  std::vector<int32_t> o2h((size_t)gB, -1);
+  for (int32_t j = 0; j < gB; ++j) {
     uint32_t pk = (uint32_t)std::abs(bs[j]);  // sign bit is a flag, every consumer takes abs (mod_mg_lvl_uns.f90:421-433)
     int32_t e = (int32_t)(pk >> 5) - 1, lf = (int32_t)(pk & 31u);
-    if (e < 0 || e >= N || lf < 1 || lf > p.row_ptr[e + 1] - p.row_ptr[e]) return fail(CFDL_ERR_MESH, "cfdl_create: bs(%d) invalid", N + 1 + j);
-    int32_t idx = p.row_ptr[e] + lf - 1;
-    if (o_nb[idx] != N + j) return fail(CFDL_ERR_MESH, "cfdl_create: bs(%d) does not point back to its halo", N + 1 + j);
-    int32_t f = o_fg[idx] - 1;
-    if (p.o2f[f] != -1) return fail(CFDL_ERR_MESH, "cfdl_create: boundary face %d used twice", f + 1);
-    p.o2f[f] = nfi + j; p.f2o[nfi + j] = f;
-    p.halo_cell[j] = p.o2c[e]; p.halo_slot[j] = (uint8_t)(lf - 1); p.halo_face[j] = nfi + j;
+    if (e < 0 || e >= gN || lf < 1 || lf > p.row_ptr[e + 1] - p.row_ptr[e]) return fail(CFDL_ERR_MESH, "cfdl_create: bs(%d) invalid", gN + 1 + j);
+    if (o_nb[p.row_ptr[e] + lf - 1] != gN + j) return fail(CFDL_ERR_MESH, "cfdl_create: bs(%d) does not point back to its halo", gN + 1 + j);
+    if (owner(e) == rank) { o2h[j] = (int32_t)p.h2o.size(); p.h2o.push_back(j); }
   }
-  for (int32_t f = 0; f < F; ++f) if (p.o2f[f] < 0) return fail(CFDL_ERR_MESH, "cfdl_create: face %d is referenced by no cell", f + 1);
-  // s2g consistency (owner side carries +fg; calc_mip/update_uvwp start from it)
-  for (int32_t f = 0; f < F; ++f) {
-    uint32_t pk = (uint32_t)s2g[f];
-    int32_t e = (int32_t)(pk >> 5) - 1, lf = (int32_t)(pk & 31u);
-    if (e < 0 || e >= N || lf < 1 || p.row_ptr[e] + lf - 1 >= p.row_ptr[e + 1] || o_fg[p.row_ptr[e] + lf - 1] != f + 1)
-      return fail(CFDL_ERR_MESH, "cfdl_create: s2g(%d) is not the owner slot of the face", f + 1);
+  const int32_t B = (int32_t)p.h2o.size(), H = Nc + B;
+  p.B = B; p.H = H;
+  // ---- faces touching an owned cell: cell-cell faces first (first-touch order), then boundary -
+  std::vector<int32_t> o2f((size_t)gF, -1);
+  p.f2o.clear(); p.face_a.clear(); p.face_b.clear(); p.fown.clear();
+  for (int32_t c = 0; c < N; ++c) {
+    int32_t e = p.c2o[c];
+    for (int32_t idx = p.row_ptr[e]; idx < p.row_ptr[e + 1]; ++idx) {
+      int32_t nb = o_nb[idx], f = std::abs(o_fg[idx]) - 1;
+      if (nb >= gN || o2f[f] >= 0) continue;
+      o2f[f] = (int32_t)p.f2o.size();
+      p.f2o.push_back(f);
+      const int32_t nbd = p.o2c[nb];
+      if (nbd < 0) return fail(CFDL_ERR_INTERNAL, "cfdl_create: neighbour cell without device index");
+      const bool plus = o_fg[idx] > 0;
+      p.face_a.push_back(plus ? c : nbd);
+      p.face_b.push_back(plus ? nbd : c);
+      p.fown.push_back((plus ? c : nbd) < N ? 1 : 0);
+    }
   }
-  // ---- ELL slot arrays ---------------------------------------------------------------------
+  p.Fi = (int32_t)p.f2o.size();
+  p.halo_cell.assign(B, -1); p.halo_face.assign(B, -1); p.halo_bc.assign(B, -1); p.halo_slot.assign(B, 0);
+  for (int32_t jl = 0; jl < B; ++jl) {
+    const int32_t j = p.h2o[jl];
+    uint32_t pk = (uint32_t)std::abs(bs[j]);
+    int32_t e = (int32_t)(pk >> 5) - 1, lf = (int32_t)(pk & 31u), idx = p.row_ptr[e] + lf - 1, f = o_fg[idx] - 1;
+    if (o2f[f] != -1) return fail(CFDL_ERR_MESH, "cfdl_create: boundary face %d used twice", f + 1);
+    o2f[f] = p.Fi + jl;
+    p.f2o.push_back(f); p.face_a.push_back(p.o2c[e]); p.face_b.push_back(Nc + jl); p.fown.push_back(1);
+    p.halo_cell[jl] = p.o2c[e]; p.halo_slot[jl] = (uint8_t)(lf - 1); p.halo_face[jl] = p.Fi + jl;
+  }
+  p.F = (int32_t)p.f2o.size();
+  if (nranks == 1 && (p.F != gF || p.Fi != gF - gB)) return fail(CFDL_ERR_MESH, "cfdl_create: %d faces found, expected %d", p.F, gF);
+  int64_t zloc = 0;
+  for (int32_t c = 0; c < N; ++c) zloc += p.row_ptr[p.c2o[c] + 1] - p.row_ptr[p.c2o[c]];
+  p.Z = (int32_t)zloc;
+  // ---- ELL slot arrays (owned rows) ------------------------------------------------------------
   p.ell_nb.assign((size_t)K * Np, 0); p.ell_fs.assign((size_t)K * Np, 0); p.nfc.assign(N, 0);
-  p.face_a.assign(F, -1); p.face_b.assign(F, -1);
   for (int32_t c = 0; c < Np; ++c)
     for (int k = 0; k < K; ++k) p.ell_nb[(size_t)k * Np + c] = std::min(c, N - 1);
   for (int32_t c = 0; c < N; ++c) {
@@ -211,11 +292,10 @@ int prepare(Prep& p, int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_i
     p.nfc[c] = (uint8_t)(p.row_ptr[e + 1] - p.row_ptr[e]);
     for (int32_t idx = p.row_ptr[e]; idx < p.row_ptr[e + 1]; ++idx) {
       int k = idx - p.row_ptr[e];
-      int32_t nb = o_nb[idx], fdev = p.o2f[std::abs(o_fg[idx]) - 1];
-      int32_t nbd = (nb < N) ? p.o2c[nb] : nb;
+      int32_t nb = o_nb[idx], fdev = o2f[std::abs(o_fg[idx]) - 1];
+      int32_t nbd = (nb < gN) ? p.o2c[nb] : Nc + o2h[nb - gN];
       p.ell_nb[(size_t)k * Np + c] = nbd;
       p.ell_fs[(size_t)k * Np + c] = (o_fg[idx] > 0) ? (fdev + 1) : -(fdev + 1);
-      if (o_fg[idx] > 0) { p.face_a[fdev] = c; p.face_b[fdev] = nbd; }
     }
   }
   // ---- boundary conditions -------------------------------------------------------------------
@@ -224,27 +304,29 @@ int prepare(Prep& p, int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_i
   for (int32_t i = 0; i < nbc; ++i) {
     if (bc_kind[i] < CFDL_BC_WALL || bc_kind[i] > CFDL_BC_SYMMETRY) return fail(CFDL_ERR_UNSUPPORTED, "cfdl_create: bc kind %d", bc_kind[i]);
     int32_t a = bc_esec[2 * i], b = bc_esec[2 * i + 1];
-    if (a < N + 1 || b > H || a > b + 1) return fail(CFDL_ERR_ARG, "cfdl_create: bc %d halo range [%d,%d] invalid", i, a, b);
-    for (int32_t h = a; h <= b; ++h) p.halo_bc[h - N - 1] = i;
+    if (a < gN + 1 || b > gH || a > b + 1) return fail(CFDL_ERR_ARG, "cfdl_create: bc %d halo range [%d,%d] invalid", i, a, b);
+    for (int32_t h = a; h <= b; ++h) if (o2h[h - gN - 1] >= 0) p.halo_bc[o2h[h - gN - 1]] = i;
   }
-  // ---- level schedules reproducing the reference's sequential sweeps -------------------------
-  {
-    std::vector<int32_t> seq((size_t)N), bp = {0, N};
-    std::iota(seq.begin(), seq.end(), 0);
-    build_schedule(p, o_nb, seq, bp, p.natural);
-  }
-  if (n_subdomains > 1) {
-    if (!g2gf_p || !g2gf_idx) return fail(CFDL_ERR_ARG, "cfdl_create: n_subdomains>1 needs g2gf_p and g2gf_idx");
-    std::vector<int32_t> seq((size_t)N), bp((size_t)n_subdomains + 1);
-    std::vector<uint8_t> seen((size_t)N, 0);
-    for (int b = 0; b <= n_subdomains; ++b) bp[b] = g2gf_idx[b] - 1;
-    if (bp[0] != 0 || bp[n_subdomains] != N) return fail(CFDL_ERR_ARG, "cfdl_create: g2gf_idx must span 1..ne+1");
-    for (int32_t i = 0; i < N; ++i) {
-      int32_t e = g2gf_p[i] - 1;
-      if (e < 0 || e >= N || seen[e]) return fail(CFDL_ERR_ARG, "cfdl_create: g2gf_p is not a permutation of the cells");
-      seen[e] = 1; seq[i] = e;
+  // ---- level schedules reproducing the reference's sequential sweeps (single rank) -----------
+  if (nranks == 1) {
+    {
+      std::vector<int32_t> seq((size_t)N), bp = {0, N};
+      std::iota(seq.begin(), seq.end(), 0);
+      build_schedule(p, o_nb, seq, bp, p.natural);
     }
-    build_schedule(p, o_nb, seq, bp, p.blocks);
+    if (n_subdomains > 1) {
+      if (!g2gf_p || !g2gf_idx) return fail(CFDL_ERR_ARG, "cfdl_create: n_subdomains>1 needs g2gf_p and g2gf_idx");
+      std::vector<int32_t> seq((size_t)N), bp((size_t)n_subdomains + 1);
+      std::vector<uint8_t> seen((size_t)N, 0);
+      for (int b = 0; b <= n_subdomains; ++b) bp[b] = g2gf_idx[b] - 1;
+      if (bp[0] != 0 || bp[n_subdomains] != N) return fail(CFDL_ERR_ARG, "cfdl_create: g2gf_idx must span 1..ne+1");
+      for (int32_t i = 0; i < N; ++i) {
+        int32_t e = g2gf_p[i] - 1;
+        if (e < 0 || e >= N || seen[e]) return fail(CFDL_ERR_ARG, "cfdl_create: g2gf_p is not a permutation of the cells");
+        seen[e] = 1; seq[i] = e;
+      }
+      build_schedule(p, o_nb, seq, bp, p.blocks);
+    }
   }
   return CFDL_OK;
 }

@@ -36,13 +36,13 @@ struct Handle {
   Prep prep;
   int device = 0, num_sms = 0;
   cudaStream_t stream = nullptr;
-  int32_t N = 0, F = 0, B = 0, H = 0, Z = 0, K = 0, Np = 0, Fi = 0;
+  int32_t N = 0, G = 0, Nc = 0, F = 0, B = 0, H = 0, Z = 0, K = 0, Np = 0, Fi = 0;  // owned, ghost, owned+ghost cells; local faces, halos
   int solver_mode = CFDL_SOLVER_PARITY;
   std::vector<void*> allocs;  // everything cudaMalloc'ed, freed in destroy
   // mesh
   int32_t *ell_nb = nullptr, *ell_fs = nullptr, *face_a = nullptr, *face_b = nullptr;
   int32_t *halo_cell = nullptr, *halo_face = nullptr, *halo_bc = nullptr, *bc_kind = nullptr;
-  int32_t *c2o = nullptr, *o2c = nullptr, *f2o = nullptr, *row_ptr = nullptr;
+  int32_t *c2o = nullptr, *cellmap = nullptr, *f2o = nullptr, *row_ptr = nullptr;  // cellmap: device cell|halo -> global index (size H)
   uint8_t *nfc = nullptr, *halo_slot = nullptr;
   double *bc_uvw = nullptr, *xc = nullptr, *yc = nullptr, *zc = nullptr, *aip = nullptr, *rip = nullptr;
   double *vol = nullptr, *rho = nullptr, *mu = nullptr;
@@ -62,6 +62,13 @@ struct Handle {
   DevSchedule natural, blocks;
   double *ap_s = nullptr, *b_s = nullptr, *anb_s = nullptr, *phi_s = nullptr, *rr = nullptr, *rsig = nullptr;
   int coop_ctas = 0;
+  // multi-GPU (one process per GPU): NCCL communicator and interface buffers
+  void* comm = nullptr;            // ncclComm_t
+  int nnbr = 0;
+  int32_t* send_cells = nullptr;   // device copy of prep.send_cells
+  double* send_buf = nullptr;      // 9 doubles per send cell
+  double* recv_buf = nullptr;      // 9 doubles per ghost (multi-component receives)
+  int64_t ne_global = 0;
   // instrumentation
   int64_t launches = 0;         // kernels launched since the last reset ("gpu_launches")
   int profile = 0;              // 1: bracket every launch of the profiled kernel kinds with CUDA events
@@ -111,6 +118,13 @@ int solver_init(Handle* h);
 int solve_equation(Handle* h, int eq, double* phi, const double* rhs, int nit, double* out4, bool dispatch);
 
 int residual_plain(Handle* h, const double* phi, const double* rhs, bool signed_max, double* res, double* res_max);
+// ---- comm.cu (no-ops on a single rank)
+// refresh the ghost-cell entries of a device field from their owner ranks; ncomp doubles per
+// cell (AoS); color >= 0 restricts the exchange to ghosts/sends of that colour
+int comm_exchange(Handle* h, double* field, int ncomp, int color);
+int comm_allreduce_sum_max(Handle* h, double* dev2);  // dev2[0] summed, dev2[1] maxed over ranks
+int comm_bcast(Handle* h, double* dev, int count, int root);
+void comm_destroy(Handle* h);
 
 }  // namespace cfdl
 

@@ -108,13 +108,45 @@ def mesh_build(raw):
     return g
 
 
-def partition_rcb(geom, P):
-    """The reference's RCB blocks: (cell2sub, g2gf_p, g2gf_idx), all 1-based."""
+def partition_rcb(geom, P, want_order=True):
+    """The reference's RCB blocks: (cell2sub, g2gf_p, g2gf_idx), all 1-based.  want_order=False
+    skips the block-local order (the reference's unstable quicksort, quadratic in cells per
+    block), which only the exact pc block solver needs."""
     ne = int(geom["ne"])
-    c2s, p, idx = np.zeros(ne, np.int32), np.zeros(ne, np.int32), np.zeros(P + 1, np.int32)
+    c2s = np.zeros(ne, np.int32)
+    p, idx = (np.zeros(ne, np.int32), np.zeros(P + 1, np.int32)) if want_order else (None, None)
     xc, yc, zc, vol = (_f64(geom[k]) for k in ("xc", "yc", "zc", "vol"))
     _chk(lib().cfdl_partition_rcb(C.c_int32(ne), _d(xc), _d(yc), _d(zc), _d(vol), C.c_int32(P), _i(c2s), _i(p), _i(idx)))
     return c2s, p, idx
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (create on rank 0, broadcast to the other ranks)."""
+    buf = (C.c_uint8 * 128)()
+    _chk(lib().cfdl_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def partition_plan(geom, cell2rank, nranks, rank):
+    """Host-only view of rank's partition: owned/ghost cells (1-based global ids, device order),
+    neighbour ranks and the send/receive lists."""
+    ne = int(geom["ne"])
+    a = {k: _i32(geom[k]) for k in ("ef2nb_idx", "ef2nb_nb", "ef2nb_fg", "s2g", "bs")}
+    r = {k: _f64(geom[k]) for k in ("xc", "yc", "zc")}
+    c2r = _i32(cell2rank)
+    owned, ghost, send = (np.zeros(ne, np.int32) for _ in range(3))
+    nbr = np.zeros(nranks, np.int32)
+    sp, rp = np.zeros(nranks + 1, np.int32), np.zeros(nranks + 1, np.int32)
+    cp = np.zeros(33, np.int32)
+    no, ng, nn, nc = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    _chk(lib().cfdl_partition_plan(C.c_int32(ne), C.c_int32(int(geom["nf"])), C.c_int32(int(geom["nbf"])),
+                                   _i(a["ef2nb_idx"]), _i(a["ef2nb_nb"]), _i(a["ef2nb_fg"]), _i(a["s2g"]), _i(a["bs"]),
+                                   _d(r["xc"]), _d(r["yc"]), _d(r["zc"]), _i(c2r), C.c_int32(nranks), C.c_int32(rank),
+                                   C.byref(no), _i(owned), C.byref(ng), _i(ghost), C.byref(nn), _i(nbr), _i(sp), _i(send), _i(rp),
+                                   C.byref(nc), _i(cp)))
+    k = nn.value
+    return dict(owned=owned[:no.value].copy(), ghost=ghost[:ng.value].copy(), nbr_rank=nbr[:k].copy(), send_ptr=sp[:k + 1].copy(),
+                send_cells=send[:sp[k]].copy(), recv_ptr=rp[:k + 1].copy(), ncolors=nc.value, color_ptr=cp[:nc.value + 1].copy())
 
 
 def default_bcs(raw):
@@ -153,8 +185,12 @@ class PinnedBuffer:
 class Solver:
     """Device-resident SIMPLE hot path for one mesh (one GPU).  Mirrors phys_t + uvwp_t."""
 
-    def __init__(self, geom, bcs, rho=5.0, mu=0.01, n_subdomains=1, g2gf_p=None, g2gf_idx=None, device=0):
+    def __init__(self, geom, bcs, rho=5.0, mu=0.01, n_subdomains=1, g2gf_p=None, g2gf_idx=None, device=0,
+                 cell2rank=None, rank=0, nranks=1):
+        """geom: the GLOBAL mesh in the reference's array format.  With nranks > 1 this handle is
+        rank `rank`'s partition (cell2rank in 1..nranks); call comm_init() before computing."""
         L = lib()
+        self.rank, self.nranks = rank, nranks
         self.ne, self.nf, self.nbf = int(geom["ne"]), int(geom["nf"]), int(geom["nbf"])
         self.H = self.ne + self.nbf
         self.Z = 2 * self.nf - self.nbf
@@ -166,11 +202,19 @@ class Solver:
         p = _i32(g2gf_p) if n_subdomains > 1 else None
         pi = _i32(g2gf_idx) if n_subdomains > 1 else None
         h = C.c_void_p()
-        _chk(L.cfdl_create(C.byref(h), C.c_int32(self.ne), C.c_int32(self.nf), C.c_int32(self.nbf),
-                           _i(a["ef2nb_idx"]), _i(a["ef2nb_nb"]), _i(a["ef2nb_fg"]), _i(a["s2g"]), _i(a["bs"]),
-                           _d(r["xc"]), _d(r["yc"]), _d(r["zc"]), _d(r["aip"]), _d(r["rip"]), _d(r["vol"]),
-                           _d(rho), _d(mu), C.c_int32(len(kind)), _i(esec), _i(kind), _d(uvw),
-                           C.c_int32(n_subdomains), _i(p), _i(pi), C.c_int32(device)))
+        if nranks > 1:
+            c2r = _i32(cell2rank)
+            _chk(L.cfdl_create_distributed(C.byref(h), C.c_int32(self.ne), C.c_int32(self.nf), C.c_int32(self.nbf),
+                                           _i(a["ef2nb_idx"]), _i(a["ef2nb_nb"]), _i(a["ef2nb_fg"]), _i(a["s2g"]), _i(a["bs"]),
+                                           _d(r["xc"]), _d(r["yc"]), _d(r["zc"]), _d(r["aip"]), _d(r["rip"]), _d(r["vol"]),
+                                           _d(rho), _d(mu), C.c_int32(len(kind)), _i(esec), _i(kind), _d(uvw),
+                                           _i(c2r), C.c_int32(rank), C.c_int32(nranks), C.c_int32(device)))
+        else:
+            _chk(L.cfdl_create(C.byref(h), C.c_int32(self.ne), C.c_int32(self.nf), C.c_int32(self.nbf),
+                               _i(a["ef2nb_idx"]), _i(a["ef2nb_nb"]), _i(a["ef2nb_fg"]), _i(a["s2g"]), _i(a["bs"]),
+                               _d(r["xc"]), _d(r["yc"]), _d(r["zc"]), _d(r["aip"]), _d(r["rip"]), _d(r["vol"]),
+                               _d(rho), _d(mu), C.c_int32(len(kind)), _i(esec), _i(kind), _d(uvw),
+                               C.c_int32(n_subdomains), _i(p), _i(pi), C.c_int32(device)))
         self.h = h
         self.n_subdomains = n_subdomains
 
@@ -210,6 +254,25 @@ class Solver:
         cp = np.zeros(nc + 1, np.int32)
         _chk(lib().cfdl_get_cell_order(self.h, _i(c2o), _i(cp)))
         return c2o, cp
+
+    def comm_init(self, unique_id):
+        """Collective: join the NCCL communicator identified by the 128-byte id of rank 0."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        _chk(lib().cfdl_comm_init(self.h, buf, C.c_int32(self.rank), C.c_int32(self.nranks)))
+
+    def local_size(self, name):
+        n = C.c_int64()
+        _chk(lib().cfdl_field_local_size(self.h, C.c_int(FIELD_ID[name]), C.byref(n)))
+        return n.value
+
+    def upload_local(self, name, arr):
+        assert arr.size == self.local_size(name) and arr.dtype == np.float64
+        _chk(lib().cfdl_upload_field_local(self.h, C.c_int(FIELD_ID[name]), _d(arr)))
+
+    def download_local(self, name, out):
+        assert out.size == self.local_size(name) and out.dtype == np.float64
+        _chk(lib().cfdl_download_field_local(self.h, C.c_int(FIELD_ID[name]), _d(out)))
+        return out
 
     def timer_record(self, slot):
         _chk(lib().cfdl_timer_record(self.h, C.c_int32(slot)))

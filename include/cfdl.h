@@ -160,19 +160,45 @@ int cfdl_host_calc_residual(cfdl_handle h, const double* phi, const double* ap, 
 int cfdl_host_solve(cfdl_handle h, int eq, double* phi, const double* ap, const double* anb,
                     const double* b, int32_t nit, double* out4);
 
-/* ---- multi-GPU: one process per GPU, one partition per process.
- * A partition is a mesh in the same format whose halo range additionally contains the cells
- * owned by other ranks; the interface description tells which halos they are. */
+/* ---- multi-GPU: one process per GPU (the reference is one process; launch P copies of the
+ * driver, e.g. under mpirun/torchrun).  Every rank passes the same GLOBAL mesh, in the format
+ * of cfdl_create, plus cell2rank(ne) in 1..nranks (e.g. from cfdl_partition_rcb) and its own
+ * 0-based rank.  The library keeps the rank's cells, adds the adjacent cells of other ranks as
+ * ghost cells and derives matching send/receive lists on every rank without communication.
+ * Ghost values move by NCCL send/recv, residual norms by NCCL all-reduce, pc(1) by broadcast —
+ * the GPU analogue of update_halos (mod_subdomains.f90:191-212) and of the residual loop of
+ * multi_subdomain_solver (mod_solver.f90:144-150).  Solver: multicolour SGS with a global
+ * colouring and a ghost refresh after every colour sweep, i.e. exactly the single-GPU MCSGS
+ * iteration.  Field upload/download keep the global reference numbering: upload reads the
+ * rank's entries of the global host array, download writes only the entries the rank owns. */
+int cfdl_create_distributed(cfdl_handle* out, int32_t ne, int32_t nf, int32_t nbf,
+                            const int32_t* ef2nb_idx, const int32_t* ef2nb_nb, const int32_t* ef2nb_fg,
+                            const int32_t* s2g, const int32_t* bs,
+                            const double* xc, const double* yc, const double* zc,
+                            const double* aip, const double* rip, const double* vol,
+                            const double* rho, const double* mu,
+                            int32_t nbc, const int32_t* bc_esec, const int32_t* bc_kind, const double* bc_uvw,
+                            const int32_t* cell2rank, int32_t rank, int32_t nranks, int32_t device);
 /* 128-byte NCCL unique id, created on rank 0 and broadcast by the caller (MPI / torch) */
 int cfdl_comm_unique_id(uint8_t id[128]);
+/* collective over all ranks; must precede any compute call on a distributed handle */
 int cfdl_comm_init(cfdl_handle h, const uint8_t id[128], int32_t rank, int32_t nranks);
-/* per neighbour rank r (nnbr of them): send_cells[send_ptr[r]:send_ptr[r+1]] are local owned
- * cells (1-based) whose values go to r; recv_halos[...] the local halo ids (ne+1..) filled
- * from r; both sides list the shared faces in the same order. */
-int cfdl_set_interfaces(cfdl_handle h, int32_t nnbr, const int32_t* nbr_rank,
-                        const int32_t* send_ptr, const int32_t* send_cells,
-                        const int32_t* recv_ptr, const int32_t* recv_halos,
-                        int64_t ne_global, int32_t owns_ref_cell);
+/* partition-local host I/O (device numbering: owned cells, ghosts, halos): the bytes a rank
+ * actually needs to move per step in a distributed host driver */
+int cfdl_field_local_size(cfdl_handle h, int field, int64_t* n);
+int cfdl_upload_field_local(cfdl_handle h, int field, const double* host);
+int cfdl_download_field_local(cfdl_handle h, int field, double* host);
+/* host-only view of the partition a rank would get (tests, tooling): owned and ghost cells in
+ * device order (1-based global ids; arrays of capacity ne), neighbour ranks (capacity nranks),
+ * send_ptr/recv_ptr (capacity nranks+1), send_cells (capacity ne), owned_color_ptr (capacity 33).
+ * Any output pointer may be NULL. */
+int cfdl_partition_plan(int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_idx,
+                        const int32_t* ef2nb_nb, const int32_t* ef2nb_fg, const int32_t* s2g,
+                        const int32_t* bs, const double* xc, const double* yc, const double* zc,
+                        const int32_t* cell2rank, int32_t nranks, int32_t rank,
+                        int32_t* n_owned, int32_t* owned, int32_t* n_ghost, int32_t* ghost,
+                        int32_t* n_nbr, int32_t* nbr_rank, int32_t* send_ptr, int32_t* send_cells,
+                        int32_t* recv_ptr, int32_t* ncolors, int32_t* owned_color_ptr);
 
 /* ---- host-side mesh tooling (no GPU needed) ------------------------------------------- */
 enum { CFDL_MESH_HEX = 0, CFDL_MESH_TET = 1 };

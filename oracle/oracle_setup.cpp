@@ -430,7 +430,7 @@ struct SeedGen {
 
 // generate_seeds (mod_mg_lvl_uns.f90:95-118) with nl = (n_subdomains, 1), npmax = 2
 // (cell_input.f90:131-137), then add_transformation_bt's block ordering (:873-903)
-void rcb_partition(Mesh& m, int n_subdomains) {
+void rcb_partition(Mesh& m, int n_subdomains, bool stable_order) {
   const int ne = m.ne;
   SeedGen sg;
   sg.m = &m;
@@ -455,7 +455,15 @@ void rcb_partition(Mesh& m, int n_subdomains) {
   m.g2gf_p.alloc(ne, 0);
   for (int gf = 1; gf <= ne; ++gf) m.g2gf_p(gf) = gf;
   std::vector<int> key(m.gf2g.d);
-  qsort_key_nRec(key.data(), m.g2gf_p.data(), ne);
+  if (stable_order) {  // TIMING RUNS ONLY: same blocks, cells ascending inside a block (the reference sort is quadratic here)
+    std::vector<int> perm(ne);
+    for (int i = 0; i < ne; ++i) perm[i] = i + 1;
+    std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return key[a - 1] < key[b - 1]; });
+    for (int i = 0; i < ne; ++i) m.g2gf_p(i + 1) = perm[i];
+    std::sort(key.begin(), key.end());
+  } else {
+    qsort_key_nRec(key.data(), m.g2gf_p.data(), ne);
+  }
   int ng_tmp = key[ne - 1];
   m.g2gf_idx.alloc(ng_tmp + 1, 0);
   int g = 0;

@@ -97,7 +97,7 @@ void setup_mesh(Mesh& m, int n_subdomains);
 void find_element_nb(Mesh& m);
 void calc_aip_xyzip_uns(Mesh& m);
 void calc_vol_cv_centers_uns(Mesh& m);
-void rcb_partition(Mesh& m, int n_subdomains);          // generate_seeds + grow
+void rcb_partition(Mesh& m, int n_subdomains, bool stable_order = false);  // generate_seeds + grow (+ block order)
 void qsort_key_nRec(int* key, int* b, int n);           // mod_util.f90:1683-1730
 void qsort_key(int* key, int* b, int i, int f);         // mod_util.f90:1602-1623 (1-based i,f)
 

@@ -50,9 +50,8 @@ def test_cuda_reproduces_golden(cfdl, name):
     geom = cfdl.mesh_build(raw)
     P = kw["n_subdomains"]
     if P > 1:
-        p = gold["g2gf_p"]
-        # blocks are contiguous in g2gf_p; sizes from the RCB on these meshes are equal
-        idx = np.linspace(0, geom["ne"], P + 1).astype(np.int32) + 1
+        _, p, idx = cfdl.partition_rcb(geom, P)  # the product's own RCB + block order
+        assert np.array_equal(p, gold["g2gf_p"])
         s = cfdl.Solver(geom, cfdl.default_bcs(raw), n_subdomains=P, g2gf_p=p, g2gf_idx=idx)
     else:
         s = cfdl.Solver(geom, cfdl.default_bcs(raw))
