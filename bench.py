@@ -28,6 +28,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "cfd-lite_b200", "python"))
+# NCCL's "NCCL version ..." banner goes to stdout by default; stdout carries exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 SOLVERS = {"parity": 0, "mcsgs": 1, "pcg": 2}
 DT, NIT, NCOEF = 0.01, 100, 3  # reference defaults, src/modules/mod_physics.f90:15-18
