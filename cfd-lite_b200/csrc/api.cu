@@ -262,6 +262,7 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
     h->solver_mode = m;
     return CFDL_OK;
   }
+  if (!std::strcmp(key, "fused")) { h->fused_rb = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "profile")) {
     int rc = prof_collect(h);
     h->profile = value != 0.0;

@@ -62,6 +62,8 @@ struct Handle {
   DevSchedule natural, blocks;
   double *ap_s = nullptr, *b_s = nullptr, *anb_s = nullptr, *phi_s = nullptr, *rr = nullptr, *rsig = nullptr;
   int coop_ctas = 0;
+  double* rb_work = nullptr;   // second value array of the fused two-colour solver (H doubles)
+  int fused_rb = 1;            // 0: always use one launch per colour + residual pass
   // multi-GPU (one process per GPU): NCCL communicator and interface buffers
   void* comm = nullptr;            // ncclComm_t
   int nnbr = 0;

@@ -208,14 +208,24 @@ def test_mcsgs_equals_solve_gs_on_colour_permuted_system(case, oracle):
     perm_phi = np.concatenate([phi0[c2o - 1], phi0[ne:]])
     s.set_option("solver", 1)
     try:
-        for eq, is_pc in ((0, False), (3, True)):
-            want_phi, want = oracle.flat_solve_gs(is_pc, perm_phi, ap[c2o - 1], p_anb, b[c2o - 1], (p_idx + 1).astype(np.int32),
-                                                  p_nb.astype(np.int32), nit=9)
-            got_phi, got = s.host_solve_gs(eq, phi0, ap, anb, b, nit=9)
-            assert got[0] == want[0], (got, want)
-            assert np.array_equal(got_phi[c2o - 1], want_phi[:ne]), "phi differs by %.3e" % rel_err(got_phi[c2o - 1], want_phi[:ne])
-            check("res_f", got[2], want[2], 1e-12)
+        # fused=1: two-colour meshes run the fused red/black passes (two updates + residual from one
+        # evaluation of the neighbour sum); fused=0: one launch per colour + a residual pass.  Both
+        # must equal the sequential reference sweeps on the permuted system bit for bit.
+        for fused in (1, 0):
+            s.set_option("fused", fused)
+            for eq, is_pc in ((0, False), (3, True)):
+                for nit in (1, 2, 9):
+                    want_phi, want = oracle.flat_solve_gs(is_pc, perm_phi, ap[c2o - 1], p_anb, b[c2o - 1], (p_idx + 1).astype(np.int32),
+                                                          p_nb.astype(np.int32), nit=nit)
+                    got_phi, got = s.host_solve_gs(eq, phi0, ap, anb, b, nit=nit)
+                    assert got[0] == want[0], (fused, eq, nit, got, want)
+                    assert np.array_equal(got_phi[c2o - 1], want_phi[:ne]), "phi differs by %.3e" % rel_err(got_phi[c2o - 1], want_phi[:ne])
+                    check("res_i", got[1], want[1], 1e-12)
+                    check("res_f", got[2], want[2], 1e-12)
+                    if want[0] > 0:
+                        check("res_max", got[3], want[3], 1e-12)
     finally:
+        s.set_option("fused", 1)
         s.set_option("solver", 0)
 
 
