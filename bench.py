@@ -266,7 +266,7 @@ def main():
     ncol = int(s.get_info("ncolors"))
     roof = None
     extra_roof = {}
-    fused = ncol == 2 and world == 1 and args.solver != "parity" and not args.unfused
+    fused = ncol == 2 and args.solver != "parity" and not args.unfused
     if prof["sgs"][1] > 0:
         if fused:
             # fused two-colour passes: a red pass reads ap,b,anb,idx (16+12K B/row), its own value,

@@ -263,6 +263,7 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
     return CFDL_OK;
   }
   if (!std::strcmp(key, "fused")) { h->fused_rb = value != 0.0; return CFDL_OK; }
+  if (!std::strcmp(key, "ctas_per_sm")) { h->tune_ctas = std::max(1, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "profile")) {
     int rc = prof_collect(h);
     h->profile = value != 0.0;

@@ -410,10 +410,10 @@ __global__ void __launch_bounds__(TPB) rb_red_kernel(int c0, int c1, int Np, con
   const double sm1 = sor - 1.0;
   double s = 0.0, m = 0.0;
   for (int c = c0 + blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += gridDim.x * blockDim.x) {
-    double sumnb = b[c];
+    double sumnb = __ldcs(&b[c]);
 #pragma unroll
-    for (int k = 0; k < K; ++k) sumnb = sumnb + anb[(size_t)k * Np + c] * black_src[nbi[(size_t)k * Np + c]];
-    const double a = ap[c];
+    for (int k = 0; k < K; ++k) sumnb = sumnb + __ldcs(&anb[(size_t)k * Np + c]) * black_src[__ldcs(&nbi[(size_t)k * Np + c])];
+    const double a = __ldcs(&ap[c]);
     double x = red_new[c];
     if (!first) {
       x = (sumnb + sm1 * a * x) / a / sor;  // R2 of iteration k
@@ -440,16 +440,16 @@ __global__ void __launch_bounds__(TPB) rb_black_kernel(int c0, int c1, int Np, c
   const double sm1 = sor - 1.0;
   double s = 0.0, m = 0.0;
   for (int c = c0 + blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += gridDim.x * blockDim.x) {
-    const double bb = b[c];
+    const double bb = __ldcs(&b[c]);
     double s_new = bb, s_mid = bb;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      const double an = anb[(size_t)k * Np + c];
-      const int i = nbi[(size_t)k * Np + c];
+      const double an = __ldcs(&anb[(size_t)k * Np + c]);
+      const int i = __ldcs(&nbi[(size_t)k * Np + c]);
       s_new = s_new + an * red_new[i];
       if (!first) s_mid = s_mid + an * red_mid[i];
     }
-    const double a = ap[c];
+    const double a = __ldcs(&ap[c]);
     double x = black_old[c];
     if (!first) {  // residual of the finished iteration: black rows against the red values after R2
       const double r = fabs(s_mid - a * x);
@@ -499,16 +499,26 @@ static int rb_solve_t(Handle* h, int eq, double* phi, const double* rhs, int nit
   const int nred = cp[1], nblack = N - nred;
   const double *ap = h->fld[CFDL_F_AP], *anb = h->fld[CFDL_F_ANB];
   double *A1 = phi, *A2 = h->rb_work;
-  const int gr = grid_for(h, nred, TPB), gb = grid_for(h, nblack, TPB);
+  const int gr = grid_for(h, nred, TPB, h->tune_ctas), gb = grid_for(h, nblack, TPB, h->tune_ctas);
   double *pr = h->partial, *pb = h->partial + 2 * (size_t)gr;
   SolveCtl init = {};
   init.nit = nit;
   *h->ctl_host = init;
   CFDL_CUDA(cudaMemcpyAsync(h->ctl, h->ctl_host, sizeof(SolveCtl), cudaMemcpyHostToDevice, h->stream));
-  // halo (and ghost) values are constant during the solve: both arrays carry them
+  const bool dist = h->prep.nranks > 1;
+  int rc;
+  if (dist && (rc = comm_exchange(h, phi, 1, -1))) return rc;
+  // halo values are constant during the solve and ghost values are refreshed after every pass:
+  // both arrays carry them
   CFDL_CUDA(cudaMemcpyAsync(A2 + N, A1 + N, sizeof(double) * (size_t)(h->H - N), cudaMemcpyDeviceToDevice, h->stream));
   prof_begin(h, PROF_RESIDUAL);
-  residual_kernel<K><<<g, TPB, 0, S(h)>>>(N, Np, h->ell_nb, ap, anb, rhs, phi, h->partial, h->ctl, RES_INIT, 0, nullptr);
+  if (!dist) {
+    residual_kernel<K><<<g, TPB, 0, S(h)>>>(N, Np, h->ell_nb, ap, anb, rhs, phi, h->partial, h->ctl, RES_INIT, 0, nullptr);
+  } else {
+    residual_kernel<K><<<g, TPB, 0, S(h)>>>(N, Np, h->ell_nb, ap, anb, rhs, phi, h->partial, h->ctl, RES_LOCAL, 0, h->scal + 8);
+    if ((rc = comm_allreduce_sum_max(h, h->scal + 8))) return rc;
+    finalize_residual_kernel<<<1, 1, 0, S(h)>>>(h->ctl, h->scal + 8, (double)h->ne_global, RES_INIT);
+  }
   prof_end(h);
   // pass j (1-based): black pass of iteration j, then red pass closing iteration j; iteration j is
   // judged inside the black pass j+1, so nit iterations need nit+1 black passes
@@ -525,13 +535,24 @@ static int rb_solve_t(Handle* h, int eq, double* phi, const double* rhs, int nit
         double* bnew = (j & 1) ? A2 : A1;
         prof_begin(h, PROF_SGS_SWEEP);
         rb_black_kernel<K><<<gb, TPB, 0, S(h)>>>(nred, N, Np, h->ell_nb, ap, anb, rhs, A1, A2, bold, bnew, sor, h->ctl, pr, gr, pb, N,
-                                                 j == 1 ? 1 : 0, 0, nullptr);
+                                                 j == 1 ? 1 : 0, dist ? 1 : 0, h->scal + 8);
         prof_end(h);
+        if (dist) {  // black ghosts of the buffer just written; residual of iteration j-1 over all ranks
+          if ((rc = comm_exchange(h, bnew, 1, 1))) return rc;
+          if (j > 1) {
+            if ((rc = comm_allreduce_sum_max(h, h->scal + 8))) return rc;
+            finalize_residual_kernel<<<1, 1, 0, S(h)>>>(h->ctl, h->scal + 8, (double)h->ne_global, RES_ITER);
+          }
+        }
       }
       if (j <= nit) {  // red pass j: black neighbours from buffer j%2
         prof_begin(h, PROF_SGS_SWEEP);
         rb_red_kernel<K><<<gr, TPB, 0, S(h)>>>(0, nred, Np, h->ell_nb, ap, anb, rhs, A1, (j & 1) ? A2 : A1, A2, sor, h->ctl, pr, j == 0 ? 1 : 0);
         prof_end(h);
+        if (dist) {  // red ghosts: newest values (A1) and, once an iteration has closed, the values after R2 (A2)
+          if ((rc = comm_exchange(h, A1, 1, 0))) return rc;
+          if (j > 0 && (rc = comm_exchange(h, A2, 1, 0))) return rc;
+        }
       }
     }
     CFDL_CUDA(cudaGetLastError());
@@ -541,6 +562,7 @@ static int rb_solve_t(Handle* h, int eq, double* phi, const double* rhs, int nit
   const int it = h->ctl_host->it;
   if (it > 0) rb_final_kernel<<<g, TPB, 0, S(h)>>>(nred, N, A1, A2, it & 1);
   CFDL_CUDA(cudaGetLastError());
+  if (dist && it > 0 && (rc = comm_exchange(h, phi, 1, -1))) return rc;  // ghosts of the final state
   if (out4) { out4[0] = it; out4[1] = h->ctl_host->res_i; out4[2] = h->ctl_host->res_f; out4[3] = h->ctl_host->res_max; }
   return CFDL_OK;
 }
@@ -633,7 +655,7 @@ int solve_equation(Handle* h, int eq, double* phi, const double* rhs, int nit, d
       return k4 ? parity_solve_t<4>(h, eq, phi, rhs, nit, out4, dispatch) : parity_solve_t<6>(h, eq, phi, rhs, nit, out4, dispatch);
     case CFDL_SOLVER_MCSGS:
     case CFDL_SOLVER_PCG:  // PCG for pc is added in pcg.cu; momentum always uses MCSGS there
-      if (h->fused_rb && h->prep.ncolors == 2 && h->prep.nranks == 1)
+      if (h->fused_rb && h->prep.ncolors == 2)
         return k4 ? rb_solve_t<4>(h, eq, phi, rhs, nit, out4) : rb_solve_t<6>(h, eq, phi, rhs, nit, out4);
       return k4 ? mcsgs_solve_t<4>(h, eq, phi, rhs, nit, out4) : mcsgs_solve_t<6>(h, eq, phi, rhs, nit, out4);
   }

@@ -64,6 +64,7 @@ struct Handle {
   int coop_ctas = 0;
   double* rb_work = nullptr;   // second value array of the fused two-colour solver (H doubles)
   int fused_rb = 1;            // 0: always use one launch per colour + residual pass
+  int tune_ctas = 8;           // CTAs per SM for the solver passes (grid = min(need, num_sms * tune_ctas))
   // multi-GPU (one process per GPU): NCCL communicator and interface buffers
   void* comm = nullptr;            // ncclComm_t
   int nnbr = 0;
