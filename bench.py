@@ -30,6 +30,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "cfd-lite_b200", "python"))
 # NCCL's "NCCL version ..." banner goes to stdout by default; stdout carries exactly one JSON line
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+if not os.environ.get("CFDL_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "NONE"  # any level >= VERSION prints the banner with printf
 
 SOLVERS = {"parity": 0, "mcsgs": 1, "pcg": 2}
 DT, NIT, NCOEF = 0.01, 100, 3  # reference defaults, src/modules/mod_physics.f90:15-18
@@ -160,6 +162,7 @@ def main():
     ap.add_argument("--mesh", default="hex", choices=["hex", "tet"])
     ap.add_argument("--solver", default="mcsgs", choices=list(SOLVERS))
     ap.add_argument("--unfused", action="store_true", help="one launch per colour + residual pass (no fused two-colour passes)")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL send/recv instead of peer-to-peer ghost stores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -192,6 +195,7 @@ def main():
 
     # weak scaling: the global cube grows with the GPU count so that every GPU keeps ~n^3 cells;
     # the mesh is split by the reference's own RCB (x-slabs, columns, octants on a cube)
+    exchange = "NCCL send/recv after every pass, residual norms by NCCL all-reduce"
     n_global = args.n if world == 1 else int(round(args.n * world ** (1.0 / 3.0)))
     raw, geom = build_mesh(cfdl, args.mesh, n_global)
     if world == 1:
@@ -206,6 +210,14 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         s.comm_init(ids[0])
         s.set_option("solver", SOLVERS[args.solver])
+        if not args.no_p2p:
+            try:  # peer-to-peer ghost exchange over NVLink (CUDA IPC); NCCL send/recv stays the fallback
+                handles = [None] * world
+                dist.all_gather_object(handles, s.ipc_handle())
+                s.ipc_connect(handles)
+                exchange = "peer-to-peer stores into the neighbours' ghost cells + flag words (CUDA IPC over NVLink), residual norms through peer slots"
+            except cfdl.CfdlError as ex:
+                dbg("p2p unavailable:", ex)
     if args.unfused:
         s.set_option("fused", 0)
     ne, nf, nbf, H = s.ne, s.nf, s.nbf, s.H  # global sizes
@@ -382,8 +394,7 @@ def main():
                            "cells_per_gpu": ne // world, "l2": "working set (>1 GB per GPU) exceeds the 126 MB L2; no flush needed" if ne // world > 1000000 else
                            "working set may fit L2",
                            "parallelism": "1 GPU" if world == 1 else
-                           "%d GPUs, one RCB block of the global mesh per GPU; ghost-cell exchange by NCCL send/recv after every colour sweep, "
-                           "residual norms by NCCL all-reduce" % world,
+                           "%d GPUs, one RCB block of the global mesh per GPU; ghost-cell exchange: %s" % (world, exchange),
                            "last_step_history(it,res_i,res_f,res_max)": hist_last.tolist() if hist_last is not None else None},
                 "roofline": roof, "roofline_other": extra_roof, "phase_ms_per_step": phase_ms, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks}

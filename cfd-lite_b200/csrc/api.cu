@@ -169,7 +169,7 @@ int create_impl(cfdl_handle* out, int32_t ne, int32_t nf, int32_t nbf, const int
   UP(h->ell_nb, p.ell_nb); UP(h->ell_fs, p.ell_fs); UP(h->nfc, p.nfc); UP(h->face_a, p.face_a); UP(h->face_b, p.face_b);
   UP(h->halo_cell, p.halo_cell); UP(h->halo_face, p.halo_face); UP(h->halo_bc, p.halo_bc); UP(h->halo_slot, p.halo_slot);
   UP(h->bc_kind, p.bc_kind); UP(h->bc_uvw, p.bc_uvw); UP(h->c2o, p.c2o); UP(h->f2o, p.f2o); UP(h->row_ptr, p.row_ptr);
-  UP(h->send_cells, p.send_cells);
+  UP(h->send_cells, p.send_cells); UP(h->tgt_ptr, p.tgt_ptr); UP(h->tgt_nbr, p.tgt_nbr); UP(h->tgt_pos, p.tgt_pos);
 #undef UP
   {  // global index of every device cell | halo (host transfers), geometry in device numbering
     std::vector<int32_t> cm((size_t)H);
@@ -188,8 +188,11 @@ int create_impl(cfdl_handle* out, int32_t ne, int32_t nf, int32_t nbf, const int
     for (int32_t f = 0; f < F; ++f) for (int q = 0; q < 3; ++q) t[3 * (size_t)f + q] = rip[3 * (size_t)p.f2o[f] + q];
     if ((rc = dev_upload(h, h->rip, t.data(), 3 * (size_t)F))) return bail(rc);
   }
+  // several GPUs: u, v, w, pc and the second solver array live in one IPC-exportable slab so
+  // that neighbours can write their ghost cells directly (cfdl_comm_ipc_connect)
+  if (nranks > 1 && (rc = p2p_alloc_slab(h))) return bail(rc);
   for (int f = 0; f < CFDL_F_COUNT; ++f)
-    if ((rc = dev_zero(h, h->fld[f], field_len(h, f) + 4))) return bail(rc);
+    if (!h->fld[f] && (rc = dev_zero(h, h->fld[f], field_len(h, f) + 4))) return bail(rc);
   h->stage_len = std::max(std::max(3 * ((size_t)p.gN + p.gB), (size_t)p.gZ), (size_t)p.gF) + 4;
   if ((rc = dev_zero(h, h->stage, h->stage_len))) return bail(rc);
   h->partial_len = 4096 + 2 * 64 * (N / 8192 + 1);
@@ -263,6 +266,7 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
     return CFDL_OK;
   }
   if (!std::strcmp(key, "fused")) { h->fused_rb = value != 0.0; return CFDL_OK; }
+  if (!std::strcmp(key, "p2p")) { h->use_p2p = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "ctas_per_sm")) { h->tune_ctas = std::max(1, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "profile")) {
     int rc = prof_collect(h);

@@ -6,6 +6,7 @@
 // (src/modules/mod_subdomains.f90:191-212) and of the residual accumulation loop of
 // multi_subdomain_solver (src/modules/mod_solver.f90:144-150,172-178).
 #include <dlfcn.h>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include "state.h"
@@ -121,6 +122,221 @@ int comm_bcast(Handle* h, double* dev, int count, int root) {
 void comm_destroy(Handle* h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   h->comm = nullptr;
+  for (void* p : h->p2p.opened) cudaIpcCloseMemHandle(p);
+  h->p2p.opened.clear();
+  h->p2p.connected = false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peer-to-peer ghost exchange: the sender's kernel stores interface values directly into the
+// receiver's ghost cells over NVLink and then raises a flag word in the receiver's memory; the
+// receiver's next pass spins on that flag before it gathers.  No host round trip, no NCCL call
+// inside a solver iteration; the residual norm is combined through per-rank slots the same way.
+namespace {
+
+constexpr long long kMagic = 0x4346444C50325031ll;  // "CFDLP2P1"
+inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct PushArgs {
+  int nnbr, narr, do_reduce, nranks, rank, parity;
+  const int32_t* send_cells;
+  const double* src[2];
+  double* dst[8][2];
+  int s0[8], cnt[8], d0[8];
+  unsigned long long* peer_flag[8];
+  unsigned long long seq;
+  unsigned int* ticket;
+  SolveCtl* ctl;
+  double ne_global;
+  const double* local_sm;
+  double* peer_red_val[64];
+  unsigned long long* peer_red_seq[64];
+  const double* my_red_val;
+  const unsigned long long* my_red_seq;
+};
+
+__global__ void __launch_bounds__(256) p2p_push_kernel(const __grid_constant__ PushArgs A) {
+  if (A.ctl->done) return;
+  int total = 0;
+  for (int i = 0; i < A.nnbr; ++i) total += A.cnt[i];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    int i = 0, k = t;
+    while (k >= A.cnt[i]) { k -= A.cnt[i]; ++i; }
+    const int cell = A.send_cells[A.s0[i] + k];
+    for (int a = 0; a < A.narr; ++a) A.dst[i][a][A.d0[i] + k] = A.src[a][cell];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {  // every CTA's stores are fenced: publish "push `seq` complete" to the neighbours
+    __threadfence_system();
+    if (threadIdx.x < A.nnbr) *((volatile unsigned long long*)A.peer_flag[threadIdx.x]) = A.seq;
+    if (threadIdx.x == 0) *A.ticket = 0;
+  }
+  if (blockIdx.x != 0 || !A.do_reduce) return;
+  // all-reduce of (sum r^2, max) through the peers' slots; summed in rank order on every rank
+  const int slot = A.parity * 64;
+  if (threadIdx.x < A.nranks) {
+    const int r = threadIdx.x;
+    A.peer_red_val[r][(slot + A.rank) * 2] = A.local_sm[0];
+    A.peer_red_val[r][(slot + A.rank) * 2 + 1] = A.local_sm[1];
+    __threadfence_system();
+    *((volatile unsigned long long*)&A.peer_red_seq[r][slot + A.rank]) = A.seq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0, m = 0.0;
+    for (int r = 0; r < A.nranks; ++r) {
+      while (*((volatile const unsigned long long*)&A.my_red_seq[slot + r]) < A.seq) {}
+    }
+    __threadfence_system();
+    for (int r = 0; r < A.nranks; ++r) {
+      s += *((volatile const double*)&A.my_red_val[(slot + r) * 2]);
+      m = fmax(m, *((volatile const double*)&A.my_red_val[(slot + r) * 2 + 1]));
+    }
+    const double res = sqrt(s / A.ne_global);
+    A.ctl->it += 1;
+    A.ctl->res_f = res; A.ctl->res_max = m;
+    A.ctl->done = !(A.ctl->it < A.ctl->nit && res > A.ctl->res_target);
+  }
+}
+
+int field_id(const Handle* h, const double* p) {
+  if (p == h->fld[CFDL_F_U]) return P2P_U;
+  if (p == h->fld[CFDL_F_V]) return P2P_V;
+  if (p == h->fld[CFDL_F_W]) return P2P_W;
+  if (p == h->fld[CFDL_F_PC]) return P2P_PC;
+  if (p == h->rb_work) return P2P_WORK;
+  return -1;
+}
+
+}  // namespace
+
+int p2p_alloc_slab(Handle* h) {
+  P2P& q = h->p2p;
+  const Prep& p = h->prep;
+  if (p.ncolors > 4 || p.nbr_rank.size() > 8 || p.nranks > 64) return CFDL_OK;  // fall back to NCCL exchanges
+  const size_t arr = align256(sizeof(double) * ((size_t)h->H + 32));
+  size_t off = 4096;
+  P2PHeader& hd = q.hdr;
+  std::memset(&hd, 0, sizeof hd);
+  hd.magic = kMagic; hd.rank = p.rank; hd.nranks = p.nranks; hd.N = h->N; hd.Nc = h->Nc; hd.H = h->H;
+  hd.ncolors = p.ncolors; hd.nnbr = (int)p.nbr_rank.size();
+  hd.off_flags = off; off += align256(64 * 8);
+  hd.off_red_val = off; off += align256(2 * 64 * 2 * 8);
+  hd.off_red_seq = off; off += align256(2 * 64 * 8);
+  const size_t off_ticket = off; off += 256;
+  for (int a = 0; a < 5; ++a) { hd.off_field[a] = (long long)off; off += arr; }
+  for (int i = 0; i < hd.nnbr; ++i) hd.nbr_rank[i] = p.nbr_rank[i];
+  for (size_t i = 0; i < p.recv_ptr.size(); ++i) hd.recv_ptr[i] = p.recv_ptr[i];
+  CFDL_CUDA(cudaMalloc(&q.slab, off));
+  h->allocs.push_back(q.slab);
+  q.slab_bytes = off;
+  CFDL_CUDA(cudaMemset(q.slab, 0, off));
+  CFDL_CUDA(cudaMemcpy(q.slab, &hd, sizeof hd, cudaMemcpyHostToDevice));
+  h->fld[CFDL_F_U] = (double*)(q.slab + hd.off_field[P2P_U]);
+  h->fld[CFDL_F_V] = (double*)(q.slab + hd.off_field[P2P_V]);
+  h->fld[CFDL_F_W] = (double*)(q.slab + hd.off_field[P2P_W]);
+  h->fld[CFDL_F_PC] = (double*)(q.slab + hd.off_field[P2P_PC]);
+  h->rb_work = (double*)(q.slab + hd.off_field[P2P_WORK]);
+  q.ticket = (unsigned int*)(q.slab + off_ticket);
+  return CFDL_OK;
+}
+
+P2PWait p2p_wait_args(Handle* h, unsigned long long expect) {
+  P2PWait w;
+  w.flags = (const unsigned long long*)(h->p2p.slab + h->p2p.hdr.off_flags);
+  w.expect = expect;
+  w.n = h->nnbr;
+  for (int i = 0; i < 8; ++i) w.r[i] = i < h->nnbr ? h->prep.nbr_rank[i] : 0;
+  return w;
+}
+
+int p2p_store_args(Handle* h, int color, const double* a, const double* b, unsigned long long seq, P2PStore* out) {
+  P2P& q = h->p2p;
+  const Prep& p = h->prep;
+  if (!q.connected) return fail(CFDL_ERR_INTERNAL, "p2p_store_args without cfdl_comm_ipc_connect");
+  std::memset(out, 0, sizeof *out);
+  const int fa = field_id(h, a), fb = b ? field_id(h, b) : 0;
+  if (fa < 0 || fb < 0) return fail(CFDL_ERR_INTERNAL, "p2p_store_args: array is not part of the exported slab");
+  const int nc = p.ncolors;
+  out->tptr = h->tgt_ptr; out->tnbr = h->tgt_nbr; out->tpos = h->tgt_pos;
+  out->nnbr = h->nnbr; out->seq = seq; out->ticket = q.ticket;
+  for (int i = 0; i < h->nnbr; ++i) {
+    const int r = p.nbr_rank[i];
+    const P2PHeader& ph = q.peer_hdr[r];
+    int me = -1;
+    for (int k = 0; k < ph.nnbr; ++k) if (ph.nbr_rank[k] == p.rank) me = k;
+    if (me < 0) return fail(CFDL_ERR_INTERNAL, "p2p: rank %d does not list rank %d as a neighbour", r, p.rank);
+    const int cnt = p.send_ptr[(size_t)i * nc + color + 1] - p.send_ptr[(size_t)i * nc + color];
+    const int expect_cnt = ph.recv_ptr[me * nc + color + 1] - ph.recv_ptr[me * nc + color];
+    if (expect_cnt != cnt) return fail(CFDL_ERR_INTERNAL, "p2p: interface size mismatch with rank %d (%d vs %d)", r, cnt, expect_cnt);
+    out->d0[i] = ph.N + ph.recv_ptr[me * nc + color];
+    out->dst_a[i] = (double*)(q.peer_base[r] + ph.off_field[fa]);
+    out->dst_b[i] = b ? (double*)(q.peer_base[r] + ph.off_field[fb]) : nullptr;
+    out->peer_flag[i] = (unsigned long long*)(q.peer_base[r] + ph.off_flags) + p.rank;
+  }
+  return CFDL_OK;
+}
+
+int p2p_reduce_args(Handle* h, int parity, unsigned long long seq, P2PReduce* out) {
+  P2P& q = h->p2p;
+  const Prep& p = h->prep;
+  if (!q.connected) return fail(CFDL_ERR_INTERNAL, "p2p_reduce_args without cfdl_comm_ipc_connect");
+  std::memset(out, 0, sizeof *out);
+  out->on = 1; out->nranks = p.nranks; out->rank = p.rank; out->parity = parity; out->seq = seq; out->ne_global = (double)h->ne_global;
+  for (int r = 0; r < p.nranks; ++r) {
+    out->peer_val[r] = (double*)(q.peer_base[r] + q.peer_hdr[r].off_red_val);
+    out->peer_seq[r] = (unsigned long long*)(q.peer_base[r] + q.peer_hdr[r].off_red_seq);
+  }
+  out->my_val = (const double*)(q.slab + q.hdr.off_red_val);
+  out->my_seq = (const unsigned long long*)(q.slab + q.hdr.off_red_seq);
+  return CFDL_OK;
+}
+
+int p2p_push(Handle* h, int color, const double* a, const double* b, unsigned long long seq, int reduce_parity, const double* local_sm) {
+  P2P& q = h->p2p;
+  const Prep& p = h->prep;
+  if (!q.connected) return fail(CFDL_ERR_INTERNAL, "p2p_push without cfdl_comm_ipc_connect");
+  PushArgs A;
+  std::memset(&A, 0, sizeof A);
+  A.nnbr = h->nnbr; A.narr = b ? 2 : 1; A.do_reduce = reduce_parity >= 0; A.nranks = p.nranks; A.rank = p.rank;
+  A.parity = reduce_parity >= 0 ? reduce_parity : 0;
+  A.send_cells = h->send_cells;
+  A.src[0] = a; A.src[1] = b;
+  const int fa = field_id(h, a), fb = b ? field_id(h, b) : 0;
+  if (fa < 0 || fb < 0) return fail(CFDL_ERR_INTERNAL, "p2p_push: array is not part of the exported slab");
+  const int nc = p.ncolors;
+  int total = 0;
+  for (int i = 0; i < h->nnbr; ++i) {
+    const int r = p.nbr_rank[i];
+    const P2PHeader& ph = q.peer_hdr[r];
+    int me = -1;
+    for (int k = 0; k < ph.nnbr; ++k) if (ph.nbr_rank[k] == p.rank) me = k;
+    if (me < 0) return fail(CFDL_ERR_INTERNAL, "p2p_push: rank %d does not list rank %d as a neighbour", r, p.rank);
+    A.s0[i] = p.send_ptr[(size_t)i * nc + color];
+    A.cnt[i] = p.send_ptr[(size_t)i * nc + color + 1] - A.s0[i];
+    const int expect_cnt = ph.recv_ptr[me * nc + color + 1] - ph.recv_ptr[me * nc + color];
+    if (expect_cnt != A.cnt[i]) return fail(CFDL_ERR_INTERNAL, "p2p_push: interface size mismatch with rank %d (%d vs %d)", r, A.cnt[i], expect_cnt);
+    A.d0[i] = ph.N + ph.recv_ptr[me * nc + color];
+    A.dst[i][0] = (double*)(q.peer_base[r] + ph.off_field[fa]);
+    A.dst[i][1] = b ? (double*)(q.peer_base[r] + ph.off_field[fb]) : nullptr;
+    A.peer_flag[i] = (unsigned long long*)(q.peer_base[r] + ph.off_flags) + p.rank;
+    total += A.cnt[i];
+  }
+  A.seq = seq; A.ticket = q.ticket; A.ctl = h->ctl; A.ne_global = (double)h->ne_global; A.local_sm = local_sm;
+  for (int r = 0; r < p.nranks; ++r) {
+    A.peer_red_val[r] = (double*)(q.peer_base[r] + q.peer_hdr[r].off_red_val);
+    A.peer_red_seq[r] = (unsigned long long*)(q.peer_base[r] + q.peer_hdr[r].off_red_seq);
+  }
+  A.my_red_val = (const double*)(q.slab + q.hdr.off_red_val);
+  A.my_red_seq = (const unsigned long long*)(q.slab + q.hdr.off_red_seq);
+  const int ctas = std::max(1, std::min(32, (total + 255) / 256));
+  p2p_push_kernel<<<ctas, 256, 0, S(h)>>>(A);
+  CFDL_CUDA(cudaGetLastError());
+  return CFDL_OK;
 }
 
 }  // namespace cfdl
@@ -150,6 +366,41 @@ int cfdl_comm_init(cfdl_handle h, const uint8_t id[128], int32_t rank, int32_t n
   NcclComm c = nullptr;
   CFDL_NCCL(g_nccl.CommInitRank(&c, nranks, u, rank));
   h->comm = c;
+  return CFDL_OK;
+}
+
+int cfdl_comm_ipc_handle(cfdl_handle h, uint8_t handle[64]) {
+  if (!h || !handle) return fail(CFDL_ERR_ARG, "cfdl_comm_ipc_handle: NULL argument");
+  if (!h->p2p.slab) return fail(CFDL_ERR_UNSUPPORTED, "cfdl_comm_ipc_handle: this handle has no exportable slab (single rank, or too many colours/neighbours)");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CFDL_CUDA(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t m;
+  CFDL_CUDA(cudaIpcGetMemHandle(&m, h->p2p.slab));
+  std::memcpy(handle, &m, 64);
+  return CFDL_OK;
+}
+
+int cfdl_comm_ipc_connect(cfdl_handle h, const uint8_t* handles) {
+  if (!h || !handles) return fail(CFDL_ERR_ARG, "cfdl_comm_ipc_connect: NULL argument");
+  P2P& q = h->p2p;
+  if (!q.slab) return fail(CFDL_ERR_UNSUPPORTED, "cfdl_comm_ipc_connect: this handle has no exportable slab");
+  CFDL_CUDA(cudaSetDevice(h->device));
+  const int P = h->prep.nranks;
+  q.peer_base.assign(P, nullptr);
+  q.peer_hdr.assign(P, P2PHeader());
+  for (int r = 0; r < P; ++r) {
+    if (r == h->prep.rank) { q.peer_base[r] = q.slab; q.peer_hdr[r] = q.hdr; continue; }
+    cudaIpcMemHandle_t m;
+    std::memcpy(&m, handles + 64 * (size_t)r, 64);
+    void* base = nullptr;
+    CFDL_CUDA(cudaIpcOpenMemHandle(&base, m, cudaIpcMemLazyEnablePeerAccess));
+    q.opened.push_back(base);
+    q.peer_base[r] = (char*)base;
+    CFDL_CUDA(cudaMemcpy(&q.peer_hdr[r], base, sizeof(P2PHeader), cudaMemcpyDeviceToHost));
+    if (q.peer_hdr[r].magic != kMagic || q.peer_hdr[r].rank != r || q.peer_hdr[r].nranks != P)
+      return fail(CFDL_ERR_ARG, "cfdl_comm_ipc_connect: handle %d is not the slab of rank %d", r, r);
+  }
+  q.connected = true;
   return CFDL_OK;
 }
 

@@ -12,6 +12,8 @@
 //          colour-permuted system.
 //  PCG     Jacobi-preconditioned conjugate gradients for the symmetric pc system, with the
 //          reference's stopping rule (10x RMS-residual drop or nit iterations).
+#include <cstdlib>
+#include <cstring>
 #include "state.h"
 
 namespace cfdl {
@@ -288,7 +290,7 @@ int solver_init(Handle* h) {
   if ((rc = dalloc(h->anb_s, (size_t)h->K * h->Np))) return rc;
   if ((rc = dalloc(h->phi_s, (size_t)h->H + h->N + 32))) return rc;
   if ((rc = dalloc(h->rr, h->Np))) return rc;
-  if ((rc = dalloc(h->rb_work, (size_t)h->H + 32))) return rc;
+  if (!h->rb_work && (rc = dalloc(h->rb_work, (size_t)h->H + 32))) return rc;
   h->coop_ctas = (h->K <= 4) ? coop_ctas_for<4>(h) : coop_ctas_for<6>(h);
   return CFDL_OK;
 }
@@ -388,184 +390,7 @@ static int parity_solve_t(Handle* h, int eq, double* phi, const double* rhs, int
   return CFDL_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Two-colour meshes (every hex mesh): the symmetric colour sequence R B | B R, R B | B R ... has
-// the same colour twice in a row at both ends of an iteration, and a cell's second update sees
-// the very same neighbour values as its first.  The two updates are therefore applied in
-// registers from ONE evaluation of b + sum(anb*phi_nb) — bit-identical to sweeping twice — and
-// the residual of iteration k is assembled from quantities the sweeps already hold:
-//   red pass   R2 of iteration k, its residual (red rows), then R1 of iteration k+1
-//   black pass residual of iteration k for black rows (needs the red values after R2, kept in
-//              `mid`), then B1+B2 of iteration k+1 written to the other black buffer
-// One iteration = one pass over the red rows + one pass over the black rows (~120 B/cell)
-// instead of four colour launches and a residual pass (316 B/cell).  The stopping test of
-// iteration k completes in the black pass of k+1, whose update is simply discarded when it fires.
-//   A1 = [red: newest | black: buffer 0 | halos]   A2 = [red: mid (state after R2) | black: buffer 1 | halos]
-template <int K>
-__global__ void __launch_bounds__(TPB) rb_red_kernel(int c0, int c1, int Np, const int32_t* __restrict__ nbi,
-                                                     const double* __restrict__ ap, const double* __restrict__ anb,
-                                                     const double* __restrict__ b, double* red_new, const double* __restrict__ black_src,
-                                                     double* red_mid, double sor, const SolveCtl* __restrict__ ctl, double* partial, int first) {
-  if (ctl->done) return;
-  const double sm1 = sor - 1.0;
-  double s = 0.0, m = 0.0;
-  for (int c = c0 + blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += gridDim.x * blockDim.x) {
-    double sumnb = __ldcs(&b[c]);
-#pragma unroll
-    for (int k = 0; k < K; ++k) sumnb = sumnb + __ldcs(&anb[(size_t)k * Np + c]) * black_src[__ldcs(&nbi[(size_t)k * Np + c])];
-    const double a = __ldcs(&ap[c]);
-    double x = red_new[c];
-    if (!first) {
-      x = (sumnb + sm1 * a * x) / a / sor;  // R2 of iteration k
-      red_mid[c] = x;
-      const double r = fabs(sumnb - a * x);
-      m = fmax(m, r);
-      s = s + r * r;
-    }
-    red_new[c] = (sumnb + sm1 * a * x) / a / sor;  // R1 of iteration k+1
-  }
-  if (first) return;
-  block_sum_max<TPB>(s, m);
-  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = s; partial[2 * blockIdx.x + 1] = m; }
-}
-
-template <int K>
-__global__ void __launch_bounds__(TPB) rb_black_kernel(int c0, int c1, int Np, const int32_t* __restrict__ nbi,
-                                                       const double* __restrict__ ap, const double* __restrict__ anb,
-                                                       const double* __restrict__ b, const double* __restrict__ red_new,
-                                                       const double* __restrict__ red_mid, const double* __restrict__ black_old,
-                                                       double* black_new, double sor, SolveCtl* ctl, double* partial_red, int nred,
-                                                       double* partial_black, int ncells_total, int first, int local_only, double* out2) {
-  if (ctl->done) return;
-  const double sm1 = sor - 1.0;
-  double s = 0.0, m = 0.0;
-  for (int c = c0 + blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += gridDim.x * blockDim.x) {
-    const double bb = __ldcs(&b[c]);
-    double s_new = bb, s_mid = bb;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const double an = __ldcs(&anb[(size_t)k * Np + c]);
-      const int i = __ldcs(&nbi[(size_t)k * Np + c]);
-      s_new = s_new + an * red_new[i];
-      if (!first) s_mid = s_mid + an * red_mid[i];
-    }
-    const double a = __ldcs(&ap[c]);
-    double x = black_old[c];
-    if (!first) {  // residual of the finished iteration: black rows against the red values after R2
-      const double r = fabs(s_mid - a * x);
-      m = fmax(m, r);
-      s = s + r * r;
-    }
-    x = (s_new + sm1 * a * x) / a / sor;               // B1
-    black_new[c] = (s_new + sm1 * a * x) / a / sor;    // B2
-  }
-  if (first) return;
-  block_sum_max<TPB>(s, m);
-  __shared__ bool last;
-  if (threadIdx.x == 0) {
-    partial_black[2 * blockIdx.x] = s;
-    partial_black[2 * blockIdx.x + 1] = m;
-    __threadfence();
-    last = (atomicAdd(&ctl->ticket, 1u) == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
-  s = 0.0; m = 0.0;
-  for (int i = threadIdx.x; i < nred; i += blockDim.x) { s += __ldcg(&partial_red[2 * i]); m = fmax(m, __ldcg(&partial_red[2 * i + 1])); }
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) { s += __ldcg(&partial_black[2 * i]); m = fmax(m, __ldcg(&partial_black[2 * i + 1])); }
-  block_sum_max<TPB>(s, m);
-  if (threadIdx.x == 0) {
-    ctl->ticket = 0;
-    if (local_only) { out2[0] = s; out2[1] = m; return; }  // several GPUs: all-reduce, then finalize_residual_kernel
-    const double res = sqrt(s / ncells_total);
-    ctl->it += 1;
-    ctl->res_f = res; ctl->res_max = m;
-    ctl->done = !(ctl->it < ctl->nit && res > ctl->res_target);
-  }
-}
-
-// final state of a two-colour solve that stopped after `it` iterations: red = mid, black = buffer it%2
-__global__ void __launch_bounds__(TPB) rb_final_kernel(int nred, int N, double* a1, const double* __restrict__ a2, int it_odd) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x)
-    if (c < nred || it_odd) a1[c] = a2[c];
-}
-
-template <int K>
-static int rb_solve_t(Handle* h, int eq, double* phi, const double* rhs, int nit, double* out4) {
-  const double sor = (eq == CFDL_EQ_PC) ? 1.02 : 1.0;
-  const int N = h->N, Np = h->Np, g = grid_for(h, N, TPB);
-  const int32_t* cp = h->prep.color_ptr.data();
-  const int nred = cp[1], nblack = N - nred;
-  const double *ap = h->fld[CFDL_F_AP], *anb = h->fld[CFDL_F_ANB];
-  double *A1 = phi, *A2 = h->rb_work;
-  const int gr = grid_for(h, nred, TPB, h->tune_ctas), gb = grid_for(h, nblack, TPB, h->tune_ctas);
-  double *pr = h->partial, *pb = h->partial + 2 * (size_t)gr;
-  SolveCtl init = {};
-  init.nit = nit;
-  *h->ctl_host = init;
-  CFDL_CUDA(cudaMemcpyAsync(h->ctl, h->ctl_host, sizeof(SolveCtl), cudaMemcpyHostToDevice, h->stream));
-  const bool dist = h->prep.nranks > 1;
-  int rc;
-  if (dist && (rc = comm_exchange(h, phi, 1, -1))) return rc;
-  // halo values are constant during the solve and ghost values are refreshed after every pass:
-  // both arrays carry them
-  CFDL_CUDA(cudaMemcpyAsync(A2 + N, A1 + N, sizeof(double) * (size_t)(h->H - N), cudaMemcpyDeviceToDevice, h->stream));
-  prof_begin(h, PROF_RESIDUAL);
-  if (!dist) {
-    residual_kernel<K><<<g, TPB, 0, S(h)>>>(N, Np, h->ell_nb, ap, anb, rhs, phi, h->partial, h->ctl, RES_INIT, 0, nullptr);
-  } else {
-    residual_kernel<K><<<g, TPB, 0, S(h)>>>(N, Np, h->ell_nb, ap, anb, rhs, phi, h->partial, h->ctl, RES_LOCAL, 0, h->scal + 8);
-    if ((rc = comm_allreduce_sum_max(h, h->scal + 8))) return rc;
-    finalize_residual_kernel<<<1, 1, 0, S(h)>>>(h->ctl, h->scal + 8, (double)h->ne_global, RES_INIT);
-  }
-  prof_end(h);
-  // pass j (1-based): black pass of iteration j, then red pass closing iteration j; iteration j is
-  // judged inside the black pass j+1, so nit iterations need nit+1 black passes
-  int next = 0;  // passes enqueued so far; pass 0 = the opening red update R1
-  int batch = 1;
-  for (;;) {
-    CFDL_CUDA(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(SolveCtl), cudaMemcpyDeviceToHost, h->stream));
-    CFDL_CUDA(cudaStreamSynchronize(h->stream));
-    if (h->ctl_host->done || next > nit + 1) break;
-    const int last = std::min(next + batch - 1, nit + 1);
-    for (int j = next; j <= last; ++j) {
-      if (j > 0) {  // black pass j: reads black buffer (j-1)%2, writes buffer j%2
-        const double* bold = ((j - 1) & 1) ? A2 : A1;
-        double* bnew = (j & 1) ? A2 : A1;
-        prof_begin(h, PROF_SGS_SWEEP);
-        rb_black_kernel<K><<<gb, TPB, 0, S(h)>>>(nred, N, Np, h->ell_nb, ap, anb, rhs, A1, A2, bold, bnew, sor, h->ctl, pr, gr, pb, N,
-                                                 j == 1 ? 1 : 0, dist ? 1 : 0, h->scal + 8);
-        prof_end(h);
-        if (dist) {  // black ghosts of the buffer just written; residual of iteration j-1 over all ranks
-          if ((rc = comm_exchange(h, bnew, 1, 1))) return rc;
-          if (j > 1) {
-            if ((rc = comm_allreduce_sum_max(h, h->scal + 8))) return rc;
-            finalize_residual_kernel<<<1, 1, 0, S(h)>>>(h->ctl, h->scal + 8, (double)h->ne_global, RES_ITER);
-          }
-        }
-      }
-      if (j <= nit) {  // red pass j: black neighbours from buffer j%2
-        prof_begin(h, PROF_SGS_SWEEP);
-        rb_red_kernel<K><<<gr, TPB, 0, S(h)>>>(0, nred, Np, h->ell_nb, ap, anb, rhs, A1, (j & 1) ? A2 : A1, A2, sor, h->ctl, pr, j == 0 ? 1 : 0);
-        prof_end(h);
-        if (dist) {  // red ghosts: newest values (A1) and, once an iteration has closed, the values after R2 (A2)
-          if ((rc = comm_exchange(h, A1, 1, 0))) return rc;
-          if (j > 0 && (rc = comm_exchange(h, A2, 1, 0))) return rc;
-        }
-      }
-    }
-    CFDL_CUDA(cudaGetLastError());
-    next = last + 1;
-    batch = std::min(batch * 2, 32);
-  }
-  const int it = h->ctl_host->it;
-  if (it > 0) rb_final_kernel<<<g, TPB, 0, S(h)>>>(nred, N, A1, A2, it & 1);
-  CFDL_CUDA(cudaGetLastError());
-  if (dist && it > 0 && (rc = comm_exchange(h, phi, 1, -1))) return rc;  // ghosts of the final state
-  if (out4) { out4[0] = it; out4[1] = h->ctl_host->res_i; out4[2] = h->ctl_host->res_f; out4[3] = h->ctl_host->res_max; }
-  return CFDL_OK;
-}
+#include "kernels_rb.inc"
 
 // MCSGS: colour-ordered symmetric Gauss-Seidel with the reference's stopping rule; iterations
 // are enqueued in growing batches, each kernel returning at once when ctl->done is set

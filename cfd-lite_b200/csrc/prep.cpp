@@ -182,12 +182,26 @@ int prepare(Prep& p, int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_i
   for (int c = 0; c < ncol; ++c) p.color_ptr[c + 1] += p.color_ptr[c];
   p.o2c.assign(gN, -1);
   p.c2o.resize(N);
+  p.color_if.assign(ncol, 0);
   {
-    std::vector<int32_t> cur(p.color_ptr.begin(), p.color_ptr.end() - 1);
+    // inside a colour the interface cells (those with a neighbour owned by another rank) come
+    // first, so a pass can compute and ship them before it sweeps the interior
+    std::vector<uint8_t> is_if;
+    if (nranks > 1) {
+      is_if.assign((size_t)gN, 0);
+      for (int32_t e = 0; e < gN; ++e) {
+        if (owner(e) != rank) continue;
+        for (int32_t idx = p.row_ptr[e]; idx < p.row_ptr[e + 1]; ++idx)
+          if (o_nb[idx] < gN && owner(o_nb[idx]) != rank) { is_if[e] = 1; break; }
+        if (is_if[e]) p.color_if[color[e]]++;
+      }
+    }
+    std::vector<int32_t> cur_if(p.color_ptr.begin(), p.color_ptr.end() - 1), cur_in(ncol);
+    for (int c = 0; c < ncol; ++c) cur_in[c] = p.color_ptr[c] + p.color_if[c];
     for (int32_t i = 0; i < gN; ++i) {
       int32_t e = base[i];
       if (owner(e) != rank) continue;
-      int32_t c = cur[color[e]]++;
+      int32_t c = (nranks > 1 && is_if[e]) ? cur_if[color[e]]++ : cur_in[color[e]]++;
       p.c2o[c] = e; p.o2c[e] = c;
     }
   }
@@ -236,6 +250,19 @@ int prepare(Prep& p, int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_i
     for (const Key& k : sends) p.send_ptr[slot_of(k) + 1]++;
     for (size_t i = 0; i < (size_t)nnbr * ncol; ++i) { p.recv_ptr[i + 1] += p.recv_ptr[i]; p.send_ptr[i + 1] += p.send_ptr[i]; }
     for (size_t i = 0; i < sends.size(); ++i) p.send_cells[i] = p.o2c[sends[i].e];
+    // the same lists seen from the cell: which ghost slots on which neighbours mirror cell c
+    p.tgt_ptr.assign((size_t)N + 1, 0);
+    for (size_t i = 0; i < sends.size(); ++i) p.tgt_ptr[p.send_cells[i] + 1]++;
+    for (int32_t c = 0; c < N; ++c) p.tgt_ptr[c + 1] += p.tgt_ptr[c];
+    p.tgt_nbr.resize(sends.size()); p.tgt_pos.resize(sends.size());
+    std::vector<int32_t> fill(p.tgt_ptr.begin(), p.tgt_ptr.end() - 1);
+    for (int r = 0; r < nnbr; ++r)
+      for (int c = 0; c < ncol; ++c)
+        for (int32_t s = p.send_ptr[(size_t)r * ncol + c]; s < p.send_ptr[(size_t)r * ncol + c + 1]; ++s) {
+          const int32_t at = fill[p.send_cells[s]]++;
+          p.tgt_nbr[at] = r;
+          p.tgt_pos[at] = s - p.send_ptr[(size_t)r * ncol + c];
+        }
   }
   // ---- halos: physical boundary faces of owned cells, in original halo order ----------------
   p.h2o.clear();

@@ -45,6 +45,10 @@ struct Prep {
   std::vector<int32_t> f2o;        // F: device face -> original face (0-based)
   std::vector<int32_t> fown;       // F: 1 when this rank reports the face on download
   std::vector<int32_t> color_ptr;  // ncolors+1 over owned cells (device cells are sorted by colour)
+  std::vector<int32_t> color_if;   // per colour: leading cells of the colour that touch another rank (interface cells)
+  // per owned device cell c: the peers' ghost slots that mirror it, tgt_nbr/tgt_pos[tgt_ptr[c]..tgt_ptr[c+1])
+  // (neighbour index into nbr_rank, position inside that neighbour's (colour) receive slice)
+  std::vector<int32_t> tgt_ptr, tgt_nbr, tgt_pos;
   std::vector<int32_t> ell_nb;     // K*Np device index of neighbour (cell, ghost or halo), pad = self
   std::vector<int32_t> ell_fs;     // K*Np signed device face id +-(f+1); 0 = padding slot
   std::vector<uint8_t> nfc;        // N faces per cell

@@ -32,8 +32,36 @@ struct DevSchedule {
   int max_level_cells = 0;
 };
 
+// Peer-to-peer ghost exchange over NVLink (multi-GPU, one process per GPU).  The solution
+// arrays whose ghost cells neighbours write into live in one cudaMalloc'ed slab that is
+// exported with cudaIpcGetMemHandle; the slab starts with this header so that a peer can find
+// the arrays, the flag words and the reduction slots of its owner.
+struct P2PHeader {
+  long long magic;
+  int rank, nranks, N, Nc, H, ncolors, nnbr, pad;
+  long long off_field[5];  // byte offsets of u, v, w, pc and the second solver array in the slab
+  long long off_flags;     // unsigned long long flags[64]: flags[r] = last push sequence completed by rank r
+  long long off_red_val;   // double red_val[2][64][2]: (sum r^2, max) of rank r, two alternating sets
+  long long off_red_seq;   // unsigned long long red_seq[2][64]
+  int nbr_rank[64];
+  int recv_ptr[64 * 4 + 1];
+};
+struct P2P {
+  bool connected = false;
+  char* slab = nullptr;
+  size_t slab_bytes = 0;
+  P2PHeader hdr;                        // this rank's header (host copy)
+  std::vector<char*> peer_base;         // per rank; own slab for self
+  std::vector<P2PHeader> peer_hdr;
+  std::vector<void*> opened;            // cudaIpcOpenMemHandle results to close
+  unsigned long long epoch = 0;
+  unsigned int* ticket = nullptr;
+};
+enum { P2P_U = 0, P2P_V = 1, P2P_W = 2, P2P_PC = 3, P2P_WORK = 4 };
+
 struct Handle {
   Prep prep;
+  P2P p2p;
   int device = 0, num_sms = 0;
   cudaStream_t stream = nullptr;
   int32_t N = 0, G = 0, Nc = 0, F = 0, B = 0, H = 0, Z = 0, K = 0, Np = 0, Fi = 0;  // owned, ghost, owned+ghost cells; local faces, halos
@@ -64,11 +92,13 @@ struct Handle {
   int coop_ctas = 0;
   double* rb_work = nullptr;   // second value array of the fused two-colour solver (H doubles)
   int fused_rb = 1;            // 0: always use one launch per colour + residual pass
+  int use_p2p = 1;             // 0: NCCL send/recv even when peer slabs are connected
   int tune_ctas = 8;           // CTAs per SM for the solver passes (grid = min(need, num_sms * tune_ctas))
   // multi-GPU (one process per GPU): NCCL communicator and interface buffers
   void* comm = nullptr;            // ncclComm_t
   int nnbr = 0;
   int32_t* send_cells = nullptr;   // device copy of prep.send_cells
+  int32_t *tgt_ptr = nullptr, *tgt_nbr = nullptr, *tgt_pos = nullptr;  // device copies of prep.tgt_*
   double* send_buf = nullptr;      // 9 doubles per send cell
   double* recv_buf = nullptr;      // 9 doubles per ghost (multi-component receives)
   int64_t ne_global = 0;
@@ -126,6 +156,38 @@ int residual_plain(Handle* h, const double* phi, const double* rhs, bool signed_
 // cell (AoS); color >= 0 restricts the exchange to ghosts/sends of that colour
 int comm_exchange(Handle* h, double* field, int ncomp, int color);
 int comm_allreduce_sum_max(Handle* h, double* dev2);  // dev2[0] summed, dev2[1] maxed over ranks
+// peer-to-peer path (after cfdl_comm_ipc_connect): write the colour-`color` interface values of
+// up to two arrays straight into the neighbours' ghost cells, then publish sequence number
+// `seq` in their flag words; with reduce_parity >= 0 also combine (sum r^2, max) in local_sm
+// over all ranks through the peers' reduction slots and advance ctl like finalize_residual_kernel
+int p2p_alloc_slab(Handle* h);  // carves u,v,w,pc and rb_work out of one exportable allocation
+int p2p_push(Handle* h, int color, const double* a, const double* b, unsigned long long seq, int reduce_parity, const double* local_sm);
+struct P2PWait { const unsigned long long* flags; unsigned long long expect; int n; int r[8]; };
+P2PWait p2p_wait_args(Handle* h, unsigned long long expect);
+// remote-store description of one launch (kernel parameter; tptr == nullptr: no remote stores):
+// cell c mirrors into ghost slot d0[i] + tpos[e] of neighbour i = tnbr[e], e in [tptr[c], tptr[c+1])
+struct P2PStore {
+  const int32_t *tptr, *tnbr, *tpos;
+  double* dst_a[8];
+  double* dst_b[8];
+  int d0[8];
+  unsigned long long* peer_flag[8];
+  int nnbr;
+  unsigned long long seq;
+  unsigned int* ticket;
+};
+// cross-rank reduction of (sum r^2, max) through peer memory (on == 0: single rank / NCCL mode)
+struct P2PReduce {
+  int on, nranks, rank, parity;
+  unsigned long long seq;
+  double ne_global;
+  double* peer_val[64];
+  unsigned long long* peer_seq[64];
+  const double* my_val;
+  const unsigned long long* my_seq;
+};
+int p2p_store_args(Handle* h, int color, const double* a, const double* b, unsigned long long seq, P2PStore* out);
+int p2p_reduce_args(Handle* h, int parity, unsigned long long seq, P2PReduce* out);
 int comm_bcast(Handle* h, double* dev, int count, int root);
 void comm_destroy(Handle* h);
 

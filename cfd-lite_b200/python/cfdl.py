@@ -260,6 +260,19 @@ class Solver:
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
         _chk(lib().cfdl_comm_init(self.h, buf, C.c_int32(self.rank), C.c_int32(self.nranks)))
 
+    def ipc_handle(self):
+        """64-byte CUDA IPC handle of this rank's exchange slab (gather over ranks, then ipc_connect)."""
+        buf = (C.c_uint8 * 64)()
+        _chk(lib().cfdl_comm_ipc_handle(self.h, buf))
+        return bytes(buf)
+
+    def ipc_connect(self, handles):
+        """handles: list of the nranks 64-byte handles in rank order.  Enables peer-to-peer ghost exchange."""
+        blob = b"".join(bytes(x) for x in handles)
+        assert len(blob) == 64 * self.nranks
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _chk(lib().cfdl_comm_ipc_connect(self.h, buf))
+
     def local_size(self, name):
         n = C.c_int64()
         _chk(lib().cfdl_field_local_size(self.h, C.c_int(FIELD_ID[name]), C.byref(n)))

@@ -183,6 +183,13 @@ int cfdl_create_distributed(cfdl_handle* out, int32_t ne, int32_t nf, int32_t nb
 int cfdl_comm_unique_id(uint8_t id[128]);
 /* collective over all ranks; must precede any compute call on a distributed handle */
 int cfdl_comm_init(cfdl_handle h, const uint8_t id[128], int32_t rank, int32_t nranks);
+/* optional peer-to-peer mode (GPUs of one node, NVLink): every rank exports the slab holding
+ * u, v, w, pc (64-byte cudaIpcMemHandle), the caller gathers the nranks handles (rank order)
+ * and every rank connects.  Afterwards the fused two-colour solver passes store interface values
+ * straight into the neighbours' ghost cells and combine residual norms through peer memory —
+ * no NCCL call inside a solver iteration.  set_option("p2p", 0) switches back to NCCL. */
+int cfdl_comm_ipc_handle(cfdl_handle h, uint8_t handle[64]);
+int cfdl_comm_ipc_connect(cfdl_handle h, const uint8_t* handles /* nranks * 64 bytes */);
 /* partition-local host I/O (device numbering: owned cells, ghosts, halos): the bytes a rank
  * actually needs to move per step in a distributed host driver */
 int cfdl_field_local_size(cfdl_handle h, int field, int64_t* n);

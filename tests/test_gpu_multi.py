@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, kind, n, out_q):
+def _worker(rank, world, port, kind, n, p2p, out_q):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ROOT, "cfd-lite_b200", "python"))
@@ -40,6 +40,10 @@ def _worker(rank, world, port, kind, n, out_q):
         dist.broadcast_object_list(ids, src=0)
         s.comm_init(ids[0])
         s.set_option("solver", cfdl.SOLVER_MCSGS)
+        if p2p:  # peer-to-peer ghost exchange through CUDA IPC instead of NCCL send/recv
+            handles = [None] * world
+            dist.all_gather_object(handles, s.ipc_handle())
+            s.ipc_connect(handles)
         hist = s.run(dt=0.01, nit=100, ntstep=2, ncoef=3)
         fields = {}
         for f in ("u", "v", "w", "p", "mip", "gp"):
@@ -77,8 +81,8 @@ def _worker(rank, world, port, kind, n, out_q):
         out_q.put((rank, "FAIL: " + "".join(traceback.format_exception(type(ex), ex, ex.__traceback__))))
 
 
-@pytest.mark.parametrize("kind,n", [(0, 10), (1, 5)])
-def test_partitioned_run_equals_single_gpu(cfdl, kind, n):
+@pytest.mark.parametrize("kind,n,p2p", [(0, 10, False), (1, 5, False), (0, 10, True), (0, 24, True)])
+def test_partitioned_run_equals_single_gpu(cfdl, kind, n, p2p):
     world = min(cfdl.device_count(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -86,7 +90,7 @@ def test_partitioned_run_equals_single_gpu(cfdl, kind, n):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, n, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, n, p2p, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=600) for _ in range(world)]
