@@ -202,6 +202,13 @@ int create_impl(cfdl_handle* out, int32_t ne, int32_t nf, int32_t nbf, const int
   if (cudaMallocHost(&h->ctl_host, sizeof(SolveCtl)) != cudaSuccess || cudaMallocHost(&h->scal_host, sizeof(double) * 512) != cudaSuccess)
     return bail(fail(CFDL_ERR_CUDA, "cudaMallocHost failed"));
   if ((rc = solver_init(h))) return bail(rc);
+  {  // static face geometry, evaluated once with the reference's own expressions (kernels_statics.cu)
+    double** arrs[15] = {&h->fs_area, &h->fs_ds, &h->fs_dsp, &h->fs_dn, &h->fs_wto, &h->fs_wtn, &h->fs_n[0], &h->fs_n[1], &h->fs_n[2],
+                         &h->fs_dr[0], &h->fs_dr[1], &h->fs_dr[2], &h->fs_drp[0], &h->fs_drp[1], &h->fs_drp[2]};
+    for (double** a : arrs)
+      if ((rc = dev_zero(h, *a, (size_t)p.Fi + 4))) return bail(rc);
+    if ((rc = k_face_statics(h))) return bail(rc);
+  }
   // construct_uvwp: fields zero, mip from calc_mip(.false.), mip0 = mip (mod_uvwp.f90:57-82)
   if ((rc = k_calc_mip(h, false, 0.01))) return bail(rc);
   if (cudaMemcpyAsync(h->fld[CFDL_F_MIP0], h->fld[CFDL_F_MIP], sizeof(double) * (size_t)F, cudaMemcpyDeviceToDevice, h->stream) != cudaSuccess ||
@@ -267,6 +274,8 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   }
   if (!std::strcmp(key, "fused")) { h->fused_rb = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "p2p")) { h->use_p2p = value != 0.0; return CFDL_OK; }
+  if (!std::strcmp(key, "uvw_variant")) { h->uvw_variant = (int)value; return CFDL_OK; }
+  if (!std::strcmp(key, "statics")) { h->use_statics = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "ctas_per_sm")) { h->tune_ctas = std::max(1, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "profile")) {
     int rc = prof_collect(h);

@@ -1,0 +1,23 @@
+// Small FP64 device helpers shared by the assembly kernels.  Operation order follows the Fortran
+// expressions of the reference (no FMA contraction: the library is compiled with -fmad=false).
+#pragma once
+#include <cstdint>
+
+namespace cfdl {
+
+__device__ __forceinline__ double dot3(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// vec_weight, src/modules/mod_util.f90:729-743 — weight on the neighbour r2
+__device__ __forceinline__ double vec_weight(const double r0[3], const double r1[3], const double r2[3]) {
+  double ra0 = r1[0] - r0[0], ra1 = r1[1] - r0[1], ra2 = r1[2] - r0[2];
+  double rb0 = r2[0] - r0[0], rb1 = r2[1] - r0[1], rb2 = r2[2] - r0[2];
+  double la = sqrt(ra0 * ra0 + ra1 * ra1 + ra2 * ra2);
+  double lb = sqrt(rb0 * rb0 + rb1 * rb1 + rb2 * rb2);
+  return (la + lb > 0.0) ? la / (la + lb) : 0.5;
+}
+
+__device__ __forceinline__ void load3(const double* __restrict__ a, int64_t i, double v[3]) {
+  v[0] = a[3 * i]; v[1] = a[3 * i + 1]; v[2] = a[3 * i + 2];
+}
+
+}  // namespace cfdl

@@ -4,25 +4,11 @@
 // follows the Fortran expressions operation by operation (compiled with -fmad=false), which
 // keeps FP64 results bit-comparable with the reference's unfused evaluation.
 #include "state.h"
+#include "device_math.cuh"
 
 namespace cfdl {
 
 #define TPB 256
-
-__device__ __forceinline__ double dot3(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-
-// vec_weight, src/modules/mod_util.f90:729-743 — weight on the neighbour r2
-__device__ __forceinline__ double vec_weight(const double r0[3], const double r1[3], const double r2[3]) {
-  double ra0 = r1[0] - r0[0], ra1 = r1[1] - r0[1], ra2 = r1[2] - r0[2];
-  double rb0 = r2[0] - r0[0], rb1 = r2[1] - r0[1], rb2 = r2[2] - r0[2];
-  double la = sqrt(ra0 * ra0 + ra1 * ra1 + ra2 * ra2);
-  double lb = sqrt(rb0 * rb0 + rb1 * rb1 + rb2 * rb2);
-  return (la + lb > 0.0) ? la / (la + lb) : 0.5;
-}
-
-__device__ __forceinline__ void load3(const double* __restrict__ a, int64_t i, double v[3]) {
-  v[0] = a[3 * i]; v[1] = a[3 * i + 1]; v[2] = a[3 * i + 2];
-}
 
 // ---- update_boundaries: BC callbacks dirichlet0 / lid / symmetry, mod_uvwp.f90:493-570 --------
 __global__ void __launch_bounds__(TPB) bc_kernel(int B, int N, const int32_t* __restrict__ halo_cell,
@@ -192,6 +178,133 @@ __global__ void __launch_bounds__(TPB) coef_uvw_kernel(const UvwArgs A) {
   }
 }
 
+// Slot-parallel form of the same routine: one thread per (cell, face slot) evaluates the face
+// terms (the ~19 FP64 divisions / square roots per face that made the one-thread-per-cell kernel
+// latency bound at 12 % occupancy), the per-slot results go through shared memory, and one thread
+// per cell adds them up in the reference's slot order, applies the boundary faces and writes the
+// row.  Same operations in the same order => same bits as coef_uvw_kernel.
+#define UVW_CELLS 64
+template <int K>
+__global__ void __launch_bounds__(UVW_CELLS* K, 2) coef_uvw_slots_kernel(const UvwArgs A) {
+  // per slot: d, fnb, f_in, ss[3], defc[3]
+  __shared__ double sh[9][K][UVW_CELLS];
+  const int N = A.N, Nc = A.Nc, Np = A.Np;
+  const int k = threadIdx.x / UVW_CELLS, cl = threadIdx.x % UVW_CELLS;
+  for (int base = blockIdx.x * UVW_CELLS; base < N; base += gridDim.x * UVW_CELLS) {
+    const int c = base + cl;
+    double d = 0.0, fnb = 0.0, f_in = 0.0, ss[3] = {0, 0, 0}, dfc[3] = {0, 0, 0};
+    if (c < N && k < A.nfc[c]) {
+      const int nb = A.ell_nb[(size_t)k * Np + c];
+      if (nb < Nc) {  // lfnb > 0 (owned or ghost cell)
+        const int fs = A.ell_fs[(size_t)k * Np + c];
+        const int f = abs(fs) - 1;
+        const double sg = fs > 0 ? 1.0 : -1.0;
+        const double rp[3] = {A.xc[c], A.yc[c], A.zc[c]};
+        double a[3], rip[3];
+        load3(A.aip, f, a); load3(A.rip, f, rip);
+        const double area = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+        const double norm[3] = {sg * a[0] / area, sg * a[1] / area, sg * a[2] / area};
+        const double rpnb[3] = {A.xc[nb], A.yc[nb], A.zc[nb]};
+        const double dr[3] = {rpnb[0] - rp[0], rpnb[1] - rp[1], rpnb[2] - rp[2]};
+        const double ds = sqrt(dot3(dr, dr));
+        const double wt = vec_weight(rip, rp, rpnb);
+        double drip[3] = {rip[0] - rp[0], rip[1] - rp[1], rip[2] - rp[2]};
+        double t = dot3(drip, norm);
+        const double rp_p[3] = {rip[0] - t * norm[0], rip[1] - t * norm[1], rip[2] - t * norm[2]};
+        drip[0] = rip[0] - rpnb[0]; drip[1] = rip[1] - rpnb[1]; drip[2] = rip[2] - rpnb[2];
+        t = dot3(drip, norm);
+        const double rpnb_p[3] = {rip[0] - t * norm[0], rip[1] - t * norm[1], rip[2] - t * norm[2]};
+        const double dr_p[3] = {rpnb_p[0] - rp_p[0], rpnb_p[1] - rp_p[1], rpnb_p[2] - rp_p[2]};
+        const double ds_p = sqrt(dot3(dr_p, dr_p));
+        f_in = -sg * A.mip[f];
+        fnb = fmax(f_in, 0.0);
+        const double muip = (1.0 - wt) * A.mu[c] + wt * A.mu[nb];
+        d = muip * area / ds;
+        double gue[3], gve[3], gwe[3], gun[3], gvn[3], gwn[3];
+        load3(A.gu, c, gue); load3(A.gv, c, gve); load3(A.gw, c, gwe);
+        load3(A.gu, nb, gun); load3(A.gv, nb, gvn); load3(A.gw, nb, gwn);
+        const double w1 = 1.0 - wt;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+          const double gip[3] = {w1 * gue[m] + wt * gun[m], w1 * gve[m] + wt * gvn[m], w1 * gwe[m] + wt * gwn[m]};
+          ss[m] = muip * area * dot3(gip, dr) / ds;
+        }
+        double gip[3] = {w1 * gue[0] + wt * gun[0], w1 * gue[1] + wt * gun[1], w1 * gue[2] + wt * gun[2]};
+        dfc[0] = muip * area * (dot3(gip, dr_p) / ds_p - dot3(gip, dr) / ds);
+        gip[0] = w1 * gve[0] + wt * gvn[0]; gip[1] = w1 * gve[1] + wt * gvn[1]; gip[2] = w1 * gve[2] + wt * gvn[2];
+        dfc[1] = muip * area * (dot3(gip, dr_p) / ds_p - dot3(gip, dr) / ds);
+        gip[0] = w1 * gwe[0] + wt * gwn[0]; gip[1] = w1 * gwe[1] + wt * gwn[1]; gip[2] = w1 * gwe[2] + wt * gwn[2];
+        dfc[2] = muip * area * (dot3(gip, dr_p) / ds_p - dot3(gip, dr) / ds);
+      }
+    }
+    sh[0][k][cl] = d; sh[1][k][cl] = fnb; sh[2][k][cl] = f_in;
+    sh[3][k][cl] = ss[0]; sh[4][k][cl] = ss[1]; sh[5][k][cl] = ss[2];
+    sh[6][k][cl] = dfc[0]; sh[7][k][cl] = dfc[1]; sh[8][k][cl] = dfc[2];
+    __syncthreads();
+    if (k == 0 && c < N) {  // one thread per cell: sums in slot order, boundary faces, row output
+      const int n = A.nfc[c];
+      double ap = 0.0, sumf = 0.0, sumss[3] = {0, 0, 0}, sumdefc[3] = {0, 0, 0};
+      for (int kk = 0; kk < n; ++kk) {
+        sumf = sumf + sh[2][kk][cl];
+        sumss[0] = sumss[0] + sh[3][kk][cl]; sumss[1] = sumss[1] + sh[4][kk][cl]; sumss[2] = sumss[2] + sh[5][kk][cl];
+        sumdefc[0] = sumdefc[0] + sh[6][kk][cl]; sumdefc[1] = sumdefc[1] + sh[7][kk][cl]; sumdefc[2] = sumdefc[2] + sh[8][kk][cl];
+        ap = ap + sh[0][kk][cl] + sh[1][kk][cl];
+      }
+      const double vol = A.vol[c];
+      const double ap0 = A.rho[c] * vol / A.dt;
+      ap = ap + ap0;
+      const double ue = A.u[c], ve = A.v[c], we = A.w[c];
+      double bu = ap0 * A.u0[c] + sumf * ue - vol * A.gp[3 * (size_t)c] + sumss[0] + sumdefc[0];
+      double bv = ap0 * A.v0[c] + sumf * ve - vol * A.gp[3 * (size_t)c + 1] + sumss[1] + sumdefc[1];
+      double bw = ap0 * A.w0[c] + sumf * we - vol * A.gp[3 * (size_t)c + 2] + sumss[2] + sumdefc[2];
+      int last = -1;  // boundary faces in halo order, like the reference's BC loop (:243-273)
+      for (int tt = 0; tt < n; ++tt) {
+        int best = 0x7fffffff, bk = -1;
+        for (int kk = 0; kk < n; ++kk) {
+          const int nbk = A.ell_nb[(size_t)kk * Np + c];
+          if (nbk >= Nc && nbk > last && nbk < best) { best = nbk; bk = kk; }
+        }
+        if (bk < 0) break;
+        last = best;
+        const int bc = A.halo_bc[best - Nc];
+        if (bc < 0) continue;
+        const int f = A.ell_fs[(size_t)bk * Np + c] - 1;
+        double a[3];
+        load3(A.aip, f, a);
+        const double area = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+        const double norm[3] = {a[0] / area, a[1] / area, a[2] / area};
+        const double dr[3] = {A.xc[best] - A.xc[c], A.yc[best] - A.yc[c], A.zc[best] - A.zc[c]};
+        const double ds = sqrt(dot3(dr, dr));
+        const double db = A.mu[c] * area / ds;
+        if (A.bc_kind[bc] != CFDL_BC_SYMMETRY) {  // 'dirichlet'
+          const double vbnc[3] = {A.u[best], A.v[best], A.w[best]};
+          double vrel[3] = {ue, ve, we};
+          const double vn = dot3(vrel, norm);
+          vrel[0] = vrel[0] - vn * norm[0]; vrel[1] = vrel[1] - vn * norm[1]; vrel[2] = vrel[2] - vn * norm[2];
+          vrel[0] = vbnc[0] - vrel[0]; vrel[1] = vbnc[1] - vrel[1]; vrel[2] = vbnc[2] - vrel[2];
+          bu = bu + db * vrel[0] - db * ue;
+          bv = bv + db * vrel[1] - db * ve;
+          bw = bw + db * vrel[2] - db * we;
+        }
+        ap = ap + db;
+        sh[0][bk][cl] = sh[0][bk][cl] + sh[1][bk][cl] + db;  // anb(idx) = anb(idx) + d + f with anb(idx) = 0 + 0
+        sh[1][bk][cl] = 0.0;
+      }
+      double dcv = ap;
+      for (int kk = 0; kk < n; ++kk) {
+        const double anbk = sh[0][kk][cl] + sh[1][kk][cl];
+        dcv = dcv - anbk;
+        A.anb[(size_t)kk * Np + c] = anbk;
+      }
+      A.ap[c] = ap;
+      A.bu[c] = bu; A.bv[c] = bv; A.bw[c] = bw;
+      A.d[c] = vol / ap;
+      A.dc[c] = vol / dcv;
+    }
+    __syncthreads();
+  }
+}
+
 int k_calc_coef_uvw(Handle* h, double dt) {
   UvwArgs A;
   A.N = h->N; A.Nc = h->Nc; A.Np = h->Np;
@@ -205,10 +318,19 @@ int k_calc_coef_uvw(Handle* h, double dt) {
   A.bw = h->fld[CFDL_F_BW]; A.d = h->fld[CFDL_F_D]; A.dc = h->fld[CFDL_F_DC];
   A.dt = dt;
   const int g = grid_for(h, h->N, TPB);
+  const int gs = grid_for(h, h->N, UVW_CELLS, 16);
+  if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
   prof_begin(h, PROF_COEF_UVW);
-  if (h->K <= 4) coef_uvw_kernel<4><<<g, TPB, 0, S(h)>>>(A);
-  else if (h->K <= 6) coef_uvw_kernel<6><<<g, TPB, 0, S(h)>>>(A);
-  else return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
+  if (h->uvw_variant == 2 && h->use_statics && h->fs_area) {
+    int rc = k_calc_coef_uvw_statics(h, dt);
+    if (rc) return rc;
+  } else if (h->uvw_variant == 0) {
+    if (h->K <= 4) coef_uvw_kernel<4><<<g, TPB, 0, S(h)>>>(A);
+    else coef_uvw_kernel<6><<<g, TPB, 0, S(h)>>>(A);
+  } else {
+    if (h->K <= 4) coef_uvw_slots_kernel<4><<<gs, UVW_CELLS * 4, 0, S(h)>>>(A);
+    else coef_uvw_slots_kernel<6><<<gs, UVW_CELLS * 6, 0, S(h)>>>(A);
+  }
   prof_end(h);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
@@ -279,7 +401,8 @@ int k_calc_coef_p(Handle* h) {
 #define CP_ARGS h->N, h->Nc, h->Np, h->ell_nb, h->ell_fs, h->nfc, h->halo_bc, h->xc, h->yc, h->zc, h->aip, h->rip, h->rho, \
                 h->fld[CFDL_F_DC], h->fld[CFDL_F_MIP], h->fld[CFDL_F_AP], h->fld[CFDL_F_ANB], h->fld[CFDL_F_B]
   prof_begin(h, PROF_COEF_P);
-  if (h->K <= 4) coef_p_kernel<4><<<g, TPB, 0, S(h)>>>(CP_ARGS);
+  if (h->use_statics && h->fs_area && h->K <= 6) { int rc = k_calc_coef_p_statics(h); if (rc) return rc; }
+  else if (h->K <= 4) coef_p_kernel<4><<<g, TPB, 0, S(h)>>>(CP_ARGS);
   else if (h->K <= 6) coef_p_kernel<6><<<g, TPB, 0, S(h)>>>(CP_ARGS);
   else return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
   prof_end(h);
@@ -337,7 +460,8 @@ int k_calc_mip(Handle* h, bool rhie_chow, double dt) {
   A.p = h->fld[CFDL_F_P]; A.gp = h->fld[CFDL_F_GP]; A.d = h->fld[CFDL_F_D]; A.mip0 = h->fld[CFDL_F_MIP0];
   A.mip = h->fld[CFDL_F_MIP]; A.dt = dt; A.rhie_chow = rhie_chow ? 1 : 0;
   prof_begin(h, PROF_MIP);
-  mip_kernel<<<grid_for(h, h->Fi, TPB), TPB, 0, S(h)>>>(A);
+  if (h->use_statics && h->fs_area) { int rc = k_calc_mip_statics(h, rhie_chow, dt); if (rc) return rc; }
+  else mip_kernel<<<grid_for(h, h->Fi, TPB), TPB, 0, S(h)>>>(A);
   prof_end(h);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
@@ -402,7 +526,8 @@ __global__ void __launch_bounds__(TPB) correct_faces_kernel(int Fi, const int32_
 int k_update_uvwp(Handle* h) {
   correct_cells_kernel<<<grid_for(h, h->Nc, TPB), TPB, 0, S(h)>>>(h->N, h->Nc, h->fld[CFDL_F_P], h->fld[CFDL_F_PC], h->fld[CFDL_F_GP],
                                                                        h->fld[CFDL_F_GPC]);
-  if (h->Fi)
+  if (h->Fi && h->use_statics && h->fs_area) { int rc = k_correct_faces_statics(h); if (rc) return rc; }
+  else if (h->Fi)
     correct_faces_kernel<<<grid_for(h, h->Fi, TPB), TPB, 0, S(h)>>>(h->Fi, h->face_a, h->face_b, h->xc, h->yc, h->zc, h->aip,
                                                                           h->rip, h->rho, h->fld[CFDL_F_DC], h->fld[CFDL_F_PC],
                                                                           h->fld[CFDL_F_MIP]);

@@ -1,0 +1,345 @@
+// Assembly kernels on precomputed face statics (sm_100a).
+//
+// The reference recomputes, for every face of every cell in every iteration, quantities that
+// depend on the mesh only: |A|, the unit normal, |dr|, the distance weights, the projected
+// points and |dr_p| (src/equations/mod_uvwp.f90:188-201,321-326,401-407,461-464).  On the GPU
+// those 5 square roots and 4 divisions per face made calc_coef_uvw instruction bound (ncu: XU pipe
+// saturated, DRAM at 11 %).  face_statics_kernel evaluates exactly those expressions ONCE, in the
+// owner's orientation; seen from the other cell every vector is the exact negation and every
+// scalar identical (IEEE negation is exact), so the kernels below produce the same bits as the
+// recomputing kernels in kernels_assembly.cu — the tests check that with array_equal.
+#include "state.h"
+#include "device_math.cuh"
+
+namespace cfdl {
+
+#define TPB 256
+
+struct FaceStatics {
+  const double *area, *ds, *dsp, *dn, *wto, *wtn;
+  const double *n[3], *dr[3], *drp[3];
+};
+
+static FaceStatics statics_of(const Handle* h) {
+  FaceStatics S;
+  S.area = h->fs_area; S.ds = h->fs_ds; S.dsp = h->fs_dsp; S.dn = h->fs_dn; S.wto = h->fs_wto; S.wtn = h->fs_wtn;
+  for (int i = 0; i < 3; ++i) { S.n[i] = h->fs_n[i]; S.dr[i] = h->fs_dr[i]; S.drp[i] = h->fs_drp[i]; }
+  return S;
+}
+
+__global__ void __launch_bounds__(TPB) face_statics_kernel(int Fi, const int32_t* __restrict__ face_a, const int32_t* __restrict__ face_b,
+                                                           const double* __restrict__ xc, const double* __restrict__ yc,
+                                                           const double* __restrict__ zc, const double* __restrict__ aip,
+                                                           const double* __restrict__ rip_, double* area_o, double* ds_o, double* dsp_o,
+                                                           double* dn_o, double* wto_o, double* wtn_o, double* n0, double* n1, double* n2,
+                                                           double* d0, double* d1, double* d2, double* p0, double* p1, double* p2) {
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < Fi; f += gridDim.x * blockDim.x) {
+    const int e = face_a[f], nb = face_b[f];
+    const double rp[3] = {xc[e], yc[e], zc[e]};
+    const double rpnb[3] = {xc[nb], yc[nb], zc[nb]};
+    double a[3], rip[3];
+    load3(aip, f, a); load3(rip_, f, rip);
+    const double area = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    const double norm[3] = {a[0] / area, a[1] / area, a[2] / area};
+    const double dr[3] = {rpnb[0] - rp[0], rpnb[1] - rp[1], rpnb[2] - rp[2]};
+    const double ds = sqrt(dot3(dr, dr));
+    double drip[3] = {rip[0] - rp[0], rip[1] - rp[1], rip[2] - rp[2]};
+    double t = dot3(drip, norm);
+    const double rp_p[3] = {rip[0] - t * norm[0], rip[1] - t * norm[1], rip[2] - t * norm[2]};
+    drip[0] = rip[0] - rpnb[0]; drip[1] = rip[1] - rpnb[1]; drip[2] = rip[2] - rpnb[2];
+    t = dot3(drip, norm);
+    const double rpnb_p[3] = {rip[0] - t * norm[0], rip[1] - t * norm[1], rip[2] - t * norm[2]};
+    const double dr_p[3] = {rpnb_p[0] - rp_p[0], rpnb_p[1] - rp_p[1], rpnb_p[2] - rp_p[2]};
+    area_o[f] = area; ds_o[f] = ds; dsp_o[f] = sqrt(dot3(dr_p, dr_p)); dn_o[f] = dot3(dr, norm);
+    wto_o[f] = vec_weight(rip, rp, rpnb);   // weight seen from the owner
+    wtn_o[f] = vec_weight(rip, rpnb, rp);   // weight seen from the neighbour
+    n0[f] = norm[0]; n1[f] = norm[1]; n2[f] = norm[2];
+    d0[f] = dr[0]; d1[f] = dr[1]; d2[f] = dr[2];
+    p0[f] = dr_p[0]; p1[f] = dr_p[1]; p2[f] = dr_p[2];
+  }
+}
+
+int k_face_statics(Handle* h) {
+  if (h->Fi == 0) return CFDL_OK;
+  face_statics_kernel<<<grid_for(h, h->Fi, TPB), TPB, 0, S(h)>>>(h->Fi, h->face_a, h->face_b, h->xc, h->yc, h->zc, h->aip, h->rip, h->fs_area,
+                                                                 h->fs_ds, h->fs_dsp, h->fs_dn, h->fs_wto, h->fs_wtn, h->fs_n[0], h->fs_n[1],
+                                                                 h->fs_n[2], h->fs_dr[0], h->fs_dr[1], h->fs_dr[2], h->fs_drp[0], h->fs_drp[1],
+                                                                 h->fs_drp[2]);
+  CFDL_CUDA(cudaGetLastError());
+  return CFDL_OK;
+}
+
+// ---- calc_coef_uvw on statics (mod_uvwp.f90:161-286) ------------------------------------------
+struct UvwArgsS {
+  int N, Nc, Np;
+  const int32_t *ell_nb, *ell_fs, *halo_bc, *bc_kind;
+  const uint8_t* nfc;
+  const double *xc, *yc, *zc, *aip, *vol, *rho, *mu;
+  const double *u, *v, *w, *u0, *v0, *w0, *gu, *gv, *gw, *gp, *mip;
+  double *ap, *anb, *bu, *bv, *bw, *d, *dc;
+  double dt;
+  FaceStatics S;
+};
+
+template <int K>
+__global__ void __launch_bounds__(TPB) coef_uvw_statics_kernel(const UvwArgsS A) {
+  const int N = A.N, Nc = A.Nc, Np = A.Np;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
+    const int n = A.nfc[c];
+    const double mu_e = A.mu[c];
+    double gue[3], gve[3], gwe[3];
+    load3(A.gu, c, gue); load3(A.gv, c, gve); load3(A.gw, c, gwe);
+    double ap = 0.0, sumf = 0.0, sumss[3] = {0, 0, 0}, sumdefc[3] = {0, 0, 0};
+    double anbk[K];
+    int nbk[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      anbk[k] = 0.0;
+      nbk[k] = -1;
+      if (k < n) {
+        const int nb = A.ell_nb[(size_t)k * Np + c];
+        const int fs = A.ell_fs[(size_t)k * Np + c];
+        nbk[k] = nb;
+        double d = 0.0, fnb = 0.0;
+        if (nb < Nc) {
+          const int f = abs(fs) - 1;
+          const bool own = fs > 0;
+          const double sg = own ? 1.0 : -1.0;
+          const double area = A.S.area[f], ds = A.S.ds[f], ds_p = A.S.dsp[f];
+          const double wt = own ? A.S.wto[f] : A.S.wtn[f];
+          const double dr[3] = {sg * A.S.dr[0][f], sg * A.S.dr[1][f], sg * A.S.dr[2][f]};
+          const double dr_p[3] = {sg * A.S.drp[0][f], sg * A.S.drp[1][f], sg * A.S.drp[2][f]};
+          const double f_in = -sg * A.mip[f];
+          fnb = fmax(f_in, 0.0);
+          sumf = sumf + f_in;
+          const double muip = (1.0 - wt) * mu_e + wt * A.mu[nb];
+          d = muip * area / ds;
+          double gun[3], gvn[3], gwn[3];
+          load3(A.gu, nb, gun); load3(A.gv, nb, gvn); load3(A.gw, nb, gwn);
+          const double w1 = 1.0 - wt;
+#pragma unroll
+          for (int m = 0; m < 3; ++m) {
+            const double gip[3] = {w1 * gue[m] + wt * gun[m], w1 * gve[m] + wt * gvn[m], w1 * gwe[m] + wt * gwn[m]};
+            sumss[m] = sumss[m] + muip * area * dot3(gip, dr) / ds;
+          }
+          {
+            double gip[3] = {w1 * gue[0] + wt * gun[0], w1 * gue[1] + wt * gun[1], w1 * gue[2] + wt * gun[2]};
+            sumdefc[0] = sumdefc[0] + muip * area * (dot3(gip, dr_p) / ds_p - dot3(gip, dr) / ds);
+            gip[0] = w1 * gve[0] + wt * gvn[0]; gip[1] = w1 * gve[1] + wt * gvn[1]; gip[2] = w1 * gve[2] + wt * gvn[2];
+            sumdefc[1] = sumdefc[1] + muip * area * (dot3(gip, dr_p) / ds_p - dot3(gip, dr) / ds);
+            gip[0] = w1 * gwe[0] + wt * gwn[0]; gip[1] = w1 * gwe[1] + wt * gwn[1]; gip[2] = w1 * gwe[2] + wt * gwn[2];
+            sumdefc[2] = sumdefc[2] + muip * area * (dot3(gip, dr_p) / ds_p - dot3(gip, dr) / ds);
+          }
+        }
+        anbk[k] = d + fnb;
+        ap = ap + d + fnb;
+      }
+    }
+    const double vol = A.vol[c];
+    const double ap0 = A.rho[c] * vol / A.dt;
+    ap = ap + ap0;
+    const double ue = A.u[c], ve = A.v[c], we = A.w[c];
+    double bu = ap0 * A.u0[c] + sumf * ue - vol * A.gp[3 * (size_t)c] + sumss[0] + sumdefc[0];
+    double bv = ap0 * A.v0[c] + sumf * ve - vol * A.gp[3 * (size_t)c + 1] + sumss[1] + sumdefc[1];
+    double bw = ap0 * A.w0[c] + sumf * we - vol * A.gp[3 * (size_t)c + 2] + sumss[2] + sumdefc[2];
+    int last = -1;  // boundary faces in halo order (rare: geometry evaluated on the fly as in the reference)
+    for (int t = 0; t < K; ++t) {
+      int best = 0x7fffffff, bk = -1;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (nbk[k] >= Nc && nbk[k] > last && nbk[k] < best) { best = nbk[k]; bk = k; }
+      if (bk < 0) break;
+      last = best;
+      const int bc = A.halo_bc[best - Nc];
+      if (bc < 0) continue;
+      const int f = A.ell_fs[(size_t)bk * Np + c] - 1;
+      double a[3];
+      load3(A.aip, f, a);
+      const double area = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+      const double norm[3] = {a[0] / area, a[1] / area, a[2] / area};
+      const double dr[3] = {A.xc[best] - A.xc[c], A.yc[best] - A.yc[c], A.zc[best] - A.zc[c]};
+      const double ds = sqrt(dot3(dr, dr));
+      const double d = mu_e * area / ds;
+      if (A.bc_kind[bc] != CFDL_BC_SYMMETRY) {
+        const double vbnc[3] = {A.u[best], A.v[best], A.w[best]};
+        double vrel[3] = {ue, ve, we};
+        const double vn = dot3(vrel, norm);
+        vrel[0] = vrel[0] - vn * norm[0]; vrel[1] = vrel[1] - vn * norm[1]; vrel[2] = vrel[2] - vn * norm[2];
+        vrel[0] = vbnc[0] - vrel[0]; vrel[1] = vbnc[1] - vrel[1]; vrel[2] = vbnc[2] - vrel[2];
+        bu = bu + d * vrel[0] - d * ue;
+        bv = bv + d * vrel[1] - d * ve;
+        bw = bw + d * vrel[2] - d * we;
+      }
+      ap = ap + d;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (k == bk) anbk[k] = anbk[k] + d;
+    }
+    double dcv = ap;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (k < n) { dcv = dcv - anbk[k]; A.anb[(size_t)k * Np + c] = anbk[k]; }
+    A.ap[c] = ap;
+    A.bu[c] = bu; A.bv[c] = bv; A.bw[c] = bw;
+    A.d[c] = vol / ap;
+    A.dc[c] = vol / dcv;
+  }
+}
+
+int k_calc_coef_uvw_statics(Handle* h, double dt) {
+  UvwArgsS A;
+  A.N = h->N; A.Nc = h->Nc; A.Np = h->Np;
+  A.ell_nb = h->ell_nb; A.ell_fs = h->ell_fs; A.halo_bc = h->halo_bc; A.bc_kind = h->bc_kind; A.nfc = h->nfc;
+  A.xc = h->xc; A.yc = h->yc; A.zc = h->zc; A.aip = h->aip; A.vol = h->vol; A.rho = h->rho; A.mu = h->mu;
+  A.u = h->fld[CFDL_F_U]; A.v = h->fld[CFDL_F_V]; A.w = h->fld[CFDL_F_W];
+  A.u0 = h->fld[CFDL_F_U0]; A.v0 = h->fld[CFDL_F_V0]; A.w0 = h->fld[CFDL_F_W0];
+  A.gu = h->fld[CFDL_F_GU]; A.gv = h->fld[CFDL_F_GV]; A.gw = h->fld[CFDL_F_GW]; A.gp = h->fld[CFDL_F_GP];
+  A.mip = h->fld[CFDL_F_MIP];
+  A.ap = h->fld[CFDL_F_AP]; A.anb = h->fld[CFDL_F_ANB]; A.bu = h->fld[CFDL_F_BU]; A.bv = h->fld[CFDL_F_BV];
+  A.bw = h->fld[CFDL_F_BW]; A.d = h->fld[CFDL_F_D]; A.dc = h->fld[CFDL_F_DC];
+  A.dt = dt;
+  A.S = statics_of(h);
+  const int g = grid_for(h, h->N, TPB);
+  if (h->K <= 4) coef_uvw_statics_kernel<4><<<g, TPB, 0, S(h)>>>(A);
+  else coef_uvw_statics_kernel<6><<<g, TPB, 0, S(h)>>>(A);
+  CFDL_CUDA(cudaGetLastError());
+  return CFDL_OK;
+}
+
+// ---- calc_coef_p on statics (mod_uvwp.f90:289-368) ---------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(TPB) coef_p_statics_kernel(int N, int Nc, int Np, const int32_t* __restrict__ ell_nb,
+                                                             const int32_t* __restrict__ ell_fs, const uint8_t* __restrict__ nfc,
+                                                             const int32_t* __restrict__ halo_bc, const double* __restrict__ rho,
+                                                             const double* __restrict__ dc, const double* __restrict__ mip, const FaceStatics S,
+                                                             double* __restrict__ ap_o, double* __restrict__ anb_o, double* __restrict__ b_o) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
+    const int n = nfc[c];
+    const double rho_e = rho[c], dc_e = dc[c];
+    double ap = 0.0, sumf = 0.0;
+    int nbk[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      nbk[k] = -1;
+      if (k < n) {
+        const int nb = ell_nb[(size_t)k * Np + c];
+        const int fs = ell_fs[(size_t)k * Np + c];
+        nbk[k] = nb;
+        double d = 0.0;
+        if (nb < Nc) {
+          const int f = abs(fs) - 1;
+          const bool own = fs > 0;
+          const double sg = own ? 1.0 : -1.0;
+          const double wt = own ? S.wto[f] : S.wtn[f];
+          const double f_in = -sg * mip[f];
+          sumf = sumf + f_in;
+          const double rhoip = (1.0 - wt) * rho_e + wt * rho[nb];
+          d = ((1.0 - wt) * dc_e + wt * dc[nb]) / S.dn[f] * rhoip * S.area[f];
+        }
+        anb_o[(size_t)k * Np + c] = d;
+        ap = ap + d;
+      }
+    }
+    double b = sumf;
+    int last = -1;
+    for (int t = 0; t < K; ++t) {
+      int best = 0x7fffffff, bk = -1;
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (nbk[k] >= Nc && nbk[k] > last && nbk[k] < best) { best = nbk[k]; bk = k; }
+      if (bk < 0) break;
+      last = best;
+      if (halo_bc[best - Nc] < 0) continue;
+      b = b - mip[ell_fs[(size_t)bk * Np + c] - 1];
+    }
+    ap_o[c] = ap;
+    b_o[c] = b;
+  }
+}
+
+int k_calc_coef_p_statics(Handle* h) {
+  const int g = grid_for(h, h->N, TPB);
+  const FaceStatics fst = statics_of(h);
+  if (h->K <= 4)
+    coef_p_statics_kernel<4><<<g, TPB, 0, S(h)>>>(h->N, h->Nc, h->Np, h->ell_nb, h->ell_fs, h->nfc, h->halo_bc, h->rho, h->fld[CFDL_F_DC],
+                                                  h->fld[CFDL_F_MIP], fst, h->fld[CFDL_F_AP], h->fld[CFDL_F_ANB], h->fld[CFDL_F_B]);
+  else
+    coef_p_statics_kernel<6><<<g, TPB, 0, S(h)>>>(h->N, h->Nc, h->Np, h->ell_nb, h->ell_fs, h->nfc, h->halo_bc, h->rho, h->fld[CFDL_F_DC],
+                                                  h->fld[CFDL_F_MIP], fst, h->fld[CFDL_F_AP], h->fld[CFDL_F_ANB], h->fld[CFDL_F_B]);
+  CFDL_CUDA(cudaGetLastError());
+  return CFDL_OK;
+}
+
+// ---- calc_mip on statics (mod_uvwp.f90:438-490) ------------------------------------------------
+struct MipArgsS {
+  int Fi;
+  const int32_t *face_a, *face_b;
+  const double* rho;
+  const double *u, *v, *w, *u0, *v0, *w0, *p, *gp, *d, *mip0;
+  double* mip;
+  double dt;
+  int rhie_chow;
+  FaceStatics S;
+};
+
+__global__ void __launch_bounds__(TPB) mip_statics_kernel(const MipArgsS A) {
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < A.Fi; f += gridDim.x * blockDim.x) {
+    const int e = A.face_a[f], nb = A.face_b[f];
+    const double area = A.S.area[f];
+    const double norm[3] = {A.S.n[0][f], A.S.n[1][f], A.S.n[2][f]};
+    const double wt = A.S.wto[f];
+    const double w1 = 1.0 - wt;
+    const double velip[3] = {w1 * A.u[e] + wt * A.u[nb], w1 * A.v[e] + wt * A.v[nb], w1 * A.w[e] + wt * A.w[nb]};
+    const double rhoip = A.rho[e] * w1 + A.rho[nb] * wt;
+    double m = dot3(velip, norm) * rhoip * area;
+    if (A.rhie_chow) {
+      const double dr[3] = {A.S.dr[0][f], A.S.dr[1][f], A.S.dr[2][f]};
+      double ge[3], gn[3];
+      load3(A.gp, e, ge); load3(A.gp, nb, gn);
+      const double gpip[3] = {w1 * ge[0] + wt * gn[0], w1 * ge[1] + wt * gn[1], w1 * ge[2] + wt * gn[2]};
+      const double dip = w1 * A.d[e] + wt * A.d[nb];
+      const double velip0[3] = {w1 * A.u0[e] + wt * A.u0[nb], w1 * A.v0[e] + wt * A.v0[nb], w1 * A.w0[e] + wt * A.w0[nb]};
+      m = m - rhoip * area * dip / A.S.dn[f] * (A.p[nb] - A.p[e] - dot3(gpip, dr))
+            - rhoip / A.dt * dip * (A.mip0[f] - dot3(velip0, norm) * rhoip * area);
+    }
+    A.mip[f] = m;
+  }
+}
+
+int k_calc_mip_statics(Handle* h, bool rhie_chow, double dt) {
+  if (h->Fi == 0) return CFDL_OK;
+  MipArgsS A;
+  A.Fi = h->Fi; A.face_a = h->face_a; A.face_b = h->face_b; A.rho = h->rho;
+  A.u = h->fld[CFDL_F_U]; A.v = h->fld[CFDL_F_V]; A.w = h->fld[CFDL_F_W];
+  A.u0 = h->fld[CFDL_F_U0]; A.v0 = h->fld[CFDL_F_V0]; A.w0 = h->fld[CFDL_F_W0];
+  A.p = h->fld[CFDL_F_P]; A.gp = h->fld[CFDL_F_GP]; A.d = h->fld[CFDL_F_D]; A.mip0 = h->fld[CFDL_F_MIP0];
+  A.mip = h->fld[CFDL_F_MIP]; A.dt = dt; A.rhie_chow = rhie_chow ? 1 : 0;
+  A.S = statics_of(h);
+  mip_statics_kernel<<<grid_for(h, h->Fi, TPB), TPB, 0, S(h)>>>(A);
+  CFDL_CUDA(cudaGetLastError());
+  return CFDL_OK;
+}
+
+// ---- face part of update_uvwp on statics (mod_uvwp.f90:394-415) ----------------------------------
+__global__ void __launch_bounds__(TPB) correct_faces_statics_kernel(int Fi, const int32_t* __restrict__ face_a, const int32_t* __restrict__ face_b,
+                                                                    const double* __restrict__ rho, const double* __restrict__ dc,
+                                                                    const double* __restrict__ pc, const FaceStatics S, double* mip) {
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < Fi; f += gridDim.x * blockDim.x) {
+    const int e = face_a[f], nb = face_b[f];
+    const double wt = S.wto[f];
+    const double dip = (1.0 - wt) * dc[e] + wt * dc[nb];
+    const double rhoip = (rho[e] + rho[nb]) / 2.0;
+    const double dmip = rhoip * S.area[f] * dip * (pc[nb] - pc[e]) / S.dn[f];
+    mip[f] = mip[f] - dmip;
+  }
+}
+
+int k_correct_faces_statics(Handle* h) {
+  if (h->Fi == 0) return CFDL_OK;
+  correct_faces_statics_kernel<<<grid_for(h, h->Fi, TPB), TPB, 0, S(h)>>>(h->Fi, h->face_a, h->face_b, h->rho, h->fld[CFDL_F_DC],
+                                                                          h->fld[CFDL_F_PC], statics_of(h), h->fld[CFDL_F_MIP]);
+  CFDL_CUDA(cudaGetLastError());
+  return CFDL_OK;
+}
+
+}  // namespace cfdl

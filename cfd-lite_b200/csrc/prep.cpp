@@ -277,22 +277,37 @@ int prepare(Prep& p, int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_i
   const int32_t B = (int32_t)p.h2o.size(), H = Nc + B;
   p.B = B; p.H = H;
   // ---- faces touching an owned cell: cell-cell faces first (first-touch order), then boundary -
+  // A face belongs to the first device cell that touches it; faces are then numbered SLOT-MAJOR
+  // over those cells (all slot-0 faces in cell order, then slot 1, ...), so that for a fixed slot
+  // consecutive cells read consecutive faces — on a two-colour mesh every face is first touched
+  // by a colour-0 cell, and the other colour meets them through consecutive neighbours as well.
   std::vector<int32_t> o2f((size_t)gF, -1);
   p.f2o.clear(); p.face_a.clear(); p.face_b.clear(); p.fown.clear();
-  for (int32_t c = 0; c < N; ++c) {
-    int32_t e = p.c2o[c];
-    for (int32_t idx = p.row_ptr[e]; idx < p.row_ptr[e + 1]; ++idx) {
-      int32_t nb = o_nb[idx], f = std::abs(o_fg[idx]) - 1;
-      if (nb >= gN || o2f[f] >= 0) continue;
-      o2f[f] = (int32_t)p.f2o.size();
-      p.f2o.push_back(f);
-      const int32_t nbd = p.o2c[nb];
-      if (nbd < 0) return fail(CFDL_ERR_INTERNAL, "cfdl_create: neighbour cell without device index");
-      const bool plus = o_fg[idx] > 0;
-      p.face_a.push_back(plus ? c : nbd);
-      p.face_b.push_back(plus ? nbd : c);
-      p.fown.push_back((plus ? c : nbd) < N ? 1 : 0);
+  {
+    std::vector<int32_t> toucher((size_t)gF, -1);
+    for (int32_t c = 0; c < N; ++c) {
+      int32_t e = p.c2o[c];
+      for (int32_t idx = p.row_ptr[e]; idx < p.row_ptr[e + 1]; ++idx) {
+        int32_t f = std::abs(o_fg[idx]) - 1;
+        if (o_nb[idx] < gN && toucher[f] < 0) toucher[f] = c;
+      }
     }
+    for (int k = 0; k < K; ++k)
+      for (int32_t c = 0; c < N; ++c) {
+        int32_t e = p.c2o[c];
+        if (k >= p.row_ptr[e + 1] - p.row_ptr[e]) continue;
+        const int32_t idx = p.row_ptr[e] + k;
+        int32_t nb = o_nb[idx], f = std::abs(o_fg[idx]) - 1;
+        if (nb >= gN || toucher[f] != c || o2f[f] >= 0) continue;
+        o2f[f] = (int32_t)p.f2o.size();
+        p.f2o.push_back(f);
+        const int32_t nbd = p.o2c[nb];
+        if (nbd < 0) return fail(CFDL_ERR_INTERNAL, "cfdl_create: neighbour cell without device index");
+        const bool plus = o_fg[idx] > 0;
+        p.face_a.push_back(plus ? c : nbd);
+        p.face_b.push_back(plus ? nbd : c);
+        p.fown.push_back((plus ? c : nbd) < N ? 1 : 0);
+      }
   }
   p.Fi = (int32_t)p.f2o.size();
   p.halo_cell.assign(B, -1); p.halo_face.assign(B, -1); p.halo_bc.assign(B, -1); p.halo_slot.assign(B, 0);

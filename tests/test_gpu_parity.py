@@ -66,9 +66,17 @@ def test_calc_coef_uvw(case):
     _, raw, oc, geom, s = case
     randomize(oc, s, seed=11)
     oc.update_boundaries(); s.update_boundaries()
-    oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)
-    for f in ("ap", "anb", "bu", "bv", "bw", "d", "dc"):
-        check(f, s.download(f), oc[f])
+    oc.calc_coef_uvw()
+    try:
+        for variant in (2, 1, 0):  # 2: precomputed face statics; 1: thread per (cell, slot); 0: thread per cell — same bits
+            s.set_option("uvw_variant", variant)
+            s.calc_coef_uvw(dt=0.01)
+            for f in ("ap", "anb", "bu", "bv", "bw", "d", "dc"):
+                got = s.download(f)
+                check(f, got, oc[f])
+                assert np.array_equal(got, oc[f]), "%s (variant %d) is not bit-identical: %.3e" % (f, variant, rel_err(got, oc[f]))
+    finally:
+        s.set_option("uvw_variant", 2)
 
 
 def test_calc_grad(case):
@@ -98,8 +106,16 @@ def test_calc_mip(case, rhie_chow):
     _, raw, oc, geom, s = case
     randomize(oc, s, seed=17)
     oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)  # provides d
-    oc.calc_mip(rhie_chow); s.calc_mip(rhie_chow, dt=0.01)
-    check("mip", s.download("mip"), oc["mip"])
+    oc.calc_mip(rhie_chow)
+    try:
+        for statics in (1, 0):  # precomputed face geometry vs recomputed in the kernel: same bits
+            s.set_option("statics", statics)
+            s.calc_mip(rhie_chow, dt=0.01)
+            got = s.download("mip")
+            check("mip", got, oc["mip"])
+            assert np.array_equal(got, oc["mip"]), "mip (statics=%d) not bit-identical: %.3e" % (statics, rel_err(got, oc["mip"]))
+    finally:
+        s.set_option("statics", 1)
 
 
 def test_calc_coef_p(case):
@@ -107,9 +123,17 @@ def test_calc_coef_p(case):
     randomize(oc, s, seed=19)
     oc.update_boundaries(); s.update_boundaries()
     oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)
-    oc.calc_coef_p(); s.calc_coef_p()
-    for f in ("ap", "anb", "b"):
-        check(f, s.download(f), oc[f])
+    oc.calc_coef_p()
+    try:
+        for statics in (0, 1):
+            s.set_option("statics", statics)
+            s.calc_coef_p()
+            for f in ("ap", "anb", "b"):
+                got = s.download(f)
+                check(f, got, oc[f])
+                assert np.array_equal(got, oc[f]), "%s (statics=%d) not bit-identical" % (f, statics)
+    finally:
+        s.set_option("statics", 1)
     # KAT pc-matrix: ap == sum anb (singular Neumann operator), anb symmetric
     ap, anb = s.download("ap"), s.download("anb")
     idx = geom["ef2nb_idx"] - 1
@@ -119,14 +143,22 @@ def test_calc_coef_p(case):
 
 def test_adjust_pc_and_update_uvwp(case):
     _, raw, oc, geom, s = case
-    randomize(oc, s, seed=23)
-    oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)  # provides dc
-    oc.adjust_pc(); s.adjust_pc()
-    assert np.array_equal(s.download("pc"), oc["phic"])
-    oc["gpc"][:] = oc.calc_grad(oc["phic"]); s.calc_grad("pc", "gpc")
-    oc.update_uvwp(); s.update_uvwp()
-    for f in ("p", "gp", "mip"):
-        check(f, s.download(f)[:len(oc[f])], oc[f])
+    for statics in (1, 0):
+        randomize(oc, s, seed=23)
+        s.set_option("statics", statics)
+        try:
+            oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)  # provides dc
+            oc.adjust_pc(); s.adjust_pc()
+            assert np.array_equal(s.download("pc"), oc["phic"])
+            oc["gpc"][:] = oc.calc_grad(oc["phic"]); s.calc_grad("pc", "gpc")
+            oc.update_uvwp(); s.update_uvwp()
+            for f in ("p", "gp", "mip"):
+                got = s.download(f)[:len(oc[f])]
+                check(f, got, oc[f])
+                if f == "mip":
+                    assert np.array_equal(got, oc[f]), "mip (statics=%d) not bit-identical" % statics
+        finally:
+            s.set_option("statics", 1)
 
 
 def assembled_system(oc):
