@@ -152,6 +152,25 @@ int create_impl(cfdl_handle* out, int32_t ne, int32_t nf, int32_t nbf, const int
   int rc = prepare(h->prep, ne, nf, nbf, ef2nb_idx, ef2nb_nb, ef2nb_fg, s2g, bs, xc, yc, zc, nbc, bc_esec, bc_kind, bc_uvw,
                    n_subdomains, g2gf_p, g2gf_idx, /*reorder auto*/ 2, cell2rank, rank, nranks);
   if (rc) { delete h; return rc; }
+  GeomSource G;  // geometry straight from the caller's (global, reference-numbered) arrays
+  G.cell_xyz = [=](int32_t g, double* o) { o[0] = xc[g]; o[1] = yc[g]; o[2] = zc[g]; };
+  G.vol = [=](int32_t g) { return vol[g]; };
+  G.rho = [=](int32_t g) { return rho[g]; };
+  G.mu = [=](int32_t g) { return mu[g]; };
+  G.face = [=](int32_t f, double* a, double* r) {
+    for (int q = 0; q < 3; ++q) { a[q] = aip[3 * (size_t)f + q]; r[q] = rip[3 * (size_t)f + q]; }
+  };
+  return create_from_prep(h, G, out);
+}
+
+}  // namespace
+
+namespace cfdl {
+
+// Device side of cfdl_create*: everything after the host-side mesh preparation.
+int create_from_prep(cfdl_handle_s* h, const GeomSource& G, cfdl_handle* out) {
+  int rc;
+  const int device = h->device, nranks = h->prep.nranks;
   auto bail = [&](int code) { cfdl_destroy(h); return code; };
   if ((rc = use_device(h))) return bail(rc);
   cudaDeviceProp prop;
@@ -176,17 +195,19 @@ int create_impl(cfdl_handle* out, int32_t ne, int32_t nf, int32_t nbf, const int
     for (int32_t c = 0; c < Nc; ++c) cm[c] = p.c2o[c];
     for (int32_t j = 0; j < B; ++j) cm[Nc + j] = p.gN + p.h2o[j];
     if ((rc = dev_upload(h, h->cellmap, cm.data(), cm.size()))) return bail(rc);
-    std::vector<double> t((size_t)3 * std::max(H, F));
-    auto cells = [&](const double* src, double*& dst, int32_t count) -> int {
-      for (int32_t i = 0; i < count; ++i) t[i] = src[cm[i]];
-      return dev_upload(h, dst, t.data(), (size_t)count);
-    };
-    if ((rc = cells(xc, h->xc, H)) || (rc = cells(yc, h->yc, H)) || (rc = cells(zc, h->zc, H))) return bail(rc);
-    if ((rc = cells(vol, h->vol, N)) || (rc = cells(rho, h->rho, Nc)) || (rc = cells(mu, h->mu, Nc))) return bail(rc);
-    for (int32_t f = 0; f < F; ++f) for (int q = 0; q < 3; ++q) t[3 * (size_t)f + q] = aip[3 * (size_t)p.f2o[f] + q];
-    if ((rc = dev_upload(h, h->aip, t.data(), 3 * (size_t)F))) return bail(rc);
-    for (int32_t f = 0; f < F; ++f) for (int q = 0; q < 3; ++q) t[3 * (size_t)f + q] = rip[3 * (size_t)p.f2o[f] + q];
-    if ((rc = dev_upload(h, h->rip, t.data(), 3 * (size_t)F))) return bail(rc);
+    std::vector<double> tx((size_t)H), ty((size_t)H), tz((size_t)H), t((size_t)std::max(Nc, 1)), ta(3 * (size_t)F), tr(3 * (size_t)F);
+    for (int32_t i = 0; i < H; ++i) { double o[3]; G.cell_xyz(cm[i], o); tx[i] = o[0]; ty[i] = o[1]; tz[i] = o[2]; }
+    if ((rc = dev_upload(h, h->xc, tx.data(), (size_t)H)) || (rc = dev_upload(h, h->yc, ty.data(), (size_t)H)) ||
+        (rc = dev_upload(h, h->zc, tz.data(), (size_t)H)))
+      return bail(rc);
+    for (int32_t i = 0; i < N; ++i) t[i] = G.vol(cm[i]);
+    if ((rc = dev_upload(h, h->vol, t.data(), (size_t)N))) return bail(rc);
+    for (int32_t i = 0; i < Nc; ++i) t[i] = G.rho(cm[i]);
+    if ((rc = dev_upload(h, h->rho, t.data(), (size_t)Nc))) return bail(rc);
+    for (int32_t i = 0; i < Nc; ++i) t[i] = G.mu(cm[i]);
+    if ((rc = dev_upload(h, h->mu, t.data(), (size_t)Nc))) return bail(rc);
+    for (int32_t f = 0; f < F; ++f) G.face(p.f2o[f], &ta[3 * (size_t)f], &tr[3 * (size_t)f]);
+    if ((rc = dev_upload(h, h->aip, ta.data(), 3 * (size_t)F)) || (rc = dev_upload(h, h->rip, tr.data(), 3 * (size_t)F))) return bail(rc);
   }
   // several GPUs: u, v, w, pc and the second solver array live in one IPC-exportable slab so
   // that neighbours can write their ghost cells directly (cfdl_comm_ipc_connect)

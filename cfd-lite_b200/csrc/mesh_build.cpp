@@ -14,6 +14,10 @@
 #include <cstring>
 #include <vector>
 #include "cfdl_common.h"
+#include "geom_formulas.h"
+
+using cfdl::face_area_centroid;
+using cfdl::CellAccumulator;
 
 namespace {
 
@@ -57,11 +61,6 @@ struct Pair {
   int32_t vmin, e1, f1, e2, f2;
 };
 
-inline void cross(double* a, const double* b, const double* c) {
-  a[0] = b[1] * c[2] - b[2] * c[1];
-  a[1] = b[2] * c[0] - b[0] * c[2];
-  a[2] = b[0] * c[1] - b[1] * c[0];
-}
 
 }  // namespace
 
@@ -171,37 +170,19 @@ extern "C" int cfdl_mesh_build(int64_t nvx, const double* x, const double* y, co
     const int32_t e = (int32_t)((uint32_t)s2g[fg] >> 5), fl = s2g[fg] & 31;
     int32_t lst[4];
     const int nl = face_vx(e2vx + (size_t)w * (e - 1), et[e], fl - 1, lst);
-    double r1[3], r2[3], r3[3], r4[3], dr1[3], dr2[3], areavec[3], subcntr[3], sumcntr[3][3], A[3];
-    P(lst[0], r1); P(lst[1], r2); P(lst[2], r3);
-    for (int i = 0; i < 3; ++i) { dr1[i] = r2[i] - r1[i]; dr2[i] = r3[i] - r1[i]; }
-    cross(areavec, dr1, dr2);
-    for (int i = 0; i < 3; ++i) { areavec[i] = 0.5 * areavec[i]; A[i] = areavec[i]; }
-    for (int i = 0; i < 3; ++i) subcntr[i] = (r1[i] + r2[i] + r3[i]) / 3.0;
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) sumcntr[i][j] = subcntr[i] * areavec[j];
-    if (nl == 4) {
-      P(lst[3], r4);
-      for (int i = 0; i < 3; ++i) { dr1[i] = r3[i] - r1[i]; dr2[i] = r4[i] - r1[i]; }
-      cross(areavec, dr1, dr2);
-      for (int i = 0; i < 3; ++i) { areavec[i] = 0.5 * areavec[i]; A[i] = A[i] + areavec[i]; }
-      for (int i = 0; i < 3; ++i) subcntr[i] = (r1[i] + r3[i] + r4[i]) / 3.0;
-      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) sumcntr[i][j] = sumcntr[i][j] + subcntr[i] * areavec[j];
-    }
-    const double aa = A[0] * A[0] + A[1] * A[1] + A[2] * A[2];
-    for (int i = 0; i < 3; ++i) {
-      double c = 0.0;
-      for (int j = 0; j < 3; ++j) c = c + sumcntr[i][j] * A[j];
-      aip[3 * (size_t)fg + i] = A[i];
-      rip[3 * (size_t)fg + i] = c / aa;
-    }
+    double r[4][3];
+    for (int i = 0; i < nl; ++i) P(lst[i], r[i]);
+    face_area_centroid(r, nl, aip + 3 * (size_t)fg, rip + 3 * (size_t)fg);
   }
   // ---- cell volumes / centroids by face pyramids; halo centre = face centroid ----------------
   for (int32_t e = 1; e <= ne; ++e) {
     const int nv = nvx_of(et[e]);
     const int32_t* vx = e2vx + (size_t)w * (e - 1);
-    double gc[3] = {0, 0, 0};
+    CellAccumulator acc;
+    double* gc = acc.gc;
+    gc[0] = gc[1] = gc[2] = 0.0;
     for (int i = 0; i < nv; ++i) { gc[0] = gc[0] + x[vx[i] - 1]; gc[1] = gc[1] + y[vx[i] - 1]; gc[2] = gc[2] + z[vx[i] - 1]; }
     for (int i = 0; i < 3; ++i) gc[i] = gc[i] / nv;
-    double sum_vol = 0.0, rc[3] = {0, 0, 0};
     for (int32_t idx = ef2nb_idx[e - 1]; idx <= ef2nb_idx[e] - 1; ++idx) {
       int32_t gf = ef2nb_fg[idx - 1];
       const int sg = gf >= 0 ? 1 : -1;
@@ -210,13 +191,11 @@ extern "C" int cfdl_mesh_build(int64_t nvx, const double* x, const double* y, co
       const double* a = aip + 3 * (size_t)(gf - 1);
       const int32_t enb = (int32_t)((uint32_t)ef2nb_nb[idx - 1] >> 5), lf = ef2nb_nb[idx - 1] & 31;
       if (lf == 0) { xc[enb - 1] = cs[0]; yc[enb - 1] = cs[1]; zc[enb - 1] = cs[2]; }
-      const double h[3] = {cs[0] - gc[0], cs[1] - gc[1], cs[2] - gc[2]};
-      const double sub_vol = ((sg * a[0]) * h[0] + (sg * a[1]) * h[1] + (sg * a[2]) * h[2]) / 3.0;
-      sum_vol = sum_vol + sub_vol;
-      for (int i = 0; i < 3; ++i) rc[i] = rc[i] + (0.25 * gc[i] + 0.75 * cs[i]) * sub_vol;
+      acc.add_face(sg, a, cs);
     }
-    xc[e - 1] = rc[0] / sum_vol; yc[e - 1] = rc[1] / sum_vol; zc[e - 1] = rc[2] / sum_vol;
-    vol[e - 1] = sum_vol;
+    double ctr[3];
+    acc.finish(ctr, &vol[e - 1]);
+    xc[e - 1] = ctr[0]; yc[e - 1] = ctr[1]; zc[e - 1] = ctr[2];
   }
   return CFDL_OK;
 }

@@ -136,6 +136,29 @@ int prepare(Prep& p, int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_i
     if (e < 0 || e >= gN || lf < 1 || p.row_ptr[e] + lf - 1 >= p.row_ptr[e + 1] || o_fg[p.row_ptr[e] + lf - 1] != f + 1)
       return fail(CFDL_ERR_MESH, "cfdl_create: s2g(%d) is not the owner slot of the face", f + 1);
   }
+  // halo -> (interior cell, local face); the sign bit of bs is a flag, every consumer takes abs
+  // (mod_mg_lvl_uns.f90:421-433)
+  std::vector<int32_t> halo_e((size_t)gB), halo_lf((size_t)gB);
+  for (int32_t j = 0; j < gB; ++j) {
+    uint32_t pk = (uint32_t)std::abs(bs[j]);
+    halo_e[j] = (int32_t)(pk >> 5) - 1;
+    halo_lf[j] = (int32_t)(pk & 31u);
+  }
+  return prepare_core(p, o_nb, o_fg, halo_e, halo_lf, xc, yc, zc, nbc, bc_esec, bc_kind, bc_uvw, n_subdomains, g2gf_p, g2gf_idx,
+                      reorder_mode, cell2rank, rank, nranks);
+}
+
+// Everything after unpacking: works on plain int32 arrays, so meshes beyond the reference's
+// 2^26 (cell<<5|face) packing limit can be prepared too (cfdl_create_structured_hex).
+//   o_nb[slot]  0-based neighbour cell, or gN + halo index for a boundary slot
+//   o_fg[slot]  signed 1-based global face id (+ on the owner = lower-numbered cell)
+//   p.gN, p.gF, p.gB, p.gZ, p.K, p.row_ptr, p.rank, p.nranks, p.n_subdomains are already set
+int prepare_core(Prep& p, const std::vector<int32_t>& o_nb, const std::vector<int32_t>& o_fg, const std::vector<int32_t>& halo_e,
+                 const std::vector<int32_t>& halo_lf, const double* xc, const double* yc, const double* zc, int32_t nbc,
+                 const int32_t* bc_esec, const int32_t* bc_kind, const double* bc_uvw, int32_t n_subdomains, const int32_t* g2gf_p,
+                 const int32_t* g2gf_idx, int reorder_mode, const int32_t* cell2rank, int32_t rank, int32_t nranks) {
+  const int32_t gN = p.gN, gF = p.gF, gB = p.gB, gH = p.gN + p.gB;
+  const int K = p.K;
   // ---- global base order (natural | Morton) and global greedy colouring --------------------
   std::vector<int32_t> base((size_t)gN), brank((size_t)gN);
   std::iota(base.begin(), base.end(), 0);
@@ -268,8 +291,7 @@ int prepare(Prep& p, int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_i
   p.h2o.clear();
   std::vector<int32_t> o2h((size_t)gB, -1);
   for (int32_t j = 0; j < gB; ++j) {
-    uint32_t pk = (uint32_t)std::abs(bs[j]);  // sign bit is a flag, every consumer takes abs (mod_mg_lvl_uns.f90:421-433)
-    int32_t e = (int32_t)(pk >> 5) - 1, lf = (int32_t)(pk & 31u);
+    const int32_t e = halo_e[j], lf = halo_lf[j];
     if (e < 0 || e >= gN || lf < 1 || lf > p.row_ptr[e + 1] - p.row_ptr[e]) return fail(CFDL_ERR_MESH, "cfdl_create: bs(%d) invalid", gN + 1 + j);
     if (o_nb[p.row_ptr[e] + lf - 1] != gN + j) return fail(CFDL_ERR_MESH, "cfdl_create: bs(%d) does not point back to its halo", gN + 1 + j);
     if (owner(e) == rank) { o2h[j] = (int32_t)p.h2o.size(); p.h2o.push_back(j); }
@@ -313,8 +335,7 @@ int prepare(Prep& p, int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_i
   p.halo_cell.assign(B, -1); p.halo_face.assign(B, -1); p.halo_bc.assign(B, -1); p.halo_slot.assign(B, 0);
   for (int32_t jl = 0; jl < B; ++jl) {
     const int32_t j = p.h2o[jl];
-    uint32_t pk = (uint32_t)std::abs(bs[j]);
-    int32_t e = (int32_t)(pk >> 5) - 1, lf = (int32_t)(pk & 31u), idx = p.row_ptr[e] + lf - 1, f = o_fg[idx] - 1;
+    const int32_t e = halo_e[j], lf = halo_lf[j], idx = p.row_ptr[e] + lf - 1, f = o_fg[idx] - 1;
     if (o2f[f] != -1) return fail(CFDL_ERR_MESH, "cfdl_create: boundary face %d used twice", f + 1);
     o2f[f] = p.Fi + jl;
     p.f2o.push_back(f); p.face_a.push_back(p.o2c[e]); p.face_b.push_back(Nc + jl); p.fown.push_back(1);

@@ -77,4 +77,10 @@ int prepare(Prep& p, int32_t ne, int32_t nf, int32_t nbf, const int32_t* ef2nb_i
             const int32_t* g2gf_p, const int32_t* g2gf_idx, int reorder_mode,
             const int32_t* cell2rank, int32_t rank, int32_t nranks);
 
+// the part of prepare() after unpacking (plain int32 connectivity; see prep.cpp)
+int prepare_core(Prep& p, const std::vector<int32_t>& o_nb, const std::vector<int32_t>& o_fg, const std::vector<int32_t>& halo_e,
+                 const std::vector<int32_t>& halo_lf, const double* xc, const double* yc, const double* zc, int32_t nbc,
+                 const int32_t* bc_esec, const int32_t* bc_kind, const double* bc_uvw, int32_t n_subdomains, const int32_t* g2gf_p,
+                 const int32_t* g2gf_idx, int reorder_mode, const int32_t* cell2rank, int32_t rank, int32_t nranks);
+
 }  // namespace cfdl

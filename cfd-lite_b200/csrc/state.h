@@ -209,3 +209,15 @@ void comm_destroy(Handle* h);
 }  // namespace cfdl
 
 struct cfdl_handle_s : public cfdl::Handle {};
+
+#include <functional>
+namespace cfdl {
+// where create_from_prep takes geometry from: indices are 0-based ids of the GLOBAL mesh
+// (cells 0..gN-1, halo j as gN + j, faces 0..gF-1)
+struct GeomSource {
+  std::function<void(int32_t, double*)> cell_xyz;
+  std::function<double(int32_t)> vol, rho, mu;
+  std::function<void(int32_t, double*, double*)> face;  // area vector (owner -> neighbour) and centroid
+};
+int create_from_prep(cfdl_handle_s* h, const GeomSource& G, cfdl_handle* out);
+}  // namespace cfdl
