@@ -177,6 +177,9 @@ def main():
     ap.add_argument("--solver", default="mcsgs", choices=list(SOLVERS))
     ap.add_argument("--unfused", action="store_true", help="one launch per colour + residual pass (no fused two-colour passes)")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL send/recv instead of peer-to-peer ghost stores")
+    ap.add_argument("--global-size", type=int, default=None, help="cells per edge of the WHOLE cube (overrides the weak-scaling rule), e.g. 512 with --gpus 8")
+    ap.add_argument("--structured", action="store_true",
+                    help="hex cavity generated per rank without the reference's packed int32 arrays (automatic beyond their 2^26 limit)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -210,16 +213,24 @@ def main():
     # weak scaling: the global cube grows with the GPU count so that every GPU keeps ~n^3 cells;
     # the mesh is split by the reference's own RCB (x-slabs, columns, octants on a cube)
     exchange = "NCCL send/recv after every pass, residual norms by NCCL all-reduce"
-    n_global = args.n if world == 1 else int(round(args.n * world ** (1.0 / 3.0)))
-    raw, geom = build_mesh(cfdl, args.mesh, n_global)
+    n_global = args.global_size or (args.n if world == 1 else int(round(args.n * world ** (1.0 / 3.0))))
+    structured = args.mesh == "hex" and (args.structured or n_global ** 3 + 6 * n_global ** 2 >= 2 ** 26)
+    if world > 1 and args.solver == "parity":
+        raise SystemExit("bench.py: the exact natural-order solver is single-GPU; use --solver mcsgs with --gpus > 1")
+    raw = geom = None
+    t_setup = time.perf_counter()
+    if structured:  # same mesh, same numbering, generated analytically on every rank (cfdl_create_structured_hex)
+        s = cfdl.Solver.structured_hex(n_global, device=local_rank, rank=rank, nranks=world)
+    else:
+        raw, geom = build_mesh(cfdl, args.mesh, n_global)
+        if world == 1:
+            s = cfdl.Solver(geom, cfdl.default_bcs(raw), device=local_rank)
+        else:
+            c2r, _, _ = cfdl.partition_rcb(geom, world, want_order=False)
+            s = cfdl.Solver(geom, cfdl.default_bcs(raw), device=local_rank, cell2rank=c2r, rank=rank, nranks=world)
     if world == 1:
-        s = cfdl.Solver(geom, cfdl.default_bcs(raw), device=local_rank)
         s.set_option("solver", SOLVERS[args.solver])
     else:
-        if args.solver == "parity":
-            raise SystemExit("bench.py: the exact natural-order solver is single-GPU; use --solver mcsgs with --gpus > 1")
-        c2r, _, _ = cfdl.partition_rcb(geom, world, want_order=False)
-        s = cfdl.Solver(geom, cfdl.default_bcs(raw), device=local_rank, cell2rank=c2r, rank=rank, nranks=world)
         ids = [cfdl.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         s.comm_init(ids[0])
@@ -247,7 +258,8 @@ def main():
             dist.barrier()
 
     # ---- value: device-resident steps, CUDA events on the library's stream -------------------
-    dbg("solver ready; owned", int(s.get_info("owned_cells")), "ghost", int(s.get_info("ghost_cells")))
+    setup_s = time.perf_counter() - t_setup
+    dbg("setup %.1f s;" % setup_s, "solver ready; owned", int(s.get_info("owned_cells")), "ghost", int(s.get_info("ghost_cells")))
     # the clock sampler (nvidia-smi takes a few 100 ms to come up) starts before the warm-up and
     # covers the timed region; it samples the GPU under the same load throughout
     sampler = ClockSampler(local_rank)
@@ -390,9 +402,11 @@ def main():
 
     # ---- cpu_baseline: the oracle on a bounded sample of the same workload (rank 0, N=1) -------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and n_global ** 3 + 6 * n_global ** 2 < 2 ** 26:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle
+        if raw is None:
+            raw, geom = build_mesh(cfdl, args.mesh, n_global)
         oc = oracle.OracleCase(raw, n_subdomains=4, geom=geom)
         nsamp = 2 if ne > 500000 else 6
         _, sec = oc.run(1, nsamp)
@@ -406,8 +420,8 @@ def main():
         line = {"metric": "cell-iterations/s (SIMPLE)", "value": value, "unit": "cell-iterations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args.mesh, n_global, ne), "solver": args.solver, "ncolors": ncol, "fused_two_colour_passes": bool(fused),
-                           "cells_per_gpu": ne // world, "l2": "working set (>1 GB per GPU) exceeds the 126 MB L2; no flush needed" if ne // world > 1000000 else
+                "config": {"workload": workload_name(args.mesh, n_global, ne), "solver": args.solver, "ncolors": ncol, "mesh_source": "structured per-rank generator" if structured else "reference-format arrays", "fused_two_colour_passes": bool(fused),
+                           "cells_per_gpu": ne // world, "setup_seconds": round(setup_s, 1), "l2": "working set (>1 GB per GPU) exceeds the 126 MB L2; no flush needed" if ne // world > 1000000 else
                            "working set may fit L2",
                            "parallelism": "1 GPU" if world == 1 else
                            "%d GPUs, one RCB block of the global mesh per GPU; ghost-cell exchange: %s" % (world, exchange),

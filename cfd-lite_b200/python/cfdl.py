@@ -120,6 +120,16 @@ def partition_rcb(geom, P, want_order=True):
     return c2s, p, idx
 
 
+def structured_hex_arrays(n, nranks=1):
+    """The connectivity / geometry Solver.structured_hex(n) is built from (CPU only)."""
+    ne, nbf, nf = n ** 3, 6 * n * n, 3 * n * n * (n + 1)
+    o = dict(nb=np.empty(6 * ne, np.int32), fg=np.empty(6 * ne, np.int32), xc=np.empty(ne + nbf), yc=np.empty(ne + nbf),
+             zc=np.empty(ne + nbf), vol=np.empty(ne), aip=np.empty(3 * nf), rip=np.empty(3 * nf), cell2rank=np.empty(ne, np.int32))
+    _chk(lib().cfdl_structured_hex_arrays(C.c_int32(n), C.c_int32(nranks), _i(o["nb"]), _i(o["fg"]), _d(o["xc"]), _d(o["yc"]),
+                                          _d(o["zc"]), _d(o["vol"]), _d(o["aip"]), _d(o["rip"]), _i(o["cell2rank"])))
+    return o
+
+
 def comm_unique_id():
     """128-byte NCCL unique id (create on rank 0, broadcast to the other ranks)."""
     buf = (C.c_uint8 * 128)()
@@ -217,6 +227,25 @@ class Solver:
                                C.c_int32(n_subdomains), _i(p), _i(pi), C.c_int32(device)))
         self.h = h
         self.n_subdomains = n_subdomains
+
+    @classmethod
+    def structured_hex(cls, n, rho=5.0, mu=0.01, device=0, rank=0, nranks=1):
+        """The n^3 lid-driven cavity generated per rank without the packed int32 arrays
+        (cfdl_create_structured_hex): the way to the 512^3 target, identical to
+        Solver(mesh_build(meshgen("hex", n)), default_bcs(...)) in everything but the host-side
+        numbering of face fields."""
+        self = cls.__new__(cls)
+        self.rank, self.nranks = rank, nranks
+        self.ne, self.nbf = n ** 3, 6 * n * n
+        self.nf = 3 * n * n * (n + 1)
+        self.H = self.ne + self.nbf
+        self.Z = 6 * self.ne
+        self.n_subdomains = 1
+        h = C.c_void_p()
+        _chk(lib().cfdl_create_structured_hex(C.byref(h), C.c_int32(n), C.c_double(rho), C.c_double(mu), C.c_int32(rank),
+                                              C.c_int32(nranks), C.c_int32(device)))
+        self.h = h
+        return self
 
     def close(self):
         if getattr(self, "h", None):

@@ -179,6 +179,24 @@ int cfdl_create_distributed(cfdl_handle* out, int32_t ne, int32_t nf, int32_t nb
                             const double* rho, const double* mu,
                             int32_t nbc, const int32_t* bc_esec, const int32_t* bc_kind, const double* bc_uvw,
                             const int32_t* cell2rank, int32_t rank, int32_t nranks, int32_t device);
+/* The synthetic n^3 lid-driven cavity (BASELINE.json configs 2, 3 and 5) created without the
+ * reference's packed (id<<5)|face int32 arrays, whose 2^26 id limit (ef2nb/bs/s2g
+ * of mod_mg_lvl_uns.f90) stops at 406^3: the mesh cfdl_meshgen_fill(HEX, n, 0, 0) +
+ * cfdl_mesh_build + cfdl_default cavity BCs would give (same cell/halo numbering, same
+ * geometry bits, constant rho/mu, top section = lid (1,0,0)), generated analytically on each
+ * rank and partitioned by recursive coordinate bisection (x, y, z in turn).  nranks must be a
+ * power of two, n <= 700.  Differences from cfdl_create_distributed: host-side FACE fields
+ * (CFDL_F_MIP, CFDL_F_MIP0) are numbered x-normal faces, then y, then z, not in the
+ * reference's face order; everything else, including comm_init / ipc_connect, is the same. */
+int cfdl_create_structured_hex(cfdl_handle* out, int32_t n, double rho, double mu,
+                               int32_t rank, int32_t nranks, int32_t device);
+/* The arrays cfdl_create_structured_hex works from, for inspection and CPU tests (any output may
+ * be NULL): nb/fg 6 n^3 slots (0-based neighbour cell, or n^3 + halo offset; signed 1-based face
+ * id in the numbering described above), xc/yc/zc n^3 + 6 n^2, vol n^3, aip/rip 3 per face,
+ * cell2rank n^3 entries in 1..nranks. */
+int cfdl_structured_hex_arrays(int32_t n, int32_t nranks, int32_t* nb, int32_t* fg,
+                               double* xc, double* yc, double* zc, double* vol,
+                               double* aip, double* rip, int32_t* cell2rank);
 /* 128-byte NCCL unique id, created on rank 0 and broadcast by the caller (MPI / torch) */
 int cfdl_comm_unique_id(uint8_t id[128]);
 /* collective over all ranks; must precede any compute call on a distributed handle */

@@ -15,6 +15,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+STRUCTURED = 2  # "kind" of the cases built with cfdl_create_structured_hex
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -31,11 +34,17 @@ def _worker(rank, world, port, kind, n, p2p, out_q):
     try:
         torch.cuda.set_device(rank)
         dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+        structured = kind == STRUCTURED
+        if structured:  # per-rank analytic generator; the reference run below uses the general builder
+            kind = 0
         raw = cfdl.meshgen(kind, n, jitter=0.2 if kind else 0.0, shuffle=bool(kind))
         geom = cfdl.mesh_build(raw)
         bcs = cfdl.default_bcs(raw)
-        c2r, _, _ = cfdl.partition_rcb(geom, world)
-        s = cfdl.Solver(geom, bcs, device=rank, cell2rank=c2r, rank=rank, nranks=world)
+        if structured:
+            s = cfdl.Solver.structured_hex(n, device=rank, rank=rank, nranks=world)
+        else:
+            c2r, _, _ = cfdl.partition_rcb(geom, world)
+            s = cfdl.Solver(geom, bcs, device=rank, cell2rank=c2r, rank=rank, nranks=world)
         ids = [cfdl.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         s.comm_init(ids[0])
@@ -46,7 +55,7 @@ def _worker(rank, world, port, kind, n, p2p, out_q):
             s.ipc_connect(handles)
         hist = s.run(dt=0.01, nit=100, ntstep=2, ncoef=3)
         fields = {}
-        for f in ("u", "v", "w", "p", "mip", "gp"):
+        for f in ("u", "v", "w", "p", "gp") + (() if structured else ("mip",)):  # structured: own face numbering
             a = np.full(s.field_size(f), np.nan)
             s.download_into(f, a)  # writes only the entries this rank owns
             fields[f] = a
@@ -81,11 +90,13 @@ def _worker(rank, world, port, kind, n, p2p, out_q):
         out_q.put((rank, "FAIL: " + "".join(traceback.format_exception(type(ex), ex, ex.__traceback__))))
 
 
-@pytest.mark.parametrize("kind,n,p2p", [(0, 10, False), (1, 5, False), (0, 10, True), (0, 24, True)])
+@pytest.mark.parametrize("kind,n,p2p", [(0, 10, False), (1, 5, False), (0, 10, True), (0, 24, True), (STRUCTURED, 12, False), (STRUCTURED, 16, True)])
 def test_partitioned_run_equals_single_gpu(cfdl, kind, n, p2p):
     world = min(cfdl.device_count(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
+    if kind == STRUCTURED and world == 3:
+        world = 2  # the structured generator bisects: power-of-two rank counts
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
