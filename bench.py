@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--global-size", type=int, default=None, help="cells per edge of the WHOLE cube (overrides the weak-scaling rule), e.g. 512 with --gpus 8")
     ap.add_argument("--structured", action="store_true",
                     help="hex cavity generated per rank without the reference's packed int32 arrays (automatic beyond their 2^26 limit)")
+    ap.add_argument("--no-pdl", action="store_true", help="fused passes fully serialised (no programmatic dependent launch)")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="cfdl_set_option(KEY, VALUE) after creation (tuning experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -245,6 +247,11 @@ def main():
                 dbg("p2p unavailable:", ex)
     if args.unfused:
         s.set_option("fused", 0)
+    if args.no_pdl:
+        s.set_option("pdl", 0)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        s.set_option(k, float(v))
     ne, nf, nbf, H = s.ne, s.nf, s.nbf, s.H  # global sizes
 
     def step(i):
@@ -420,7 +427,7 @@ def main():
         line = {"metric": "cell-iterations/s (SIMPLE)", "value": value, "unit": "cell-iterations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args.mesh, n_global, ne), "solver": args.solver, "ncolors": ncol, "mesh_source": "structured per-rank generator" if structured else "reference-format arrays", "fused_two_colour_passes": bool(fused),
+                "config": {"workload": workload_name(args.mesh, n_global, ne), "solver": args.solver, "ncolors": ncol, "options": args.opt, "mesh_source": "structured per-rank generator" if structured else "reference-format arrays", "fused_two_colour_passes": bool(fused), "programmatic_dependent_launch": bool(fused and not args.no_pdl),
                            "cells_per_gpu": ne // world, "setup_seconds": round(setup_s, 1), "l2": "working set (>1 GB per GPU) exceeds the 126 MB L2; no flush needed" if ne // world > 1000000 else
                            "working set may fit L2",
                            "parallelism": "1 GPU" if world == 1 else

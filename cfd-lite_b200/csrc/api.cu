@@ -185,7 +185,7 @@ int create_from_prep(cfdl_handle_s* h, const GeomSource& G, cfdl_handle* out) {
   if (nranks > 1) h->solver_mode = CFDL_SOLVER_MCSGS;
   const int32_t N = p.N, Nc = p.Nc, F = p.F, B = p.B, H = p.H;
 #define UP(dst, vec) if ((rc = dev_upload(h, dst, (vec).data(), (vec).size()))) return bail(rc)
-  UP(h->ell_nb, p.ell_nb); UP(h->ell_fs, p.ell_fs); UP(h->nfc, p.nfc); UP(h->face_a, p.face_a); UP(h->face_b, p.face_b);
+  UP(h->ell_nb, p.ell_nb); UP(h->ell_fs, p.ell_fs); UP(h->nfc, p.nfc); UP(h->ftouch, p.ftouch); UP(h->face_a, p.face_a); UP(h->face_b, p.face_b);
   UP(h->halo_cell, p.halo_cell); UP(h->halo_face, p.halo_face); UP(h->halo_bc, p.halo_bc); UP(h->halo_slot, p.halo_slot);
   UP(h->bc_kind, p.bc_kind); UP(h->bc_uvw, p.bc_uvw); UP(h->c2o, p.c2o); UP(h->f2o, p.f2o); UP(h->row_ptr, p.row_ptr);
   UP(h->send_cells, p.send_cells); UP(h->tgt_ptr, p.tgt_ptr); UP(h->tgt_nbr, p.tgt_nbr); UP(h->tgt_pos, p.tgt_pos);
@@ -295,6 +295,9 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   }
   if (!std::strcmp(key, "fused")) { h->fused_rb = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "p2p")) { h->use_p2p = value != 0.0; return CFDL_OK; }
+  if (!std::strcmp(key, "mip_variant")) { h->mip_variant = (int)value; return CFDL_OK; }
+  if (!std::strcmp(key, "occ_grids")) { h->occ_grids = value != 0.0; return CFDL_OK; }
+  if (!std::strcmp(key, "pdl")) { h->use_pdl = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "uvw_variant")) { h->uvw_variant = (int)value; return CFDL_OK; }
   if (!std::strcmp(key, "statics")) { h->use_statics = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "ctas_per_sm")) { h->tune_ctas = std::max(1, (int)value); return CFDL_OK; }

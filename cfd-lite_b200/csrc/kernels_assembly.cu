@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(TPB) grad_kernel(int N, int Np, const int32_t*
 }
 
 int k_calc_grad(Handle* h, const double* phi, double* grad) {
-  const int g = grid_for(h, h->N, TPB);
+  const int g = (h->K <= 4) ? occ_grid<grad_kernel<4, 1>>(h, h->N, TPB) : occ_grid<grad_kernel<6, 1>>(h, h->N, TPB);
   if (h->K <= 4) grad_kernel<4, 1><<<g, TPB, 0, S(h)>>>(h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, phi, phi, phi, grad, grad, grad);
   else if (h->K <= 6) grad_kernel<6, 1><<<g, TPB, 0, S(h)>>>(h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, phi, phi, phi, grad, grad, grad);
   else return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
@@ -615,7 +615,7 @@ int k_calc_grad(Handle* h, const double* phi, double* grad) {
 }
 
 int k_calc_grad3(Handle* h) {  // the three calc_grad calls of mod_uvwp.f90:118-120 in one pass over the mesh
-  const int g = grid_for(h, h->N, TPB);
+  const int g = (h->K <= 4) ? occ_grid<grad_kernel<4, 3>>(h, h->N, TPB) : occ_grid<grad_kernel<6, 3>>(h, h->N, TPB);
 #define G3 h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, h->fld[CFDL_F_U], h->fld[CFDL_F_V], h->fld[CFDL_F_W], \
            h->fld[CFDL_F_GU], h->fld[CFDL_F_GV], h->fld[CFDL_F_GW]
   prof_begin(h, PROF_GRAD);

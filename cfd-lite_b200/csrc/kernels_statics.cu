@@ -199,9 +199,8 @@ int k_calc_coef_uvw_statics(Handle* h, double dt) {
   A.bw = h->fld[CFDL_F_BW]; A.d = h->fld[CFDL_F_D]; A.dc = h->fld[CFDL_F_DC];
   A.dt = dt;
   A.S = statics_of(h);
-  const int g = grid_for(h, h->N, TPB);
-  if (h->K <= 4) coef_uvw_statics_kernel<4><<<g, TPB, 0, S(h)>>>(A);
-  else coef_uvw_statics_kernel<6><<<g, TPB, 0, S(h)>>>(A);
+  if (h->K <= 4) coef_uvw_statics_kernel<4><<<occ_grid<coef_uvw_statics_kernel<4>>(h, h->N, TPB), TPB, 0, S(h)>>>(A);
+  else coef_uvw_statics_kernel<6><<<occ_grid<coef_uvw_statics_kernel<6>>(h, h->N, TPB), TPB, 0, S(h)>>>(A);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
@@ -258,7 +257,7 @@ __global__ void __launch_bounds__(TPB) coef_p_statics_kernel(int N, int Nc, int 
 }
 
 int k_calc_coef_p_statics(Handle* h) {
-  const int g = grid_for(h, h->N, TPB);
+  const int g = (h->K <= 4) ? occ_grid<coef_p_statics_kernel<4>>(h, h->N, TPB) : occ_grid<coef_p_statics_kernel<6>>(h, h->N, TPB);
   const FaceStatics fst = statics_of(h);
   if (h->K <= 4)
     coef_p_statics_kernel<4><<<g, TPB, 0, S(h)>>>(h->N, h->Nc, h->Np, h->ell_nb, h->ell_fs, h->nfc, h->halo_bc, h->rho, h->fld[CFDL_F_DC],
@@ -306,8 +305,89 @@ __global__ void __launch_bounds__(TPB) mip_statics_kernel(const MipArgsS A) {
   }
 }
 
+// The same faces visited from the cells: a thread takes one cell and the cell-cell faces that are
+// numbered from it (ftouch; on a two-colour mesh every face of a first-colour cell).  Faces are
+// numbered slot-major over exactly these cells, so for a fixed slot consecutive threads read
+// consecutive statics and write consecutive mip entries, the cell's own fields are read once,
+// and the neighbours' fields come from L2 instead of one DRAM pass per face slot.  Each face
+// evaluates the expression of mip_statics_kernel on (owner, neighbour) in the reference's
+// orientation, hence the same bits.
+struct MipCellArgs {
+  int n_cells, Np, K;
+  const int32_t *ell_nb, *ell_fs;
+  const uint8_t* ftouch;
+  const double* rho;
+  const double *u, *v, *w, *u0, *v0, *w0, *p, *gp, *d, *mip0;
+  double* mip;
+  double dt;
+  int rhie_chow;
+  FaceStatics S;
+};
+
+struct MipCellVals { double u, v, w, u0, v0, w0, p, d, rho, g[3]; };
+
+__device__ __forceinline__ void mip_load_cell(const MipCellArgs& A, int c, bool rc, MipCellVals& x) {
+  x.u = A.u[c]; x.v = A.v[c]; x.w = A.w[c]; x.rho = A.rho[c];
+  if (rc) {
+    x.u0 = A.u0[c]; x.v0 = A.v0[c]; x.w0 = A.w0[c]; x.p = A.p[c]; x.d = A.d[c];
+    load3(A.gp, c, x.g);
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(TPB, 3) mip_cells_kernel(const MipCellArgs A) {
+  const bool rc = A.rhie_chow != 0;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.n_cells; c += gridDim.x * blockDim.x) {
+    const unsigned mask = A.ftouch[c];
+    if (!mask) continue;
+    MipCellVals me;
+    mip_load_cell(A, c, rc, me);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (!(mask >> k & 1u)) continue;
+      const int other = A.ell_nb[(size_t)k * A.Np + c];
+      const int fs = A.ell_fs[(size_t)k * A.Np + c];
+      const int f = abs(fs) - 1;
+      MipCellVals ot;
+      mip_load_cell(A, other, rc, ot);
+      const bool own = fs > 0;  // this cell is the face's owner (reference orientation e -> nb)
+      const MipCellVals& E = own ? me : ot;
+      const MipCellVals& NB = own ? ot : me;
+      const double area = A.S.area[f];
+      const double norm[3] = {A.S.n[0][f], A.S.n[1][f], A.S.n[2][f]};
+      const double wt = A.S.wto[f];
+      const double w1 = 1.0 - wt;
+      const double velip[3] = {w1 * E.u + wt * NB.u, w1 * E.v + wt * NB.v, w1 * E.w + wt * NB.w};
+      const double rhoip = E.rho * w1 + NB.rho * wt;
+      double m = dot3(velip, norm) * rhoip * area;
+      if (rc) {
+        const double dr[3] = {A.S.dr[0][f], A.S.dr[1][f], A.S.dr[2][f]};
+        const double gpip[3] = {w1 * E.g[0] + wt * NB.g[0], w1 * E.g[1] + wt * NB.g[1], w1 * E.g[2] + wt * NB.g[2]};
+        const double dip = w1 * E.d + wt * NB.d;
+        const double velip0[3] = {w1 * E.u0 + wt * NB.u0, w1 * E.v0 + wt * NB.v0, w1 * E.w0 + wt * NB.w0};
+        m = m - rhoip * area * dip / A.S.dn[f] * (NB.p - E.p - dot3(gpip, dr))
+              - rhoip / A.dt * dip * (A.mip0[f] - dot3(velip0, norm) * rhoip * area);
+      }
+      A.mip[f] = m;
+    }
+  }
+}
+
 int k_calc_mip_statics(Handle* h, bool rhie_chow, double dt) {
   if (h->Fi == 0) return CFDL_OK;
+  if (h->mip_variant == 1 && h->K <= 6) {
+    MipCellArgs A;
+    A.n_cells = h->prep.touch_end; A.Np = h->Np; A.K = h->K; A.ell_nb = h->ell_nb; A.ell_fs = h->ell_fs; A.ftouch = h->ftouch; A.rho = h->rho;
+    A.u = h->fld[CFDL_F_U]; A.v = h->fld[CFDL_F_V]; A.w = h->fld[CFDL_F_W];
+    A.u0 = h->fld[CFDL_F_U0]; A.v0 = h->fld[CFDL_F_V0]; A.w0 = h->fld[CFDL_F_W0];
+    A.p = h->fld[CFDL_F_P]; A.gp = h->fld[CFDL_F_GP]; A.d = h->fld[CFDL_F_D]; A.mip0 = h->fld[CFDL_F_MIP0];
+    A.mip = h->fld[CFDL_F_MIP]; A.dt = dt; A.rhie_chow = rhie_chow ? 1 : 0;
+    A.S = statics_of(h);
+    if (h->K <= 4) mip_cells_kernel<4><<<occ_grid<mip_cells_kernel<4>>(h, A.n_cells, TPB), TPB, 0, S(h)>>>(A);
+    else mip_cells_kernel<6><<<occ_grid<mip_cells_kernel<6>>(h, A.n_cells, TPB), TPB, 0, S(h)>>>(A);
+    CFDL_CUDA(cudaGetLastError());
+    return CFDL_OK;
+  }
   MipArgsS A;
   A.Fi = h->Fi; A.face_a = h->face_a; A.face_b = h->face_b; A.rho = h->rho;
   A.u = h->fld[CFDL_F_U]; A.v = h->fld[CFDL_F_V]; A.w = h->fld[CFDL_F_W];
@@ -315,7 +395,7 @@ int k_calc_mip_statics(Handle* h, bool rhie_chow, double dt) {
   A.p = h->fld[CFDL_F_P]; A.gp = h->fld[CFDL_F_GP]; A.d = h->fld[CFDL_F_D]; A.mip0 = h->fld[CFDL_F_MIP0];
   A.mip = h->fld[CFDL_F_MIP]; A.dt = dt; A.rhie_chow = rhie_chow ? 1 : 0;
   A.S = statics_of(h);
-  mip_statics_kernel<<<grid_for(h, h->Fi, TPB), TPB, 0, S(h)>>>(A);
+  mip_statics_kernel<<<occ_grid<mip_statics_kernel>(h, h->Fi, TPB), TPB, 0, S(h)>>>(A);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
@@ -336,7 +416,7 @@ __global__ void __launch_bounds__(TPB) correct_faces_statics_kernel(int Fi, cons
 
 int k_correct_faces_statics(Handle* h) {
   if (h->Fi == 0) return CFDL_OK;
-  correct_faces_statics_kernel<<<grid_for(h, h->Fi, TPB), TPB, 0, S(h)>>>(h->Fi, h->face_a, h->face_b, h->rho, h->fld[CFDL_F_DC],
+  correct_faces_statics_kernel<<<occ_grid<correct_faces_statics_kernel>(h, h->Fi, TPB), TPB, 0, S(h)>>>(h->Fi, h->face_a, h->face_b, h->rho, h->fld[CFDL_F_DC],
                                                                           h->fld[CFDL_F_PC], statics_of(h), h->fld[CFDL_F_MIP]);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;

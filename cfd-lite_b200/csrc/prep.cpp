@@ -307,6 +307,8 @@ int prepare_core(Prep& p, const std::vector<int32_t>& o_nb, const std::vector<in
   p.f2o.clear(); p.face_a.clear(); p.face_b.clear(); p.fown.clear();
   {
     std::vector<int32_t> toucher((size_t)gF, -1);
+    p.ftouch.assign((size_t)N, 0);
+    p.touch_end = 0;
     for (int32_t c = 0; c < N; ++c) {
       int32_t e = p.c2o[c];
       for (int32_t idx = p.row_ptr[e]; idx < p.row_ptr[e + 1]; ++idx) {
@@ -321,6 +323,8 @@ int prepare_core(Prep& p, const std::vector<int32_t>& o_nb, const std::vector<in
         const int32_t idx = p.row_ptr[e] + k;
         int32_t nb = o_nb[idx], f = std::abs(o_fg[idx]) - 1;
         if (nb >= gN || toucher[f] != c || o2f[f] >= 0) continue;
+        p.ftouch[c] |= (uint8_t)(1u << k);
+        p.touch_end = std::max(p.touch_end, c + 1);
         o2f[f] = (int32_t)p.f2o.size();
         p.f2o.push_back(f);
         const int32_t nbd = p.o2c[nb];

@@ -52,6 +52,8 @@ struct Prep {
   std::vector<int32_t> ell_nb;     // K*Np device index of neighbour (cell, ghost or halo), pad = self
   std::vector<int32_t> ell_fs;     // K*Np signed device face id +-(f+1); 0 = padding slot
   std::vector<uint8_t> nfc;        // N faces per cell
+  std::vector<uint8_t> ftouch;     // N: bit k set when slot k's cell-cell face is numbered from this cell (its first toucher)
+  int32_t touch_end = 0;           // cells [touch_end, N) have ftouch == 0 (two-colour mesh: the whole second colour)
   std::vector<int32_t> face_a, face_b;  // per device face: reference owner / neighbour (device idx; halo for boundary)
   std::vector<int32_t> halo_cell, halo_face, halo_bc;  // per halo: interior device cell, device face, bc index
   std::vector<uint8_t> halo_slot;  // per halo: ELL slot k in its interior cell

@@ -71,7 +71,7 @@ struct Handle {
   int32_t *ell_nb = nullptr, *ell_fs = nullptr, *face_a = nullptr, *face_b = nullptr;
   int32_t *halo_cell = nullptr, *halo_face = nullptr, *halo_bc = nullptr, *bc_kind = nullptr;
   int32_t *c2o = nullptr, *cellmap = nullptr, *f2o = nullptr, *row_ptr = nullptr;  // cellmap: device cell|halo -> global index (size H)
-  uint8_t *nfc = nullptr, *halo_slot = nullptr;
+  uint8_t *nfc = nullptr, *halo_slot = nullptr, *ftouch = nullptr;
   double *bc_uvw = nullptr, *xc = nullptr, *yc = nullptr, *zc = nullptr, *aip = nullptr, *rip = nullptr;
   double *vol = nullptr, *rho = nullptr, *mu = nullptr;
   // fields, indexed by CFDL_F_*
@@ -94,6 +94,9 @@ struct Handle {
   int last_passes[4] = {1, 1, 1, 1};  // per equation: passes the previous solve needed (first-batch size estimate)
   int fused_rb = 1;            // 0: always use one launch per colour + residual pass
   int use_p2p = 1;             // 0: NCCL send/recv even when peer slabs are connected
+  int mip_variant = 1;         // calc_mip on statics: 1 = from the cells that number the faces, 0 = one thread per face
+  int occ_grids = 1;           // assembly kernels: grid = resident CTAs (occupancy API) instead of 8 per SM
+  int use_pdl = 1;             // fused passes: programmatic dependent launch (a pass loads its first matrix rows while the previous one drains)
   int uvw_variant = 2;         // calc_coef_uvw: 0 = one thread per cell, 1 = one thread per (cell, face slot),
                                // 2 = one thread per cell on precomputed face statics
   // per cell-cell face, owner orientation, computed once with the very expressions the reference
@@ -137,6 +140,20 @@ inline int grid_for(const Handle* h, int64_t n, int threads, int ctas_per_sm = 8
   int64_t cap = (int64_t)h->num_sms * ctas_per_sm;
   if (need < 1) need = 1;
   return (int)(need < cap ? need : cap);
+}
+
+// grid for a grid-stride kernel: exactly the CTAs that are resident at once (one wave), as the
+// occupancy calculator reports for this kernel — a fixed 8 per SM leaves register-heavy assembly
+// kernels (4-5 resident CTAs) with a second, partly filled wave
+template <auto Kern>
+inline int occ_grid(const Handle* h, int64_t n, int threads) {
+  static int occ = 0;
+  if (occ == 0) {
+    int o = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, Kern, threads, 0) != cudaSuccess || o < 1) o = 8;
+    occ = o;
+  }
+  return grid_for(h, n, threads, h->occ_grids ? occ : 8);
 }
 
 // ---- kernels_assembly.cu

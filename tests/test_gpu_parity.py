@@ -106,16 +106,23 @@ def test_calc_mip(case, rhie_chow):
     _, raw, oc, geom, s = case
     randomize(oc, s, seed=17)
     oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)  # provides d
+    mip_in = oc["mip"].copy()
     oc.calc_mip(rhie_chow)
     try:
-        for statics in (1, 0):  # precomputed face geometry vs recomputed in the kernel: same bits
+        # precomputed face geometry (visited from the cells that number the faces, or one thread per
+        # face) vs geometry recomputed in the kernel: same bits
+        for statics, variant in ((1, 1), (1, 0), (0, 0)):
             s.set_option("statics", statics)
+            s.set_option("mip_variant", variant)
+            s.upload("mip", mip_in)  # every variant starts from the same faces (boundary ones are not written)
             s.calc_mip(rhie_chow, dt=0.01)
             got = s.download("mip")
             check("mip", got, oc["mip"])
-            assert np.array_equal(got, oc["mip"]), "mip (statics=%d) not bit-identical: %.3e" % (statics, rel_err(got, oc["mip"]))
+            assert np.array_equal(got, oc["mip"]), "mip (statics=%d, variant=%d) not bit-identical: %.3e" % (
+                statics, variant, rel_err(got, oc["mip"]))
     finally:
         s.set_option("statics", 1)
+        s.set_option("mip_variant", 1)
 
 
 def test_calc_coef_p(case):
@@ -306,3 +313,26 @@ def test_create_rejects_bad_mesh(cfdl, oracle):
     bad["ef2nb_fg"][0] = 0
     with pytest.raises(cfdl.CfdlError):
         cfdl.Solver(bad, oc.bc_table())
+
+
+def test_overlapped_passes_equal_serialised_passes(cfdl):
+    """Fused passes launched with programmatic dependent launch (a pass starts while the previous
+    one drains, option pdl=1) against the same passes fully serialised (pdl=0) and against one
+    launch per colour (fused=0): identical bits over ~100-iteration pc solves on a mesh large
+    enough (64^3) for every SM to hold several CTAs of consecutive passes at once."""
+    raw = cfdl.meshgen(cfdl.MESH_HEX, 64)
+    geom = cfdl.mesh_build(raw)
+    out = []
+    for opts in ({"pdl": 1}, {"pdl": 0}, {"fused": 0}):
+        s = cfdl.Solver(geom, cfdl.default_bcs(raw))
+        s.set_option("solver", cfdl.SOLVER_MCSGS)
+        for k, v in opts.items():
+            s.set_option(k, v)
+        hist = s.run(dt=0.01, nit=100, ntstep=2, ncoef=2)
+        out.append((hist, {f: s.download(f) for f in ("u", "v", "w", "p", "pc", "mip")}))
+        s.close()
+    assert out[0][0][:, 3, 0].max() >= 50, "pc solves too short to exercise the overlap"
+    for hist, fields in out[1:]:
+        assert np.array_equal(hist[:, :, 0], out[0][0][:, :, 0])
+        for f in fields:
+            assert np.array_equal(fields[f], out[0][1][f]), f
