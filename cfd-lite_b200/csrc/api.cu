@@ -297,6 +297,7 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "p2p")) { h->use_p2p = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "mip_variant")) { h->mip_variant = (int)value; return CFDL_OK; }
   if (!std::strcmp(key, "occ_grids")) { h->occ_grids = value != 0.0; return CFDL_OK; }
+  if (!std::strcmp(key, "pdl_rows")) { h->pdl_rows = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "pdl")) { h->use_pdl = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "uvw_variant")) { h->uvw_variant = (int)value; return CFDL_OK; }
   if (!std::strcmp(key, "statics")) { h->use_statics = value != 0.0; return CFDL_OK; }

@@ -96,6 +96,7 @@ struct Handle {
   int use_p2p = 1;             // 0: NCCL send/recv even when peer slabs are connected
   int mip_variant = 1;         // calc_mip on statics: 1 = from the cells that number the faces, 0 = one thread per face
   int occ_grids = 1;           // assembly kernels: grid = resident CTAs (occupancy API) instead of 8 per SM
+  int pdl_rows = 1;            // rows per thread prefetched to L2 ahead of the dependency wait
   int use_pdl = 1;             // fused passes: programmatic dependent launch (a pass loads its first matrix rows while the previous one drains)
   int uvw_variant = 2;         // calc_coef_uvw: 0 = one thread per cell, 1 = one thread per (cell, face slot),
                                // 2 = one thread per cell on precomputed face statics
