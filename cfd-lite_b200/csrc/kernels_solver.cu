@@ -435,11 +435,16 @@ static int mcsgs_solve_t(Handle* h, int eq, double* phi, const double* rhs, int 
   };
   if (dist && (rc = comm_exchange(h, phi, 1, -1))) return rc;
   if ((rc = residual(RES_INIT))) return rc;
-  int launched = 0, batch = 1;
-  for (;;) {
-    CFDL_CUDA(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(SolveCtl), cudaMemcpyDeviceToHost, h->stream));
-    CFDL_CUDA(cudaStreamSynchronize(h->stream));
-    if (h->ctl_host->done || launched >= nit) break;
+  // first batch: the iteration count of this equation's previous solve (consecutive SIMPLE
+  // iterations need about the same), enqueued without waiting for the opening residual — every
+  // kernel returns at once when ctl->done is set; an overshoot continues in small batches
+  int launched = 0, batch = std::max(1, std::min(h->last_passes[eq], nit));
+  for (bool opening = true;; opening = false) {
+    if (!opening) {
+      CFDL_CUDA(cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(SolveCtl), cudaMemcpyDeviceToHost, h->stream));
+      CFDL_CUDA(cudaStreamSynchronize(h->stream));
+      if (h->ctl_host->done || launched >= nit) break;
+    }
     const int m = std::min(batch, nit - launched);
     for (int i = 0; i < m; ++i) {
       for (int c = 0; c < nc; ++c) if ((rc = sweep(c))) return rc;
@@ -448,8 +453,9 @@ static int mcsgs_solve_t(Handle* h, int eq, double* phi, const double* rhs, int 
     }
     CFDL_CUDA(cudaGetLastError());
     launched += m;
-    batch = std::min(batch * 2, 32);
+    batch = (launched > 8) ? 8 : 2;
   }
+  h->last_passes[eq] = h->ctl_host->it;
   if (out4) { out4[0] = h->ctl_host->it; out4[1] = h->ctl_host->res_i; out4[2] = h->ctl_host->res_f; out4[3] = h->ctl_host->res_max; }
   return CFDL_OK;
 }
