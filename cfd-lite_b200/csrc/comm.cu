@@ -77,8 +77,12 @@ __global__ void __launch_bounds__(256) pack_kernel(double* __restrict__ buf, con
 
 }  // namespace
 
+static int p2p_exchange(Handle* h, double* field, int ncomp);
+static int p2p_mail(Handle* h, double* dev, int mode, int root);
+
 int comm_exchange(Handle* h, double* field, int ncomp, int color) {
   if (h->prep.nranks == 1 || h->nnbr == 0) return CFDL_OK;
+  if (color < 0 && ncomp <= 3 && h->p2p.connected && h->use_p2p) return p2p_exchange(h, field, ncomp);
   if (!h->comm) return fail(CFDL_ERR_NCCL, "this handle is one partition of %d: call cfdl_comm_init before computing", h->prep.nranks);
   if (ncomp < 1 || ncomp > 9) return fail(CFDL_ERR_ARG, "comm_exchange: ncomp %d", ncomp);
   const Prep& p = h->prep;
@@ -104,6 +108,7 @@ int comm_exchange(Handle* h, double* field, int ncomp, int color) {
 
 int comm_allreduce_sum_max(Handle* h, double* dev2) {
   if (h->prep.nranks == 1) return CFDL_OK;
+  if (h->p2p.connected && h->use_p2p) return p2p_mail(h, dev2, /*sum,max*/ 0, 0);
   if (!h->comm) return fail(CFDL_ERR_NCCL, "cfdl_comm_init has not been called");
   CFDL_NCCL(g_nccl.GroupStart());
   CFDL_NCCL(g_nccl.AllReduce(dev2, dev2, 1, kNcclDouble, kNcclSum, h->comm, h->stream));
@@ -114,6 +119,7 @@ int comm_allreduce_sum_max(Handle* h, double* dev2) {
 
 int comm_bcast(Handle* h, double* dev, int count, int root) {
   if (h->prep.nranks == 1) return CFDL_OK;
+  if (count == 1 && h->p2p.connected && h->use_p2p) return p2p_mail(h, dev, /*pick root*/ 1, root);
   if (!h->comm) return fail(CFDL_ERR_NCCL, "cfdl_comm_init has not been called");
   CFDL_NCCL(g_nccl.Broadcast(dev, dev, (size_t)count, kNcclDouble, root, h->comm, h->stream));
   return CFDL_OK;
@@ -228,6 +234,10 @@ int p2p_alloc_slab(Handle* h) {
   hd.off_red_val = off; off += align256(2 * 64 * 2 * 8);
   hd.off_red_seq = off; off += align256(2 * 64 * 8);
   const size_t off_ticket = off; off += 256;
+  hd.off_xflag = off; off += align256(64 * 8);
+  hd.off_mail_val = off; off += align256(2 * 64 * 2 * 8);
+  hd.off_mail_seq = off; off += align256(2 * 64 * 8);
+  for (int b = 0; b < 2; ++b) { hd.off_stage[b] = (long long)off; off += align256(sizeof(double) * 3 * ((size_t)h->G + 32)); }
   for (int a = 0; a < 5; ++a) { hd.off_field[a] = (long long)off; off += arr; }
   for (int i = 0; i < hd.nnbr; ++i) hd.nbr_rank[i] = p.nbr_rank[i];
   for (size_t i = 0; i < p.recv_ptr.size(); ++i) hd.recv_ptr[i] = p.recv_ptr[i];
@@ -242,6 +252,7 @@ int p2p_alloc_slab(Handle* h) {
   h->fld[CFDL_F_PC] = (double*)(q.slab + hd.off_field[P2P_PC]);
   h->rb_work = (double*)(q.slab + hd.off_field[P2P_WORK]);
   q.ticket = (unsigned int*)(q.slab + off_ticket);
+  q.xticket = q.ticket + 8;
   return CFDL_OK;
 }
 
@@ -335,6 +346,155 @@ int p2p_push(Handle* h, int color, const double* a, const double* b, unsigned lo
   A.my_red_seq = (const unsigned long long*)(q.slab + q.hdr.off_red_seq);
   const int ctas = std::max(1, std::min(32, (total + 255) / 256));
   p2p_push_kernel<<<ctas, 256, 0, S(h)>>>(A);
+  CFDL_CUDA(cudaGetLastError());
+  return CFDL_OK;
+}
+
+// ---- staged exchange of any field (all colours at once) -----------------------------------------
+// One launch per exchange: every CTA copies its share of the interface values into the
+// neighbours' landing zones (laid out like their ghost range), the last CTA to finish raises the
+// neighbours' flag words, then all CTAs wait for the neighbours' flags and move the landed values
+// into the field's ghost cells.  Two landing zones alternate: a rank can only deliver exchange k+2
+// after it has consumed k+1, which its neighbour sent after consuming k.  The grid is far below
+// one wave, so the CTAs that spin never keep a publishing CTA from running.
+namespace {
+
+struct StageArgs {
+  int nnbr, ncomp, N, G;
+  const int32_t* send_cells;
+  const double* src;          // field (device numbering, ncomp interleaved)
+  double* field;
+  int s0[8], cnt[8], d0[8];   // per neighbour: first send cell, count, first ghost slot at the neighbour
+  double* peer_stage[8];
+  unsigned long long* peer_flag[8];
+  const double* my_stage;
+  const unsigned long long* my_flags;
+  int nbr_rank[8];
+  unsigned long long seq;
+  unsigned int* ticket;
+};
+
+__global__ void __launch_bounds__(256) stage_exchange_kernel(const __grid_constant__ StageArgs A) {
+  int total = 0;
+  for (int i = 0; i < A.nnbr; ++i) total += A.cnt[i];
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    int i = 0, k = t;
+    while (k >= A.cnt[i]) { k -= A.cnt[i]; ++i; }
+    const int cell = A.send_cells[A.s0[i] + k];
+    for (int q = 0; q < A.ncomp; ++q) A.peer_stage[i][(size_t)(A.d0[i] + k) * A.ncomp + q] = A.src[(size_t)cell * A.ncomp + q];
+  }
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    last = (atomicAdd(A.ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    if ((int)threadIdx.x < A.nnbr) *((volatile unsigned long long*)A.peer_flag[threadIdx.x]) = A.seq;
+    if (threadIdx.x == 0) *A.ticket = 0;
+  }
+  if ((int)threadIdx.x < A.nnbr) {
+    const volatile unsigned long long* f = (const volatile unsigned long long*)A.my_flags + A.nbr_rank[threadIdx.x];
+    while (*f < A.seq) {}
+    __threadfence_system();
+  }
+  __syncthreads();
+  const size_t n = (size_t)A.G * A.ncomp;
+  double* ghosts = A.field + (size_t)A.N * A.ncomp;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) ghosts[t] = __ldcg(&A.my_stage[t]);
+}
+
+// small all-to-all through the peers' mailboxes: every rank posts two doubles to every rank,
+// waits for all, and combines in rank order (identical result everywhere)
+struct MailArgs {
+  int nranks, rank, mode, root, parity;
+  unsigned long long seq;
+  double* dev;  // in: this rank's two values; out: the combination
+  double* peer_val[64];
+  unsigned long long* peer_seq[64];
+  const double* my_val;
+  const unsigned long long* my_seq;
+};
+
+__global__ void __launch_bounds__(64) mail_kernel(const __grid_constant__ MailArgs A) {
+  const int slot = A.parity * 64;
+  const double v0 = A.dev[0], v1 = A.mode == 0 ? A.dev[1] : 0.0;
+  if ((int)threadIdx.x < A.nranks) {
+    const int r = threadIdx.x;
+    A.peer_val[r][(slot + A.rank) * 2] = v0;
+    A.peer_val[r][(slot + A.rank) * 2 + 1] = v1;
+    __threadfence_system();
+    *((volatile unsigned long long*)&A.peer_seq[r][slot + A.rank]) = A.seq;
+    while (*((volatile const unsigned long long*)&A.my_seq[slot + r]) < A.seq) {}
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (A.mode == 0) {
+      double s = 0.0, m = 0.0;
+      for (int r = 0; r < A.nranks; ++r) {
+        s += *((volatile const double*)&A.my_val[(slot + r) * 2]);
+        m = fmax(m, *((volatile const double*)&A.my_val[(slot + r) * 2 + 1]));
+      }
+      A.dev[0] = s; A.dev[1] = m;
+    } else {
+      A.dev[0] = *((volatile const double*)&A.my_val[(slot + A.root) * 2]);
+    }
+  }
+}
+
+}  // namespace
+
+static int p2p_exchange(Handle* h, double* field, int ncomp) {
+  P2P& q = h->p2p;
+  const Prep& p = h->prep;
+  StageArgs A;
+  std::memset(&A, 0, sizeof A);
+  const int nc = p.ncolors;
+  const unsigned long long seq = ++q.xseq;
+  const int buf = (int)(seq & 1);
+  A.nnbr = h->nnbr; A.ncomp = ncomp; A.N = h->N; A.G = h->G; A.send_cells = h->send_cells; A.src = field; A.field = field;
+  int total = 0;
+  for (int i = 0; i < h->nnbr; ++i) {
+    const int r = p.nbr_rank[i];
+    const P2PHeader& ph = q.peer_hdr[r];
+    int me = -1;
+    for (int k = 0; k < ph.nnbr; ++k) if (ph.nbr_rank[k] == p.rank) me = k;
+    if (me < 0) return fail(CFDL_ERR_INTERNAL, "p2p_exchange: rank %d does not list rank %d as a neighbour", r, p.rank);
+    A.s0[i] = p.send_ptr[(size_t)i * nc];
+    A.cnt[i] = p.send_ptr[(size_t)(i + 1) * nc] - A.s0[i];
+    if (ph.recv_ptr[(me + 1) * nc] - ph.recv_ptr[me * nc] != A.cnt[i]) return fail(CFDL_ERR_INTERNAL, "p2p_exchange: interface size mismatch with rank %d", r);
+    A.d0[i] = ph.recv_ptr[me * nc];
+    A.peer_stage[i] = (double*)(q.peer_base[r] + ph.off_stage[buf]);
+    A.peer_flag[i] = (unsigned long long*)(q.peer_base[r] + ph.off_xflag) + p.rank;
+    A.nbr_rank[i] = r;
+    total += A.cnt[i];
+  }
+  A.my_stage = (const double*)(q.slab + q.hdr.off_stage[buf]);
+  A.my_flags = (const unsigned long long*)(q.slab + q.hdr.off_xflag);
+  A.seq = seq; A.ticket = q.xticket;
+  const int ctas = std::max(1, std::min(64, (std::max(total, h->G) * ncomp + 255) / 256));
+  stage_exchange_kernel<<<ctas, 256, 0, S(h)>>>(A);
+  CFDL_CUDA(cudaGetLastError());
+  return CFDL_OK;
+}
+
+static int p2p_mail(Handle* h, double* dev, int mode, int root) {
+  P2P& q = h->p2p;
+  const Prep& p = h->prep;
+  MailArgs A;
+  std::memset(&A, 0, sizeof A);
+  A.nranks = p.nranks; A.rank = p.rank; A.mode = mode; A.root = root;
+  A.seq = ++q.mseq; A.parity = (int)(A.seq & 1); A.dev = dev;
+  for (int r = 0; r < p.nranks; ++r) {
+    A.peer_val[r] = (double*)(q.peer_base[r] + q.peer_hdr[r].off_mail_val);
+    A.peer_seq[r] = (unsigned long long*)(q.peer_base[r] + q.peer_hdr[r].off_mail_seq);
+  }
+  A.my_val = (const double*)(q.slab + q.hdr.off_mail_val);
+  A.my_seq = (const unsigned long long*)(q.slab + q.hdr.off_mail_seq);
+  mail_kernel<<<1, 64, 0, S(h)>>>(A);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }

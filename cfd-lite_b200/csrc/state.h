@@ -43,6 +43,10 @@ struct P2PHeader {
   long long off_flags;     // unsigned long long flags[64]: flags[r] = last push sequence completed by rank r
   long long off_red_val;   // double red_val[2][64][2]: (sum r^2, max) of rank r, two alternating sets
   long long off_red_seq;   // unsigned long long red_seq[2][64]
+  long long off_stage[2];  // double stage[G][3]: landing zones for staged ghost exchanges, two alternating
+  long long off_xflag;     // unsigned long long xflag[64]: xflag[r] = last staged exchange rank r has delivered
+  long long off_mail_val;  // double mail_val[2][64][2]: small all-to-all mailbox (all-reduce / broadcast), alternating sets
+  long long off_mail_seq;  // unsigned long long mail_seq[2][64]
   int nbr_rank[64];
   int recv_ptr[64 * 4 + 1];
 };
@@ -55,7 +59,9 @@ struct P2P {
   std::vector<P2PHeader> peer_hdr;
   std::vector<void*> opened;            // cudaIpcOpenMemHandle results to close
   unsigned long long epoch = 0;
+  unsigned long long xseq = 0, mseq = 0;  // staged exchanges / mailbox rounds done (every rank performs the same sequence)
   unsigned int* ticket = nullptr;
+  unsigned int* xticket = nullptr;
 };
 enum { P2P_U = 0, P2P_V = 1, P2P_W = 2, P2P_PC = 3, P2P_WORK = 4 };
 

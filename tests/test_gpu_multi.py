@@ -90,7 +90,7 @@ def _worker(rank, world, port, kind, n, p2p, out_q):
         out_q.put((rank, "FAIL: " + "".join(traceback.format_exception(type(ex), ex, ex.__traceback__))))
 
 
-@pytest.mark.parametrize("kind,n,p2p", [(0, 10, False), (1, 5, False), (0, 10, True), (0, 24, True), (STRUCTURED, 12, False), (STRUCTURED, 16, True)])
+@pytest.mark.parametrize("kind,n,p2p", [(0, 10, False), (1, 5, False), (0, 10, True), (0, 24, True), (STRUCTURED, 12, False), (STRUCTURED, 16, True), (1, 5, True)])
 def test_partitioned_run_equals_single_gpu(cfdl, kind, n, p2p):
     world = min(cfdl.device_count(), 4)
     if world < 2:
