@@ -304,7 +304,7 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "ctas_per_sm")) { h->tune_ctas = std::max(1, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "profile")) {
     int rc = prof_collect(h);
-    h->profile = value != 0.0;
+    h->profile = (value == 2.0) ? 2 : (value != 0.0);
     return rc;
   }
   if (!std::strcmp(key, "reset_counters")) {

@@ -5,20 +5,25 @@
 
 namespace cfdl {
 
-int prof_begin(Handle* h, int kind) {
-  if (!h->profile) return CFDL_OK;
+// level 1 (profile=1): every launch of the profiled kinds is bracketed by its own event pair.
+// level 2 (profile=2): only whole batches of back-to-back solver passes are bracketed, so the
+// passes keep overlapping as they do in production; the batch owner adds the launch count.
+int prof_begin(Handle* h, int kind, int level) {
+  if (h->profile != level) return CFDL_OK;
   if (h->prof_used + 2 > h->prof_ev.size()) {
     const size_t old = h->prof_ev.size(), grow = 4096;
     h->prof_ev.resize(old + grow, nullptr);
     h->prof_kind.resize((old + grow) / 2, 0);
+    h->prof_cnt.resize((old + grow) / 2, 1);
     for (size_t i = old; i < old + grow; ++i) CFDL_CUDA(cudaEventCreate(&h->prof_ev[i]));
   }
   h->prof_kind[h->prof_used / 2] = kind;
   CFDL_CUDA(cudaEventRecord(h->prof_ev[h->prof_used], h->stream));
   return CFDL_OK;
 }
-int prof_end(Handle* h) {
-  if (!h->profile) return CFDL_OK;
+int prof_end(Handle* h, int count, int level) {
+  if (h->profile != level) return CFDL_OK;
+  h->prof_cnt[h->prof_used / 2] = count;
   CFDL_CUDA(cudaEventRecord(h->prof_ev[h->prof_used + 1], h->stream));
   h->prof_used += 2;
   return CFDL_OK;
@@ -31,7 +36,7 @@ int prof_collect(Handle* h) {
     CFDL_CUDA(cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]));
     const int k = h->prof_kind[i / 2];
     h->prof_ms[k] += ms;
-    h->prof_n[k] += 1;
+    h->prof_n[k] += h->prof_cnt[i / 2];
   }
   h->prof_used = 0;
   return CFDL_OK;

@@ -125,7 +125,7 @@ struct Handle {
   int64_t launches = 0;         // kernels launched since the last reset ("gpu_launches")
   int profile = 0;              // 1: bracket every launch of the profiled kernel kinds with CUDA events
   std::vector<cudaEvent_t> prof_ev;  // pairs (begin, end)
-  std::vector<int> prof_kind;
+  std::vector<int> prof_kind, prof_cnt;  // per pair: kernel kind, launches it covers
   size_t prof_used = 0;
   double prof_ms[8] = {0};
   int64_t prof_n[8] = {0};
@@ -137,8 +137,8 @@ inline cudaStream_t S(Handle* h) { h->launches++; return h->stream; }
 
 // profiled kernel kinds (per-launch CUDA-event timing when h->profile is on)
 enum { PROF_SGS_SWEEP = 0, PROF_RESIDUAL = 1, PROF_COEF_UVW = 2, PROF_COEF_P = 3, PROF_MIP = 4, PROF_GRAD = 5, PROF_LEVELS = 6, PROF_PCG = 7 };
-int prof_begin(Handle* h, int kind);
-int prof_end(Handle* h);
+int prof_begin(Handle* h, int kind, int level = 1);
+int prof_end(Handle* h, int count = 1, int level = 1);
 int prof_collect(Handle* h);  // after a stream sync: fold finished event pairs into prof_ms / prof_n
 
 // launch geometry helper: grids are sized as a multiple of the SM count (B200: 148)
