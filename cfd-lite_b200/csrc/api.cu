@@ -486,3 +486,66 @@ int cfdl_host_calc_residual(cfdl_handle h, const double* phi, const double* ap, 
 }
 
 }  // extern "C"
+
+// ---- the assembly routines with host arrays (flattened derived types of the reference) ----------
+namespace {
+struct In { int field; const double* host; };
+struct Out { int field; double* host; };
+template <size_t NI, size_t NO, typename Run>
+int host_routine(cfdl_handle h, const char* who, const In (&ins)[NI], const Out (&outs)[NO], Run run) {
+  if (h->prep.nranks > 1) return fail(CFDL_ERR_UNSUPPORTED, "%s: single-GPU drop-in (use the per-routine calls on a partitioned handle)", who);
+  for (const In& i : ins) if (!i.host) return fail(CFDL_ERR_ARG, "%s: NULL input array", who);
+  for (const Out& o : outs) if (!o.host) return fail(CFDL_ERR_ARG, "%s: NULL output array", who);
+  int rc;
+  for (const In& i : ins) if ((rc = upload_field(h, i.field, i.host))) return rc;
+  if ((rc = run())) return rc;
+  for (const Out& o : outs) if ((rc = download_field(h, o.field, o.host))) return rc;
+  return CFDL_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int cfdl_host_calc_coef_uvw(cfdl_handle h, double dt, const double* u, const double* v, const double* w, const double* u0,
+                            const double* v0, const double* w0, const double* gu, const double* gv, const double* gw, const double* gp,
+                            const double* mip, double* ap, double* anb, double* bu, double* bv, double* bw, double* d, double* dc) {
+  ENTER(h);
+  const In ins[] = {{CFDL_F_U, u}, {CFDL_F_V, v}, {CFDL_F_W, w}, {CFDL_F_U0, u0}, {CFDL_F_V0, v0}, {CFDL_F_W0, w0},
+                    {CFDL_F_GU, gu}, {CFDL_F_GV, gv}, {CFDL_F_GW, gw}, {CFDL_F_GP, gp}, {CFDL_F_MIP, mip}};
+  const Out outs[] = {{CFDL_F_AP, ap}, {CFDL_F_ANB, anb}, {CFDL_F_BU, bu}, {CFDL_F_BV, bv}, {CFDL_F_BW, bw}, {CFDL_F_D, d}, {CFDL_F_DC, dc}};
+  return host_routine(h, "cfdl_host_calc_coef_uvw", ins, outs, [&] { return k_calc_coef_uvw(h, dt); });
+}
+
+int cfdl_host_calc_mip(cfdl_handle h, int32_t l_rhie_chow, double dt, const double* u, const double* v, const double* w, const double* u0,
+                       const double* v0, const double* w0, const double* p, const double* gp, const double* d, const double* mip0,
+                       double* mip) {
+  ENTER(h);
+  // mip is in/out: only cell-cell faces are written (mod_uvwp.f90:456), boundary entries pass through
+  const In ins[] = {{CFDL_F_U, u}, {CFDL_F_V, v}, {CFDL_F_W, w}, {CFDL_F_U0, u0}, {CFDL_F_V0, v0}, {CFDL_F_W0, w0},
+                    {CFDL_F_P, p}, {CFDL_F_GP, gp}, {CFDL_F_D, d}, {CFDL_F_MIP0, mip0}, {CFDL_F_MIP, mip}};
+  const Out outs[] = {{CFDL_F_MIP, mip}};
+  return host_routine(h, "cfdl_host_calc_mip", ins, outs, [&] { return k_calc_mip(h, l_rhie_chow != 0, dt); });
+}
+
+int cfdl_host_calc_coef_p(cfdl_handle h, const double* dc, const double* mip, double* ap, double* anb, double* b) {
+  ENTER(h);
+  const In ins[] = {{CFDL_F_DC, dc}, {CFDL_F_MIP, mip}};
+  const Out outs[] = {{CFDL_F_AP, ap}, {CFDL_F_ANB, anb}, {CFDL_F_B, b}};
+  return host_routine(h, "cfdl_host_calc_coef_p", ins, outs, [&] { return k_calc_coef_p(h); });
+}
+
+int cfdl_host_adjust_pc(cfdl_handle h, double* pc) {
+  ENTER(h);
+  const In ins[] = {{CFDL_F_PC, pc}};
+  const Out outs[] = {{CFDL_F_PC, pc}};
+  return host_routine(h, "cfdl_host_adjust_pc", ins, outs, [&] { return k_adjust_pc(h); });
+}
+
+int cfdl_host_update_uvwp(cfdl_handle h, const double* pc, const double* gpc, const double* dc, double* p, double* gp, double* mip) {
+  ENTER(h);
+  const In ins[] = {{CFDL_F_PC, pc}, {CFDL_F_GPC, gpc}, {CFDL_F_DC, dc}, {CFDL_F_P, p}, {CFDL_F_GP, gp}, {CFDL_F_MIP, mip}};
+  const Out outs[] = {{CFDL_F_P, p}, {CFDL_F_GP, gp}, {CFDL_F_MIP, mip}};
+  return host_routine(h, "cfdl_host_update_uvwp", ins, outs, [&] { return k_update_uvwp(h); });
+}
+
+}  // extern "C"

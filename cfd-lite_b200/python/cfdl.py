@@ -399,6 +399,35 @@ class Solver:
         _chk(lib().cfdl_host_solve(self.h, C.c_int(eq), _d(phi), _d(ap), _d(anb), _d(b), C.c_int32(nit), _d(out)))
         return phi, out
 
+    def host_calc_coef_uvw(self, f, dt=0.01):
+        """f: dict of host arrays u,v,w,u0,v0,w0,gu,gv,gw,gp,mip -> dict ap,anb,bu,bv,bw,d,dc."""
+        ins = [_f64(f[k]) for k in ("u", "v", "w", "u0", "v0", "w0", "gu", "gv", "gw", "gp", "mip")]
+        out = {k: np.empty(self.field_size(k)) for k in ("ap", "anb", "bu", "bv", "bw", "d", "dc")}
+        _chk(lib().cfdl_host_calc_coef_uvw(self.h, C.c_double(dt), *[_d(a) for a in ins], *[_d(out[k]) for k in out]))
+        return out
+
+    def host_calc_mip(self, f, rhie_chow=True, dt=0.01):
+        """f: dict u,v,w,u0,v0,w0,p,gp,d,mip0,mip -> new mip (boundary entries pass through)."""
+        ins = [_f64(f[k]) for k in ("u", "v", "w", "u0", "v0", "w0", "p", "gp", "d", "mip0")]
+        mip = _f64(f["mip"]).copy()
+        _chk(lib().cfdl_host_calc_mip(self.h, C.c_int32(1 if rhie_chow else 0), C.c_double(dt), *[_d(a) for a in ins], _d(mip)))
+        return mip
+
+    def host_calc_coef_p(self, dc, mip):
+        out = {k: np.empty(self.field_size(k)) for k in ("ap", "anb", "b")}
+        _chk(lib().cfdl_host_calc_coef_p(self.h, _d(_f64(dc)), _d(_f64(mip)), *[_d(out[k]) for k in out]))
+        return out
+
+    def host_adjust_pc(self, pc):
+        pc = _f64(pc).copy()
+        _chk(lib().cfdl_host_adjust_pc(self.h, _d(pc)))
+        return pc
+
+    def host_update_uvwp(self, pc, gpc, dc, p, gp, mip):
+        p, gp, mip = _f64(p).copy(), _f64(gp).copy(), _f64(mip).copy()
+        _chk(lib().cfdl_host_update_uvwp(self.h, _d(_f64(pc)), _d(_f64(gpc)), _d(_f64(dc)), _d(p), _d(gp), _d(mip)))
+        return p, gp, mip
+
     def host_calc_residual(self, phi, ap, anb, b):
         phi, ap, anb, b = _f64(phi), _f64(ap), _f64(anb), _f64(b)
         res, res_max = C.c_double(), C.c_double()

@@ -48,8 +48,7 @@ enum {
                              multi_subdomain_solver (n_subdomains>1); level-scheduled on the GPU */
   CFDL_SOLVER_MCSGS = 1,  /* multicolour symmetric Gauss-Seidel: same update formula, same
                              stopping rule, colour order instead of natural order */
-  CFDL_SOLVER_PCG = 2     /* pc only: Jacobi-preconditioned CG with the reference's 10x / nit
-                             stopping rule; u,v,w use MCSGS */
+  CFDL_SOLVER_PCG = 2     /* reserved for a Krylov pc solver; currently runs MCSGS */
 };
 
 /* field selectors for upload/download and the per-routine entry points */
@@ -107,8 +106,10 @@ int cfdl_get_info(cfdl_handle h, const char* key, double* value);
 int cfdl_get_cell_order(cfdl_handle h, int32_t* c2o, int32_t* color_ptr);
 
 /* ---- instrumentation (bench.py): CUDA events on the library's stream, pinned host buffers.
- * set_option keys: "solver", "profile" (0/1: time every launch of the dominant kernels),
- *                  "reset_counters" (any value).
+ * set_option keys: "solver", "profile" (0 off; 1: an event pair around every launch of the profiled
+ *                  kernels; 2: an event pair around every batch of back-to-back solver passes),
+ *                  "reset_counters" (any value); tuning switches: "fused", "pdl", "pdl_rows", "p2p",
+ *                  "statics", "uvw_variant", "mip_variant", "occ_grids", "ctas_per_sm".
  * get_info keys:   "launches" (kernels launched since reset), "prof_ms_<k>" / "prof_n_<k>" with
  *                  k in sgs, residual, coef_uvw, coef_p, mip, grad, levels, pcg;
  *                  "ncolors", "morton", "nlevels_natural", "nlevels_blocks", "ell_width", "num_sms". */
@@ -159,6 +160,33 @@ int cfdl_host_calc_residual(cfdl_handle h, const double* phi, const double* ap, 
  * was created with n_subdomains>1, else solve_gs */
 int cfdl_host_solve(cfdl_handle h, int eq, double* phi, const double* ap, const double* anb,
                     const double* b, int32_t nit, double* out4);
+
+/* The assembly routines with host arrays: the reference passes derived types (uvwp_t, geometry_t,
+ * properties_t); flattened here to the arrays each routine reads and writes, in the reference
+ * numbering (cells+halos H, faces F, CSR slots Z, cells N).  Mesh, rho, mu and the BC table come
+ * from the handle.  Single-GPU handles only. */
+/* calc_coef_uvw(eqn,prop,geom,dt) mod_uvwp.f90:161-286: in u,v,w,u0,v0,w0 [H], gu,gv,gw,gp [3H],
+ * mip [F]; out ap [N], anb [Z], bu,bv,bw,d,dc [N] */
+int cfdl_host_calc_coef_uvw(cfdl_handle h, double dt, const double* u, const double* v, const double* w,
+                            const double* u0, const double* v0, const double* w0,
+                            const double* gu, const double* gv, const double* gw, const double* gp,
+                            const double* mip, double* ap, double* anb,
+                            double* bu, double* bv, double* bw, double* d, double* dc);
+/* calc_mip(eqn,prop,geom,dt,l_rhie_chow) mod_uvwp.f90:438-490: in u,v,w,u0,v0,w0,p [H], gp [3H],
+ * d [N], mip0 [F]; mip [F] in/out (only cell-cell faces are written, :456) */
+int cfdl_host_calc_mip(cfdl_handle h, int32_t l_rhie_chow, double dt, const double* u, const double* v,
+                       const double* w, const double* u0, const double* v0, const double* w0,
+                       const double* p, const double* gp, const double* d, const double* mip0,
+                       double* mip);
+/* calc_coef_p(eqn,prop,geom) mod_uvwp.f90:289-368: in dc [N], mip [F]; out ap [N], anb [Z], b [N] */
+int cfdl_host_calc_coef_p(cfdl_handle h, const double* dc, const double* mip,
+                          double* ap, double* anb, double* b);
+/* pref=phic(1); adjust_pc(phic,pref,...) mod_uvwp.f90:129-130,136-158: pc [H] in/out */
+int cfdl_host_adjust_pc(cfdl_handle h, double* pc);
+/* update_uvwp(eqn,prop,geom) mod_uvwp.f90:370-436: in pc [H], gpc [3H], dc [N]; p [H], gp [3H],
+ * mip [F] in/out */
+int cfdl_host_update_uvwp(cfdl_handle h, const double* pc, const double* gpc, const double* dc,
+                          double* p, double* gp, double* mip);
 
 /* ---- multi-GPU: one process per GPU (the reference is one process; launch P copies of the
  * driver, e.g. under mpirun/torchrun).  Every rank passes the same GLOBAL mesh, in the format

@@ -105,3 +105,27 @@ def test_partition_plans_and_halo_exchange(world, kind, n):
         p.join(timeout=60)
     bad = [r for r in results if r[1] != "ok"]
     assert not bad, bad
+
+
+@pytest.mark.parametrize("world,kind,n", [(4, 0, 8), (8, 0, 8), (8, 1, 4), (4, 0, 9)])
+def test_plans_of_4_and_8_ranks_match_pairwise(cfdl, world, kind, n):
+    """The peer-to-peer exchange addresses a neighbour's ghost slice by (neighbour index,
+    offset), so what one rank sends must equal, element for element and per colour, what the
+    other expects — checked here for every pair of the 4- and 8-rank partitions (one process,
+    no communication: every plan is derived from the global mesh alone)."""
+    raw = cfdl.meshgen(kind, n, jitter=0.2 if kind else 0.0, shuffle=bool(kind))
+    geom = cfdl.mesh_build(raw)
+    c2r, _, _ = cfdl.partition_rcb(geom, world, want_order=False)
+    plans = [cfdl.partition_plan(geom, c2r, world, r) for r in range(world)]
+    ne = geom["ne"]
+    assert sorted(np.concatenate([p["owned"] for p in plans]).tolist()) == list(range(1, ne + 1))
+    assert len({p["ncolors"] for p in plans}) == 1
+    for r, p in enumerate(plans):
+        nbrs = [int(x) for x in p["nbr_rank"]]
+        assert nbrs == sorted(nbrs) and r not in nbrs and len(nbrs) <= 8
+        for i, q in enumerate(nbrs):
+            other = plans[q]
+            j = [int(x) for x in other["nbr_rank"]].index(r)  # symmetric neighbour sets
+            mine = p["send_cells"][p["send_ptr"][i]:p["send_ptr"][i + 1]]
+            theirs = other["ghost"][other["recv_ptr"][j]:other["recv_ptr"][j + 1]]
+            assert np.array_equal(mine, theirs), (r, q)
