@@ -16,6 +16,22 @@ __device__ __forceinline__ double vec_weight(const double r0[3], const double r1
   return (la + lb > 0.0) ? la / (la + lb) : 0.5;
 }
 
+// a / b from y = RN(1/b): one multiply and two fused multiply-adds give the correctly rounded
+// quotient (Markstein's correction: q0 = RN(a*y), r = a - b*q0 exactly, q = RN(q0 + r*y)) — the
+// same bits as the division, for 3 FP64 instructions instead of the ~25 of the division routine.
+// Checked against IEEE division on 4e8 random and adversarial operand pairs (all-ones significands,
+// powers of two, near-ties): tools/check_fast_div.cpp.  Needs |a| >= 2^-969 or a == 0 so that r is
+// exact (a == -0 returns +0).  FAST = false is the plain division.
+template <bool FAST>
+__device__ __forceinline__ double quot(double a, double b, double y) {
+  if (FAST) {
+    const double q0 = a * y;
+    const double r = fma(-b, q0, a);
+    return fma(r, y, q0);
+  }
+  return a / b;
+}
+
 __device__ __forceinline__ void load3(const double* __restrict__ a, int64_t i, double v[3]) {
   v[0] = a[3 * i]; v[1] = a[3 * i + 1]; v[2] = a[3 * i + 2];
 }

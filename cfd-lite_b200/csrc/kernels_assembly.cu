@@ -321,7 +321,7 @@ int k_calc_coef_uvw(Handle* h, double dt) {
   const int gs = grid_for(h, h->N, UVW_CELLS, 16);
   if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
   prof_begin(h, PROF_COEF_UVW);
-  if (h->uvw_variant == 2 && h->use_statics && h->fs_area) {
+  if (h->uvw_variant >= 2 && h->uvw_variant <= 4 && h->use_statics && h->fs_area) {
     int rc = k_calc_coef_uvw_statics(h, dt);
     if (rc) return rc;
   } else if (h->uvw_variant == 0) {

@@ -105,7 +105,8 @@ struct Handle {
   int pdl_rows = 1;            // rows per thread prefetched to L2 ahead of the dependency wait
   int use_pdl = 1;             // fused passes: programmatic dependent launch (a pass loads its first matrix rows while the previous one drains)
   int uvw_variant = 2;         // calc_coef_uvw: 0 = one thread per cell, 1 = one thread per (cell, face slot),
-                               // 2 = one thread per cell on precomputed face statics
+                               // 2 = one thread per cell on precomputed face statics, 3 = as 2 with the ten quotients
+                               // per face formed from two reciprocals + FMA corrections (same bits; not yet timed)
   // per cell-cell face, owner orientation, computed once with the very expressions the reference
   // evaluates every iteration (area, unit normal, |dr|, projected |dr_p|, dr.n, both distance
   // weights, dr, dr_p): the assembly kernels then need 10 instead of 19 FP64 div/sqrt per face

@@ -55,3 +55,20 @@ def test_host_assembly_chain(case):
     p, gp, mip2 = s.host_update_uvwp(pc, oc["gpc"], f["dc"], p_in, gp_in, mip)
     assert rel_err(p, oc["p"]) <= 1e-12 and rel_err(gp, oc["gp"]) <= 1e-12
     assert np.array_equal(mip2, oc["mip"])
+
+
+def test_coef_uvw_reciprocal_variants_keep_the_bits(case):
+    """uvw_variant 3 (quotients from two reciprocals + FMA corrections) and 4 (the same with three
+    resident CTAs per SM) against the oracle: same bits as the dividing kernel."""
+    oc, s = case
+    for name in STATE:
+        s.upload(name, oc[name])
+    oc.calc_coef_uvw()
+    try:
+        for variant in (3, 4):
+            s.set_option("uvw_variant", variant)
+            s.calc_coef_uvw(dt=0.01)
+            for f in ("ap", "anb", "bu", "bv", "bw", "d", "dc"):
+                assert np.array_equal(s.download(f), oc[f]), (variant, f)
+    finally:
+        s.set_option("uvw_variant", 2)
