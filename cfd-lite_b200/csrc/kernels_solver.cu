@@ -306,9 +306,9 @@ static int launch_levels(Handle* h, const DevSchedule& D, double sor, int niter)
   void* args[] = {&nlevels, &lvl_ptr, &Np, &H, &nbs, &ap, &anb, &b, &phi, &sor, &niter, &nlag, &lag_src, &counter};
   // no more CTAs than the widest level can feed
   int ctas = std::min(h->coop_ctas, std::max(1, (D.max_level_cells + TPB - 1) / TPB));
-  const void* fn = (h->K <= 4) ? (const void*)level_sgs_kernel<4> : (const void*)level_sgs_kernel<6>;
+  auto go = [&](auto kern) { return cudaLaunchCooperativeKernel(kern, dim3(ctas), dim3(TPB), args, 0, S(h)); };
   prof_begin(h, PROF_LEVELS);
-  CFDL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(ctas), dim3(TPB), args, 0, S(h)));
+  CFDL_CUDA(h->K <= 4 ? go(level_sgs_kernel<4>) : go(level_sgs_kernel<6>));
   prof_end(h);
   return CFDL_OK;
 }

@@ -10,8 +10,36 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, ROOT)
 
 
+def pytest_addoption(parser):
+    parser.addoption("--emul", action="store_true", default=False,
+                     help="run the gpu-marked tests against tests/emul/_build/libcfdl_emul.so (host emulation of the "
+                          "CUDA sources, test infrastructure only) instead of the real library")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    if config.getoption("--emul"):
+        use_emulated_library()
+
+
+EMUL_LIB = os.path.join(ROOT, "tests", "emul", "_build", "libcfdl_emul.so")
+
+
+def build_emulated_library():
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emul"), "-j", "8"])
+    return EMUL_LIB
+
+
+def use_emulated_library():
+    """Point the ctypes mirror at the cuemu build for THIS test process (never done by the product)."""
+    import ctypes
+    import cfdl as m
+    build_emulated_library()
+    m._lib = ctypes.CDLL(EMUL_LIB)
+    m._lib.cfdl_last_error.restype = ctypes.c_char_p
+    assert m._lib.cfdl_emulated() == 1
+    m.LIB_PATH = EMUL_LIB
 
 
 @pytest.fixture(scope="session")

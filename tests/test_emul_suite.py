@@ -1,0 +1,24 @@
+"""The gpu-marked parity tests, executed on the host against the cuemu build of the CUDA sources.
+
+tests/emul/ compiles cfd-lite_b200/csrc/*.cu for the host (kernel launches rewritten, CUDA
+runtime and device intrinsics emulated with fibers, guard pages behind every device allocation)
+into tests/emul/_build/libcfdl_emul.so.  Running the GPU parity suite against it checks, in a
+container without a GPU, that the kernels' arithmetic and indexing and the orchestration in
+api.cu / kernels_solver.cu reproduce the oracle — it is a checker for the sources, not a way
+to run the product: the product library has no CPU path and nothing outside tests/ can load the
+emulated one.  Timing, occupancy and memory-ordering across CTAs are of course NOT covered; the
+`-m gpu` run on the B200 remains the parity gate.
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_gpu_suite_passes_under_emulation():
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-m", "gpu", "--emul", "-x", "-q",
+                        "-p", "no:cacheprovider"], cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    tail = "\n".join(r.stdout.splitlines()[-25:])
+    assert r.returncode == 0, "gpu suite under emulation failed:\n%s\n%s" % (tail, r.stderr[-2000:])
+    assert " passed" in tail
