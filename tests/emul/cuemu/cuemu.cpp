@@ -249,7 +249,11 @@ void warp_exchange(const void* mine, void* out, size_t bytes) {
   while (w.gen == g) yield_to_sched();
 }
 
-void spin_pause() { sched_yield(); }
+// a spinning thread lets its siblings in the CTA run (independent thread scheduling), then the core
+void spin_pause() {
+  if (t_cta) yield_to_sched();
+  sched_yield();
+}
 
 void run_grid(dim3 grid, dim3 block, Body body, bool cooperative) {
   const uint3 s_t = threadIdx, s_b = blockIdx;

@@ -1,0 +1,90 @@
+#!/usr/bin/env python3
+"""Partitioned run on the cuemu build: the ranks of a multi-GPU job are THREADS of this process,
+every rank owns a handle of the emulated library, and the "IPC handle" of a slab is its address —
+so the peer-to-peer path of comm.cu / kernels_rb.inc (interface CTAs storing into the neighbours'
+ghost cells, flag words, mailbox all-reduce) runs for real, concurrently, on the host.  The merged
+result must equal the single-rank run like in tests/test_gpu_multi.py.  TEST INFRASTRUCTURE ONLY.
+usage: multirank_check.py <world> <n> [structured]
+"""
+import os
+import sys
+import threading
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(ROOT, "cfd-lite_b200", "python"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cfdl  # noqa: E402
+import conftest  # noqa: E402
+
+
+def main():
+    world, n = int(sys.argv[1]), int(sys.argv[2])
+    structured = len(sys.argv) > 3 and sys.argv[3] == "structured"
+    conftest.use_emulated_library()
+    raw = cfdl.meshgen(0, n)
+    geom = cfdl.mesh_build(raw)
+    bcs = cfdl.default_bcs(raw)
+    c2r, _, _ = cfdl.partition_rcb(geom, world)
+    bar = threading.Barrier(world)
+    handles = [None] * world
+    out = [None] * world
+    errs = []
+    fields_wanted = ("u", "v", "w", "p", "gp") + (() if structured else ("mip",))
+
+    def rank_main(rank):
+        try:
+            if structured:
+                s = cfdl.Solver.structured_hex(n, device=0, rank=rank, nranks=world)
+            else:
+                s = cfdl.Solver(geom, bcs, device=0, cell2rank=c2r, rank=rank, nranks=world)
+            s.set_option("solver", cfdl.SOLVER_MCSGS)
+            handles[rank] = s.ipc_handle()
+            bar.wait()
+            s.ipc_connect(handles)
+            bar.wait()
+            hist = s.run(dt=0.01, nit=100, ntstep=2, ncoef=2)
+            fields = {}
+            for f in fields_wanted:
+                a = np.full(s.field_size(f), np.nan)
+                s.download_into(f, a)
+                fields[f] = a
+            out[rank] = (hist, fields)
+            bar.wait()
+            s.close()
+        except Exception as ex:  # a failing rank must not leave the others at the barrier
+            errs.append((rank, repr(ex)))
+            bar.abort()
+
+    th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    one = cfdl.Solver(geom, bcs, device=0)
+    one.set_option("solver", cfdl.SOLVER_MCSGS)
+    want_hist = one.run(dt=0.01, nit=100, ntstep=2, ncoef=2)
+    for r in range(world):
+        hist = out[r][0]
+        assert np.array_equal(hist[:, :, 0], want_hist[:, :, 0]), (r, hist[:, :, 0], want_hist[:, :, 0])
+        err_h = np.abs(hist[:, :, 1:3] - want_hist[:, :, 1:3]).max() / np.abs(want_hist[:, :, 1:3]).max()
+        assert err_h < 1e-10, err_h
+    worst = 0.0
+    for f in fields_wanted:
+        m = np.full_like(out[0][1][f], np.nan)
+        for r in range(world):
+            ok = ~np.isnan(out[r][1][f])
+            m[ok] = out[r][1][f][ok]
+        assert not np.isnan(m).any(), f + ": some entries were reported by no rank"
+        w = one.download(f)
+        err = np.abs(m - w).max() / max(np.abs(w).max(), 1e-300)
+        assert err < 1e-12, (f, err)
+        worst = max(worst, err)
+    one.close()
+    print("multirank emulation ok: world=%d n=%d structured=%s worst field err %.2e" % (world, n, structured, worst))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,20 @@
+"""Partitioned peer-to-peer runs on the cuemu build (ranks = threads of one process, see
+tests/emul/multirank_check.py): 2, 4 and 8 ranks must reproduce the single-rank fields, like
+tests/test_gpu_multi.py asserts on real GPUs.  Covers the interface-CTA stores, flag words,
+staged exchanges and the mailbox all-reduce on the host; NVLink ordering itself is only
+exercised by the gpu test."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("world,n,structured", [(2, 8, False), (4, 10, False), (8, 12, False), (4, 12, True)])
+def test_partitioned_p2p_run_equals_single_rank_under_emulation(world, n, structured):
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "emul", "multirank_check.py"), str(world), str(n)] + (["structured"] if structured else [])
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "multirank emulation ok" in r.stdout
