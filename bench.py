@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="cfdl_set_option(KEY, VALUE) after creation (tuning experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-separate", action="store_true", help="e2e through separate upload/solve/download calls instead of cfdl_step_host")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -397,17 +398,30 @@ def main():
         ne2e = min(args.steps, 10)
         base = args.warmup + args.steps + 2 * nprof
 
+        # one C-ABI call per step (cfdl_step_host: the transfers that the iteration allows run beside the
+        # computation); the separate upload/solve/download calls remain as the fallback and are named in the line
+        e2e_path = {"how": "cfdl_step_host (mip0 uploaded during the momentum phase; u,v,w,gu,gv,gw downloaded during the pc solve)"}
+        in_arrays = {k: bufs[k].array for k in ins}
+        out_arrays = {k: bufs[k].array for k in outs}
+
         def e2e_step(i):
-            for k in ins:
-                up(k, bufs[k].array)
-            s.update_boundaries()
-            s.solve_uvwp(DT, NIT)
+            if "failed" not in e2e_path and not args.e2e_separate:
+                try:
+                    s.step_host(in_arrays, out_arrays, dt=DT, nit=NIT, apply_bcs=True, local=(world > 1))
+                except cfdl.CfdlError as ex:
+                    e2e_path["failed"] = str(ex)
+                    e2e_path["how"] = "separate cfdl_upload_field / cfdl_solve_uvwp / cfdl_download_field calls"
+            if "failed" in e2e_path or args.e2e_separate:
+                for k in ins:
+                    up(k, bufs[k].array)
+                s.update_boundaries()
+                s.solve_uvwp(DT, NIT)
+                for k in outs:
+                    down(k, bufs[k].array)
             if (i + 1) % NCOEF == 0:
                 s.update_time()
                 for k in ("u0", "v0", "w0", "mip0"):
                     down(k, bufs[k].array)
-            for k in outs:
-                down(k, bufs[k].array)
 
         e2e_step(base)
         barrier()
@@ -427,7 +441,9 @@ def main():
         e2e = {"value": ne * ne2e / (ms_e * 1e-3), "unit": "cell-iterations/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": ne2e, "ms_per_step": ms_e / ne2e,
                "what": "per step: upload u,v,w,p,u0,v0,w0,gu,gv,gw,gp,mip,mip0 from pinned host memory, update_boundaries + "
-                       "solve_uvwp through the C ABI, download u,v,w,p,gu,gv,gw,gp,gpc,mip and the residual history"}
+                       "solve_uvwp through the C ABI, download u,v,w,p,gu,gv,gw,gp,gpc,mip and the residual history",
+               "path": ("separate cfdl_upload_field / cfdl_solve_uvwp / cfdl_download_field calls" if args.e2e_separate else e2e_path["how"]),
+               "path_error": e2e_path.get("failed")}
         for b in bufs.values():
             b.free()
 

@@ -110,16 +110,25 @@ int phi_field(int eq) { return eq == CFDL_EQ_U ? CFDL_F_U : eq == CFDL_EQ_V ? CF
 
 // solve_uvwp, src/equations/mod_uvwp.f90:95-134.  On several GPUs the ghost-cell copies of the
 // fields a later kernel gathers are refreshed right after the kernel that produces them.
-int solve_uvwp_impl(Handle* h, double dt, int nit, double* hist) {
+// `hook`, when given, is called at the points of the iteration where a host driver's transfers
+// can run beside the computation (cfdl_step_host): after the momentum solves (u, v, w are final —
+// the reference's velocity correction is disabled, mod_uvwp.f90:387-391), after their gradients
+// (gu, gv, gw are final) and right before calc_mip (the first reader of mip0).
+enum { STEP_MOMENTUM_DONE = 0, STEP_GRAD_DONE = 1, STEP_BEFORE_MIP = 2 };
+struct StepHook { virtual int at(int stage) = 0; virtual ~StepHook() {} };
+
+int solve_uvwp_impl(Handle* h, double dt, int nit, double* hist, StepHook* hook = nullptr) {
   int rc;
   double st[16] = {0};
   if ((rc = k_calc_coef_uvw(h, dt))) return rc;                                              // :111
   if ((rc = comm_exchange(h, h->fld[CFDL_F_D], 1, -1)) || (rc = comm_exchange(h, h->fld[CFDL_F_DC], 1, -1))) return rc;
   for (int eq = CFDL_EQ_U; eq <= CFDL_EQ_W; ++eq)                                            // :114-116
     if ((rc = solve_equation(h, eq, h->fld[phi_field(eq)], h->fld[rhs_field(eq)], nit, st + 4 * eq, false))) return rc;
+  if (hook && (rc = hook->at(STEP_MOMENTUM_DONE))) return rc;
   if ((rc = k_calc_grad3(h))) return rc;                                                     // :118-120
   for (int f = CFDL_F_GU; f <= CFDL_F_GW; ++f)
     if ((rc = comm_exchange(h, h->fld[f], 3, -1))) return rc;
+  if (hook && ((rc = hook->at(STEP_GRAD_DONE)) || (rc = hook->at(STEP_BEFORE_MIP)))) return rc;
   if ((rc = k_calc_mip(h, true, dt))) return rc;                                             // :122
   if ((rc = k_calc_coef_p(h))) return rc;                                                    // :124
   CFDL_CUDA(cudaMemsetAsync(h->fld[CFDL_F_PC], 0, sizeof(double) * (size_t)h->H, h->stream)); // :126 set_a_0
@@ -275,6 +284,9 @@ int cfdl_destroy(cfdl_handle h) {
   comm_destroy(h);
   for (cudaEvent_t e : h->prof_ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->timer_ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->xfer_ev) if (e) cudaEventDestroy(e);
+  if (h->xfer_in) { cudaStreamSynchronize(h->xfer_in); cudaStreamDestroy(h->xfer_in); }
+  if (h->xfer_out) { cudaStreamSynchronize(h->xfer_out); cudaStreamDestroy(h->xfer_out); }
   for (void* p : h->allocs) cudaFree(p);
   if (h->ctl_host) cudaFreeHost(h->ctl_host);
   if (h->scal_host) cudaFreeHost(h->scal_host);
@@ -549,3 +561,139 @@ int cfdl_host_update_uvwp(cfdl_handle h, const double* pc, const double* gpc, co
 }
 
 }  // extern "C"
+
+// ---- one SIMPLE iteration with host arrays, transfers overlapped with the computation -----------
+namespace {
+
+// host <-> device copy of one field in the reference numbering through a staging buffer of its
+// own; `map`/`ncomp`/`n` describe the permutation (device index i <-> host index map[i])
+struct FieldMap { const int32_t* map; int64_t n; int ncomp; };
+FieldMap field_map(const Handle* h, int f) {
+  if (f <= CFDL_F_PC) return {h->cellmap, h->H, 1};
+  if (f <= CFDL_F_GPC) return {h->cellmap, h->H, 3};
+  if (f <= CFDL_F_MIP0) return {h->f2o, h->F, 1};
+  return {h->c2o, h->N, 1};
+}
+
+int ensure_xfer(Handle* h) {
+  if (!h->xfer_in && cudaStreamCreateWithFlags(&h->xfer_in, cudaStreamNonBlocking) != cudaSuccess) return fail(CFDL_ERR_CUDA, "cudaStreamCreate failed");
+  if (!h->xfer_out && cudaStreamCreateWithFlags(&h->xfer_out, cudaStreamNonBlocking) != cudaSuccess) return fail(CFDL_ERR_CUDA, "cudaStreamCreate failed");
+  for (cudaEvent_t& e : h->xfer_ev)
+    if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(CFDL_ERR_CUDA, "cudaEventCreate failed");
+  if (!h->xstage) {  // mip0 | u v w | gu gv gw, each in the host's numbering
+    const Prep& p = h->prep;
+    h->xstage_len = (size_t)p.gF + 12 * ((size_t)p.gN + p.gB) + 16;
+    int rc = dev_zero(h, h->xstage, h->xstage_len);
+    if (rc) return rc;
+  }
+  return CFDL_OK;
+}
+
+struct HostStepHook : StepHook {
+  Handle* h;
+  bool local;
+  const double* late_mip0 = nullptr;  // host source of mip0 when it travels beside the momentum phase
+  double* early[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // host targets of u,v,w,gu,gv,gw
+  // where field f is staged inside xstage (host numbering)
+  double* slot(int f) const {
+    const size_t Hh = (size_t)h->prep.gN + h->prep.gB;
+    if (f == CFDL_F_MIP0) return h->xstage;
+    if (f <= CFDL_F_W) return h->xstage + h->prep.gF + (size_t)(f - CFDL_F_U) * Hh;
+    return h->xstage + h->prep.gF + 3 * Hh + (size_t)(f - CFDL_F_GU) * 3 * Hh;
+  }
+  // device -> host of fields [f0, f1] beside the computation: permute into the staging slots on the
+  // compute stream, then copy out on the download stream once the permutation has finished
+  int send_out(int f0, int f1, int e0, cudaEvent_t ev) {
+    bool any = false;
+    for (int f = f0; f <= f1; ++f) {
+      if (!early[e0 + f - f0]) continue;
+      any = true;
+      if (!local) {
+        const FieldMap m = field_map(h, f);
+        int rc = k_scatter(h, slot(f), h->fld[f], m.map, m.n, m.ncomp);
+        if (rc) return rc;
+      }
+    }
+    if (!any) return CFDL_OK;
+    CFDL_CUDA(cudaEventRecord(ev, h->stream));
+    CFDL_CUDA(cudaStreamWaitEvent(h->xfer_out, ev, 0));
+    for (int f = f0; f <= f1; ++f) {
+      double* dst = early[e0 + f - f0];
+      if (!dst) continue;
+      // partition-local arrays need no permutation: later kernels of the step do not write these fields
+      const double* src = local ? h->fld[f] : slot(f);
+      const size_t n = local ? field_len(h, f) : host_len(h, f);
+      CFDL_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyDeviceToHost, h->xfer_out));
+    }
+    return CFDL_OK;
+  }
+  int at(int stage) override {
+    if (stage == STEP_MOMENTUM_DONE) return send_out(CFDL_F_U, CFDL_F_W, 0, h->xfer_ev[1]);
+    if (stage == STEP_GRAD_DONE) return send_out(CFDL_F_GU, CFDL_F_GW, 3, h->xfer_ev[2]);
+    if (stage == STEP_BEFORE_MIP && late_mip0) {
+      CFDL_CUDA(cudaStreamWaitEvent(h->stream, h->xfer_ev[0], 0));
+      if (!local) return k_gather(h, h->fld[CFDL_F_MIP0], slot(CFDL_F_MIP0), h->f2o, h->F, 1);
+    }
+    return CFDL_OK;
+  }
+};
+
+}  // namespace
+
+extern "C" int cfdl_step_host(cfdl_handle h, double dt, int32_t nit, int32_t apply_bcs, int32_t local_numbering, int32_t n_in,
+                              const int32_t* in_fields, const double* const* in_ptrs, int32_t n_out, const int32_t* out_fields,
+                              double* const* out_ptrs, double* hist) {
+  ENTER(h);
+  if (n_in < 0 || n_out < 0 || (n_in && (!in_fields || !in_ptrs)) || (n_out && (!out_fields || !out_ptrs)))
+    return fail(CFDL_ERR_ARG, "cfdl_step_host: bad field lists");
+  for (int i = 0; i < n_in; ++i)
+    if (in_fields[i] < 0 || in_fields[i] >= CFDL_F_COUNT || !in_ptrs[i]) return fail(CFDL_ERR_ARG, "cfdl_step_host: bad input %d", i);
+  for (int i = 0; i < n_out; ++i)
+    if (out_fields[i] < 0 || out_fields[i] >= CFDL_F_COUNT || !out_ptrs[i]) return fail(CFDL_ERR_ARG, "cfdl_step_host: bad output %d", i);
+  const bool local = local_numbering != 0;
+  if (!local && h->prep.nranks > 1)
+    return fail(CFDL_ERR_UNSUPPORTED, "cfdl_step_host: on a partitioned handle pass partition-local arrays (local_numbering = 1)");
+  int rc;
+  if ((rc = ensure_xfer(h))) return rc;
+  HostStepHook hook;
+  hook.h = h;
+  hook.local = local;
+  // inputs: everything the first kernels read goes first, on the compute stream; mip0 (read by
+  // calc_mip only) follows on the upload stream while the momentum equations are assembled and solved
+  for (int i = 0; i < n_in; ++i) {
+    const int f = in_fields[i];
+    if (f == CFDL_F_MIP0) { hook.late_mip0 = in_ptrs[i]; continue; }
+    if (local) CFDL_CUDA(cudaMemcpyAsync(h->fld[f], in_ptrs[i], sizeof(double) * field_len(h, f), cudaMemcpyHostToDevice, h->stream));
+    else if ((rc = upload_field(h, f, in_ptrs[i]))) return rc;
+  }
+  if (hook.late_mip0) {
+    double* dst = local ? h->fld[CFDL_F_MIP0] : hook.slot(CFDL_F_MIP0);
+    const size_t n = local ? field_len(h, CFDL_F_MIP0) : host_len(h, CFDL_F_MIP0);
+    CFDL_CUDA(cudaMemcpyAsync(dst, hook.late_mip0, sizeof(double) * n, cudaMemcpyHostToDevice, h->xfer_in));
+    CFDL_CUDA(cudaEventRecord(h->xfer_ev[0], h->xfer_in));
+  }
+  // outputs that are final before the pressure-correction solve travel during it
+  bool late_out[CFDL_F_COUNT] = {false};
+  double* late_ptr[CFDL_F_COUNT] = {nullptr};
+  for (int i = 0; i < n_out; ++i) {
+    const int f = out_fields[i];
+    if (f >= CFDL_F_U && f <= CFDL_F_W) hook.early[f - CFDL_F_U] = out_ptrs[i];
+    else if (f >= CFDL_F_GU && f <= CFDL_F_GW) hook.early[3 + f - CFDL_F_GU] = out_ptrs[i];
+    else { late_out[f] = true; late_ptr[f] = out_ptrs[i]; }
+  }
+  if (apply_bcs && (rc = k_update_boundaries(h))) return rc;
+  double st[16];
+  rc = solve_uvwp_impl(h, dt, nit, st, &hook);
+  if (!rc)
+    for (int f = 0; f < CFDL_F_COUNT && !rc; ++f) {
+      if (!late_out[f]) continue;
+      if (local) { if (cudaMemcpyAsync(late_ptr[f], h->fld[f], sizeof(double) * field_len(h, f), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) rc = fail(CFDL_ERR_CUDA, "cfdl_step_host: download failed"); }
+      else rc = download_field(h, f, late_ptr[f]);
+    }
+  // both transfer streams are drained before the call returns, also on failure
+  cudaError_t e1 = cudaStreamSynchronize(h->xfer_in), e2 = cudaStreamSynchronize(h->xfer_out), e3 = cudaStreamSynchronize(h->stream);
+  if (rc) return rc;
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return fail(CFDL_ERR_CUDA, "cfdl_step_host: %s", cudaGetErrorString(cudaGetLastError()));
+  if (hist) std::memcpy(hist, st, sizeof st);
+  return CFDL_OK;
+}

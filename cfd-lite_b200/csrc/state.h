@@ -114,6 +114,12 @@ struct Handle {
   double *fs_n[3] = {nullptr, nullptr, nullptr}, *fs_dr[3] = {nullptr, nullptr, nullptr}, *fs_drp[3] = {nullptr, nullptr, nullptr};
   int use_statics = 1;         // 0: recompute face geometry in every kernel (the reference's way)
   int tune_ctas = 8;           // CTAs per SM for the solver passes (grid = min(need, num_sms * tune_ctas))
+  // cfdl_step_host: transfer streams that run beside the compute stream, and a staging area of
+  // its own (reference-numbered copies of the late input and the early outputs)
+  cudaStream_t xfer_in = nullptr, xfer_out = nullptr;
+  cudaEvent_t xfer_ev[3] = {nullptr, nullptr, nullptr};  // late input landed; u,v,w staged; gu,gv,gw staged
+  double* xstage = nullptr;
+  size_t xstage_len = 0;
   // multi-GPU (one process per GPU): NCCL communicator and interface buffers
   void* comm = nullptr;            // ncclComm_t
   int nnbr = 0;

@@ -350,6 +350,23 @@ class Solver:
         _chk(lib().cfdl_solve_uvwp(self.h, C.c_double(dt), C.c_int32(nit), _d(hist)))
         return hist.reshape(4, 4)
 
+    def step_host(self, ins, outs, dt=0.01, nit=100, apply_bcs=True, local=False):
+        """One SIMPLE iteration with host arrays (cfdl_step_host): ins/outs map field names to float64
+        arrays (page-locked ones let the transfers overlap the computation)."""
+        def pack(d, const):
+            ids = (C.c_int32 * len(d))(*[FIELD_ID[k] for k in d])
+            ptrs = (_dp * len(d))(*[_d(a) for a in d.values()])
+            return ids, ptrs
+        size = self.local_size if local else self.field_size
+        for k, a in list(ins.items()) + list(outs.items()):
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.size == size(k), k
+        iid, iptr = pack(ins, True)
+        oid, optr = pack(outs, False)
+        hist = np.zeros(16)
+        _chk(lib().cfdl_step_host(self.h, C.c_double(dt), C.c_int32(nit), C.c_int32(1 if apply_bcs else 0), C.c_int32(1 if local else 0),
+                                  C.c_int32(len(ins)), iid, iptr, C.c_int32(len(outs)), oid, optr, _d(hist)))
+        return hist.reshape(4, 4)
+
     def run(self, dt=0.01, nit=100, ntstep=10, ncoef=3, want_hist=True):
         hist = np.zeros(ntstep * ncoef * 16) if want_hist else None
         _chk(lib().cfdl_run(self.h, C.c_double(dt), C.c_int32(nit), C.c_int32(ntstep), C.c_int32(ncoef), _d(hist)))

@@ -134,6 +134,22 @@ int cfdl_update_time(cfdl_handle h);
  * hist (ntstep*ncoef*16 doubles) may be NULL. */
 int cfdl_run(cfdl_handle h, double dt, int32_t nit, int32_t ntstep, int32_t ncoef, double* hist);
 
+/* One SIMPLE iteration for a driver whose HOST arrays stay authoritative (the reference's situation:
+ * uvwp_t lives in Fortran-owned memory): [update_boundaries, mod_physics.f90:38-50, when apply_bcs != 0]
+ * + solve_uvwp, mod_uvwp.f90:95-134, with the listed input fields (CFDL_F_* ids) uploaded first and
+ * the listed output fields written back — the same as cfdl_upload_field x n_in, cfdl_update_boundaries,
+ * cfdl_solve_uvwp, cfdl_download_field x n_out, except that transfers run beside the computation
+ * where the iteration allows it: mip0 (first read by calc_mip) travels while the momentum equations
+ * are assembled and solved; u, v, w and gu, gv, gw are final before the pressure-correction solve
+ * (the reference's velocity correction is disabled, mod_uvwp.f90:387-391) and are copied back
+ * during it.  Use page-locked host arrays (cfdl_host_alloc) for the overlap to take place.
+ * local_numbering = 0: host arrays in the reference numbering (single-GPU handles);
+ * local_numbering = 1: partition-local arrays as in cfdl_upload_field_local (any handle).
+ * The call returns when every transfer has completed. */
+int cfdl_step_host(cfdl_handle h, double dt, int32_t nit, int32_t apply_bcs, int32_t local_numbering,
+                   int32_t n_in, const int32_t* in_fields, const double* const* in_ptrs,
+                   int32_t n_out, const int32_t* out_fields, double* const* out_ptrs, double* hist);
+
 /* ---- per-routine path on the handle's device-resident state (one reference routine each) */
 int cfdl_calc_coef_uvw(cfdl_handle h, double dt);                 /* mod_uvwp.f90:161-286 */
 int cfdl_calc_mip(cfdl_handle h, int32_t l_rhie_chow, double dt); /* mod_uvwp.f90:438-490 */

@@ -22,3 +22,18 @@ def test_gpu_suite_passes_under_emulation():
     tail = "\n".join(r.stdout.splitlines()[-25:])
     assert r.returncode == 0, "gpu suite under emulation failed:\n%s\n%s" % (tail, r.stderr[-2000:])
     assert " passed" in tail
+
+
+def test_bench_script_runs_under_emulation():
+    """Plumbing check of bench.py (argument handling, step loop, e2e through cfdl_step_host, JSON line) on a
+    tiny mesh against the cuemu build; the numbers are host-emulation artefacts and are not looked at."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "run_bench_emul.py"), "--size", "8", "--steps", "3", "--warmup", "3"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["e2e"]["path"].startswith("cfdl_step_host") and line["e2e"]["path_error"] is None
+    assert line["gpu_launches"] > 0 and line["cpu_baseline"]["kind"] == "port"

@@ -336,3 +336,41 @@ def test_overlapped_passes_equal_serialised_passes(cfdl):
         assert np.array_equal(hist[:, :, 0], out[0][0][:, :, 0])
         for f in fields:
             assert np.array_equal(fields[f], out[0][1][f]), f
+
+
+@pytest.mark.parametrize("solver", ["parity", "mcsgs"])
+def test_step_host_equals_separate_calls(case, cfdl, solver):
+    """cfdl_step_host (uploads, update_boundaries, solve_uvwp, downloads in one call, transfers beside
+    the computation) against the same sequence of separate C-ABI calls: identical bits."""
+    _, raw, oc, geom, s = case
+    ins = "u v w p u0 v0 w0 gu gv gw gp mip mip0".split()
+    outs = "u v w p gu gv gw gp gpc mip".split()
+    rng = np.random.default_rng(23)
+    state = {k: rng.standard_normal(s.field_size(k)) * (0.01 if k.startswith("mip") else 0.1) for k in ins}
+    s.set_option("solver", cfdl.SOLVER_PARITY if solver == "parity" else cfdl.SOLVER_MCSGS)
+    try:
+        for k in ins:
+            s.upload(k, state[k])
+        s.update_boundaries()
+        want_hist = s.solve_uvwp(0.01, 20)
+        want = {k: s.download(k) for k in outs}
+        # scramble the device state so that the second path must really transfer everything
+        for k in ins:
+            s.upload(k, np.full(s.field_size(k), 3.25))
+        bufs_in = {k: cfdl.PinnedBuffer(s.field_size(k)) for k in ins}
+        bufs_out = {k: cfdl.PinnedBuffer(s.field_size(k)) for k in outs}
+        for k in ins:
+            bufs_in[k].array[:] = state[k]
+        got_hist = s.step_host({k: bufs_in[k].array for k in ins}, {k: bufs_out[k].array for k in outs}, dt=0.01, nit=20)
+        assert np.array_equal(got_hist, want_hist)
+        for k in outs:
+            assert np.array_equal(bufs_out[k].array, want[k]), k
+        # a second call on the same handle reuses the transfer streams and staging area
+        got_hist2 = s.step_host({k: bufs_in[k].array for k in ins}, {k: bufs_out[k].array for k in outs}, dt=0.01, nit=20)
+        assert np.array_equal(got_hist2, want_hist)
+        for k in outs:
+            assert np.array_equal(bufs_out[k].array, want[k]), k
+        for b in list(bufs_in.values()) + list(bufs_out.values()):
+            b.free()
+    finally:
+        s.set_option("solver", cfdl.SOLVER_PARITY)
