@@ -1,6 +1,7 @@
 // C ABI of libcfdl (include/cfdl.h): lifecycle, host<->device field sync, the whole-step path
 // (update_boundaries / solve_uvwp / update_time, src/main.f90:50-63) and the per-routine path.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "state.h"
@@ -233,8 +234,8 @@ int create_from_prep(cfdl_handle_s* h, const GeomSource& G, cfdl_handle* out) {
     return bail(fail(CFDL_ERR_CUDA, "cudaMallocHost failed"));
   if ((rc = solver_init(h))) return bail(rc);
   {  // static face geometry, evaluated once with the reference's own expressions (kernels_statics.cu)
-    double** arrs[15] = {&h->fs_area, &h->fs_ds, &h->fs_dsp, &h->fs_dn, &h->fs_wto, &h->fs_wtn, &h->fs_n[0], &h->fs_n[1], &h->fs_n[2],
-                         &h->fs_dr[0], &h->fs_dr[1], &h->fs_dr[2], &h->fs_drp[0], &h->fs_drp[1], &h->fs_drp[2]};
+    double** arrs[17] = {&h->fs_area, &h->fs_ds, &h->fs_dsp, &h->fs_dn, &h->fs_wto, &h->fs_wtn, &h->fs_n[0], &h->fs_n[1], &h->fs_n[2],
+                         &h->fs_dr[0], &h->fs_dr[1], &h->fs_dr[2], &h->fs_drp[0], &h->fs_drp[1], &h->fs_drp[2], &h->fs_rds, &h->fs_rdsp};
     for (double** a : arrs)
       if ((rc = dev_zero(h, *a, (size_t)p.Fi + 4))) return bail(rc);
     if ((rc = k_face_statics(h))) return bail(rc);
@@ -311,7 +312,12 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "occ_grids")) { h->occ_grids = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "pdl_rows")) { h->pdl_rows = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "pdl")) { h->use_pdl = value != 0.0; return CFDL_OK; }
-  if (!std::strcmp(key, "uvw_variant")) { h->uvw_variant = (int)value; return CFDL_OK; }
+  if (!std::strcmp(key, "uvw_variant")) { h->uvw_variant = (int)value; h->tune_uvw.done = 1; return CFDL_OK; }  // pinned by hand
+  if (!std::strcmp(key, "autotune")) {
+    h->autotune = value != 0.0;
+    if (value == 2.0) { h->tune_uvw = Handle::Tuned(); h->tune_grad3 = Handle::Tuned(); h->tune_grad1 = Handle::Tuned(); h->tune_coef_p = Handle::Tuned(); h->tune_mip = Handle::Tuned(); }
+    return CFDL_OK;
+  }
   if (!std::strcmp(key, "statics")) { h->use_statics = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "ctas_per_sm")) { h->tune_ctas = std::max(1, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "profile")) {
@@ -338,6 +344,26 @@ int cfdl_get_info(cfdl_handle h, const char* key, double* value) {
   else if (!std::strcmp(key, "num_sms")) *value = h->num_sms;
   else if (!std::strcmp(key, "solver")) *value = h->solver_mode;
   else if (!std::strcmp(key, "launches")) *value = (double)h->launches;
+  else if (!std::strcmp(key, "uvw_variant")) *value = h->uvw_variant;
+  else if (!std::strncmp(key, "tuned_", 6)) {
+    // "tuned_<routine>" = chosen variant (-1: not tuned); "tuned_<routine>_ms<i>" / "_cand<i>" = the measurements
+    const Handle::Tuned* T = nullptr;
+    const char* r = key + 6;
+    size_t len = 0;
+    static const char* names[5] = {"uvw", "grad3", "grad1", "coef_p", "mip"};
+    const Handle::Tuned* all[5] = {&h->tune_uvw, &h->tune_grad3, &h->tune_grad1, &h->tune_coef_p, &h->tune_mip};
+    for (int i = 0; i < 5; ++i) {
+      const size_t l = std::strlen(names[i]);
+      if (!std::strncmp(r, names[i], l) && (r[l] == 0 || r[l] == '_') && l > len) { T = all[i]; len = l; }
+    }
+    if (!T) return fail(CFDL_ERR_ARG, "cfdl_get_info: unknown key '%s'", key);
+    r += len;
+    if (*r == 0) *value = T->ncand ? T->choice : -1;
+    else if (!std::strncmp(r, "_ms", 3)) { const int i = std::atoi(r + 3); *value = (i >= 0 && i < T->ncand) ? T->ms[i] : -1; }
+    else if (!std::strncmp(r, "_cand", 5)) { const int i = std::atoi(r + 5); *value = (i >= 0 && i < T->ncand) ? T->cand[i] : -1; }
+    else if (!std::strcmp(r, "_n")) *value = T->ncand;
+    else return fail(CFDL_ERR_ARG, "cfdl_get_info: unknown key '%s'", key);
+  }
   else if (!std::strcmp(key, "owned_cells")) *value = h->N;
   else if (!std::strcmp(key, "ghost_cells")) *value = h->G;
   else if (!std::strcmp(key, "local_halos")) *value = h->B;

@@ -8,6 +8,7 @@
 // owner's orientation; seen from the other cell every vector is the exact negation and every
 // scalar identical (IEEE negation is exact), so the kernels below produce the same bits as the
 // recomputing kernels in kernels_assembly.cu — the tests check that with array_equal.
+#include <algorithm>
 #include "state.h"
 #include "device_math.cuh"
 
@@ -17,12 +18,14 @@ namespace cfdl {
 
 struct FaceStatics {
   const double *area, *ds, *dsp, *dn, *wto, *wtn;
+  const double *rds, *rdsp;  // RN(1/ds), RN(1/dsp): the reciprocals quot<true> needs (uvw_variant 5, 6)
   const double *n[3], *dr[3], *drp[3];
 };
 
 static FaceStatics statics_of(const Handle* h) {
   FaceStatics S;
   S.area = h->fs_area; S.ds = h->fs_ds; S.dsp = h->fs_dsp; S.dn = h->fs_dn; S.wto = h->fs_wto; S.wtn = h->fs_wtn;
+  S.rds = h->fs_rds; S.rdsp = h->fs_rdsp;
   for (int i = 0; i < 3; ++i) { S.n[i] = h->fs_n[i]; S.dr[i] = h->fs_dr[i]; S.drp[i] = h->fs_drp[i]; }
   return S;
 }
@@ -32,7 +35,8 @@ __global__ void __launch_bounds__(TPB) face_statics_kernel(int Fi, const int32_t
                                                            const double* __restrict__ zc, const double* __restrict__ aip,
                                                            const double* __restrict__ rip_, double* area_o, double* ds_o, double* dsp_o,
                                                            double* dn_o, double* wto_o, double* wtn_o, double* n0, double* n1, double* n2,
-                                                           double* d0, double* d1, double* d2, double* p0, double* p1, double* p2) {
+                                                           double* d0, double* d1, double* d2, double* p0, double* p1, double* p2,
+                                                           double* rds_o, double* rdsp_o) {
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < Fi; f += gridDim.x * blockDim.x) {
     const int e = face_a[f], nb = face_b[f];
     const double rp[3] = {xc[e], yc[e], zc[e]};
@@ -50,7 +54,9 @@ __global__ void __launch_bounds__(TPB) face_statics_kernel(int Fi, const int32_t
     t = dot3(drip, norm);
     const double rpnb_p[3] = {rip[0] - t * norm[0], rip[1] - t * norm[1], rip[2] - t * norm[2]};
     const double dr_p[3] = {rpnb_p[0] - rp_p[0], rpnb_p[1] - rp_p[1], rpnb_p[2] - rp_p[2]};
-    area_o[f] = area; ds_o[f] = ds; dsp_o[f] = sqrt(dot3(dr_p, dr_p)); dn_o[f] = dot3(dr, norm);
+    const double dsp = sqrt(dot3(dr_p, dr_p));
+    area_o[f] = area; ds_o[f] = ds; dsp_o[f] = dsp; dn_o[f] = dot3(dr, norm);
+    rds_o[f] = 1.0 / ds; rdsp_o[f] = 1.0 / dsp;
     wto_o[f] = vec_weight(rip, rp, rpnb);   // weight seen from the owner
     wtn_o[f] = vec_weight(rip, rpnb, rp);   // weight seen from the neighbour
     n0[f] = norm[0]; n1[f] = norm[1]; n2[f] = norm[2];
@@ -64,14 +70,14 @@ int k_face_statics(Handle* h) {
   face_statics_kernel<<<grid_for(h, h->Fi, TPB), TPB, 0, S(h)>>>(h->Fi, h->face_a, h->face_b, h->xc, h->yc, h->zc, h->aip, h->rip, h->fs_area,
                                                                  h->fs_ds, h->fs_dsp, h->fs_dn, h->fs_wto, h->fs_wtn, h->fs_n[0], h->fs_n[1],
                                                                  h->fs_n[2], h->fs_dr[0], h->fs_dr[1], h->fs_dr[2], h->fs_drp[0], h->fs_drp[1],
-                                                                 h->fs_drp[2]);
+                                                                 h->fs_drp[2], h->fs_rds, h->fs_rdsp);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
 
 // ---- calc_coef_uvw on statics (mod_uvwp.f90:161-286) ------------------------------------------
 struct UvwArgsS {
-  int N, Nc, Np;
+  int N, Nc, Np, ncol0;  // ncol0: cells of the first colour (paired order)
   const int32_t *ell_nb, *ell_fs, *halo_bc, *bc_kind;
   const uint8_t* nfc;
   const double *xc, *yc, *zc, *aip, *vol, *rho, *mu;
@@ -84,25 +90,32 @@ struct UvwArgsS {
 // FASTDIV (uvw_variant=3): the ten quotients per face share two divisors (|dr| and |dr_p|); their
 // reciprocals are taken once and every quotient is formed with quot<true> — same bits, ~35 % fewer
 // instructions in a kernel that ncu shows issue-bound at 25 % occupancy.
-template <int K, bool FASTDIV>
-__device__ __forceinline__ void coef_uvw_statics_body(const UvwArgsS& A) {
-  const int N = A.N, Nc = A.Nc, Np = A.Np;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
+// DIV: 0 = plain divisions; 1 = quot<true> with the two reciprocals taken in the kernel; 2 = quot<true>
+// with the reciprocals read from the statics (two divisions per face side less, 16 bytes more)
+// LEAN: the K coefficients and neighbour ids are not held in registers across the cell — anb is stored
+// slot by slot and read back (this thread's own stores: L1) for dc, boundary slots are remembered in a
+// bit mask and their ids re-read; fewer live registers for the face loop.
+template <int K, int DIV, bool LEAN = false>
+__device__ __forceinline__ void coef_uvw_statics_cell(const UvwArgsS& A, const int c) {
+  constexpr bool FASTDIV = DIV != 0;
+  const int Nc = A.Nc, Np = A.Np;
+  {
     const int n = A.nfc[c];
     const double mu_e = A.mu[c];
     double gue[3], gve[3], gwe[3];
     load3(A.gu, c, gue); load3(A.gv, c, gve); load3(A.gw, c, gwe);
     double ap = 0.0, sumf = 0.0, sumss[3] = {0, 0, 0}, sumdefc[3] = {0, 0, 0};
-    double anbk[K];
-    int nbk[K];
+    double anbk[LEAN ? 1 : K];
+    int nbk[LEAN ? 1 : K];
+    unsigned bmask = 0;  // LEAN: slots whose neighbour is a boundary halo
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      anbk[k] = 0.0;
-      nbk[k] = -1;
+      if (!LEAN) { anbk[k] = 0.0; nbk[k] = -1; }
       if (k < n) {
         const int nb = A.ell_nb[(size_t)k * Np + c];
         const int fs = A.ell_fs[(size_t)k * Np + c];
-        nbk[k] = nb;
+        if (LEAN) { if (nb >= Nc) bmask |= 1u << k; }
+        else nbk[k] = nb;
         double d = 0.0, fnb = 0.0;
         if (nb < Nc) {
           const int f = abs(fs) - 1;
@@ -116,7 +129,7 @@ __device__ __forceinline__ void coef_uvw_statics_body(const UvwArgsS& A) {
           fnb = fmax(f_in, 0.0);
           sumf = sumf + f_in;
           const double muip = (1.0 - wt) * mu_e + wt * A.mu[nb];
-          const double rds = FASTDIV ? 1.0 / ds : 0.0, rdsp = FASTDIV ? 1.0 / ds_p : 0.0;
+          const double rds = DIV == 2 ? A.S.rds[f] : (DIV == 1 ? 1.0 / ds : 0.0), rdsp = DIV == 2 ? A.S.rdsp[f] : (DIV == 1 ? 1.0 / ds_p : 0.0);
           d = quot<FASTDIV>(muip * area, ds, rds);
           double gun[3], gvn[3], gwn[3];
           load3(A.gu, nb, gun); load3(A.gv, nb, gvn); load3(A.gw, nb, gwn);
@@ -135,7 +148,8 @@ __device__ __forceinline__ void coef_uvw_statics_body(const UvwArgsS& A) {
             sumdefc[2] = sumdefc[2] + muip * area * (quot<FASTDIV>(dot3(gip, dr_p), ds_p, rdsp) - quot<FASTDIV>(dot3(gip, dr), ds, rds));
           }
         }
-        anbk[k] = d + fnb;
+        if (LEAN) A.anb[(size_t)k * Np + c] = d + fnb;
+        else anbk[k] = d + fnb;
         ap = ap + d + fnb;
       }
     }
@@ -149,9 +163,18 @@ __device__ __forceinline__ void coef_uvw_statics_body(const UvwArgsS& A) {
     int last = -1;  // boundary faces in halo order (rare: geometry evaluated on the fly as in the reference)
     for (int t = 0; t < K; ++t) {
       int best = 0x7fffffff, bk = -1;
+      if (LEAN) {
+        if (!bmask) break;
+        for (int k = 0; k < K; ++k) {
+          if (!(bmask >> k & 1u)) continue;
+          const int nb = A.ell_nb[(size_t)k * Np + c];
+          if (nb > last && nb < best) { best = nb; bk = k; }
+        }
+      } else {
 #pragma unroll
-      for (int k = 0; k < K; ++k)
-        if (nbk[k] >= Nc && nbk[k] > last && nbk[k] < best) { best = nbk[k]; bk = k; }
+        for (int k = 0; k < K; ++k)
+          if (nbk[k] >= Nc && nbk[k] > last && nbk[k] < best) { best = nbk[k]; bk = k; }
+      }
       if (bk < 0) break;
       last = best;
       const int bc = A.halo_bc[best - Nc];
@@ -175,14 +198,24 @@ __device__ __forceinline__ void coef_uvw_statics_body(const UvwArgsS& A) {
         bw = bw + d * vrel[2] - d * we;
       }
       ap = ap + d;
+      if (LEAN) {
+        A.anb[(size_t)bk * Np + c] = 0.0 + d;  // the face loop stored d + fnb = 0 for a boundary slot
+      } else {
 #pragma unroll
-      for (int k = 0; k < K; ++k)
-        if (k == bk) anbk[k] = anbk[k] + d;
+        for (int k = 0; k < K; ++k)
+          if (k == bk) anbk[k] = anbk[k] + d;
+      }
     }
     double dcv = ap;
+    if (LEAN) {
 #pragma unroll
-    for (int k = 0; k < K; ++k)
-      if (k < n) { dcv = dcv - anbk[k]; A.anb[(size_t)k * Np + c] = anbk[k]; }
+      for (int k = 0; k < K; ++k)
+        if (k < n) dcv = dcv - A.anb[(size_t)k * Np + c];
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        if (k < n) { dcv = dcv - anbk[k]; A.anb[(size_t)k * Np + c] = anbk[k]; }
+    }
     A.ap[c] = ap;
     A.bu[c] = bu; A.bv[c] = bv; A.bw[c] = bw;
     A.d[c] = vol / ap;
@@ -190,11 +223,55 @@ __device__ __forceinline__ void coef_uvw_statics_body(const UvwArgsS& A) {
   }
 }
 
-template <int K, bool FASTDIV>
-__global__ void __launch_bounds__(TPB) coef_uvw_statics_kernel(const UvwArgsS A) { coef_uvw_statics_body<K, FASTDIV>(A); }
+template <int K, int DIV>
+__device__ __forceinline__ void coef_uvw_statics_body(const UvwArgsS& A) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.N; c += gridDim.x * blockDim.x) coef_uvw_statics_cell<K, DIV>(A, c);
+}
+// Two-colour meshes, colour-major numbering: a CTA takes TPB cells of the first colour and then the
+// TPB cells at the same position of the second colour.  On meshes numbered with some locality these
+// are each other's neighbours, so the statics of their common faces — which the linear order reads a
+// second time half a kernel later, from DRAM — are still in L1/L2.  Same cells, same per-cell code.
+template <int K, int DIV, bool LEAN>
+__device__ __forceinline__ void coef_uvw_statics_body_paired(const UvwArgsS& A) {
+  const int n0 = A.ncol0, n1 = A.N - A.ncol0;
+  const int nq = (max(n0, n1) + (int)blockDim.x - 1) / (int)blockDim.x;
+  for (int q = blockIdx.x; q < nq; q += gridDim.x) {
+    const int i = q * blockDim.x + threadIdx.x;
+#pragma unroll 1
+    for (int col = 0; col < 2; ++col)
+      if (i < (col ? n1 : n0)) coef_uvw_statics_cell<K, DIV, LEAN>(A, col ? n0 + i : i);
+  }
+}
+
+template <int K, int DIV>
+__global__ void __launch_bounds__(TPB) coef_uvw_statics_kernel(const UvwArgsS A) { coef_uvw_statics_body<K, DIV>(A); }
 // uvw_variant=4: FASTDIV with three resident CTAs per SM requested (80 registers, some spills): occupancy experiment
 template <int K>
-__global__ void __launch_bounds__(TPB, 3) coef_uvw_statics_occ3_kernel(const UvwArgsS A) { coef_uvw_statics_body<K, true>(A); }
+__global__ void __launch_bounds__(TPB, 3) coef_uvw_statics_occ3_kernel(const UvwArgsS A) { coef_uvw_statics_body<K, 1>(A); }
+template <int K, int DIV>
+__global__ void __launch_bounds__(TPB) coef_uvw_statics_paired_kernel(const UvwArgsS A) { coef_uvw_statics_body_paired<K, DIV, false>(A); }
+// uvw_variant 9/10: stored reciprocals, lean register use (linear / paired order); 11: 9 with three CTAs per SM requested
+template <int K>
+__global__ void __launch_bounds__(TPB) coef_uvw_statics_lean_kernel(const UvwArgsS A) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.N; c += gridDim.x * blockDim.x) coef_uvw_statics_cell<K, 2, true>(A, c);
+}
+template <int K>
+__global__ void __launch_bounds__(TPB) coef_uvw_statics_lean_paired_kernel(const UvwArgsS A) { coef_uvw_statics_body_paired<K, 2, true>(A); }
+template <int K>
+__global__ void __launch_bounds__(TPB, 3) coef_uvw_statics_lean_occ3_kernel(const UvwArgsS A) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.N; c += gridDim.x * blockDim.x) coef_uvw_statics_cell<K, 2, true>(A, c);
+}
+template <int K>
+__global__ void __launch_bounds__(TPB, 4) coef_uvw_statics_lean_occ4_kernel(const UvwArgsS A) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.N; c += gridDim.x * blockDim.x) coef_uvw_statics_cell<K, 2, true>(A, c);
+}
+
+// tets (K = 4) and hexes/prisms/pyramids (K = 6) get their own instantiation of every variant
+template <auto K4, auto K6>
+static void launch_uvw(Handle* h, const UvwArgsS& A, int cells) {
+  if (h->K <= 4) K4<<<occ_grid<K4>(h, cells, TPB), TPB, 0, S(h)>>>(A);
+  else K6<<<occ_grid<K6>(h, cells, TPB), TPB, 0, S(h)>>>(A);
+}
 
 int k_calc_coef_uvw_statics(Handle* h, double dt) {
   UvwArgsS A;
@@ -209,15 +286,22 @@ int k_calc_coef_uvw_statics(Handle* h, double dt) {
   A.bw = h->fld[CFDL_F_BW]; A.d = h->fld[CFDL_F_D]; A.dc = h->fld[CFDL_F_DC];
   A.dt = dt;
   A.S = statics_of(h);
-  if (h->uvw_variant == 4) {
-    if (h->K <= 4) coef_uvw_statics_occ3_kernel<4><<<occ_grid<coef_uvw_statics_occ3_kernel<4>>(h, h->N, TPB), TPB, 0, S(h)>>>(A);
-    else coef_uvw_statics_occ3_kernel<6><<<occ_grid<coef_uvw_statics_occ3_kernel<6>>(h, h->N, TPB), TPB, 0, S(h)>>>(A);
-  } else if (h->uvw_variant == 3) {
-    if (h->K <= 4) coef_uvw_statics_kernel<4, true><<<occ_grid<coef_uvw_statics_kernel<4, true>>(h, h->N, TPB), TPB, 0, S(h)>>>(A);
-    else coef_uvw_statics_kernel<6, true><<<occ_grid<coef_uvw_statics_kernel<6, true>>(h, h->N, TPB), TPB, 0, S(h)>>>(A);
-  } else {
-    if (h->K <= 4) coef_uvw_statics_kernel<4, false><<<occ_grid<coef_uvw_statics_kernel<4, false>>(h, h->N, TPB), TPB, 0, S(h)>>>(A);
-    else coef_uvw_statics_kernel<6, false><<<occ_grid<coef_uvw_statics_kernel<6, false>>(h, h->N, TPB), TPB, 0, S(h)>>>(A);
+  A.ncol0 = h->prep.ncolors == 2 ? h->prep.color_ptr[1] : h->N;
+  const int paired_cells = std::max(A.ncol0, h->N - A.ncol0);  // a CTA of the paired order covers TPB cells of each colour
+  int v = h->uvw_variant;
+  if (h->prep.ncolors != 2) v = (v == 6) ? 5 : (v == 7 ? 3 : (v == 8 ? 2 : (v == 10 ? 9 : v)));  // the paired order needs two colours
+  switch (v) {
+    case 3: launch_uvw<coef_uvw_statics_kernel<4, 1>, coef_uvw_statics_kernel<6, 1>>(h, A, h->N); break;
+    case 4: launch_uvw<coef_uvw_statics_occ3_kernel<4>, coef_uvw_statics_occ3_kernel<6>>(h, A, h->N); break;
+    case 5: launch_uvw<coef_uvw_statics_kernel<4, 2>, coef_uvw_statics_kernel<6, 2>>(h, A, h->N); break;
+    case 6: launch_uvw<coef_uvw_statics_paired_kernel<4, 2>, coef_uvw_statics_paired_kernel<6, 2>>(h, A, paired_cells); break;
+    case 7: launch_uvw<coef_uvw_statics_paired_kernel<4, 1>, coef_uvw_statics_paired_kernel<6, 1>>(h, A, paired_cells); break;
+    case 8: launch_uvw<coef_uvw_statics_paired_kernel<4, 0>, coef_uvw_statics_paired_kernel<6, 0>>(h, A, paired_cells); break;
+    case 9: launch_uvw<coef_uvw_statics_lean_kernel<4>, coef_uvw_statics_lean_kernel<6>>(h, A, h->N); break;
+    case 10: launch_uvw<coef_uvw_statics_lean_paired_kernel<4>, coef_uvw_statics_lean_paired_kernel<6>>(h, A, paired_cells); break;
+    case 11: launch_uvw<coef_uvw_statics_lean_occ3_kernel<4>, coef_uvw_statics_lean_occ3_kernel<6>>(h, A, h->N); break;
+    case 12: launch_uvw<coef_uvw_statics_lean_occ4_kernel<4>, coef_uvw_statics_lean_occ4_kernel<6>>(h, A, h->N); break;
+    default: launch_uvw<coef_uvw_statics_kernel<4, 0>, coef_uvw_statics_kernel<6, 0>>(h, A, h->N); break;
   }
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;

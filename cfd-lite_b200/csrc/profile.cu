@@ -42,6 +42,37 @@ int prof_collect(Handle* h) {
   return CFDL_OK;
 }
 
+int autotune_pick(Handle* h, Handle::Tuned& T, const int* cands, int n, const std::function<int(int)>& run, int reps) {
+  T.done = 1;
+  T.ncand = 0;
+  T.choice = cands[0];
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+    if (e0) cudaEventDestroy(e0);
+    cudaGetLastError();
+    return CFDL_OK;  // no timing possible: keep the first candidate
+  }
+  float best = 0.f;
+  bool have = false;
+  for (int i = 0; i < n && T.ncand < 12; ++i) {
+    const int c = cands[i];
+    float ms = -1.f;
+    bool ok = run(c) == CFDL_OK && cudaStreamSynchronize(h->stream) == cudaSuccess;  // warm-up (and a check that it launches)
+    if (ok) ok = cudaEventRecord(e0, h->stream) == cudaSuccess;
+    for (int r = 0; ok && r < reps; ++r) ok = run(c) == CFDL_OK;
+    if (ok) ok = cudaEventRecord(e1, h->stream) == cudaSuccess && cudaEventSynchronize(e1) == cudaSuccess &&
+                 cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); ms = -1.f; }
+    T.cand[T.ncand] = c;
+    T.ms[T.ncand] = ok ? ms / reps : -1.f;
+    T.ncand++;
+    if (ok && (!have || ms < best)) { best = ms; have = true; T.choice = c; }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return CFDL_OK;
+}
+
 }  // namespace cfdl
 
 using namespace cfdl;

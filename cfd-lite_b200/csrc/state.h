@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <functional>
 #include <vector>
 #include "cfdl_common.h"
 #include "prep.h"
@@ -111,8 +112,15 @@ struct Handle {
   // evaluates every iteration (area, unit normal, |dr|, projected |dr_p|, dr.n, both distance
   // weights, dr, dr_p): the assembly kernels then need 10 instead of 19 FP64 div/sqrt per face
   double *fs_area = nullptr, *fs_ds = nullptr, *fs_dsp = nullptr, *fs_dn = nullptr, *fs_wto = nullptr, *fs_wtn = nullptr;
+  double *fs_rds = nullptr, *fs_rdsp = nullptr;  // RN(1/ds), RN(1/dsp)
   double *fs_n[3] = {nullptr, nullptr, nullptr}, *fs_dr[3] = {nullptr, nullptr, nullptr}, *fs_drp[3] = {nullptr, nullptr, nullptr};
   int use_statics = 1;         // 0: recompute face geometry in every kernel (the reference's way)
+  // Variant selection by measurement: the first call of a routine times its bit-identical kernel
+  // variants on the handle's own data (CUDA events, a few launches each) and keeps the fastest.
+  // Setting a *_variant option by hand pins that routine.  autotune = 0 keeps the defaults.
+  int autotune = 1;
+  struct Tuned { int done = 0, choice = -1, ncand = 0, cand[12] = {0}; float ms[12] = {0}; };
+  Tuned tune_uvw, tune_grad3, tune_grad1, tune_coef_p, tune_mip;
   int tune_ctas = 8;           // CTAs per SM for the solver passes (grid = min(need, num_sms * tune_ctas))
   // cfdl_step_host: transfer streams that run beside the compute stream, and a staging area of
   // its own (reference-numbered copies of the late input and the early outputs)
@@ -147,6 +155,9 @@ enum { PROF_SGS_SWEEP = 0, PROF_RESIDUAL = 1, PROF_COEF_UVW = 2, PROF_COEF_P = 3
 int prof_begin(Handle* h, int kind, int level = 1);
 int prof_end(Handle* h, int count = 1, int level = 1);
 int prof_collect(Handle* h);  // after a stream sync: fold finished event pairs into prof_ms / prof_n
+// times run(cand) for every candidate (one warm-up launch, then `reps` timed ones between two events on
+// the handle's stream) and records the fastest in T; a candidate whose launch fails is skipped
+int autotune_pick(Handle* h, Handle::Tuned& T, const int* cands, int n, const std::function<int(int)>& run, int reps = 3);
 
 // launch geometry helper: grids are sized as a multiple of the SM count (B200: 148)
 inline int grid_for(const Handle* h, int64_t n, int threads, int ctas_per_sm = 8) {

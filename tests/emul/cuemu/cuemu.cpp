@@ -346,7 +346,17 @@ cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cu
 cudaError_t cudaEventDestroy(cudaEvent_t e) { std::free(e); return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 1e-3f; return cudaSuccess; }
+// CUEMU_RANDOM_TIMES=<seed>: event intervals become pseudo-random, so that code which chooses between
+// (bit-identical) kernel variants by timing them takes a different choice in every run of the tests
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) {
+  static const char* e = std::getenv("CUEMU_RANDOM_TIMES");
+  static std::atomic<unsigned long long> state{e ? std::strtoull(e, nullptr, 10) * 2654435761ull + 12345ull : 0ull};
+  if (!e) { *ms = 1e-3f; return cudaSuccess; }
+  unsigned long long x = state.fetch_add(0x9E3779B97F4A7C15ull) + 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; x ^= x >> 31;
+  *ms = 0.5f + (float)(x >> 40) / (float)(1 << 24);
+  return cudaSuccess;
+}
 // "ranks" of an emulated multi-GPU run are threads of one process: the handle is the pointer
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { std::memset(h, 0, sizeof *h); std::memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
 cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }

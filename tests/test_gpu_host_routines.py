@@ -3,8 +3,9 @@ _adjust_pc, _update_uvwp): the flattened form of the reference's derived-type si
 (SURVEY §8b).  Each is upload -> the routine tested in test_gpu_parity.py -> download, so the
 results must again equal the oracle's bit for bit.
 
-These entry points were added after the round's GPU budget was spent: the expectation is
-recorded as non-strict xfail until a GPU run has confirmed it (an XPASS is the confirmation)."""
+These entry points were added after the round's GPU budget was spent: they pass on the host
+emulation of the CUDA sources (tests/emul, `pytest -m gpu --emul`); on the GPU the expectation is
+recorded as non-strict xfail until a run has confirmed it (an XPASS is the confirmation)."""
 import numpy as np
 import pytest
 
@@ -58,14 +59,15 @@ def test_host_assembly_chain(case):
 
 
 def test_coef_uvw_reciprocal_variants_keep_the_bits(case):
-    """uvw_variant 3 (quotients from two reciprocals + FMA corrections) and 4 (the same with three
-    resident CTAs per SM) against the oracle: same bits as the dividing kernel."""
+    """uvw_variant 3 (quotients from two reciprocals + FMA corrections), 4 (the same with three resident
+    CTAs per SM), 5 (reciprocals read from the face statics) 6/7/8 (5/3/2 in the paired colour order) and 9/10/11/12 (lean register use)
+    against the oracle: same bits as the dividing kernel."""
     oc, s = case
     for name in STATE:
         s.upload(name, oc[name])
     oc.calc_coef_uvw()
     try:
-        for variant in (3, 4):
+        for variant in (3, 4, 5, 6, 7, 8, 9, 10, 11, 12):
             s.set_option("uvw_variant", variant)
             s.calc_coef_uvw(dt=0.01)
             for f in ("ap", "anb", "bu", "bv", "bw", "d", "dc"):
