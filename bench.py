@@ -276,6 +276,16 @@ def main():
         step(i)
         dbg("warmup step", i)
     hist_last = None
+    # kernel variants chosen by measurement during the first warm-up step (bit-identical candidates)
+    tuned = {}
+    for r in ("uvw", "grad3", "grad1", "coef_p"):
+        try:
+            n_c = int(s.get_info("tuned_%s_n" % r))
+            if n_c > 0:
+                tuned[r] = {"chosen": int(s.get_info("tuned_" + r)),
+                            "ms": {str(int(s.get_info("tuned_%s_cand%d" % (r, i)))): round(s.get_info("tuned_%s_ms%d" % (r, i)), 4) for i in range(n_c)}}
+        except cfdl.CfdlError as ex:
+            dbg("tuning info unavailable:", ex)
     barrier()
     s.set_option("reset_counters", 1)
     s.timer_record(0)
@@ -467,7 +477,7 @@ def main():
         line = {"metric": "cell-iterations/s (SIMPLE)", "value": value, "unit": "cell-iterations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args.mesh, n_global, ne), "solver": args.solver, "ncolors": ncol, "options": args.opt, "mesh_source": "structured per-rank generator" if structured else "reference-format arrays", "fused_two_colour_passes": bool(fused), "programmatic_dependent_launch": bool(fused and not args.no_pdl),
+                "config": {"workload": workload_name(args.mesh, n_global, ne), "solver": args.solver, "ncolors": ncol, "options": args.opt, "mesh_source": "structured per-rank generator" if structured else "reference-format arrays", "fused_two_colour_passes": bool(fused), "kernel_variants_chosen_by_timing": tuned, "programmatic_dependent_launch": bool(fused and not args.no_pdl),
                            "cells_per_gpu": ne // world, "setup_seconds": round(setup_s, 1), "l2": "working set (>1 GB per GPU) exceeds the 126 MB L2; no flush needed" if ne // world > 1000000 else
                            "working set may fit L2",
                            "parallelism": "1 GPU" if world == 1 else

@@ -313,6 +313,8 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "pdl_rows")) { h->pdl_rows = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "pdl")) { h->use_pdl = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "uvw_variant")) { h->uvw_variant = (int)value; h->tune_uvw.done = 1; return CFDL_OK; }  // pinned by hand
+  if (!std::strcmp(key, "grad_variant")) { h->grad_variant = (int)value; return CFDL_OK; }
+  if (!std::strcmp(key, "coef_p_variant")) { h->coef_p_variant = (int)value; return CFDL_OK; }
   if (!std::strcmp(key, "autotune")) {
     h->autotune = value != 0.0;
     if (value == 2.0) { h->tune_uvw = Handle::Tuned(); h->tune_grad3 = Handle::Tuned(); h->tune_grad1 = Handle::Tuned(); h->tune_coef_p = Handle::Tuned(); h->tune_mip = Handle::Tuned(); }

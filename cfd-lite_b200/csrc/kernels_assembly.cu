@@ -615,28 +615,173 @@ __global__ void __launch_bounds__(TPB) grad_kernel(int N, int Np, const int32_t*
   }
 }
 
-int k_calc_grad(Handle* h, const double* phi, double* grad) {
-  const int g = (h->K <= 4) ? occ_grid<grad_kernel<4, 1>>(h, h->N, TPB) : occ_grid<grad_kernel<6, 1>>(h, h->N, TPB);
-  if (h->K <= 4) grad_kernel<4, 1><<<g, TPB, 0, S(h)>>>(h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, phi, phi, phi, grad, grad, grad);
-  else if (h->K <= 6) grad_kernel<6, 1><<<g, TPB, 0, S(h)>>>(h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, phi, phi, phi, grad, grad, grad);
-  else return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
+// ---- calc_grad on precomputed least-squares statics (grad_variant 1) --------------------------------
+// The matrix A = sum w dr dr^T, its inverse (matinv3, with the trace fallback) and the weights
+// w = 1/|dr|^2 depend on the mesh only; the reference rebuilds them in each of its four calc_grad calls
+// per iteration.  lsq_statics_kernel evaluates the very same expressions once (inverse entries b11..b33
+// per cell, w per slot); grad_lsq_kernel then needs neither the division per face nor the inversion and
+// produces the same bits (same operands, same operation order) for 15 more doubles read per cell.
+template <int K>
+__global__ void __launch_bounds__(TPB) lsq_statics_kernel(int N, int Np, const int32_t* __restrict__ ell_nb, const uint8_t* __restrict__ nfc,
+                                                          const double* __restrict__ xc, const double* __restrict__ yc,
+                                                          const double* __restrict__ zc, double* binv, double* wslot) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
+    const int n = nfc[c];
+    const double rp[3] = {xc[c], yc[c], zc[c]};
+    double A[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (k < n) {
+        const int nb = ell_nb[(size_t)k * Np + c];
+        const double dr[3] = {xc[nb] - rp[0], yc[nb] - rp[1], zc[nb] - rp[2]};
+        const double wt = 1.0 / (dr[0] * dr[0] + dr[1] * dr[1] + dr[2] * dr[2]);
+        wslot[(size_t)k * Np + c] = wt;
+        A[0] = A[0] + wt * dr[0] * dr[0];
+        A[1] = A[1] + wt * dr[0] * dr[1];
+        A[2] = A[2] + wt * dr[0] * dr[2];
+        A[3] = A[3] + wt * dr[1] * dr[1];
+        A[4] = A[4] + wt * dr[1] * dr[2];
+        A[5] = A[5] + wt * dr[2] * dr[2];
+      }
+    }
+    // matinv3 (mod_solver.f90:8-38): the expressions of matinv3_apply, entries stored instead of applied
+    const double a11 = A[0], a12 = A[1], a13 = A[2], a21 = A[1], a22 = A[3], a23 = A[4], a31 = A[2], a32 = A[4], a33 = A[5];
+    const double det = (a11 * a22 * a33 - a11 * a23 * a32 - a12 * a21 * a33 + a12 * a23 * a31 + a13 * a21 * a32 - a13 * a22 * a31);
+    double b[9];
+    if (fabs(det) > 2.2250738585072014e-308) {
+      const double detinv = 1.0 / det;
+      b[0] = +detinv * (a22 * a33 - a23 * a32);
+      b[3] = -detinv * (a21 * a33 - a23 * a31);
+      b[6] = +detinv * (a21 * a32 - a22 * a31);
+      b[1] = -detinv * (a12 * a33 - a13 * a32);
+      b[4] = +detinv * (a11 * a33 - a13 * a31);
+      b[7] = -detinv * (a11 * a32 - a12 * a31);
+      b[2] = +detinv * (a12 * a23 - a13 * a22);
+      b[5] = -detinv * (a11 * a23 - a13 * a21);
+      b[8] = +detinv * (a11 * a22 - a12 * a21);
+    } else {
+      const double detinv = 1.0 / (a11 + a22 + a33);
+      b[0] = detinv; b[4] = detinv; b[8] = detinv;
+      b[1] = b[2] = b[3] = b[5] = b[6] = b[7] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 9; ++j) binv[(size_t)j * Np + c] = b[j];  // row-major b11 b12 b13 b21 ...
+  }
+}
+
+template <int K, int NF>
+__global__ void __launch_bounds__(TPB) grad_lsq_kernel(int N, int Np, const int32_t* __restrict__ ell_nb, const uint8_t* __restrict__ nfc,
+                                                       const double* __restrict__ xc, const double* __restrict__ yc,
+                                                       const double* __restrict__ zc, const double* __restrict__ binv,
+                                                       const double* __restrict__ wslot, const double* phi0, const double* phi1,
+                                                       const double* phi2, double* g0, double* g1, double* g2) {
+  const double* phis[3] = {phi0, phi1, phi2};
+  double* gs[3] = {g0, g1, g2};
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
+    const int n = nfc[c];
+    const double rp[3] = {xc[c], yc[c], zc[c]};
+    double pe[NF], g[NF][3];
+#pragma unroll
+    for (int q = 0; q < NF; ++q) { pe[q] = phis[q][c]; g[q][0] = g[q][1] = g[q][2] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (k < n) {
+        const int nb = ell_nb[(size_t)k * Np + c];
+        const double dr[3] = {xc[nb] - rp[0], yc[nb] - rp[1], zc[nb] - rp[2]};
+        const double wt = wslot[(size_t)k * Np + c];
+#pragma unroll
+        for (int q = 0; q < NF; ++q) {
+          const double dphi = phis[q][nb] - pe[q];
+          g[q][0] = g[q][0] + wt * dphi * dr[0];
+          g[q][1] = g[q][1] + wt * dphi * dr[1];
+          g[q][2] = g[q][2] + wt * dphi * dr[2];
+        }
+      }
+    }
+    double b[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) b[j] = binv[(size_t)j * Np + c];
+#pragma unroll
+    for (int q = 0; q < NF; ++q) {
+      gs[q][3 * (size_t)c] = 0.0 + b[0] * g[q][0] + b[1] * g[q][1] + b[2] * g[q][2];
+      gs[q][3 * (size_t)c + 1] = 0.0 + b[3] * g[q][0] + b[4] * g[q][1] + b[5] * g[q][2];
+      gs[q][3 * (size_t)c + 2] = 0.0 + b[6] * g[q][0] + b[7] * g[q][1] + b[8] * g[q][2];
+    }
+  }
+}
+
+// allocates and fills the least-squares statics on first use
+static int ensure_lsq_statics(Handle* h) {
+  if (h->lsq_binv) return CFDL_OK;
+  double *b = nullptr, *w = nullptr;
+  CFDL_CUDA(cudaMalloc(&b, sizeof(double) * 9 * (size_t)h->Np));
+  h->allocs.push_back(b);
+  CFDL_CUDA(cudaMalloc(&w, sizeof(double) * (size_t)h->K * h->Np));
+  h->allocs.push_back(w);
+  CFDL_CUDA(cudaMemsetAsync(b, 0, sizeof(double) * 9 * (size_t)h->Np, h->stream));
+  CFDL_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * (size_t)h->K * h->Np, h->stream));
+  const int g = grid_for(h, h->N, TPB);
+  if (h->K <= 4) lsq_statics_kernel<4><<<g, TPB, 0, S(h)>>>(h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, b, w);
+  else lsq_statics_kernel<6><<<g, TPB, 0, S(h)>>>(h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, b, w);
+  CFDL_CUDA(cudaGetLastError());
+  h->lsq_binv = b; h->lsq_w = w;
+  return CFDL_OK;
+}
+
+template <auto K4, auto K6, typename... Args>
+static void launch_k46(Handle* h, int cells, Args... args) {
+  if (h->K <= 4) K4<<<occ_grid<K4>(h, cells, TPB), TPB, 0, S(h)>>>(args...);
+  else K6<<<occ_grid<K6>(h, cells, TPB), TPB, 0, S(h)>>>(args...);
+}
+
+static int grad1_launch(Handle* h, int variant, const double* phi, double* grad) {
+  if (variant == 1) {
+    int rc = ensure_lsq_statics(h);
+    if (rc) return rc;
+    launch_k46<grad_lsq_kernel<4, 1>, grad_lsq_kernel<6, 1>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, h->lsq_binv, h->lsq_w, phi, phi, phi, grad, grad, grad);
+  } else {
+    launch_k46<grad_kernel<4, 1>, grad_kernel<6, 1>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, phi, phi, phi, grad, grad, grad);
+  }
+  CFDL_CUDA(cudaGetLastError());
+  return CFDL_OK;
+}
+static int grad3_launch(Handle* h, int variant) {
+  const double *u = h->fld[CFDL_F_U], *v = h->fld[CFDL_F_V], *w = h->fld[CFDL_F_W];
+  double *gu = h->fld[CFDL_F_GU], *gv = h->fld[CFDL_F_GV], *gw = h->fld[CFDL_F_GW];
+  if (variant == 1) {
+    int rc = ensure_lsq_statics(h);
+    if (rc) return rc;
+    launch_k46<grad_lsq_kernel<4, 3>, grad_lsq_kernel<6, 3>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, h->lsq_binv, h->lsq_w, u, v, w, gu, gv, gw);
+  } else {
+    launch_k46<grad_kernel<4, 3>, grad_kernel<6, 3>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, u, v, w, gu, gv, gw);
+  }
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
 
-int k_calc_grad3(Handle* h) {  // the three calc_grad calls of mod_uvwp.f90:118-120 in one pass over the mesh
-  const int g = (h->K <= 4) ? occ_grid<grad_kernel<4, 3>>(h, h->N, TPB) : occ_grid<grad_kernel<6, 3>>(h, h->N, TPB);
-#define G3 h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, h->fld[CFDL_F_U], h->fld[CFDL_F_V], h->fld[CFDL_F_W], \
-           h->fld[CFDL_F_GU], h->fld[CFDL_F_GV], h->fld[CFDL_F_GW]
-  prof_begin(h, PROF_GRAD);
-  if (h->K <= 4) grad_kernel<4, 3><<<g, TPB, 0, S(h)>>>(G3);
-  else if (h->K <= 6) grad_kernel<6, 3><<<g, TPB, 0, S(h)>>>(G3);
-  else return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
-  prof_end(h);
-#undef G3
-  CFDL_CUDA(cudaGetLastError());
-  return CFDL_OK;
+int k_calc_grad(Handle* h, const double* phi, double* grad) {
+  if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
+  if (h->autotune && !h->tune_grad1.done && h->profile == 0 && h->grad_variant < 0) {
+    static const int cands[] = {0, 1};
+    int rc = autotune_pick(h, h->tune_grad1, cands, 2, [&](int v) { return grad1_launch(h, v, phi, grad); });
+    if (rc) return rc;
+  }
+  return grad1_launch(h, h->grad_variant >= 0 ? h->grad_variant : (h->tune_grad1.ncand ? h->tune_grad1.choice : 0), phi, grad);
 }
+
+int k_calc_grad3(Handle* h) {  // the three calc_grad calls of mod_uvwp.f90:118-120 in one pass over the mesh
+  if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
+  if (h->autotune && !h->tune_grad3.done && h->profile == 0 && h->grad_variant < 0) {
+    static const int cands[] = {0, 1};
+    int rc = autotune_pick(h, h->tune_grad3, cands, 2, [&](int v) { return grad3_launch(h, v); });
+    if (rc) return rc;
+  }
+  prof_begin(h, PROF_GRAD);
+  int rc = grad3_launch(h, h->grad_variant >= 0 ? h->grad_variant : (h->tune_grad3.ncand ? h->tune_grad3.choice : 0));
+  prof_end(h);
+  return rc;
+}
+
 
 // ---- update_time, mod_physics.f90:101-112 ------------------------------------------------------
 int k_update_time(Handle* h) {

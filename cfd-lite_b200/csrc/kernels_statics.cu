@@ -308,67 +308,106 @@ int k_calc_coef_uvw_statics(Handle* h, double dt) {
 }
 
 // ---- calc_coef_p on statics (mod_uvwp.f90:289-368) ---------------------------------------------
+struct CoefPArgs {
+  int N, Nc, Np, ncol0;
+  const int32_t *ell_nb, *ell_fs, *halo_bc;
+  const uint8_t* nfc;
+  const double *rho, *dc, *mip;
+  double *ap, *anb, *b;
+  FaceStatics S;
+};
+
 template <int K>
-__global__ void __launch_bounds__(TPB) coef_p_statics_kernel(int N, int Nc, int Np, const int32_t* __restrict__ ell_nb,
-                                                             const int32_t* __restrict__ ell_fs, const uint8_t* __restrict__ nfc,
-                                                             const int32_t* __restrict__ halo_bc, const double* __restrict__ rho,
-                                                             const double* __restrict__ dc, const double* __restrict__ mip, const FaceStatics S,
-                                                             double* __restrict__ ap_o, double* __restrict__ anb_o, double* __restrict__ b_o) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
-    const int n = nfc[c];
-    const double rho_e = rho[c], dc_e = dc[c];
-    double ap = 0.0, sumf = 0.0;
-    int nbk[K];
+__device__ __forceinline__ void coef_p_statics_cell(const CoefPArgs& A, const int c) {
+  const int Nc = A.Nc, Np = A.Np;
+  const int n = A.nfc[c];
+  const double rho_e = A.rho[c], dc_e = A.dc[c];
+  double ap = 0.0, sumf = 0.0;
+  int nbk[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      nbk[k] = -1;
-      if (k < n) {
-        const int nb = ell_nb[(size_t)k * Np + c];
-        const int fs = ell_fs[(size_t)k * Np + c];
-        nbk[k] = nb;
-        double d = 0.0;
-        if (nb < Nc) {
-          const int f = abs(fs) - 1;
-          const bool own = fs > 0;
-          const double sg = own ? 1.0 : -1.0;
-          const double wt = own ? S.wto[f] : S.wtn[f];
-          const double f_in = -sg * mip[f];
-          sumf = sumf + f_in;
-          const double rhoip = (1.0 - wt) * rho_e + wt * rho[nb];
-          d = ((1.0 - wt) * dc_e + wt * dc[nb]) / S.dn[f] * rhoip * S.area[f];
-        }
-        anb_o[(size_t)k * Np + c] = d;
-        ap = ap + d;
+  for (int k = 0; k < K; ++k) {
+    nbk[k] = -1;
+    if (k < n) {
+      const int nb = A.ell_nb[(size_t)k * Np + c];
+      const int fs = A.ell_fs[(size_t)k * Np + c];
+      nbk[k] = nb;
+      double d = 0.0;
+      if (nb < Nc) {
+        const int f = abs(fs) - 1;
+        const bool own = fs > 0;
+        const double sg = own ? 1.0 : -1.0;
+        const double wt = own ? A.S.wto[f] : A.S.wtn[f];
+        const double f_in = -sg * A.mip[f];
+        sumf = sumf + f_in;
+        const double rhoip = (1.0 - wt) * rho_e + wt * A.rho[nb];
+        d = ((1.0 - wt) * dc_e + wt * A.dc[nb]) / A.S.dn[f] * rhoip * A.S.area[f];
       }
+      A.anb[(size_t)k * Np + c] = d;
+      ap = ap + d;
     }
-    double b = sumf;
-    int last = -1;
-    for (int t = 0; t < K; ++t) {
-      int best = 0x7fffffff, bk = -1;
+  }
+  double b = sumf;
+  int last = -1;
+  for (int t = 0; t < K; ++t) {
+    int best = 0x7fffffff, bk = -1;
 #pragma unroll
-      for (int k = 0; k < K; ++k)
-        if (nbk[k] >= Nc && nbk[k] > last && nbk[k] < best) { best = nbk[k]; bk = k; }
-      if (bk < 0) break;
-      last = best;
-      if (halo_bc[best - Nc] < 0) continue;
-      b = b - mip[ell_fs[(size_t)bk * Np + c] - 1];
-    }
-    ap_o[c] = ap;
-    b_o[c] = b;
+    for (int k = 0; k < K; ++k)
+      if (nbk[k] >= Nc && nbk[k] > last && nbk[k] < best) { best = nbk[k]; bk = k; }
+    if (bk < 0) break;
+    last = best;
+    if (A.halo_bc[best - Nc] < 0) continue;
+    b = b - A.mip[A.ell_fs[(size_t)bk * Np + c] - 1];
+  }
+  A.ap[c] = ap;
+  A.b[c] = b;
+}
+
+template <int K>
+__global__ void __launch_bounds__(TPB) coef_p_statics_kernel(const CoefPArgs A) {
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.N; c += gridDim.x * blockDim.x) coef_p_statics_cell<K>(A, c);
+}
+// coef_p_variant 1: the paired colour order of coef_uvw_statics_body_paired (face statics and mip of a
+// face are read by both of its cells within one CTA's pass instead of half a kernel apart)
+template <int K>
+__global__ void __launch_bounds__(TPB) coef_p_statics_paired_kernel(const CoefPArgs A) {
+  const int n0 = A.ncol0, n1 = A.N - A.ncol0;
+  const int nq = (max(n0, n1) + (int)blockDim.x - 1) / (int)blockDim.x;
+  for (int q = blockIdx.x; q < nq; q += gridDim.x) {
+    const int i = q * blockDim.x + threadIdx.x;
+#pragma unroll 1
+    for (int col = 0; col < 2; ++col)
+      if (i < (col ? n1 : n0)) coef_p_statics_cell<K>(A, col ? n0 + i : i);
   }
 }
 
-int k_calc_coef_p_statics(Handle* h) {
-  const int g = (h->K <= 4) ? occ_grid<coef_p_statics_kernel<4>>(h, h->N, TPB) : occ_grid<coef_p_statics_kernel<6>>(h, h->N, TPB);
-  const FaceStatics fst = statics_of(h);
-  if (h->K <= 4)
-    coef_p_statics_kernel<4><<<g, TPB, 0, S(h)>>>(h->N, h->Nc, h->Np, h->ell_nb, h->ell_fs, h->nfc, h->halo_bc, h->rho, h->fld[CFDL_F_DC],
-                                                  h->fld[CFDL_F_MIP], fst, h->fld[CFDL_F_AP], h->fld[CFDL_F_ANB], h->fld[CFDL_F_B]);
+template <auto K4, auto K6>
+static void launch_coef_p(Handle* h, const CoefPArgs& A, int cells) {
+  if (h->K <= 4) K4<<<occ_grid<K4>(h, cells, TPB), TPB, 0, S(h)>>>(A);
+  else K6<<<occ_grid<K6>(h, cells, TPB), TPB, 0, S(h)>>>(A);
+}
+
+static int coef_p_launch(Handle* h, int variant) {
+  CoefPArgs A;
+  A.N = h->N; A.Nc = h->Nc; A.Np = h->Np; A.ncol0 = h->prep.ncolors == 2 ? h->prep.color_ptr[1] : h->N;
+  A.ell_nb = h->ell_nb; A.ell_fs = h->ell_fs; A.halo_bc = h->halo_bc; A.nfc = h->nfc;
+  A.rho = h->rho; A.dc = h->fld[CFDL_F_DC]; A.mip = h->fld[CFDL_F_MIP];
+  A.ap = h->fld[CFDL_F_AP]; A.anb = h->fld[CFDL_F_ANB]; A.b = h->fld[CFDL_F_B];
+  A.S = statics_of(h);
+  if (variant == 1 && h->prep.ncolors == 2)
+    launch_coef_p<coef_p_statics_paired_kernel<4>, coef_p_statics_paired_kernel<6>>(h, A, std::max(A.ncol0, h->N - A.ncol0));
   else
-    coef_p_statics_kernel<6><<<g, TPB, 0, S(h)>>>(h->N, h->Nc, h->Np, h->ell_nb, h->ell_fs, h->nfc, h->halo_bc, h->rho, h->fld[CFDL_F_DC],
-                                                  h->fld[CFDL_F_MIP], fst, h->fld[CFDL_F_AP], h->fld[CFDL_F_ANB], h->fld[CFDL_F_B]);
+    launch_coef_p<coef_p_statics_kernel<4>, coef_p_statics_kernel<6>>(h, A, h->N);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
+}
+
+int k_calc_coef_p_statics(Handle* h) {
+  if (h->autotune && !h->tune_coef_p.done && h->profile == 0 && h->coef_p_variant < 0 && h->prep.ncolors == 2) {
+    static const int cands[] = {0, 1};
+    int rc = autotune_pick(h, h->tune_coef_p, cands, 2, [&](int v) { return coef_p_launch(h, v); });
+    if (rc) return rc;
+  }
+  return coef_p_launch(h, h->coef_p_variant >= 0 ? h->coef_p_variant : (h->tune_coef_p.ncand ? h->tune_coef_p.choice : 0));
 }
 
 // ---- calc_mip on statics (mod_uvwp.f90:438-490) ------------------------------------------------

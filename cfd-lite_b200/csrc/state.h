@@ -113,6 +113,11 @@ struct Handle {
   // weights, dr, dr_p): the assembly kernels then need 10 instead of 19 FP64 div/sqrt per face
   double *fs_area = nullptr, *fs_ds = nullptr, *fs_dsp = nullptr, *fs_dn = nullptr, *fs_wto = nullptr, *fs_wtn = nullptr;
   double *fs_rds = nullptr, *fs_rdsp = nullptr;  // RN(1/ds), RN(1/dsp)
+  // least-squares gradient statics (filled on first use by grad_variant 1): inverse LSQ matrix per cell
+  // (9 x Np, entry-major) and the weight 1/|dr|^2 per slot (K x Np)
+  double *lsq_binv = nullptr, *lsq_w = nullptr;
+  int coef_p_variant = -1;     // calc_coef_p on statics: -1 = chosen by measurement, 0 = linear cell order, 1 = paired colour order
+  int grad_variant = -1;       // calc_grad: -1 = chosen by measurement (0 when autotune is off), 0 = reference form, 1 = on the LSQ statics
   double *fs_n[3] = {nullptr, nullptr, nullptr}, *fs_dr[3] = {nullptr, nullptr, nullptr}, *fs_drp[3] = {nullptr, nullptr, nullptr};
   int use_statics = 1;         // 0: recompute face geometry in every kernel (the reference's way)
   // Variant selection by measurement: the first call of a routine times its bit-identical kernel

@@ -374,3 +374,55 @@ def test_step_host_equals_separate_calls(case, cfdl, solver):
             b.free()
     finally:
         s.set_option("solver", cfdl.SOLVER_PARITY)
+
+
+def test_calc_grad_variants_keep_the_bits(case):
+    """grad_variant 1 (inverse least-squares matrix and weights precomputed once with the reference's
+    expressions) against variant 0 (everything rebuilt per call, as the reference does): same bits, for
+    the single-field kernel and for the fused u,v,w pass inside solve_uvwp."""
+    _, raw, oc, geom, s = case
+    randomize(oc, s, seed=29)
+    got = {}
+    try:
+        for variant in (0, 1):
+            s.set_option("grad_variant", variant)
+            s.calc_grad("p", "gp")
+            got[variant, "gp"] = s.download("gp")[:3 * oc.ne]
+            s.calc_grad("pc", "gpc")
+            got[variant, "gpc"] = s.download("gpc")[:3 * oc.ne]
+        want = oc.calc_grad(oc["p"])[:3 * oc.ne]
+        check("gp", got[0, "gp"], want)
+        for f in ("gp", "gpc"):
+            assert np.array_equal(got[0, f], got[1, f]), f
+        # the fused three-field pass runs inside solve_uvwp: two iterations from the same state
+        hist = {}
+        for variant in (0, 1):
+            s.set_option("grad_variant", variant)
+            randomize(oc, s, seed=31)
+            s.update_boundaries()
+            hist[variant] = s.solve_uvwp(0.01, 5)
+            for f in ("gu", "gv", "gw", "gp", "mip", "p"):
+                got[variant, f] = s.download(f)
+        assert np.array_equal(hist[0], hist[1])
+        for f in ("gu", "gv", "gw", "gp", "mip", "p"):
+            assert np.array_equal(got[0, f], got[1, f]), f
+    finally:
+        s.set_option("grad_variant", -1)
+
+
+def test_calc_coef_p_variants_keep_the_bits(case):
+    """coef_p_variant 1 (paired colour order) against variant 0 and the oracle: same bits."""
+    _, raw, oc, geom, s = case
+    randomize(oc, s, seed=37)
+    oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)  # provides dc
+    oc.calc_coef_p()
+    try:
+        for variant in (0, 1):
+            s.set_option("coef_p_variant", variant)
+            for f in ("ap", "anb", "b"):
+                s.upload(f, np.full(s.field_size(f), 7.5))  # stale values must be overwritten
+            s.calc_coef_p()
+            for f in ("ap", "anb", "b"):
+                assert np.array_equal(s.download(f), oc[f]), (variant, f)
+    finally:
+        s.set_option("coef_p_variant", -1)
