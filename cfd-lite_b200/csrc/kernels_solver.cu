@@ -11,7 +11,7 @@
 //          each colour is one fully coalesced launch); identical to solve_gs applied to the
 //          colour-permuted system.
 //  PCG     Jacobi-preconditioned conjugate gradients for the symmetric pc system, with the
-//          reference's stopping rule (10x RMS-residual drop or nit iterations).
+//          reference's stopping rule (10x RMS-residual drop or nit iterations); kernels_pcg.inc.
 #include <cstdlib>
 #include <cstring>
 #include "state.h"
@@ -391,6 +391,7 @@ static int parity_solve_t(Handle* h, int eq, double* phi, const double* rhs, int
 }
 
 #include "kernels_rb.inc"
+#include "kernels_pcg.inc"
 
 // MCSGS: colour-ordered symmetric Gauss-Seidel with the reference's stopping rule; iterations
 // are enqueued in growing batches, each kernel returning at once when ctl->done is set
@@ -484,8 +485,10 @@ int solve_equation(Handle* h, int eq, double* phi, const double* rhs, int nit, d
   switch (h->solver_mode) {
     case CFDL_SOLVER_PARITY:
       return k4 ? parity_solve_t<4>(h, eq, phi, rhs, nit, out4, dispatch) : parity_solve_t<6>(h, eq, phi, rhs, nit, out4, dispatch);
+    case CFDL_SOLVER_PCG:  // conjugate gradients for the (symmetric) pc system; the momentum equations stay on MCSGS
+      if (eq == CFDL_EQ_PC) return k4 ? pcg_solve_t<4>(h, eq, phi, rhs, nit, out4) : pcg_solve_t<6>(h, eq, phi, rhs, nit, out4);
+      // fall through
     case CFDL_SOLVER_MCSGS:
-    case CFDL_SOLVER_PCG:  // PCG for pc is added in pcg.cu; momentum always uses MCSGS there
       if (h->fused_rb && h->prep.ncolors == 2)
         return k4 ? rb_solve_t<4>(h, eq, phi, rhs, nit, out4) : rb_solve_t<6>(h, eq, phi, rhs, nit, out4);
       return k4 ? mcsgs_solve_t<4>(h, eq, phi, rhs, nit, out4) : mcsgs_solve_t<6>(h, eq, phi, rhs, nit, out4);

@@ -98,6 +98,7 @@ struct Handle {
   double *ap_s = nullptr, *b_s = nullptr, *anb_s = nullptr, *phi_s = nullptr, *rr = nullptr, *rsig = nullptr;
   int coop_ctas = 0;
   double* rb_work = nullptr;   // second value array of the fused two-colour solver (H doubles)
+  double *pcg_r = nullptr, *pcg_q = nullptr, *pcg_p = nullptr;  // conjugate-gradient work vectors (first use)
   int last_passes[4] = {1, 1, 1, 1};  // per equation: passes the previous solve needed (first-batch size estimate)
   int fused_rb = 1;            // 0: always use one launch per colour + residual pass
   int use_p2p = 1;             // 0: NCCL send/recv even when peer slabs are connected

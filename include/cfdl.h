@@ -48,7 +48,8 @@ enum {
                              multi_subdomain_solver (n_subdomains>1); level-scheduled on the GPU */
   CFDL_SOLVER_MCSGS = 1,  /* multicolour symmetric Gauss-Seidel: same update formula, same
                              stopping rule, colour order instead of natural order */
-  CFDL_SOLVER_PCG = 2     /* reserved for a Krylov pc solver; currently runs MCSGS */
+  CFDL_SOLVER_PCG = 2     /* pc: Jacobi-preconditioned conjugate gradients with the reference's stopping rule (not a
+                             restatement of solve_gs: same interface, fewer matrix passes); u,v,w: MCSGS; one GPU */
 };
 
 /* field selectors for upload/download and the per-routine entry points */

@@ -426,3 +426,73 @@ def test_calc_coef_p_variants_keep_the_bits(case):
                 assert np.array_equal(s.download(f), oc[f]), (variant, f)
     finally:
         s.set_option("coef_p_variant", -1)
+
+
+def _numpy_pcg(ne, idx, nb_packed, ap, anb, b, phi0, nit):
+    """Jacobi-preconditioned CG with the reference's residual definition and stopping rule, in plain
+    numpy on the reference-format (CSR, packed neighbour ids) system: the model of solver=pcg."""
+    rows = np.repeat(np.arange(ne), np.diff(idx))
+    cols = (nb_packed >> 5) - 1  # cells and halos share the id space of phi
+    x = phi0.copy()
+
+    def nbsum(v):
+        return np.bincount(rows, weights=anb * v[cols], minlength=ne)
+
+    r = b + nbsum(x) - ap * x[:ne]
+    res_i = np.sqrt(np.sum(r * r) / ne)
+    res_f, res_max, it = res_i, 0.0, 0
+    p = np.zeros_like(x)
+    p[:ne] = r / ap
+    rz = np.sum(r * r / ap)
+    while it < nit and res_f > res_i / 10.0:
+        q = ap * p[:ne] - nbsum(p)
+        pq = np.sum(p[:ne] * q)
+        if not pq > 0.0:
+            break
+        alpha = rz / pq
+        x[:ne] += alpha * p[:ne]
+        r = r - alpha * q
+        it += 1
+        res_f, res_max = np.sqrt(np.sum(r * r) / ne), np.abs(r).max()
+        rz_new = np.sum(r * r / ap)
+        p[:ne] = r / ap + (rz_new / rz) * p[:ne]
+        rz = rz_new
+    return x, (it, res_i, res_f, res_max)
+
+
+def test_pcg_solves_the_pc_system_like_its_numpy_model(case, cfdl):
+    """solver=pcg (conjugate gradients for pc; not a reference algorithm, see kernels_pcg.inc): same
+    iterates as the numpy model up to summation order (1e-9), same iteration counts and stopping rule,
+    and the residual really drops by the factor the reference asks for."""
+    name, raw, oc, geom, s = case
+    rng = np.random.default_rng(41)
+    for nm in STATE:
+        a = oc[nm]
+        a[:] = rng.standard_normal(a.size) * (0.01 if nm.startswith("mip") else 0.1)
+    oc.update_boundaries(); oc.calc_coef_uvw(); oc.calc_mip(True); oc.calc_coef_p()
+    ap, anb, b = oc["ap"].copy(), oc["anb"].copy(), oc["b"].copy()
+    b -= b.mean()  # consistent right-hand side for the singular Neumann system (true in a run: boundary fluxes are zero)
+    phi0 = np.zeros(oc.ne + oc.nbf)
+    idx = geom["ef2nb_idx"].astype(np.int64) - 1
+    nbp = geom["ef2nb_nb"].astype(np.int64)
+    s.set_option("solver", cfdl.SOLVER_PCG)
+    try:
+        for nit in (1, 3, 12, 400):
+            want_phi, want = _numpy_pcg(oc.ne, idx, nbp, ap, anb, b, phi0, nit)
+            got_phi, got = s.host_solve(3, phi0, ap, anb, b, nit=nit)
+            assert got[0] == want[0], (nit, got, want)
+            scale = max(np.abs(want_phi[:oc.ne]).max(), 1e-300)
+            assert np.abs(got_phi[:oc.ne] - want_phi[:oc.ne]).max() / scale < 1e-9, nit
+            for k in (1, 2, 3):
+                if want[k] != 0.0:
+                    assert abs(got[k] - want[k]) <= 1e-9 * abs(want[k]), (nit, k, got, want)
+        assert got[2] <= got[1] / 10.0 and got[0] < 400  # converged by the reference's criterion, not by the cap
+        # momentum equations are not symmetric: solver=pcg keeps them on MCSGS
+        s.set_option("solver", cfdl.SOLVER_MCSGS)
+        ap_u, anb_u, b_u, phi_u = assembled_system(oc)
+        ref_phi, ref = s.host_solve_gs(0, phi_u, ap_u, anb_u, b_u, nit=5)
+        s.set_option("solver", cfdl.SOLVER_PCG)
+        pcg_phi, pcg = s.host_solve_gs(0, phi_u, ap_u, anb_u, b_u, nit=5)
+        assert np.array_equal(ref_phi, pcg_phi) and np.array_equal(ref, pcg)
+    finally:
+        s.set_option("solver", cfdl.SOLVER_PARITY)
