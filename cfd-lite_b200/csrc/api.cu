@@ -123,7 +123,9 @@ int solve_uvwp_impl(Handle* h, double dt, int nit, double* hist, StepHook* hook 
   double st[16] = {0};
   if ((rc = k_calc_coef_uvw(h, dt))) return rc;                                              // :111
   if ((rc = comm_exchange(h, h->fld[CFDL_F_D], 1, -1)) || (rc = comm_exchange(h, h->fld[CFDL_F_DC], 1, -1))) return rc;
-  for (int eq = CFDL_EQ_U; eq <= CFDL_EQ_W; ++eq)                                            // :114-116
+  bool fused3 = false;                                                                       // :114-116
+  if ((rc = solve_momentum_fused(h, nit, st, &fused3))) return rc;
+  for (int eq = CFDL_EQ_U; eq <= CFDL_EQ_W && !fused3; ++eq)
     if ((rc = solve_equation(h, eq, h->fld[phi_field(eq)], h->fld[rhs_field(eq)], nit, st + 4 * eq, false))) return rc;
   if (hook && (rc = hook->at(STEP_MOMENTUM_DONE))) return rc;
   if ((rc = k_calc_grad3(h))) return rc;                                                     // :118-120
@@ -290,6 +292,7 @@ int cfdl_destroy(cfdl_handle h) {
   if (h->xfer_out) { cudaStreamSynchronize(h->xfer_out); cudaStreamDestroy(h->xfer_out); }
   for (void* p : h->allocs) cudaFree(p);
   if (h->ctl_host) cudaFreeHost(h->ctl_host);
+  if (h->ctl3_host) cudaFreeHost(h->ctl3_host);
   if (h->scal_host) cudaFreeHost(h->scal_host);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -313,6 +316,7 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "pdl_rows")) { h->pdl_rows = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "pdl")) { h->use_pdl = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "uvw_variant")) { h->uvw_variant = (int)value; h->tune_uvw.done = 1; return CFDL_OK; }  // pinned by hand
+  if (!std::strcmp(key, "uvw_fused")) { h->uvw_fused = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "grad_variant")) { h->grad_variant = (int)value; return CFDL_OK; }
   if (!std::strcmp(key, "coef_p_variant")) { h->coef_p_variant = (int)value; return CFDL_OK; }
   if (!std::strcmp(key, "autotune")) {

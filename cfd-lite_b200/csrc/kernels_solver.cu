@@ -391,6 +391,7 @@ static int parity_solve_t(Handle* h, int eq, double* phi, const double* rhs, int
 }
 
 #include "kernels_rb.inc"
+#include "kernels_rb3.inc"
 #include "kernels_pcg.inc"
 
 // MCSGS: colour-ordered symmetric Gauss-Seidel with the reference's stopping rule; iterations
@@ -475,6 +476,15 @@ int residual_plain(Handle* h, const double* phi, const double* rhs, bool signed_
   *res = h->scal_host[0];
   *res_max = h->scal_host[1];
   return CFDL_OK;
+}
+
+// the three momentum solves of solve_uvwp (mod_uvwp.f90:114-116) side by side when the mode allows it
+// (multicolour SGS on a two-colour mesh, one GPU); *handled = false: the caller runs them one by one
+int solve_momentum_fused(Handle* h, int nit, double* out12, bool* handled) {
+  *handled = false;
+  if (h->K > 6 || h->prep.nranks > 1 || h->solver_mode == CFDL_SOLVER_PARITY || !h->fused_rb || h->prep.ncolors != 2 || h->uvw_fused == 0) return CFDL_OK;
+  *handled = true;
+  return h->K <= 4 ? rb3_solve_t<4>(h, nit, out12) : rb3_solve_t<6>(h, nit, out12);
 }
 
 int solve_equation(Handle* h, int eq, double* phi, const double* rhs, int nit, double* out4, bool dispatch) {

@@ -99,6 +99,12 @@ struct Handle {
   int coop_ctas = 0;
   double* rb_work = nullptr;   // second value array of the fused two-colour solver (H doubles)
   double *pcg_r = nullptr, *pcg_q = nullptr, *pcg_p = nullptr;  // conjugate-gradient work vectors (first use)
+  // the three momentum solves side by side (kernels_rb3.inc): second value arrays of v and w (u uses rb_work),
+  // one control block per equation
+  double* rb3_work[2] = {nullptr, nullptr};
+  SolveCtl* ctl3 = nullptr;       // device, 3 blocks
+  SolveCtl* ctl3_host = nullptr;  // pinned
+  int uvw_fused = 1;              // 0: u, v, w are solved one after the other as the reference does
   int last_passes[4] = {1, 1, 1, 1};  // per equation: passes the previous solve needed (first-batch size estimate)
   int fused_rb = 1;            // 0: always use one launch per colour + residual pass
   int use_p2p = 1;             // 0: NCCL send/recv even when peer slabs are connected
@@ -212,6 +218,7 @@ int solver_init(Handle* h);
 // dispatch=false: solve_gs (mod_solver.f90:255); dispatch=true: solve() (:329), i.e. the block
 // solver when the handle has n_subdomains>1
 int solve_equation(Handle* h, int eq, double* phi, const double* rhs, int nit, double* out4, bool dispatch);
+int solve_momentum_fused(Handle* h, int nit, double* out12, bool* handled);
 
 int residual_plain(Handle* h, const double* phi, const double* rhs, bool signed_max, double* res, double* res_max);
 // ---- comm.cu (no-ops on a single rank)

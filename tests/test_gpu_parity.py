@@ -496,3 +496,34 @@ def test_pcg_solves_the_pc_system_like_its_numpy_model(case, cfdl):
         assert np.array_equal(ref_phi, pcg_phi) and np.array_equal(ref, pcg)
     finally:
         s.set_option("solver", cfdl.SOLVER_PARITY)
+
+
+def test_momentum_solves_side_by_side_keep_the_bits(case, cfdl):
+    """uvw_fused=1 (u, v, w in one set of fused two-colour passes, matrix rows read once per pass,
+    kernels_rb3.inc) against uvw_fused=0 (three separate solves as the reference orders them): every
+    equation stops at its own iteration count and all fields are bit-identical."""
+    name, raw, oc, geom, s = case
+    if int(s.get_info("ncolors")) != 2:
+        pytest.skip("the side-by-side passes need a two-colour mesh")
+    s.set_option("solver", cfdl.SOLVER_MCSGS)
+    try:
+        for seed, nit in ((43, 100), (47, 2), (53, 1)):
+            res = {}
+            for fused in (0, 1):
+                s.set_option("uvw_fused", fused)
+                randomize(oc, s, seed=seed)
+                s.update_boundaries()
+                h1 = s.solve_uvwp(0.01, nit)
+                s.update_boundaries()
+                h2 = s.solve_uvwp(0.01, nit)
+                res[fused] = (h1, h2, {f: s.download(f) for f in ("u", "v", "w", "p", "gu", "gv", "gw", "mip")})
+            for i in (0, 1):
+                a, b = res[0][i], res[1][i]
+                assert np.array_equal(a[:, 0], b[:, 0]), (seed, nit, a[:, 0], b[:, 0])  # iteration counts
+                assert np.array_equal(a[:, 1], b[:, 1])                                  # opening residuals: same launch geometry
+                assert np.allclose(a[:, 2:], b[:, 2:], rtol=1e-12, atol=0.0)
+            for f, v in res[0][2].items():
+                assert np.array_equal(v, res[1][2][f]), (seed, nit, f)
+    finally:
+        s.set_option("uvw_fused", 1)
+        s.set_option("solver", cfdl.SOLVER_PARITY)
