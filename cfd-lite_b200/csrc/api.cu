@@ -123,10 +123,7 @@ int solve_uvwp_impl(Handle* h, double dt, int nit, double* hist, StepHook* hook 
   double st[16] = {0};
   if ((rc = k_calc_coef_uvw(h, dt))) return rc;                                              // :111
   if ((rc = comm_exchange(h, h->fld[CFDL_F_D], 1, -1)) || (rc = comm_exchange(h, h->fld[CFDL_F_DC], 1, -1))) return rc;
-  bool fused3 = false;                                                                       // :114-116
-  if ((rc = solve_momentum_fused(h, nit, st, &fused3))) return rc;
-  for (int eq = CFDL_EQ_U; eq <= CFDL_EQ_W && !fused3; ++eq)
-    if ((rc = solve_equation(h, eq, h->fld[phi_field(eq)], h->fld[rhs_field(eq)], nit, st + 4 * eq, false))) return rc;
+  if ((rc = solve_momentum(h, nit, st))) return rc;                                          // :114-116
   if (hook && (rc = hook->at(STEP_MOMENTUM_DONE))) return rc;
   if ((rc = k_calc_grad3(h))) return rc;                                                     // :118-120
   for (int f = CFDL_F_GU; f <= CFDL_F_GW; ++f)
@@ -316,12 +313,15 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "pdl_rows")) { h->pdl_rows = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "pdl")) { h->use_pdl = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "uvw_variant")) { h->uvw_variant = (int)value; h->tune_uvw.done = 1; return CFDL_OK; }  // pinned by hand
-  if (!std::strcmp(key, "uvw_fused")) { h->uvw_fused = value != 0.0; return CFDL_OK; }
+  if (!std::strcmp(key, "uvw_fused")) { h->uvw_fused = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
   if (!std::strcmp(key, "grad_variant")) { h->grad_variant = (int)value; return CFDL_OK; }
   if (!std::strcmp(key, "coef_p_variant")) { h->coef_p_variant = (int)value; return CFDL_OK; }
   if (!std::strcmp(key, "autotune")) {
     h->autotune = value != 0.0;
-    if (value == 2.0) { h->tune_uvw = Handle::Tuned(); h->tune_grad3 = Handle::Tuned(); h->tune_grad1 = Handle::Tuned(); h->tune_coef_p = Handle::Tuned(); h->tune_mip = Handle::Tuned(); }
+    if (value == 2.0) {
+      h->tune_uvw = Handle::Tuned(); h->tune_grad3 = Handle::Tuned(); h->tune_grad1 = Handle::Tuned(); h->tune_coef_p = Handle::Tuned();
+      h->tune_mip = Handle::Tuned(); h->tune_uvw_solve = Handle::Tuned(); h->momentum_calls = 0;
+    }
     return CFDL_OK;
   }
   if (!std::strcmp(key, "statics")) { h->use_statics = value != 0.0; return CFDL_OK; }
@@ -356,9 +356,9 @@ int cfdl_get_info(cfdl_handle h, const char* key, double* value) {
     const Handle::Tuned* T = nullptr;
     const char* r = key + 6;
     size_t len = 0;
-    static const char* names[5] = {"uvw", "grad3", "grad1", "coef_p", "mip"};
-    const Handle::Tuned* all[5] = {&h->tune_uvw, &h->tune_grad3, &h->tune_grad1, &h->tune_coef_p, &h->tune_mip};
-    for (int i = 0; i < 5; ++i) {
+    static const char* names[6] = {"uvw", "grad3", "grad1", "coef_p", "mip", "uvw_solve"};
+    const Handle::Tuned* all[6] = {&h->tune_uvw, &h->tune_grad3, &h->tune_grad1, &h->tune_coef_p, &h->tune_mip, &h->tune_uvw_solve};
+    for (int i = 0; i < 6; ++i) {
       const size_t l = std::strlen(names[i]);
       if (!std::strncmp(r, names[i], l) && (r[l] == 0 || r[l] == '_') && l > len) { T = all[i]; len = l; }
     }

@@ -478,13 +478,61 @@ int residual_plain(Handle* h, const double* phi, const double* rhs, bool signed_
   return CFDL_OK;
 }
 
-// the three momentum solves of solve_uvwp (mod_uvwp.f90:114-116) side by side when the mode allows it
-// (multicolour SGS on a two-colour mesh, one GPU); *handled = false: the caller runs them one by one
-int solve_momentum_fused(Handle* h, int nit, double* out12, bool* handled) {
-  *handled = false;
-  if (h->K > 6 || h->prep.nranks > 1 || h->solver_mode == CFDL_SOLVER_PARITY || !h->fused_rb || h->prep.ncolors != 2 || h->uvw_fused == 0) return CFDL_OK;
-  *handled = true;
-  return h->K <= 4 ? rb3_solve_t<4>(h, nit, out12) : rb3_solve_t<6>(h, nit, out12);
+// The three momentum solves of solve_uvwp (mod_uvwp.f90:114-116): side by side (kernels_rb3.inc) when
+// the mode allows it — multicolour SGS on a two-colour mesh, one GPU — else one after the other.
+// Both orders give the same bits, so with autotune on the second call of a handle measures both on
+// its own data (u, v, w are put back in between) and later calls use the faster one.
+static bool momentum_fusable(const Handle* h) {
+  return h->K <= 6 && h->prep.nranks == 1 && h->solver_mode != CFDL_SOLVER_PARITY && h->fused_rb && h->prep.ncolors == 2;
+}
+static int momentum_run(Handle* h, bool fused, int nit, double* out12) {
+  if (fused) return h->K <= 4 ? rb3_solve_t<4>(h, nit, out12) : rb3_solve_t<6>(h, nit, out12);
+  for (int eq = CFDL_EQ_U; eq <= CFDL_EQ_W; ++eq) {
+    int rc = solve_equation(h, eq, h->fld[CFDL_F_U + eq], h->fld[CFDL_F_BU + eq], nit, out12 ? out12 + 4 * eq : nullptr, false);
+    if (rc) return rc;
+  }
+  return CFDL_OK;
+}
+
+int solve_momentum(Handle* h, int nit, double* out12) {
+  if (!momentum_fusable(h)) return momentum_run(h, false, nit, out12);
+  Handle::Tuned& T = h->tune_uvw_solve;
+  if (h->autotune && h->uvw_fused < 0 && !T.done && h->profile == 0 && ++h->momentum_calls == 2) {
+    T.done = 1;
+    double* keep = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const size_t hb = sizeof(double) * (size_t)h->H;
+    bool ok = cudaMalloc(&keep, 3 * hb) == cudaSuccess && cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess;
+    auto put = [&](bool save) {
+      for (int q = 0; q < 3 && ok; ++q) {
+        double *a = keep + (size_t)q * h->H, *f = h->fld[CFDL_F_U + q];
+        ok = cudaMemcpyAsync(save ? a : f, save ? f : a, hb, cudaMemcpyDeviceToDevice, h->stream) == cudaSuccess;
+      }
+    };
+    int est[3] = {h->last_passes[0], h->last_passes[1], h->last_passes[2]};
+    put(true);
+    int rc = CFDL_OK;
+    if (ok) rc = momentum_run(h, true, nit, out12);  // untimed: first-use allocations of the side-by-side path
+    for (int cand = 0; cand < 2 && ok && !rc; ++cand) {
+      put(false);
+      for (int q = 0; q < 3; ++q) h->last_passes[q] = est[q];  // same batch estimates for both
+      float ms = -1.f;
+      ok = ok && cudaEventRecord(e0, h->stream) == cudaSuccess;
+      if (ok) rc = momentum_run(h, cand == 1, nit, out12);
+      ok = ok && !rc && cudaEventRecord(e1, h->stream) == cudaSuccess && cudaEventSynchronize(e1) == cudaSuccess &&
+           cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess;
+      T.cand[T.ncand] = cand; T.ms[T.ncand] = ms; T.ncand++;
+    }
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (keep) { cudaStreamSynchronize(h->stream); cudaFree(keep); }
+    if (rc) return rc;
+    if (!ok) { cudaGetLastError(); T.ncand = 0; return momentum_run(h, true, nit, out12); }  // u, v, w may be stale copies: solve again
+    T.choice = (T.ms[0] >= 0.f && T.ms[0] < T.ms[1]) ? 0 : 1;
+    return CFDL_OK;  // the last run (side by side) left u, v, w solved
+  }
+  const bool fused = h->uvw_fused >= 0 ? h->uvw_fused != 0 : (T.ncand ? T.choice == 1 : true);
+  return momentum_run(h, fused, nit, out12);
 }
 
 int solve_equation(Handle* h, int eq, double* phi, const double* rhs, int nit, double* out4, bool dispatch) {

@@ -104,7 +104,8 @@ struct Handle {
   double* rb3_work[2] = {nullptr, nullptr};
   SolveCtl* ctl3 = nullptr;       // device, 3 blocks
   SolveCtl* ctl3_host = nullptr;  // pinned
-  int uvw_fused = 1;              // 0: u, v, w are solved one after the other as the reference does
+  int uvw_fused = -1;             // 1: side by side, 0: one after the other as the reference does, -1: measured (autotune) else 1
+  int momentum_calls = 0;
   int last_passes[4] = {1, 1, 1, 1};  // per equation: passes the previous solve needed (first-batch size estimate)
   int fused_rb = 1;            // 0: always use one launch per colour + residual pass
   int use_p2p = 1;             // 0: NCCL send/recv even when peer slabs are connected
@@ -132,7 +133,7 @@ struct Handle {
   // Setting a *_variant option by hand pins that routine.  autotune = 0 keeps the defaults.
   int autotune = 1;
   struct Tuned { int done = 0, choice = -1, ncand = 0, cand[12] = {0}; float ms[12] = {0}; };
-  Tuned tune_uvw, tune_grad3, tune_grad1, tune_coef_p, tune_mip;
+  Tuned tune_uvw, tune_grad3, tune_grad1, tune_coef_p, tune_mip, tune_uvw_solve;
   int tune_ctas = 8;           // CTAs per SM for the solver passes (grid = min(need, num_sms * tune_ctas))
   // cfdl_step_host: transfer streams that run beside the compute stream, and a staging area of
   // its own (reference-numbered copies of the late input and the early outputs)
@@ -218,7 +219,7 @@ int solver_init(Handle* h);
 // dispatch=false: solve_gs (mod_solver.f90:255); dispatch=true: solve() (:329), i.e. the block
 // solver when the handle has n_subdomains>1
 int solve_equation(Handle* h, int eq, double* phi, const double* rhs, int nit, double* out4, bool dispatch);
-int solve_momentum_fused(Handle* h, int nit, double* out12, bool* handled);
+int solve_momentum(Handle* h, int nit, double* out12);  // u, v, w (side by side where possible)
 
 int residual_plain(Handle* h, const double* phi, const double* rhs, bool signed_max, double* res, double* res_max);
 // ---- comm.cu (no-ops on a single rank)

@@ -525,5 +525,5 @@ def test_momentum_solves_side_by_side_keep_the_bits(case, cfdl):
             for f, v in res[0][2].items():
                 assert np.array_equal(v, res[1][2][f]), (seed, nit, f)
     finally:
-        s.set_option("uvw_fused", 1)
+        s.set_option("uvw_fused", -1)
         s.set_option("solver", cfdl.SOLVER_PARITY)
