@@ -79,6 +79,17 @@ module mod_gpu_bridge
       real(c_double) :: hist(4,4)                        ! hist(:,k) = it,res_i,res_f,res_max of u,v,w,pc
       integer(c_int) :: ierr
     end function
+    function cfdl_step_host(h,dt,nit,apply_bcs,local_numbering,n_in,in_fields,in_ptrs,n_out,out_fields,out_ptrs,hist) &
+             bind(C,name='cfdl_step_host') result(ierr)
+      import :: c_ptr, c_int, c_double
+      type(c_ptr), value :: h
+      real(c_double), value :: dt
+      integer(c_int), value :: nit, apply_bcs, local_numbering, n_in, n_out
+      integer(c_int) :: in_fields(*), out_fields(*)
+      type(c_ptr) :: in_ptrs(*), out_ptrs(*)
+      real(c_double) :: hist(4,4)
+      integer(c_int) :: ierr
+    end function
     function cfdl_update_time(h) bind(C,name='cfdl_update_time') result(ierr)
       import :: c_ptr,c_int
       type(c_ptr), value :: h
@@ -162,6 +173,27 @@ contains
     do k=1,4
       write(*,"(5x,A16,x,i5,x,15x,es9.3e2,3x,es9.3e2,3x,es9.3e2)") names(k),int(hist(1,k)),hist(2,k),hist(3,k),hist(4,k)
     end do
+  end subroutine
+
+  ! update_boundaries + solve_uvwp with the HOST arrays of uvwp_t staying authoritative (for drivers
+  ! that touch the fields between iterations): one call, transfers overlapped with the computation
+  ! inside the library (cfdl_step_host).  Equivalent to upload / gpu_update_boundaries /
+  ! gpu_solve_uvwp / download of the thirteen state arrays.
+  subroutine gpu_step_host(eqn,dt,nit)
+    type(uvwp_t), target :: eqn
+    real :: dt
+    integer :: nit
+    real(c_double) :: hist(4,4)
+    integer(c_int) :: fin(13), fout(10)
+    type(c_ptr) :: pin(13), pout(10)
+    fin =[F_U,F_V,F_W,F_P,F_U0,F_V0,F_W0,F_GU,F_GV,F_GW,F_GP,F_MIP,F_MIP0]
+    pin =[c_loc(eqn%u(1)),c_loc(eqn%v(1)),c_loc(eqn%w(1)),c_loc(eqn%p(1)),c_loc(eqn%u0(1)),c_loc(eqn%v0(1)),c_loc(eqn%w0(1)), &
+          c_loc(eqn%gu(1)),c_loc(eqn%gv(1)),c_loc(eqn%gw(1)),c_loc(eqn%gp(1)),c_loc(eqn%mip(1)),c_loc(eqn%mip0(1))]
+    fout=[F_U,F_V,F_W,F_P,F_GU,F_GV,F_GW,F_GP,F_GPC,F_MIP]
+    pout=[c_loc(eqn%u(1)),c_loc(eqn%v(1)),c_loc(eqn%w(1)),c_loc(eqn%p(1)),c_loc(eqn%gu(1)),c_loc(eqn%gv(1)),c_loc(eqn%gw(1)), &
+          c_loc(eqn%gp(1)),c_loc(eqn%gpc(1)),c_loc(eqn%mip(1))]
+    call gpu_check(cfdl_step_host(cfdl_h,real(dt,c_double),int(nit,c_int),1_c_int,0_c_int,13_c_int,fin,pin,10_c_int,fout,pout,hist), &
+                   'cfdl_step_host')
   end subroutine
 
   ! drop-in for `call update_time(phys)` (main.f90:63)
