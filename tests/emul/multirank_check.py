@@ -52,6 +52,21 @@ def main():
                 fields[f] = a
             out[rank] = (hist, fields)
             bar.wait()
+            # cfdl_step_host with partition-local arrays (bench.py's e2e path on several GPUs) against the
+            # separate local upload / solve / download calls, from the same state: same bits on every rank
+            ins = "u v w p u0 v0 w0 gu gv gw gp mip mip0".split()
+            outs = "u v w p gu gv gw gp gpc mip".split()
+            state = {k: s.download_local(k, np.zeros(s.local_size(k))) for k in ins}
+            s.update_boundaries()
+            h_sep = s.solve_uvwp(0.01, 30)
+            want = {k: s.download_local(k, np.zeros(s.local_size(k))) for k in outs}
+            bar.wait()
+            got = {k: np.zeros(s.local_size(k)) for k in outs}
+            h_one = s.step_host({k: state[k] for k in ins}, got, dt=0.01, nit=30, apply_bcs=True, local=True)
+            assert np.array_equal(h_sep[:, 0], h_one[:, 0]), (rank, h_sep, h_one)
+            for k in outs:
+                assert np.array_equal(got[k], want[k]), (rank, k)
+            bar.wait()
             s.close()
         except Exception as ex:  # a failing rank must not leave the others at the barrier
             errs.append((rank, repr(ex)))
