@@ -316,7 +316,7 @@ def main():
     nprof = min(args.steps, 6)
     for i in range(nprof):
         step(args.warmup + args.steps + i)
-    kinds = ("sgs", "residual", "levels", "coef_uvw", "coef_p", "mip", "grad", "pcg")
+    kinds = ("sgs", "residual", "levels", "coef_uvw", "coef_p", "mip", "grad", "pcg", "sgs3")
     prof = {k: (s.get_info("prof_ms_" + k), int(s.get_info("prof_n_" + k))) for k in kinds}
     s.set_option("profile", 0)
     # fused passes are launched back to back and overlap head/tail (programmatic dependent launch);
@@ -371,6 +371,15 @@ def main():
         ach = ab["residual"] / (avg_ms * 1e-3) / 1e9
         extra_roof["residual_spmv"] = {"achieved": ach, "frac": ach / peak, "unit": "GB/s", "bytes_per_launch": ab["residual"],
                                        "avg_launch_ms": avg_ms, "launches_timed": prof["residual"][1]}
+    if prof["sgs3"][1] > 0:
+        # u, v, w side by side (kernels_rb3.inc): a pass reads a row's ap, anb, ids once (16+12K B) and per equation
+        # b + own value (16 B), writes 8 B (red passes 16 B) and gathers the other colour's values (8 B per cell, 16 in black passes)
+        n_r = n_owned // 2
+        per3 = (n_r * (16 + 12 * K + 3 * (16 + 16 + 8)) + (n_owned - n_r) * (16 + 12 * K + 3 * (16 + 8 + 16))) / 2.0
+        avg_ms = prof["sgs3"][0] / prof["sgs3"][1]
+        ach = per3 / (avg_ms * 1e-3) / 1e9
+        extra_roof["momentum_side_by_side_pass"] = {"achieved": ach, "frac": ach / peak, "unit": "GB/s", "bytes_per_launch": per3,
+                                                    "avg_launch_ms": avg_ms, "launches_timed": prof["sgs3"][1]}
     if roof is None and prof["levels"][1] > 0:
         # parity mode: one persistent launch = one (or two) symmetric iterations over all levels
         it_per_launch = 2 if (args.solver == "parity" and False) else 1

@@ -334,7 +334,7 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "reset_counters")) {
     int rc = prof_collect(h);
     h->launches = 0;
-    for (int k = 0; k < 8; ++k) { h->prof_ms[k] = 0.0; h->prof_n[k] = 0; }
+    for (int k = 0; k < PROF_KINDS; ++k) { h->prof_ms[k] = 0.0; h->prof_n[k] = 0; }
     return rc;
   }
   return fail(CFDL_ERR_ARG, "cfdl_set_option: unknown key '%s'", key);
@@ -376,12 +376,12 @@ int cfdl_get_info(cfdl_handle h, const char* key, double* value) {
   else if (!std::strcmp(key, "local_faces")) *value = h->F;
   else if (!std::strcmp(key, "neighbour_ranks")) *value = h->nnbr;
   else if (!std::strncmp(key, "prof_ms_", 8) || !std::strncmp(key, "prof_n_", 7)) {
-    static const char* names[8] = {"sgs", "residual", "coef_uvw", "coef_p", "mip", "grad", "levels", "pcg"};
+    static const char* names[PROF_KINDS] = {"sgs", "residual", "coef_uvw", "coef_p", "mip", "grad", "levels", "pcg", "sgs3"};
     const bool is_ms = key[5] == 'm';
     const char* nm = key + (is_ms ? 8 : 7);
     int rc = prof_collect(h);
     if (rc) return rc;
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < PROF_KINDS; ++k)
       if (!std::strcmp(nm, names[k])) { *value = is_ms ? h->prof_ms[k] : (double)h->prof_n[k]; return CFDL_OK; }
     return fail(CFDL_ERR_ARG, "cfdl_get_info: unknown kernel kind '%s'", nm);
   }

@@ -155,8 +155,8 @@ struct Handle {
   std::vector<cudaEvent_t> prof_ev;  // pairs (begin, end)
   std::vector<int> prof_kind, prof_cnt;  // per pair: kernel kind, launches it covers
   size_t prof_used = 0;
-  double prof_ms[8] = {0};
-  int64_t prof_n[8] = {0};
+  double prof_ms[10] = {0};
+  int64_t prof_n[10] = {0};
   cudaEvent_t timer_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -164,7 +164,7 @@ struct Handle {
 inline cudaStream_t S(Handle* h) { h->launches++; return h->stream; }
 
 // profiled kernel kinds (per-launch CUDA-event timing when h->profile is on)
-enum { PROF_SGS_SWEEP = 0, PROF_RESIDUAL = 1, PROF_COEF_UVW = 2, PROF_COEF_P = 3, PROF_MIP = 4, PROF_GRAD = 5, PROF_LEVELS = 6, PROF_PCG = 7 };
+enum { PROF_SGS_SWEEP = 0, PROF_RESIDUAL = 1, PROF_COEF_UVW = 2, PROF_COEF_P = 3, PROF_MIP = 4, PROF_GRAD = 5, PROF_LEVELS = 6, PROF_PCG = 7, PROF_SGS3 = 8, PROF_KINDS = 9 };
 int prof_begin(Handle* h, int kind, int level = 1);
 int prof_end(Handle* h, int count = 1, int level = 1);
 int prof_collect(Handle* h);  // after a stream sync: fold finished event pairs into prof_ms / prof_n

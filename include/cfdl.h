@@ -112,7 +112,7 @@ int cfdl_get_cell_order(cfdl_handle h, int32_t* c2o, int32_t* color_ptr);
  *                  "reset_counters" (any value); tuning switches: "fused", "pdl", "pdl_rows", "p2p",
  *                  "statics", "uvw_variant", "mip_variant", "occ_grids", "ctas_per_sm".
  * get_info keys:   "launches" (kernels launched since reset), "prof_ms_<k>" / "prof_n_<k>" with
- *                  k in sgs, residual, coef_uvw, coef_p, mip, grad, levels, pcg;
+ *                  k in sgs, residual, coef_uvw, coef_p, mip, grad, levels, pcg, sgs3 (u,v,w side-by-side passes);
  *                  "ncolors", "morton", "nlevels_natural", "nlevels_blocks", "ell_width", "num_sms". */
 int cfdl_timer_record(cfdl_handle h, int32_t slot);                 /* slot 0..3 */
 int cfdl_timer_elapsed_ms(cfdl_handle h, int32_t slot_begin, int32_t slot_end, double* ms);
