@@ -607,12 +607,12 @@ FieldMap field_map(const Handle* h, int f) {
   return {h->c2o, h->N, 1};
 }
 
-int ensure_xfer(Handle* h) {
+int ensure_xfer(Handle* h, bool need_stage) {
   if (!h->xfer_in && cudaStreamCreateWithFlags(&h->xfer_in, cudaStreamNonBlocking) != cudaSuccess) return fail(CFDL_ERR_CUDA, "cudaStreamCreate failed");
   if (!h->xfer_out && cudaStreamCreateWithFlags(&h->xfer_out, cudaStreamNonBlocking) != cudaSuccess) return fail(CFDL_ERR_CUDA, "cudaStreamCreate failed");
   for (cudaEvent_t& e : h->xfer_ev)
     if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(CFDL_ERR_CUDA, "cudaEventCreate failed");
-  if (!h->xstage) {  // mip0 | u v w | gu gv gw, each in the host's numbering
+  if (need_stage && !h->xstage) {  // mip0 | u v w | gu gv gw, each in the host's numbering (partition-local arrays need none)
     const Prep& p = h->prep;
     h->xstage_len = (size_t)p.gF + 12 * ((size_t)p.gN + p.gB) + 16;
     int rc = dev_zero(h, h->xstage, h->xstage_len);
@@ -686,7 +686,7 @@ extern "C" int cfdl_step_host(cfdl_handle h, double dt, int32_t nit, int32_t app
   if (!local && h->prep.nranks > 1)
     return fail(CFDL_ERR_UNSUPPORTED, "cfdl_step_host: on a partitioned handle pass partition-local arrays (local_numbering = 1)");
   int rc;
-  if ((rc = ensure_xfer(h))) return rc;
+  if ((rc = ensure_xfer(h, !local))) return rc;
   HostStepHook hook;
   hook.h = h;
   hook.local = local;
