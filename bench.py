@@ -346,8 +346,11 @@ def main():
             # gathers the black values, writes mid+new; a black pass gathers two red arrays and writes one value.
             n_r = n_owned // 2
             halo_vals = int(s.get_info("ghost_cells")) + n_local_halos
-            red = n_r * (16 + 12 * K + 8 + 16) + 8 * (n_owned - n_r + halo_vals)
-            black = (n_owned - n_r) * (16 + 12 * K + 8 + 8) + 16 * (n_r + halo_vals)
+            # pc passes (nearly all of them: the momentum passes have their own entry when they run side by side) rebuild
+            # ap from the row's anb instead of reading it (pc_sumap): 8 + 12K bytes of matrix per row instead of 16 + 12K
+            row = (8 if int(s.get_info("pc_sumap")) else 16) + 12 * K
+            red = n_r * (row + 8 + 16) + 8 * (n_owned - n_r + halo_vals)
+            black = (n_owned - n_r) * (row + 8 + 8) + 16 * (n_r + halo_vals)
             per_launch = (red + black) / 2.0
             kname = "rb_red_kernel / rb_black_kernel (fused two-colour SGS pass incl. residual; average of the two)"
         else:

@@ -57,6 +57,7 @@ int use_device(Handle* h) {
 
 // host (reference numbering, global mesh) -> device field (owned + ghost cells, local halos/faces)
 int upload_field(Handle* h, int f, const double* host) {
+  if (f == CFDL_F_AP || f == CFDL_F_ANB) h->pc_sumap_ok = false;  // caller-supplied matrix: the diagonal must be read
   CFDL_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * host_len(h, f), cudaMemcpyHostToDevice, h->stream));
   if (f == CFDL_F_ANB) return k_csr_to_ell(h, h->fld[f], h->stage);
   if (f <= CFDL_F_PC) return k_gather(h, h->fld[f], h->stage, h->cellmap, h->H, 1);
@@ -313,6 +314,7 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "pdl_rows")) { h->pdl_rows = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "pdl")) { h->use_pdl = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "uvw_variant")) { h->uvw_variant = (int)value; h->tune_uvw.done = 1; return CFDL_OK; }  // pinned by hand
+  if (!std::strcmp(key, "pc_sumap")) { h->pc_sumap = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "uvw_fused")) { h->uvw_fused = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
   if (!std::strcmp(key, "grad_variant")) { h->grad_variant = (int)value; return CFDL_OK; }
   if (!std::strcmp(key, "coef_p_variant")) { h->coef_p_variant = (int)value; return CFDL_OK; }
@@ -351,6 +353,7 @@ int cfdl_get_info(cfdl_handle h, const char* key, double* value) {
   else if (!std::strcmp(key, "solver")) *value = h->solver_mode;
   else if (!std::strcmp(key, "launches")) *value = (double)h->launches;
   else if (!std::strcmp(key, "uvw_variant")) *value = h->uvw_variant;
+  else if (!std::strcmp(key, "pc_sumap")) *value = h->pc_sumap;
   else if (!std::strncmp(key, "tuned_", 6)) {
     // "tuned_<routine>" = chosen variant (-1: not tuned); "tuned_<routine>_ms<i>" / "_cand<i>" = the measurements
     const Handle::Tuned* T = nullptr;
@@ -426,6 +429,7 @@ int cfdl_field_local_size(cfdl_handle h, int field, int64_t* n) {
 int cfdl_upload_field_local(cfdl_handle h, int field, const double* host) {
   ENTER(h);
   if (field < 0 || field >= CFDL_F_COUNT || !host) return fail(CFDL_ERR_ARG, "cfdl_upload_field_local: bad field/pointer");
+  if (field == CFDL_F_AP || field == CFDL_F_ANB) h->pc_sumap_ok = false;
   CFDL_CUDA(cudaMemcpyAsync(h->fld[field], host, sizeof(double) * field_len(h, field), cudaMemcpyHostToDevice, h->stream));
   FINISH(h);
 }
@@ -695,6 +699,7 @@ extern "C" int cfdl_step_host(cfdl_handle h, double dt, int32_t nit, int32_t app
   for (int i = 0; i < n_in; ++i) {
     const int f = in_fields[i];
     if (f == CFDL_F_MIP0) { hook.late_mip0 = in_ptrs[i]; continue; }
+    if (f == CFDL_F_AP || f == CFDL_F_ANB) h->pc_sumap_ok = false;
     if (local) CFDL_CUDA(cudaMemcpyAsync(h->fld[f], in_ptrs[i], sizeof(double) * field_len(h, f), cudaMemcpyHostToDevice, h->stream));
     else if ((rc = upload_field(h, f, in_ptrs[i]))) return rc;
   }

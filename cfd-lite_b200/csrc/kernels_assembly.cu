@@ -320,6 +320,7 @@ int k_calc_coef_uvw(Handle* h, double dt) {
   const int g = grid_for(h, h->N, TPB);
   const int gs = grid_for(h, h->N, UVW_CELLS, 16);
   if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
+  h->pc_sumap_ok = false;  // ap, anb become the momentum matrix
   if (h->autotune && !h->tune_uvw.done && h->profile == 0 && h->uvw_variant == 2 && h->use_statics && h->fs_area) {
     // same bits from every candidate (tests); 2 = divisions, 3 = reciprocal quotients, 5 = 3 with stored
     // reciprocals, 6/7/8 = 5/3/2 in the paired colour order, 4 = 3 with three CTAs per SM requested
@@ -410,6 +411,7 @@ int k_calc_coef_p(Handle* h) {
   const int g = grid_for(h, h->N, TPB);
 #define CP_ARGS h->N, h->Nc, h->Np, h->ell_nb, h->ell_fs, h->nfc, h->halo_bc, h->xc, h->yc, h->zc, h->aip, h->rip, h->rho, \
                 h->fld[CFDL_F_DC], h->fld[CFDL_F_MIP], h->fld[CFDL_F_AP], h->fld[CFDL_F_ANB], h->fld[CFDL_F_B]
+  h->pc_sumap_ok = true;  // every form of calc_coef_p builds ap as the slot-order sum of the anb it stores
   prof_begin(h, PROF_COEF_P);
   if (h->use_statics && h->fs_area && h->K <= 6) { int rc = k_calc_coef_p_statics(h); if (rc) return rc; }
   else if (h->K <= 4) coef_p_kernel<4><<<g, TPB, 0, S(h)>>>(CP_ARGS);

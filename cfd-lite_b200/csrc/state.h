@@ -104,6 +104,8 @@ struct Handle {
   double* rb3_work[2] = {nullptr, nullptr};
   SolveCtl* ctl3 = nullptr;       // device, 3 blocks
   SolveCtl* ctl3_host = nullptr;  // pinned
+  int pc_sumap = 1;               // fused pc passes rebuild ap as the slot-order sum of anb instead of reading it
+  bool pc_sumap_ok = false;       // true while ap/anb on the device are what calc_coef_p wrote (cleared by any other writer)
   int uvw_fused = -1;             // 1: side by side, 0: one after the other as the reference does, -1: measured (autotune) else 1
   int momentum_calls = 0;
   int last_passes[4] = {1, 1, 1, 1};  // per equation: passes the previous solve needed (first-batch size estimate)

@@ -527,3 +527,40 @@ def test_momentum_solves_side_by_side_keep_the_bits(case, cfdl):
     finally:
         s.set_option("uvw_fused", -1)
         s.set_option("solver", cfdl.SOLVER_PARITY)
+
+
+def test_pc_passes_rebuilding_the_diagonal_keep_the_bits(case, cfdl):
+    """pc_sumap=1: the fused pc passes do not read ap but rebuild it as the slot-order sum of the row's
+    coefficients — how calc_coef_p forms it — against pc_sumap=0: identical history and fields; a
+    caller-supplied matrix (host drop-in) whose diagonal is NOT that sum must still be honoured."""
+    name, raw, oc, geom, s = case
+    if int(s.get_info("ncolors")) != 2:
+        pytest.skip("fused two-colour passes only")
+    s.set_option("solver", cfdl.SOLVER_MCSGS)
+    try:
+        res = {}
+        for flag in (0, 1):
+            s.set_option("pc_sumap", flag)
+            randomize(oc, s, seed=59)
+            hs = []
+            for _ in range(2):
+                s.update_boundaries()
+                hs.append(s.solve_uvwp(0.01, 30))
+            res[flag] = (np.array(hs), {f: s.download(f) for f in ("u", "p", "pc", "gpc", "mip")})
+        assert np.array_equal(res[0][0], res[1][0])
+        for f, v in res[0][1].items():
+            assert np.array_equal(v, res[1][1][f]), f
+        # host drop-in with a diagonally dominant matrix (ap != sum anb): the flag must not apply
+        s.set_option("pc_sumap", 1)
+        s.update_boundaries(); s.solve_uvwp(0.01, 3)  # leaves the device matrix in the "written by calc_coef_p" state
+        ap, anb, b, phi0 = assembled_system(oc)
+        want_phi, want = None, None
+        for flag in (0, 1):
+            s.set_option("pc_sumap", flag)
+            got_phi, got = s.host_solve_gs(3, phi0, ap, anb, b, nit=4)
+            if want_phi is None:
+                want_phi, want = got_phi, got
+        assert np.array_equal(got_phi, want_phi) and np.array_equal(got, want)
+    finally:
+        s.set_option("pc_sumap", 1)
+        s.set_option("solver", cfdl.SOLVER_PARITY)
