@@ -37,3 +37,16 @@ def test_bench_script_runs_under_emulation():
         assert key in line, key
     assert line["e2e"]["path"].startswith("cfdl_step_host") and line["e2e"]["path_error"] is None
     assert line["gpu_launches"] > 0 and line["cpu_baseline"]["kind"] == "port"
+
+
+def test_medium_mesh_runs_under_emulation():
+    """Grids of tens of CTAs with several rows per thread (tests/emul/medium_check.py): exact mode equals the
+    oracle; the throughput mode with randomly drawn kernel variants and every post-round-1 path on equals
+    the same mode with all of them off, bit for bit."""
+    import os as _os
+    for seed in ("3", "8"):
+        env = dict(_os.environ, CUEMU_RANDOM_TIMES=seed)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "medium_check.py"), "16"], cwd=ROOT, env=env,
+                           capture_output=True, text=True, timeout=1200)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+        assert "medium emulation ok" in r.stdout
