@@ -483,10 +483,11 @@ int residual_plain(Handle* h, const double* phi, const double* rhs, bool signed_
 // Both orders give the same bits, so with autotune on the second call of a handle measures both on
 // its own data (u, v, w are put back in between) and later calls use the faster one.
 static bool momentum_fusable(const Handle* h) {
-  return h->K <= 6 && h->prep.nranks == 1 && h->solver_mode != CFDL_SOLVER_PARITY && h->fused_rb && h->prep.ncolors == 2;
+  return h->K <= 6 && h->prep.nranks == 1 && h->solver_mode != CFDL_SOLVER_PARITY;
 }
 static int momentum_run(Handle* h, bool fused, int nit, double* out12) {
-  if (fused) return h->K <= 4 ? rb3_solve_t<4>(h, nit, out12) : rb3_solve_t<6>(h, nit, out12);
+  if (fused && h->fused_rb && h->prep.ncolors == 2) return h->K <= 4 ? rb3_solve_t<4>(h, nit, out12) : rb3_solve_t<6>(h, nit, out12);
+  if (fused) return h->K <= 4 ? mcsgs3_solve_t<4>(h, nit, out12) : mcsgs3_solve_t<6>(h, nit, out12);
   for (int eq = CFDL_EQ_U; eq <= CFDL_EQ_W; ++eq) {
     int rc = solve_equation(h, eq, h->fld[CFDL_F_U + eq], h->fld[CFDL_F_BU + eq], nit, out12 ? out12 + 4 * eq : nullptr, false);
     if (rc) return rc;

@@ -499,12 +499,10 @@ def test_pcg_solves_the_pc_system_like_its_numpy_model(case, cfdl):
 
 
 def test_momentum_solves_side_by_side_keep_the_bits(case, cfdl):
-    """uvw_fused=1 (u, v, w in one set of fused two-colour passes, matrix rows read once per pass,
-    kernels_rb3.inc) against uvw_fused=0 (three separate solves as the reference orders them): every
+    """uvw_fused=1 (u, v, w in one set of passes — fused two-colour passes, or one launch per colour on
+    meshes with more colours — matrix rows read once per pass, kernels_rb3.inc) against uvw_fused=0 (three separate solves as the reference orders them): every
     equation stops at its own iteration count and all fields are bit-identical."""
     name, raw, oc, geom, s = case
-    if int(s.get_info("ncolors")) != 2:
-        pytest.skip("the side-by-side passes need a two-colour mesh")
     s.set_option("solver", cfdl.SOLVER_MCSGS)
     try:
         for seed, nit in ((43, 100), (47, 2), (53, 1)):
