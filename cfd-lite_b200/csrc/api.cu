@@ -314,6 +314,7 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "pdl_rows")) { h->pdl_rows = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "pdl")) { h->use_pdl = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "uvw_variant")) { h->uvw_variant = (int)value; h->tune_uvw.done = 1; return CFDL_OK; }  // pinned by hand
+  if (!std::strcmp(key, "rb_persistent")) { h->rb_persistent = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
   if (!std::strcmp(key, "pc_sumap")) { h->pc_sumap = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "uvw_fused")) { h->uvw_fused = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
   if (!std::strcmp(key, "grad_variant")) { h->grad_variant = (int)value; return CFDL_OK; }
@@ -323,6 +324,7 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
     if (value == 2.0) {
       h->tune_uvw = Handle::Tuned(); h->tune_grad3 = Handle::Tuned(); h->tune_grad1 = Handle::Tuned(); h->tune_coef_p = Handle::Tuned();
       h->tune_mip = Handle::Tuned(); h->tune_uvw_solve = Handle::Tuned(); h->momentum_calls = 0;
+      h->tune_rbp = Handle::Tuned(); h->pc_solves = 0;
     }
     return CFDL_OK;
   }
@@ -359,9 +361,9 @@ int cfdl_get_info(cfdl_handle h, const char* key, double* value) {
     const Handle::Tuned* T = nullptr;
     const char* r = key + 6;
     size_t len = 0;
-    static const char* names[6] = {"uvw", "grad3", "grad1", "coef_p", "mip", "uvw_solve"};
-    const Handle::Tuned* all[6] = {&h->tune_uvw, &h->tune_grad3, &h->tune_grad1, &h->tune_coef_p, &h->tune_mip, &h->tune_uvw_solve};
-    for (int i = 0; i < 6; ++i) {
+    static const char* names[7] = {"uvw", "grad3", "grad1", "coef_p", "mip", "uvw_solve", "rb_persistent"};
+    const Handle::Tuned* all[7] = {&h->tune_uvw, &h->tune_grad3, &h->tune_grad1, &h->tune_coef_p, &h->tune_mip, &h->tune_uvw_solve, &h->tune_rbp};
+    for (int i = 0; i < 7; ++i) {
       const size_t l = std::strlen(names[i]);
       if (!std::strncmp(r, names[i], l) && (r[l] == 0 || r[l] == '_') && l > len) { T = all[i]; len = l; }
     }

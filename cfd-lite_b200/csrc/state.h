@@ -104,6 +104,8 @@ struct Handle {
   double* rb3_work[2] = {nullptr, nullptr};
   SolveCtl* ctl3 = nullptr;       // device, 3 blocks
   SolveCtl* ctl3_host = nullptr;  // pinned
+  int rb_persistent = -1;         // fused passes of a batch in one cooperative launch: 1 on, 0 off, -1 measured (autotune) else off
+  int rbp_refused = 0, pc_solves = 0;
   int pc_sumap = 1;               // fused pc passes rebuild ap as the slot-order sum of anb instead of reading it
   bool pc_sumap_ok = false;       // true while ap/anb on the device are what calc_coef_p wrote (cleared by any other writer)
   int uvw_fused = -1;             // 1: side by side, 0: one after the other as the reference does, -1: measured (autotune) else 1
@@ -135,7 +137,7 @@ struct Handle {
   // Setting a *_variant option by hand pins that routine.  autotune = 0 keeps the defaults.
   int autotune = 1;
   struct Tuned { int done = 0, choice = -1, ncand = 0, cand[12] = {0}; float ms[12] = {0}; };
-  Tuned tune_uvw, tune_grad3, tune_grad1, tune_coef_p, tune_mip, tune_uvw_solve;
+  Tuned tune_uvw, tune_grad3, tune_grad1, tune_coef_p, tune_mip, tune_uvw_solve, tune_rbp;
   int tune_ctas = 8;           // CTAs per SM for the solver passes (grid = min(need, num_sms * tune_ctas))
   // cfdl_step_host: transfer streams that run beside the compute stream, and a staging area of
   // its own (reference-numbered copies of the late input and the early outputs)

@@ -44,17 +44,17 @@ def main():
         s = cfdl.Solver(geom, bcs, device=0)
         s.set_option("solver", cfdl.SOLVER_MCSGS)
         if not new:
-            for k, v in (("autotune", 0), ("uvw_fused", 0), ("pc_sumap", 0), ("grad_variant", 0), ("coef_p_variant", 0), ("uvw_variant", 2)):
+            for k, v in (("autotune", 0), ("uvw_fused", 0), ("pc_sumap", 0), ("grad_variant", 0), ("coef_p_variant", 0), ("uvw_variant", 2), ("rb_persistent", 0)):
                 s.set_option(k, v)
         h = s.run(dt=0.5, nit=100, ntstep=2, ncoef=3)
         res[new] = (h, {f: s.download(f) for f in ("u", "v", "w", "p", "gu", "gp", "mip")},
-                    [int(s.get_info("tuned_" + r)) for r in ("uvw", "grad3", "grad1", "coef_p", "uvw_solve")])
+                    [int(s.get_info("tuned_" + r)) for r in ("uvw", "grad3", "grad1", "coef_p", "uvw_solve", "rb_persistent")])
         s.close()
     assert np.array_equal(res[0][0][:, :, 0], res[1][0][:, :, 0])
     assert np.allclose(res[0][0], res[1][0], rtol=1e-12, atol=0.0)
     for f, v in res[0][1].items():
         assert np.array_equal(v, res[1][1][f]), f
-    print("medium emulation ok: n=%d exact-mode err %.1e; variants chosen (uvw, grad3, grad1, coef_p, uvw_solve) = %s; momentum its %s"
+    print("medium emulation ok: n=%d exact-mode err %.1e; variants chosen (uvw, grad3, grad1, coef_p, uvw_solve, rb_persistent) = %s; momentum its %s"
           % (n, worst, res[1][2], res[1][0][-1, :3, 0].astype(int).tolist()))
 
 

@@ -562,3 +562,33 @@ def test_pc_passes_rebuilding_the_diagonal_keep_the_bits(case, cfdl):
     finally:
         s.set_option("pc_sumap", 1)
         s.set_option("solver", cfdl.SOLVER_PARITY)
+
+
+def test_persistent_passes_keep_the_bits(case, cfdl):
+    """rb_persistent=1 (all fused passes of a batch in one cooperative launch with grid barriers,
+    kernels_rbp.inc) against rb_persistent=0 (one launch per pass): same row-to-thread mapping and
+    reductions, hence identical fields AND identical residual history."""
+    name, raw, oc, geom, s = case
+    if int(s.get_info("ncolors")) != 2:
+        pytest.skip("fused two-colour passes only")
+    s.set_option("solver", cfdl.SOLVER_MCSGS)
+    try:
+        res = {}
+        for flag in (0, 1):
+            s.set_option("rb_persistent", flag)
+            for sep in (0, 1):  # momentum one by one runs the single-equation passes too
+                s.set_option("uvw_fused", 1 - sep)
+                randomize(oc, s, seed=61)
+                hs = []
+                for nit in (1, 2, 40):
+                    s.update_boundaries()
+                    hs.append(s.solve_uvwp(0.01, nit))
+                res[flag, sep] = (np.array(hs), {f: s.download(f) for f in ("u", "v", "w", "p", "pc", "mip")})
+        for sep in (0, 1):
+            assert np.array_equal(res[0, sep][0], res[1, sep][0]), (res[0, sep][0], res[1, sep][0])
+            for f, v in res[0, sep][1].items():
+                assert np.array_equal(v, res[1, sep][1][f]), (sep, f)
+    finally:
+        s.set_option("rb_persistent", -1)
+        s.set_option("uvw_fused", -1)
+        s.set_option("solver", cfdl.SOLVER_PARITY)
