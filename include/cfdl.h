@@ -49,7 +49,8 @@ enum {
   CFDL_SOLVER_MCSGS = 1,  /* multicolour symmetric Gauss-Seidel: same update formula, same
                              stopping rule, colour order instead of natural order */
   CFDL_SOLVER_PCG = 2     /* pc: Jacobi-preconditioned conjugate gradients with the reference's stopping rule (not a
-                             restatement of solve_gs: same interface, fewer matrix passes); u,v,w: MCSGS; one GPU */
+                             restatement of solve_gs: same interface, fewer matrix passes); u,v,w: MCSGS; partitioned handles:
+                             ghost exchange of the search direction + all-reduced dot products per iteration */
 };
 
 /* field selectors for upload/download and the per-routine entry points */

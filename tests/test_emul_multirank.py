@@ -12,9 +12,10 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("world,n,structured", [(2, 8, False), (4, 10, False), (8, 12, False), (4, 12, True)])
+@pytest.mark.parametrize("world,n,structured", [(2, 8, False), (4, 10, False), (8, 12, False), (4, 12, True), (4, 10, "pcg")])
 def test_partitioned_p2p_run_equals_single_rank_under_emulation(world, n, structured):
-    cmd = [sys.executable, os.path.join(ROOT, "tests", "emul", "multirank_check.py"), str(world), str(n)] + (["structured"] if structured else [])
+    extra = [structured] if isinstance(structured, str) else (["structured"] if structured else [])
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "emul", "multirank_check.py"), str(world), str(n)] + extra
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "multirank emulation ok" in r.stdout
