@@ -150,3 +150,76 @@ extern "C" int cfdl_meshgen_fill(int kind, int n, double jitter, int shuffle, ui
   }
   return (b == ne + nbf) ? CFDL_OK : CFDL_ERR_INTERNAL;
 }
+
+// ---- raw mesh file -------------------------------------------------------------------------------
+// What cell_input.f90:36-99 obtains from the CGNS library, in one little-endian binary file, for
+// drivers built without CGNS/HDF5 (the reference needs a modified cgnslib 3.2.1): the Fortran side
+// reads it with stream access (cfd-lite_b200/fortran/mod_rawmesh.f90) instead of cgns_db_open /
+// cg_section_read_f / cgns_element_info / cgns_cell_data.  Layout:
+//   char[8] "CFDLRAW1" | int64 nvx | int64 nelem | int32 nsec | int32 ne2vx_max |
+//   nsec x { char[32] name (blank padded) | int32 etype | int32 first | int32 last } |
+//   double x[nvx] | double y[nvx] | double z[nvx] | int32 e2vx[ne2vx_max * nelem]
+#include <cstdio>
+namespace {
+const char kRawMagic[8] = {'C', 'F', 'D', 'L', 'R', 'A', 'W', '1'};
+struct File {
+  std::FILE* f;
+  explicit File(std::FILE* p) : f(p) {}
+  ~File() { if (f) std::fclose(f); }
+};
+bool put(std::FILE* f, const void* p, size_t n) { return n == 0 || std::fwrite(p, 1, n, f) == n; }
+bool get(std::FILE* f, void* p, size_t n) { return n == 0 || std::fread(p, 1, n, f) == n; }
+int raw_header(std::FILE* f, int64_t* nvx, int64_t* nelem, int32_t* nsec, int32_t* w) {
+  char magic[8];
+  if (!get(f, magic, 8) || std::memcmp(magic, kRawMagic, 8) != 0) return CFDL_ERR_ARG;
+  if (!get(f, nvx, 8) || !get(f, nelem, 8) || !get(f, nsec, 4) || !get(f, w, 4)) return CFDL_ERR_ARG;
+  if (*nvx < 0 || *nelem < 0 || *nsec < 0 || *nsec > 4096 || *w < 0 || *w > 64) return CFDL_ERR_ARG;
+  return CFDL_OK;
+}
+}  // namespace
+
+extern "C" int cfdl_rawmesh_write(const char* path, int64_t nvx, const double* x, const double* y, const double* z, int nsec,
+                                  const int32_t* etype, const int32_t* esec, const char* names, int ne2vx_max, const int32_t* e2vx,
+                                  int64_t nelem) {
+  if (!path || !x || !y || !z || !etype || !esec || !names || !e2vx || nvx < 0 || nelem < 0 || nsec < 0 || ne2vx_max < 0) return CFDL_ERR_ARG;
+  File fh(std::fopen(path, "wb"));
+  if (!fh.f) return CFDL_ERR_ARG;
+  const int32_t ns = nsec, w = ne2vx_max;
+  bool ok = put(fh.f, kRawMagic, 8) && put(fh.f, &nvx, 8) && put(fh.f, &nelem, 8) && put(fh.f, &ns, 4) && put(fh.f, &w, 4);
+  for (int s = 0; s < nsec && ok; ++s) {
+    char nm[32];
+    std::memset(nm, ' ', 32);
+    for (int i = 0; i < 32 && names[32 * s + i] != 0; ++i) nm[i] = names[32 * s + i];
+    ok = put(fh.f, nm, 32) && put(fh.f, &etype[s], 4) && put(fh.f, &esec[2 * s], 4) && put(fh.f, &esec[2 * s + 1], 4);
+  }
+  ok = ok && put(fh.f, x, 8 * (size_t)nvx) && put(fh.f, y, 8 * (size_t)nvx) && put(fh.f, z, 8 * (size_t)nvx) &&
+       put(fh.f, e2vx, 4 * (size_t)ne2vx_max * (size_t)nelem);
+  return ok ? CFDL_OK : CFDL_ERR_INTERNAL;
+}
+
+extern "C" int cfdl_rawmesh_sizes(const char* path, int64_t* nvx, int64_t* nelem, int* nsec, int* ne2vx_max) {
+  if (!path || !nvx || !nelem || !nsec || !ne2vx_max) return CFDL_ERR_ARG;
+  File fh(std::fopen(path, "rb"));
+  if (!fh.f) return CFDL_ERR_ARG;
+  int32_t ns = 0, w = 0;
+  int rc = raw_header(fh.f, nvx, nelem, &ns, &w);
+  *nsec = ns; *ne2vx_max = w;
+  return rc;
+}
+
+extern "C" int cfdl_rawmesh_read(const char* path, double* x, double* y, double* z, int32_t* etype, int32_t* esec, char* names,
+                                 int32_t* e2vx) {
+  if (!path || !x || !y || !z || !etype || !esec || !names || !e2vx) return CFDL_ERR_ARG;
+  File fh(std::fopen(path, "rb"));
+  if (!fh.f) return CFDL_ERR_ARG;
+  int64_t nvx = 0, nelem = 0;
+  int32_t ns = 0, w = 0;
+  int rc = raw_header(fh.f, &nvx, &nelem, &ns, &w);
+  if (rc) return rc;
+  bool ok = true;
+  for (int s = 0; s < ns && ok; ++s)
+    ok = get(fh.f, names + 32 * s, 32) && get(fh.f, &etype[s], 4) && get(fh.f, &esec[2 * s], 4) && get(fh.f, &esec[2 * s + 1], 4);
+  ok = ok && get(fh.f, x, 8 * (size_t)nvx) && get(fh.f, y, 8 * (size_t)nvx) && get(fh.f, z, 8 * (size_t)nvx) &&
+       get(fh.f, e2vx, 4 * (size_t)w * (size_t)nelem);
+  return ok ? CFDL_OK : CFDL_ERR_ARG;
+}

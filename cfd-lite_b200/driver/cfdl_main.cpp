@@ -22,7 +22,7 @@
   } while (0)
 
 int main(int argc, char** argv) {
-  if (argc < 3) { std::fprintf(stderr, "usage: %s <hex|tet> <n> [solver] [ntstep] [ncoef] [n_subdomains]\n", argv[0]); return 2; }
+  if (argc < 3) { std::fprintf(stderr, "usage: %s <hex|tet|file:mesh.raw> <n> [solver] [ntstep] [ncoef] [n_subdomains]\n", argv[0]); return 2; }
   const int kind = !std::strcmp(argv[1], "tet") ? CFDL_MESH_TET : CFDL_MESH_HEX;
   const int n = std::atoi(argv[2]);
   const std::string solver = argc > 3 ? argv[3] : "parity";
@@ -32,16 +32,33 @@ int main(int argc, char** argv) {
   const double dt = 0.01;
   const int nit = 100;
 
-  int64_t nvx, ne64, nbf64;
+  // the mesh: a raw mesh file (file:<path>, the CGNS-free input of cfdl_rawmesh_write / mod_rawmesh.f90) or a synthetic cube
+  int64_t nvx, ne64 = 0, nbf64 = 0;
   int nsec, w;
-  CHECK(cfdl_meshgen_sizes(kind, n, &nvx, &ne64, &nbf64, &nsec, &w));
+  std::vector<double> x, y, z;
+  std::vector<int32_t> e2vx, etype, esec;
+  std::vector<char> names;
+  int64_t faces2 = 0;  // sum of faces per 3-D cell
+  if (!std::strncmp(argv[1], "file:", 5)) {
+    int64_t nelem;
+    CHECK(cfdl_rawmesh_sizes(argv[1] + 5, &nvx, &nelem, &nsec, &w));
+    x.resize(nvx); y.resize(nvx); z.resize(nvx); e2vx.resize((size_t)w * nelem); etype.resize(nsec); esec.resize(2 * nsec); names.resize(32 * nsec);
+    CHECK(cfdl_rawmesh_read(argv[1] + 5, x.data(), y.data(), z.data(), etype.data(), esec.data(), names.data(), e2vx.data()));
+  } else {
+    CHECK(cfdl_meshgen_sizes(kind, n, &nvx, &ne64, &nbf64, &nsec, &w));
+    x.resize(nvx); y.resize(nvx); z.resize(nvx); e2vx.resize((size_t)w * (ne64 + nbf64)); etype.resize(nsec); esec.resize(2 * nsec); names.resize(32 * nsec);
+    CHECK(cfdl_meshgen_fill(kind, n, kind == CFDL_MESH_TET ? 0.2 : 0.0, kind == CFDL_MESH_TET, 12345, x.data(), y.data(), z.data(),
+                            e2vx.data(), etype.data(), esec.data(), names.data()));
+  }
+  ne64 = nbf64 = 0;
+  for (int s = 0; s < nsec; ++s) {  // cell_input.f90:58-71 (faces per cell: mod_util.f90:168)
+    const int64_t cnt = esec[2 * s + 1] - esec[2 * s] + 1;
+    const int t = etype[s];
+    if (t >= 10 && t <= 20) { ne64 += cnt; faces2 += cnt * (t == 17 ? 6 : t == 10 ? 4 : 5); }
+    else nbf64 += cnt;
+  }
   const int32_t ne = (int32_t)ne64, nbf = (int32_t)nbf64;
-  std::vector<double> x(nvx), y(nvx), z(nvx);
-  std::vector<int32_t> e2vx((size_t)w * (ne + nbf)), etype(nsec), esec(2 * nsec);
-  std::vector<char> names(32 * nsec);
-  CHECK(cfdl_meshgen_fill(kind, n, kind == CFDL_MESH_TET ? 0.2 : 0.0, kind == CFDL_MESH_TET, 12345, x.data(), y.data(), z.data(),
-                          e2vx.data(), etype.data(), esec.data(), names.data()));
-  const int32_t nf = (int32_t)(((int64_t)(kind == CFDL_MESH_HEX ? 6 : 4) * ne + nbf) / 2);
+  const int32_t nf = (int32_t)((faces2 + nbf) / 2);
   const int64_t Z = 2 * (int64_t)nf - nbf, H = (int64_t)ne + nbf;
   std::vector<int32_t> idx(ne + 1), nb(Z), fg(Z), s2g(nf), bs(nbf);
   std::vector<double> xc(H), yc(H), zc(H), aip(3 * (size_t)nf), rip(3 * (size_t)nf), vol(ne);

@@ -81,6 +81,32 @@ def meshgen(kind, n, jitter=0.0, shuffle=False, seed=12345):
                 x=x, y=y, z=z, e2vx=e2vx, etype=etype, esec=esec, names=names.raw)
 
 
+def rawmesh_write(raw, path):
+    """Write a mesh (dict as returned by meshgen) to the raw mesh file format (cfdl_rawmesh_write)."""
+    x, y, z = _f64(raw["x"]), _f64(raw["y"]), _f64(raw["z"])
+    et, es, e2vx = _i32(raw["etype"]), _i32(raw["esec"]), _i32(raw["e2vx"])
+    nelem = int(raw["ne"]) + int(raw["nbf"])
+    _chk(lib().cfdl_rawmesh_write(path.encode(), C.c_int64(len(x)), _d(x), _d(y), _d(z), C.c_int(len(et)), _i(et), _i(es),
+                                  C.c_char_p(bytes(raw["names"])), C.c_int(int(raw["ne2vx_max"])), _i(e2vx), C.c_int64(nelem)))
+
+
+def rawmesh_read(path):
+    """Read a raw mesh file into the dict format of meshgen (kind / n are not stored: None)."""
+    L = lib()
+    nvx, nelem = C.c_int64(), C.c_int64()
+    nsec, w = C.c_int(), C.c_int()
+    _chk(L.cfdl_rawmesh_sizes(path.encode(), C.byref(nvx), C.byref(nelem), C.byref(nsec), C.byref(w)))
+    x, y, z = (np.zeros(nvx.value) for _ in range(3))
+    e2vx = np.zeros(w.value * nelem.value, np.int32)
+    etype = np.zeros(nsec.value, np.int32)
+    esec = np.zeros(2 * nsec.value, np.int32)
+    names = C.create_string_buffer(32 * nsec.value)
+    _chk(L.cfdl_rawmesh_read(path.encode(), _d(x), _d(y), _d(z), _i(etype), _i(esec), names, _i(e2vx)))
+    ne = sum(int(esec[2 * s + 1] - esec[2 * s] + 1) for s in range(nsec.value) if etype[s] >= 10)
+    return dict(kind=None, n=None, nvx=nvx.value, ne=ne, nbf=nelem.value - ne, nsec=nsec.value, ne2vx_max=w.value,
+                x=x, y=y, z=z, e2vx=e2vx, etype=etype, esec=esec, names=names.raw)
+
+
 def mesh_build(raw):
     """Connectivity + geometry (find_element_nb, calc_aip_xyzip_uns, calc_vol_cv_centers_uns)."""
     L = lib()

@@ -279,6 +279,17 @@ int cfdl_meshgen_sizes(int kind, int n, int64_t* nvx, int64_t* ne, int64_t* nbf,
 int cfdl_meshgen_fill(int kind, int n, double jitter, int shuffle, uint64_t seed,
                       double* x, double* y, double* z, int32_t* e2vx, int32_t* etype,
                       int32_t* esec, char* names);
+/* raw mesh file: what cell_input.f90:36-99 obtains from the CGNS library (vertex coordinates,
+ * sections with name / element type / element range, element->vertex lists) in one little-endian
+ * binary file, so that a driver can be built without CGNS/HDF5 — the Fortran reader is
+ * cfd-lite_b200/fortran/mod_rawmesh.f90.  names: 32 characters per section; nelem = 3-D + 2-D
+ * elements; e2vx has ne2vx_max entries per element as in mg_lvl%e2vx. */
+int cfdl_rawmesh_write(const char* path, int64_t nvx, const double* x, const double* y, const double* z,
+                       int nsec, const int32_t* etype, const int32_t* esec, const char* names,
+                       int ne2vx_max, const int32_t* e2vx, int64_t nelem);
+int cfdl_rawmesh_sizes(const char* path, int64_t* nvx, int64_t* nelem, int* nsec, int* ne2vx_max);
+int cfdl_rawmesh_read(const char* path, double* x, double* y, double* z, int32_t* etype,
+                      int32_t* esec, char* names, int32_t* e2vx);
 /* fast connectivity + geometry build producing exactly the arrays of find_element_nb,
  * calc_aip_xyzip_uns and calc_vol_cv_centers_uns (mod_mg_lvl_uns.f90:283-488,
  * calc_aip_xyzip.f90, calc_vol_cv_centers.f90), including the reference's face numbering. */
