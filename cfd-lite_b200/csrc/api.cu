@@ -1,9 +1,11 @@
 // C ABI of libcfdl (include/cfdl.h): lifecycle, host<->device field sync, the whole-step path
 // (update_boundaries / solve_uvwp / update_time, src/main.f90:50-63) and the per-routine path.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
 #include "state.h"
 
 using namespace cfdl;
@@ -735,4 +737,92 @@ extern "C" int cfdl_step_host(cfdl_handle h, double dt, int32_t nit, int32_t app
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return fail(CFDL_ERR_CUDA, "cfdl_step_host: %s", cudaGetErrorString(cudaGetLastError()));
   if (hist) std::memcpy(hist, st, sizeof st);
   return CFDL_OK;
+}
+
+// ---- checkpoint / restart ---------------------------------------------------------------------------
+// The reference has no restart.  The state that carries over from one SIMPLE iteration to
+// the next is u,v,w,p,u0,v0,w0,gu,gv,gw,gp,mip,mip0 (pc, gpc, d, dc, the matrix and the right-hand
+// sides are rebuilt by every solve_uvwp): written in the reference numbering on one GPU (the file can
+// be read back by any single-GPU handle of the same mesh), partition-local on several (one file per
+// rank, same partition on restart).  Continuing from a checkpoint reproduces the uninterrupted run bit
+// for bit (test).
+namespace {
+const char kCkpMagic[8] = {'C', 'F', 'D', 'L', 'C', 'K', 'P', '1'};
+const int kCkpFields[13] = {CFDL_F_U, CFDL_F_V, CFDL_F_W, CFDL_F_P, CFDL_F_U0, CFDL_F_V0, CFDL_F_W0,
+                            CFDL_F_GU, CFDL_F_GV, CFDL_F_GW, CFDL_F_GP, CFDL_F_MIP, CFDL_F_MIP0};
+struct CkpHeader { char magic[8]; int64_t ne, nbf, nf; int32_t rank, nranks, nfields, pad; };
+std::string ckp_path(const Handle* h, const char* path) {
+  std::string p(path);
+  if (h->prep.nranks > 1) p += ".r" + std::to_string(h->prep.rank) + "of" + std::to_string(h->prep.nranks);
+  return p;
+}
+}  // namespace
+
+extern "C" int cfdl_checkpoint_write(cfdl_handle h, const char* path) {
+  ENTER(h);
+  if (!path) return fail(CFDL_ERR_ARG, "cfdl_checkpoint_write: NULL path");
+  const bool local = h->prep.nranks > 1;
+  const std::string p = ckp_path(h, path);
+  std::FILE* f = std::fopen(p.c_str(), "wb");
+  if (!f) return fail(CFDL_ERR_ARG, "cfdl_checkpoint_write: cannot open %s", p.c_str());
+  CkpHeader hd;
+  std::memset(&hd, 0, sizeof hd);
+  std::memcpy(hd.magic, kCkpMagic, 8);
+  hd.ne = h->prep.gN; hd.nbf = h->prep.gB; hd.nf = h->prep.gF; hd.rank = h->prep.rank; hd.nranks = h->prep.nranks; hd.nfields = 13;
+  bool ok = std::fwrite(&hd, sizeof hd, 1, f) == 1;
+  std::vector<double> buf;
+  int rc = CFDL_OK;
+  for (int i = 0; i < 13 && ok && !rc; ++i) {
+    const int fld = kCkpFields[i];
+    const int64_t n = (int64_t)(local ? field_len(h, fld) : host_len(h, fld));
+    buf.resize((size_t)n);
+    if (local) {
+      if (cudaMemcpyAsync(buf.data(), h->fld[fld], sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+          cudaStreamSynchronize(h->stream) != cudaSuccess)
+        rc = fail(CFDL_ERR_CUDA, "cfdl_checkpoint_write: download failed");
+    } else {
+      rc = download_field(h, fld, buf.data());
+    }
+    const int32_t id = fld;
+    ok = !rc && std::fwrite(&id, 4, 1, f) == 1 && std::fwrite(&n, 8, 1, f) == 1 && std::fwrite(buf.data(), 8, (size_t)n, f) == (size_t)n;
+  }
+  ok = (std::fclose(f) == 0) && ok;
+  if (rc) return rc;
+  if (!ok) return fail(CFDL_ERR_INTERNAL, "cfdl_checkpoint_write: short write to %s", p.c_str());
+  return CFDL_OK;
+}
+
+extern "C" int cfdl_checkpoint_read(cfdl_handle h, const char* path) {
+  ENTER(h);
+  if (!path) return fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: NULL path");
+  const bool local = h->prep.nranks > 1;
+  const std::string p = ckp_path(h, path);
+  std::FILE* f = std::fopen(p.c_str(), "rb");
+  if (!f) return fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: cannot open %s", p.c_str());
+  CkpHeader hd;
+  int rc = CFDL_OK;
+  if (std::fread(&hd, sizeof hd, 1, f) != 1 || std::memcmp(hd.magic, kCkpMagic, 8) != 0) rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: %s is not a checkpoint", p.c_str());
+  else if (hd.ne != h->prep.gN || hd.nbf != h->prep.gB || hd.nf != h->prep.gF || hd.rank != h->prep.rank || hd.nranks != h->prep.nranks)
+    rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: %s belongs to another mesh or partition (ne %lld nbf %lld nf %lld, rank %d of %d)", p.c_str(),
+              (long long)hd.ne, (long long)hd.nbf, (long long)hd.nf, hd.rank, hd.nranks);
+  std::vector<double> buf;
+  for (int i = 0; i < hd.nfields && !rc; ++i) {
+    int32_t id = -1;
+    int64_t n = -1;
+    if (std::fread(&id, 4, 1, f) != 1 || std::fread(&n, 8, 1, f) != 1 || id < 0 || id >= CFDL_F_COUNT) { rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: damaged record %d", i); break; }
+    const int64_t want = (int64_t)(local ? field_len(h, id) : host_len(h, id));
+    if (n != want) { rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: field %d has %lld entries, expected %lld", id, (long long)n, (long long)want); break; }
+    buf.resize((size_t)n);
+    if (std::fread(buf.data(), 8, (size_t)n, f) != (size_t)n) { rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: file ends inside field %d", id); break; }
+    if (local) {
+      if (cudaMemcpyAsync(h->fld[id], buf.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+          cudaStreamSynchronize(h->stream) != cudaSuccess)
+        rc = fail(CFDL_ERR_CUDA, "cfdl_checkpoint_read: upload failed");
+    } else {
+      rc = upload_field(h, id, buf.data());
+      if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(CFDL_ERR_CUDA, "cfdl_checkpoint_read: upload failed");
+    }
+  }
+  std::fclose(f);
+  return rc;
 }

@@ -393,6 +393,12 @@ class Solver:
                                   C.c_int32(len(ins)), iid, iptr, C.c_int32(len(outs)), oid, optr, _d(hist)))
         return hist.reshape(4, 4)
 
+    def checkpoint_write(self, path):
+        _chk(lib().cfdl_checkpoint_write(self.h, path.encode()))
+
+    def checkpoint_read(self, path):
+        _chk(lib().cfdl_checkpoint_read(self.h, path.encode()))
+
     def run(self, dt=0.01, nit=100, ntstep=10, ncoef=3, want_hist=True):
         hist = np.zeros(ntstep * ncoef * 16) if want_hist else None
         _chk(lib().cfdl_run(self.h, C.c_double(dt), C.c_int32(nit), C.c_int32(ntstep), C.c_int32(ncoef), _d(hist)))

@@ -152,6 +152,13 @@ int cfdl_step_host(cfdl_handle h, double dt, int32_t nit, int32_t apply_bcs, int
                    int32_t n_in, const int32_t* in_fields, const double* const* in_ptrs,
                    int32_t n_out, const int32_t* out_fields, double* const* out_ptrs, double* hist);
 
+/* Checkpoint / restart (the reference has none): the state that carries over between SIMPLE
+ * iterations — u,v,w,p,u0,v0,w0,gu,gv,gw,gp,mip,mip0 — in the reference numbering on one GPU, as
+ * one partition-local file per rank (path + ".r<rank>of<nranks>") on several.  A run continued from
+ * a checkpoint reproduces the uninterrupted run bit for bit. */
+int cfdl_checkpoint_write(cfdl_handle h, const char* path);
+int cfdl_checkpoint_read(cfdl_handle h, const char* path);
+
 /* ---- per-routine path on the handle's device-resident state (one reference routine each) */
 int cfdl_calc_coef_uvw(cfdl_handle h, double dt);                 /* mod_uvwp.f90:161-286 */
 int cfdl_calc_mip(cfdl_handle h, int32_t l_rhie_chow, double dt); /* mod_uvwp.f90:438-490 */

@@ -592,3 +592,30 @@ def test_persistent_passes_keep_the_bits(case, cfdl):
         s.set_option("rb_persistent", -1)
         s.set_option("uvw_fused", -1)
         s.set_option("solver", cfdl.SOLVER_PARITY)
+
+
+@pytest.mark.parametrize("solver", ["parity", "mcsgs"])
+def test_restart_from_checkpoint_reproduces_the_run(case, cfdl, tmp_path, solver):
+    """cfdl_checkpoint_write / _read: 2 time steps + checkpoint + 2 more == fresh handle + read + 2."""
+    name, raw, oc, geom, s = case
+    mode = cfdl.SOLVER_PARITY if solver == "parity" else cfdl.SOLVER_MCSGS
+    path = str(tmp_path / "state.ckp")
+    a = make_solver(cfdl, raw, oc, geom)
+    b = make_solver(cfdl, raw, oc, geom)
+    try:
+        a.set_option("solver", mode); b.set_option("solver", mode)
+        a.run(dt=0.01, nit=30, ntstep=2, ncoef=2, want_hist=False)
+        a.checkpoint_write(path)
+        ha = a.run(dt=0.01, nit=30, ntstep=2, ncoef=2)
+        b.checkpoint_read(path)
+        hb = b.run(dt=0.01, nit=30, ntstep=2, ncoef=2)
+        assert np.array_equal(ha, hb)
+        for f in ("u", "v", "w", "p", "gp", "mip", "mip0", "u0"):
+            assert np.array_equal(a.download(f), b.download(f)), f
+        # a checkpoint of another mesh is refused
+        with open(path, "r+b") as fh:
+            fh.seek(8); fh.write((12345).to_bytes(8, "little"))
+        with pytest.raises(cfdl.CfdlError):
+            b.checkpoint_read(path)
+    finally:
+        a.close(); b.close()
