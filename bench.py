@@ -278,7 +278,7 @@ def main():
     hist_last = None
     # kernel variants chosen by measurement during the first warm-up step (bit-identical candidates)
     tuned = {}
-    for r in ("uvw", "grad3", "grad1", "coef_p", "uvw_solve", "rb_persistent"):
+    for r in ("uvw", "grad3", "grad1", "coef_p", "mip", "uvw_solve", "rb_persistent"):
         try:
             n_c = int(s.get_info("tuned_%s_n" % r))
             if n_c > 0:

@@ -236,8 +236,8 @@ int create_from_prep(cfdl_handle_s* h, const GeomSource& G, cfdl_handle* out) {
     return bail(fail(CFDL_ERR_CUDA, "cudaMallocHost failed"));
   if ((rc = solver_init(h))) return bail(rc);
   {  // static face geometry, evaluated once with the reference's own expressions (kernels_statics.cu)
-    double** arrs[17] = {&h->fs_area, &h->fs_ds, &h->fs_dsp, &h->fs_dn, &h->fs_wto, &h->fs_wtn, &h->fs_n[0], &h->fs_n[1], &h->fs_n[2],
-                         &h->fs_dr[0], &h->fs_dr[1], &h->fs_dr[2], &h->fs_drp[0], &h->fs_drp[1], &h->fs_drp[2], &h->fs_rds, &h->fs_rdsp};
+    double** arrs[18] = {&h->fs_area, &h->fs_ds, &h->fs_dsp, &h->fs_dn, &h->fs_wto, &h->fs_wtn, &h->fs_n[0], &h->fs_n[1], &h->fs_n[2],
+                         &h->fs_dr[0], &h->fs_dr[1], &h->fs_dr[2], &h->fs_drp[0], &h->fs_drp[1], &h->fs_drp[2], &h->fs_rds, &h->fs_rdsp, &h->fs_rdn};
     for (double** a : arrs)
       if ((rc = dev_zero(h, *a, (size_t)p.Fi + 4))) return bail(rc);
     if ((rc = k_face_statics(h))) return bail(rc);
@@ -321,6 +321,8 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "uvw_fused")) { h->uvw_fused = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
   if (!std::strcmp(key, "grad_variant")) { h->grad_variant = (int)value; return CFDL_OK; }
   if (!std::strcmp(key, "coef_p_variant")) { h->coef_p_variant = (int)value; return CFDL_OK; }
+  if (!std::strcmp(key, "mip_fast")) { h->mip_fast = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
+  if (!std::strcmp(key, "correct_fast")) { h->correct_fast = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "autotune")) {
     h->autotune = value != 0.0;
     if (value == 2.0) {

@@ -19,13 +19,14 @@ namespace cfdl {
 struct FaceStatics {
   const double *area, *ds, *dsp, *dn, *wto, *wtn;
   const double *rds, *rdsp;  // RN(1/ds), RN(1/dsp): the reciprocals quot<true> needs (uvw_variant 5, 6)
+  const double* rdn;         // RN(1/dn) for the quotients by dr.n in calc_mip, calc_coef_p and the face correction
   const double *n[3], *dr[3], *drp[3];
 };
 
 static FaceStatics statics_of(const Handle* h) {
   FaceStatics S;
   S.area = h->fs_area; S.ds = h->fs_ds; S.dsp = h->fs_dsp; S.dn = h->fs_dn; S.wto = h->fs_wto; S.wtn = h->fs_wtn;
-  S.rds = h->fs_rds; S.rdsp = h->fs_rdsp;
+  S.rds = h->fs_rds; S.rdsp = h->fs_rdsp; S.rdn = h->fs_rdn;
   for (int i = 0; i < 3; ++i) { S.n[i] = h->fs_n[i]; S.dr[i] = h->fs_dr[i]; S.drp[i] = h->fs_drp[i]; }
   return S;
 }
@@ -36,7 +37,7 @@ __global__ void __launch_bounds__(TPB) face_statics_kernel(int Fi, const int32_t
                                                            const double* __restrict__ rip_, double* area_o, double* ds_o, double* dsp_o,
                                                            double* dn_o, double* wto_o, double* wtn_o, double* n0, double* n1, double* n2,
                                                            double* d0, double* d1, double* d2, double* p0, double* p1, double* p2,
-                                                           double* rds_o, double* rdsp_o) {
+                                                           double* rds_o, double* rdsp_o, double* rdn_o) {
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < Fi; f += gridDim.x * blockDim.x) {
     const int e = face_a[f], nb = face_b[f];
     const double rp[3] = {xc[e], yc[e], zc[e]};
@@ -55,8 +56,9 @@ __global__ void __launch_bounds__(TPB) face_statics_kernel(int Fi, const int32_t
     const double rpnb_p[3] = {rip[0] - t * norm[0], rip[1] - t * norm[1], rip[2] - t * norm[2]};
     const double dr_p[3] = {rpnb_p[0] - rp_p[0], rpnb_p[1] - rp_p[1], rpnb_p[2] - rp_p[2]};
     const double dsp = sqrt(dot3(dr_p, dr_p));
-    area_o[f] = area; ds_o[f] = ds; dsp_o[f] = dsp; dn_o[f] = dot3(dr, norm);
-    rds_o[f] = 1.0 / ds; rdsp_o[f] = 1.0 / dsp;
+    const double dn = dot3(dr, norm);
+    area_o[f] = area; ds_o[f] = ds; dsp_o[f] = dsp; dn_o[f] = dn;
+    rds_o[f] = 1.0 / ds; rdsp_o[f] = 1.0 / dsp; rdn_o[f] = 1.0 / dn;
     wto_o[f] = vec_weight(rip, rp, rpnb);   // weight seen from the owner
     wtn_o[f] = vec_weight(rip, rpnb, rp);   // weight seen from the neighbour
     n0[f] = norm[0]; n1[f] = norm[1]; n2[f] = norm[2];
@@ -70,7 +72,7 @@ int k_face_statics(Handle* h) {
   face_statics_kernel<<<grid_for(h, h->Fi, TPB), TPB, 0, S(h)>>>(h->Fi, h->face_a, h->face_b, h->xc, h->yc, h->zc, h->aip, h->rip, h->fs_area,
                                                                  h->fs_ds, h->fs_dsp, h->fs_dn, h->fs_wto, h->fs_wtn, h->fs_n[0], h->fs_n[1],
                                                                  h->fs_n[2], h->fs_dr[0], h->fs_dr[1], h->fs_dr[2], h->fs_drp[0], h->fs_drp[1],
-                                                                 h->fs_drp[2], h->fs_rds, h->fs_rdsp);
+                                                                 h->fs_drp[2], h->fs_rds, h->fs_rdsp, h->fs_rdn);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
@@ -317,7 +319,8 @@ struct CoefPArgs {
   FaceStatics S;
 };
 
-template <int K>
+// FAST: the quotient by dr.n through the stored reciprocal and quot<true> (same bits as the division)
+template <int K, bool FAST>
 __device__ __forceinline__ void coef_p_statics_cell(const CoefPArgs& A, const int c) {
   const int Nc = A.Nc, Np = A.Np;
   const int n = A.nfc[c];
@@ -340,7 +343,7 @@ __device__ __forceinline__ void coef_p_statics_cell(const CoefPArgs& A, const in
         const double f_in = -sg * A.mip[f];
         sumf = sumf + f_in;
         const double rhoip = (1.0 - wt) * rho_e + wt * A.rho[nb];
-        d = ((1.0 - wt) * dc_e + wt * A.dc[nb]) / A.S.dn[f] * rhoip * A.S.area[f];
+        d = quot<FAST>((1.0 - wt) * dc_e + wt * A.dc[nb], A.S.dn[f], FAST ? A.S.rdn[f] : 0.0) * rhoip * A.S.area[f];
       }
       A.anb[(size_t)k * Np + c] = d;
       ap = ap + d;
@@ -362,13 +365,13 @@ __device__ __forceinline__ void coef_p_statics_cell(const CoefPArgs& A, const in
   A.b[c] = b;
 }
 
-template <int K>
+template <int K, bool FAST>
 __global__ void __launch_bounds__(TPB) coef_p_statics_kernel(const CoefPArgs A) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.N; c += gridDim.x * blockDim.x) coef_p_statics_cell<K>(A, c);
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.N; c += gridDim.x * blockDim.x) coef_p_statics_cell<K, FAST>(A, c);
 }
 // coef_p_variant 1: the paired colour order of coef_uvw_statics_body_paired (face statics and mip of a
 // face are read by both of its cells within one CTA's pass instead of half a kernel apart)
-template <int K>
+template <int K, bool FAST>
 __global__ void __launch_bounds__(TPB) coef_p_statics_paired_kernel(const CoefPArgs A) {
   const int n0 = A.ncol0, n1 = A.N - A.ncol0;
   const int nq = (max(n0, n1) + (int)blockDim.x - 1) / (int)blockDim.x;
@@ -376,7 +379,7 @@ __global__ void __launch_bounds__(TPB) coef_p_statics_paired_kernel(const CoefPA
     const int i = q * blockDim.x + threadIdx.x;
 #pragma unroll 1
     for (int col = 0; col < 2; ++col)
-      if (i < (col ? n1 : n0)) coef_p_statics_cell<K>(A, col ? n0 + i : i);
+      if (i < (col ? n1 : n0)) coef_p_statics_cell<K, FAST>(A, col ? n0 + i : i);
   }
 }
 
@@ -393,18 +396,22 @@ static int coef_p_launch(Handle* h, int variant) {
   A.rho = h->rho; A.dc = h->fld[CFDL_F_DC]; A.mip = h->fld[CFDL_F_MIP];
   A.ap = h->fld[CFDL_F_AP]; A.anb = h->fld[CFDL_F_ANB]; A.b = h->fld[CFDL_F_B];
   A.S = statics_of(h);
-  if (variant == 1 && h->prep.ncolors == 2)
-    launch_coef_p<coef_p_statics_paired_kernel<4>, coef_p_statics_paired_kernel<6>>(h, A, std::max(A.ncol0, h->N - A.ncol0));
-  else
-    launch_coef_p<coef_p_statics_kernel<4>, coef_p_statics_kernel<6>>(h, A, h->N);
+  // 0/1 = linear / paired colour order with the division; 2/3 = the same with the stored reciprocal of dr.n
+  const bool paired = (variant == 1 || variant == 3) && h->prep.ncolors == 2, fast = variant >= 2;
+  const int pc = std::max(A.ncol0, h->N - A.ncol0);
+  if (paired && fast) launch_coef_p<coef_p_statics_paired_kernel<4, true>, coef_p_statics_paired_kernel<6, true>>(h, A, pc);
+  else if (paired) launch_coef_p<coef_p_statics_paired_kernel<4, false>, coef_p_statics_paired_kernel<6, false>>(h, A, pc);
+  else if (fast) launch_coef_p<coef_p_statics_kernel<4, true>, coef_p_statics_kernel<6, true>>(h, A, h->N);
+  else launch_coef_p<coef_p_statics_kernel<4, false>, coef_p_statics_kernel<6, false>>(h, A, h->N);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
 
 int k_calc_coef_p_statics(Handle* h) {
-  if (h->autotune && !h->tune_coef_p.done && h->profile == 0 && h->coef_p_variant < 0 && h->prep.ncolors == 2) {
-    static const int cands[] = {0, 1};
-    int rc = autotune_pick(h, h->tune_coef_p, cands, 2, [&](int v) { return coef_p_launch(h, v); });
+  if (h->autotune && !h->tune_coef_p.done && h->profile == 0 && h->coef_p_variant < 0) {
+    static const int cands2[] = {0, 1, 2, 3}, cands[] = {0, 2};
+    const bool two = h->prep.ncolors == 2;
+    int rc = autotune_pick(h, h->tune_coef_p, two ? cands2 : cands, two ? 4 : 2, [&](int v) { return coef_p_launch(h, v); });
     if (rc) return rc;
   }
   return coef_p_launch(h, h->coef_p_variant >= 0 ? h->coef_p_variant : (h->tune_coef_p.ncand ? h->tune_coef_p.choice : 0));
@@ -475,8 +482,10 @@ __device__ __forceinline__ void mip_load_cell(const MipCellArgs& A, int c, bool 
   }
 }
 
-template <int K>
+// FAST: both quotients of the Rhie-Chow term (by dr.n and by dt) through reciprocals and quot<true>
+template <int K, bool FAST>
 __global__ void __launch_bounds__(TPB, 3) mip_cells_kernel(const MipCellArgs A) {
+  const double rdt = FAST ? 1.0 / A.dt : 0.0;
   const bool rc = A.rhie_chow != 0;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.n_cells; c += gridDim.x * blockDim.x) {
     const unsigned mask = A.ftouch[c];
@@ -506,12 +515,18 @@ __global__ void __launch_bounds__(TPB, 3) mip_cells_kernel(const MipCellArgs A) 
         const double gpip[3] = {w1 * E.g[0] + wt * NB.g[0], w1 * E.g[1] + wt * NB.g[1], w1 * E.g[2] + wt * NB.g[2]};
         const double dip = w1 * E.d + wt * NB.d;
         const double velip0[3] = {w1 * E.u0 + wt * NB.u0, w1 * E.v0 + wt * NB.v0, w1 * E.w0 + wt * NB.w0};
-        m = m - rhoip * area * dip / A.S.dn[f] * (NB.p - E.p - dot3(gpip, dr))
-              - rhoip / A.dt * dip * (A.mip0[f] - dot3(velip0, norm) * rhoip * area);
+        m = m - quot<FAST>(rhoip * area * dip, A.S.dn[f], FAST ? A.S.rdn[f] : 0.0) * (NB.p - E.p - dot3(gpip, dr))
+              - quot<FAST>(rhoip, A.dt, rdt) * dip * (A.mip0[f] - dot3(velip0, norm) * rhoip * area);
       }
       A.mip[f] = m;
     }
   }
+}
+
+template <auto K4, auto K6>
+static void launch_mip(Handle* h, const MipCellArgs& A) {
+  if (h->K <= 4) K4<<<occ_grid<K4>(h, A.n_cells, TPB), TPB, 0, S(h)>>>(A);
+  else K6<<<occ_grid<K6>(h, A.n_cells, TPB), TPB, 0, S(h)>>>(A);
 }
 
 int k_calc_mip_statics(Handle* h, bool rhie_chow, double dt) {
@@ -524,10 +539,18 @@ int k_calc_mip_statics(Handle* h, bool rhie_chow, double dt) {
     A.p = h->fld[CFDL_F_P]; A.gp = h->fld[CFDL_F_GP]; A.d = h->fld[CFDL_F_D]; A.mip0 = h->fld[CFDL_F_MIP0];
     A.mip = h->fld[CFDL_F_MIP]; A.dt = dt; A.rhie_chow = rhie_chow ? 1 : 0;
     A.S = statics_of(h);
-    if (h->K <= 4) mip_cells_kernel<4><<<occ_grid<mip_cells_kernel<4>>(h, A.n_cells, TPB), TPB, 0, S(h)>>>(A);
-    else mip_cells_kernel<6><<<occ_grid<mip_cells_kernel<6>>(h, A.n_cells, TPB), TPB, 0, S(h)>>>(A);
-    CFDL_CUDA(cudaGetLastError());
-    return CFDL_OK;
+    auto go = [&](int fast) {
+      if (fast) launch_mip<mip_cells_kernel<4, true>, mip_cells_kernel<6, true>>(h, A);
+      else launch_mip<mip_cells_kernel<4, false>, mip_cells_kernel<6, false>>(h, A);
+      return cudaGetLastError() == cudaSuccess ? CFDL_OK : fail(CFDL_ERR_CUDA, "calc_mip launch failed");
+    };
+    // mip_fast: -1 = measured on first use (a Rhie-Chow call: the plain interpolation has no quotient), 0 = divisions, 1 = reciprocals
+    if (h->autotune && !h->tune_mip.done && h->profile == 0 && h->mip_fast < 0 && rhie_chow) {
+      static const int cands[] = {0, 1};
+      int rc = autotune_pick(h, h->tune_mip, cands, 2, go);
+      if (rc) return rc;
+    }
+    return go(h->mip_fast >= 0 ? h->mip_fast : (h->tune_mip.ncand ? h->tune_mip.choice : 0));
   }
   MipArgsS A;
   A.Fi = h->Fi; A.face_a = h->face_a; A.face_b = h->face_b; A.rho = h->rho;
@@ -542,6 +565,7 @@ int k_calc_mip_statics(Handle* h, bool rhie_chow, double dt) {
 }
 
 // ---- face part of update_uvwp on statics (mod_uvwp.f90:394-415) ----------------------------------
+template <bool FAST>
 __global__ void __launch_bounds__(TPB) correct_faces_statics_kernel(int Fi, const int32_t* __restrict__ face_a, const int32_t* __restrict__ face_b,
                                                                     const double* __restrict__ rho, const double* __restrict__ dc,
                                                                     const double* __restrict__ pc, const FaceStatics S, double* mip) {
@@ -550,15 +574,21 @@ __global__ void __launch_bounds__(TPB) correct_faces_statics_kernel(int Fi, cons
     const double wt = S.wto[f];
     const double dip = (1.0 - wt) * dc[e] + wt * dc[nb];
     const double rhoip = (rho[e] + rho[nb]) / 2.0;
-    const double dmip = rhoip * S.area[f] * dip * (pc[nb] - pc[e]) / S.dn[f];
+    const double dmip = quot<FAST>(rhoip * S.area[f] * dip * (pc[nb] - pc[e]), S.dn[f], FAST ? S.rdn[f] : 0.0);
     mip[f] = mip[f] - dmip;
   }
 }
 
 int k_correct_faces_statics(Handle* h) {
   if (h->Fi == 0) return CFDL_OK;
-  correct_faces_statics_kernel<<<occ_grid<correct_faces_statics_kernel>(h, h->Fi, TPB), TPB, 0, S(h)>>>(h->Fi, h->face_a, h->face_b, h->rho, h->fld[CFDL_F_DC],
-                                                                          h->fld[CFDL_F_PC], statics_of(h), h->fld[CFDL_F_MIP]);
+  // the kernel updates mip in place, so its two forms cannot be timed against each other on live data;
+  // correct_fast (default 0) selects the reciprocal form by hand
+  if (h->correct_fast)
+    correct_faces_statics_kernel<true><<<occ_grid<correct_faces_statics_kernel<true>>(h, h->Fi, TPB), TPB, 0, S(h)>>>(h->Fi, h->face_a, h->face_b, h->rho, h->fld[CFDL_F_DC],
+                                                                                          h->fld[CFDL_F_PC], statics_of(h), h->fld[CFDL_F_MIP]);
+  else
+    correct_faces_statics_kernel<false><<<occ_grid<correct_faces_statics_kernel<false>>(h, h->Fi, TPB), TPB, 0, S(h)>>>(h->Fi, h->face_a, h->face_b, h->rho, h->fld[CFDL_F_DC],
+                                                                                            h->fld[CFDL_F_PC], statics_of(h), h->fld[CFDL_F_MIP]);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }

@@ -124,7 +124,9 @@ struct Handle {
   // evaluates every iteration (area, unit normal, |dr|, projected |dr_p|, dr.n, both distance
   // weights, dr, dr_p): the assembly kernels then need 10 instead of 19 FP64 div/sqrt per face
   double *fs_area = nullptr, *fs_ds = nullptr, *fs_dsp = nullptr, *fs_dn = nullptr, *fs_wto = nullptr, *fs_wtn = nullptr;
-  double *fs_rds = nullptr, *fs_rdsp = nullptr;  // RN(1/ds), RN(1/dsp)
+  double *fs_rds = nullptr, *fs_rdsp = nullptr, *fs_rdn = nullptr;  // RN(1/ds), RN(1/dsp), RN(1/dn)
+  int mip_fast = -1;           // calc_mip from the cells: quotients by division (0), by reciprocals (1), measured (-1)
+  int correct_fast = 0;        // face correction: quotient by dr.n through the stored reciprocal
   // least-squares gradient statics (filled on first use by grad_variant 1): inverse LSQ matrix per cell
   // (9 x Np, entry-major) and the weight 1/|dr|^2 per slot (K x Np)
   double *lsq_binv = nullptr, *lsq_w = nullptr;

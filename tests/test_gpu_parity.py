@@ -411,13 +411,14 @@ def test_calc_grad_variants_keep_the_bits(case):
 
 
 def test_calc_coef_p_variants_keep_the_bits(case):
-    """coef_p_variant 1 (paired colour order) against variant 0 and the oracle: same bits."""
+    """coef_p_variant 1 (paired colour order), 2 and 3 (reciprocal quotients) against the oracle: same bits."""
     _, raw, oc, geom, s = case
     randomize(oc, s, seed=37)
+    oc.update_boundaries(); s.update_boundaries()
     oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)  # provides dc
     oc.calc_coef_p()
     try:
-        for variant in (0, 1):
+        for variant in (0, 1, 2, 3):  # 2, 3: the quotient by dr.n through the stored reciprocal (linear, paired)
             s.set_option("coef_p_variant", variant)
             for f in ("ap", "anb", "b"):
                 s.upload(f, np.full(s.field_size(f), 7.5))  # stale values must be overwritten
@@ -619,3 +620,32 @@ def test_restart_from_checkpoint_reproduces_the_run(case, cfdl, tmp_path, solver
             b.checkpoint_read(path)
     finally:
         a.close(); b.close()
+
+
+def test_reciprocal_quotients_in_mip_and_face_correction_keep_the_bits(case):
+    """mip_fast=1 / correct_fast=1: the quotients by dr.n and dt formed from reciprocals + FMA correction
+    (quot<true>, device_math.cuh) in calc_mip and in the face correction of update_uvwp — same bits as
+    the divisions, checked against the oracle."""
+    _, raw, oc, geom, s = case
+    randomize(oc, s, seed=67)
+    oc.update_boundaries(); s.update_boundaries()
+    oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)  # d, dc
+    mip_in = oc["mip"].copy()
+    oc.calc_mip(True)
+    try:
+        for fast in (0, 1):
+            s.set_option("mip_fast", fast)
+            s.upload("mip", mip_in)
+            s.calc_mip(True, dt=0.01)
+            assert np.array_equal(s.download("mip"), oc["mip"]), fast
+        oc.adjust_pc(); oc["gpc"][:] = oc.calc_grad(oc["phic"])
+        mip_before, p_before, gp_before = oc["mip"].copy(), oc["p"].copy(), oc["gp"].copy()
+        oc.update_uvwp()
+        for fast in (0, 1):
+            s.set_option("correct_fast", fast)
+            s.upload("mip", mip_before); s.upload("p", p_before); s.upload("gp", gp_before); s.upload("pc", oc["phic"]); s.upload("gpc", oc["gpc"])
+            s.update_uvwp()
+            assert np.array_equal(s.download("mip"), oc["mip"]), fast
+    finally:
+        s.set_option("mip_fast", -1)
+        s.set_option("correct_fast", 0)
