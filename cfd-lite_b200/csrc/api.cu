@@ -287,7 +287,7 @@ int cfdl_destroy(cfdl_handle h) {
   comm_destroy(h);
   for (cudaEvent_t e : h->prof_ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : h->timer_ev) if (e) cudaEventDestroy(e);
-  for (cudaEvent_t e : h->xfer_ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->xfer_evs) if (e) cudaEventDestroy(e);
   if (h->xfer_in) { cudaStreamSynchronize(h->xfer_in); cudaStreamDestroy(h->xfer_in); }
   if (h->xfer_out) { cudaStreamSynchronize(h->xfer_out); cudaStreamDestroy(h->xfer_out); }
   for (void* p : h->allocs) cudaFree(p);
@@ -617,66 +617,80 @@ FieldMap field_map(const Handle* h, int f) {
   return {h->c2o, h->N, 1};
 }
 
-int ensure_xfer(Handle* h, bool need_stage) {
+// streams, events and (reference-numbering transfers) a staging area with one slot per field of the call
+int ensure_xfer(Handle* h, size_t stage_doubles) {
   if (!h->xfer_in && cudaStreamCreateWithFlags(&h->xfer_in, cudaStreamNonBlocking) != cudaSuccess) return fail(CFDL_ERR_CUDA, "cudaStreamCreate failed");
   if (!h->xfer_out && cudaStreamCreateWithFlags(&h->xfer_out, cudaStreamNonBlocking) != cudaSuccess) return fail(CFDL_ERR_CUDA, "cudaStreamCreate failed");
-  for (cudaEvent_t& e : h->xfer_ev)
-    if (!e && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(CFDL_ERR_CUDA, "cudaEventCreate failed");
-  if (need_stage && !h->xstage) {  // mip0 | u v w | gu gv gw, each in the host's numbering (partition-local arrays need none)
-    const Prep& p = h->prep;
-    h->xstage_len = (size_t)p.gF + 12 * ((size_t)p.gN + p.gB) + 16;
-    int rc = dev_zero(h, h->xstage, h->xstage_len);
+  if (h->xfer_evs.empty()) {
+    h->xfer_evs.assign(2 * CFDL_F_COUNT, nullptr);
+    for (cudaEvent_t& e : h->xfer_evs)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail(CFDL_ERR_CUDA, "cudaEventCreate failed");
+  }
+  if (stage_doubles > h->xstage_len) {  // grows with the largest field list seen (an outgrown area is freed with the handle)
+    h->xstage = nullptr;
+    h->xstage_len = 0;
+    int rc = dev_zero(h, h->xstage, stage_doubles);
     if (rc) return rc;
+    h->xstage_len = stage_doubles;
   }
   return CFDL_OK;
 }
 
-struct HostStepHook : StepHook {
-  Handle* h;
-  bool local;
-  const double* late_mip0 = nullptr;  // host source of mip0 when it travels beside the momentum phase
-  double* early[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // host targets of u,v,w,gu,gv,gw
-  // where field f is staged inside xstage (host numbering)
-  double* slot(int f) const {
-    const size_t Hh = (size_t)h->prep.gN + h->prep.gB;
-    if (f == CFDL_F_MIP0) return h->xstage;
-    if (f <= CFDL_F_W) return h->xstage + h->prep.gF + (size_t)(f - CFDL_F_U) * Hh;
-    return h->xstage + h->prep.gF + 3 * Hh + (size_t)(f - CFDL_F_GU) * 3 * Hh;
-  }
-  // device -> host of fields [f0, f1] beside the computation: permute into the staging slots on the
-  // compute stream, then copy out on the download stream once the permutation has finished
-  int send_out(int f0, int f1, int e0, cudaEvent_t ev) {
-    bool any = false;
-    for (int f = f0; f <= f1; ++f) {
-      if (!early[e0 + f - f0]) continue;
-      any = true;
-      if (!local) {
-        const FieldMap m = field_map(h, f);
-        int rc = k_scatter(h, slot(f), h->fld[f], m.map, m.n, m.ncomp);
-        if (rc) return rc;
-      }
-    }
-    if (!any) return CFDL_OK;
-    CFDL_CUDA(cudaEventRecord(ev, h->stream));
-    CFDL_CUDA(cudaStreamWaitEvent(h->xfer_out, ev, 0));
-    for (int f = f0; f <= f1; ++f) {
-      double* dst = early[e0 + f - f0];
-      if (!dst) continue;
-      // partition-local arrays need no permutation: later kernels of the step do not write these fields
-      const double* src = local ? h->fld[f] : slot(f);
-      const size_t n = local ? field_len(h, f) : host_len(h, f);
-      CFDL_CUDA(cudaMemcpyAsync(dst, src, sizeof(double) * n, cudaMemcpyDeviceToHost, h->xfer_out));
-    }
+// The transfers of one cfdl_step_host call.  Reference numbering: every field of the call has a slot of
+// its own in the staging area; uploads are queued back to back on the upload stream (slot <- host) and
+// each is followed on the compute stream by its permutation into the device numbering, so the copy engine
+// never waits for a permutation kernel; downloads are the mirror image on the download stream.
+// Partition-local arrays need no permutation and move straight between the host and the field.
+struct HostStep : StepHook {
+  Handle* h = nullptr;
+  bool local = false;
+  size_t off[CFDL_F_COUNT];
+  const double* in[CFDL_F_COUNT];
+  double* out[CFDL_F_COUNT];
+  HostStep() { for (int f = 0; f < CFDL_F_COUNT; ++f) { off[f] = 0; in[f] = nullptr; out[f] = nullptr; } }
+  cudaEvent_t ev_in(int f) const { return h->xfer_evs[f]; }
+  cudaEvent_t ev_out(int f) const { return h->xfer_evs[CFDL_F_COUNT + f]; }
+  double* slot(int f) const { return h->xstage + off[f]; }
+  size_t count(int f) const { return local ? field_len(h, f) : host_len(h, f); }
+  static bool staged(int f) { return f != CFDL_F_ANB; }  // anb changes layout (CSR <-> ELL): the plain upload / download path
+
+  // host -> staging slot (or straight into the field) on the upload stream
+  int queue_upload(int f) {
+    if (!local && !staged(f)) return CFDL_OK;
+    CFDL_CUDA(cudaMemcpyAsync(local ? h->fld[f] : slot(f), in[f], sizeof(double) * count(f), cudaMemcpyHostToDevice, h->xfer_in));
+    CFDL_CUDA(cudaEventRecord(ev_in(f), h->xfer_in));
     return CFDL_OK;
   }
+  // compute stream: wait for the field's upload, bring it into the device numbering
+  int land(int f) {
+    if (f == CFDL_F_AP || f == CFDL_F_ANB) h->pc_sumap_ok = false;
+    if (!local && !staged(f)) return upload_field(h, f, in[f]);
+    CFDL_CUDA(cudaStreamWaitEvent(h->stream, ev_in(f), 0));
+    if (local) return CFDL_OK;
+    const FieldMap m = field_map(h, f);
+    return k_gather(h, h->fld[f], slot(f), m.map, m.n, m.ncomp);
+  }
+  // compute stream: field is final -> permute into its slot; download stream: copy out once that is done
+  int send(int f) {
+    if (!out[f]) return CFDL_OK;
+    if (!local && !staged(f)) return download_field(h, f, out[f]);
+    if (!local) {
+      const FieldMap m = field_map(h, f);
+      int rc = k_scatter(h, slot(f), h->fld[f], m.map, m.n, m.ncomp);
+      if (rc) return rc;
+    }
+    CFDL_CUDA(cudaEventRecord(ev_out(f), h->stream));
+    CFDL_CUDA(cudaStreamWaitEvent(h->xfer_out, ev_out(f), 0));
+    CFDL_CUDA(cudaMemcpyAsync(out[f], local ? h->fld[f] : slot(f), sizeof(double) * count(f), cudaMemcpyDeviceToHost, h->xfer_out));
+    return CFDL_OK;
+  }
+  static bool early_out(int f) { return (f >= CFDL_F_U && f <= CFDL_F_W) || (f >= CFDL_F_GU && f <= CFDL_F_GW); }
   int at(int stage) override {
-    if (stage == STEP_MOMENTUM_DONE) return send_out(CFDL_F_U, CFDL_F_W, 0, h->xfer_ev[1]);
-    if (stage == STEP_GRAD_DONE) return send_out(CFDL_F_GU, CFDL_F_GW, 3, h->xfer_ev[2]);
-    if (stage == STEP_BEFORE_MIP && late_mip0) {
-      CFDL_CUDA(cudaStreamWaitEvent(h->stream, h->xfer_ev[0], 0));
-      if (!local) return k_gather(h, h->fld[CFDL_F_MIP0], slot(CFDL_F_MIP0), h->f2o, h->F, 1);
-    }
-    return CFDL_OK;
+    int rc = CFDL_OK;
+    if (stage == STEP_MOMENTUM_DONE) for (int f = CFDL_F_U; f <= CFDL_F_W && !rc; ++f) rc = send(f);
+    if (stage == STEP_GRAD_DONE) for (int f = CFDL_F_GU; f <= CFDL_F_GW && !rc; ++f) rc = send(f);
+    if (stage == STEP_BEFORE_MIP && in[CFDL_F_MIP0]) rc = land(CFDL_F_MIP0);
+    return rc;
   }
 };
 
@@ -688,56 +702,39 @@ extern "C" int cfdl_step_host(cfdl_handle h, double dt, int32_t nit, int32_t app
   ENTER(h);
   if (n_in < 0 || n_out < 0 || (n_in && (!in_fields || !in_ptrs)) || (n_out && (!out_fields || !out_ptrs)))
     return fail(CFDL_ERR_ARG, "cfdl_step_host: bad field lists");
-  for (int i = 0; i < n_in; ++i)
-    if (in_fields[i] < 0 || in_fields[i] >= CFDL_F_COUNT || !in_ptrs[i]) return fail(CFDL_ERR_ARG, "cfdl_step_host: bad input %d", i);
-  for (int i = 0; i < n_out; ++i)
-    if (out_fields[i] < 0 || out_fields[i] >= CFDL_F_COUNT || !out_ptrs[i]) return fail(CFDL_ERR_ARG, "cfdl_step_host: bad output %d", i);
-  const bool local = local_numbering != 0;
-  if (!local && h->prep.nranks > 1)
+  HostStep st;
+  st.h = h;
+  st.local = local_numbering != 0;
+  if (!st.local && h->prep.nranks > 1)
     return fail(CFDL_ERR_UNSUPPORTED, "cfdl_step_host: on a partitioned handle pass partition-local arrays (local_numbering = 1)");
-  int rc;
-  if ((rc = ensure_xfer(h, !local))) return rc;
-  HostStepHook hook;
-  hook.h = h;
-  hook.local = local;
-  // inputs: everything the first kernels read goes first, on the compute stream; mip0 (read by
-  // calc_mip only) follows on the upload stream while the momentum equations are assembled and solved
   for (int i = 0; i < n_in; ++i) {
-    const int f = in_fields[i];
-    if (f == CFDL_F_MIP0) { hook.late_mip0 = in_ptrs[i]; continue; }
-    if (f == CFDL_F_AP || f == CFDL_F_ANB) h->pc_sumap_ok = false;
-    if (local) CFDL_CUDA(cudaMemcpyAsync(h->fld[f], in_ptrs[i], sizeof(double) * field_len(h, f), cudaMemcpyHostToDevice, h->stream));
-    else if ((rc = upload_field(h, f, in_ptrs[i]))) return rc;
+    if (in_fields[i] < 0 || in_fields[i] >= CFDL_F_COUNT || !in_ptrs[i] || st.in[in_fields[i]]) return fail(CFDL_ERR_ARG, "cfdl_step_host: bad input %d", i);
+    st.in[in_fields[i]] = in_ptrs[i];
   }
-  if (hook.late_mip0) {
-    double* dst = local ? h->fld[CFDL_F_MIP0] : hook.slot(CFDL_F_MIP0);
-    const size_t n = local ? field_len(h, CFDL_F_MIP0) : host_len(h, CFDL_F_MIP0);
-    CFDL_CUDA(cudaMemcpyAsync(dst, hook.late_mip0, sizeof(double) * n, cudaMemcpyHostToDevice, h->xfer_in));
-    CFDL_CUDA(cudaEventRecord(h->xfer_ev[0], h->xfer_in));
-  }
-  // outputs that are final before the pressure-correction solve travel during it
-  bool late_out[CFDL_F_COUNT] = {false};
-  double* late_ptr[CFDL_F_COUNT] = {nullptr};
   for (int i = 0; i < n_out; ++i) {
-    const int f = out_fields[i];
-    if (f >= CFDL_F_U && f <= CFDL_F_W) hook.early[f - CFDL_F_U] = out_ptrs[i];
-    else if (f >= CFDL_F_GU && f <= CFDL_F_GW) hook.early[3 + f - CFDL_F_GU] = out_ptrs[i];
-    else { late_out[f] = true; late_ptr[f] = out_ptrs[i]; }
+    if (out_fields[i] < 0 || out_fields[i] >= CFDL_F_COUNT || !out_ptrs[i] || st.out[out_fields[i]]) return fail(CFDL_ERR_ARG, "cfdl_step_host: bad output %d", i);
+    st.out[out_fields[i]] = out_ptrs[i];
   }
-  if (apply_bcs && (rc = k_update_boundaries(h))) return rc;
-  double st[16];
-  rc = solve_uvwp_impl(h, dt, nit, st, &hook);
-  if (!rc)
-    for (int f = 0; f < CFDL_F_COUNT && !rc; ++f) {
-      if (!late_out[f]) continue;
-      if (local) { if (cudaMemcpyAsync(late_ptr[f], h->fld[f], sizeof(double) * field_len(h, f), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) rc = fail(CFDL_ERR_CUDA, "cfdl_step_host: download failed"); }
-      else rc = download_field(h, f, late_ptr[f]);
-    }
-  // both transfer streams are drained before the call returns, also on failure
+  size_t need = 0;
+  for (int f = 0; f < CFDL_F_COUNT && !st.local; ++f)
+    if ((st.in[f] || st.out[f]) && HostStep::staged(f)) { st.off[f] = need; need += (host_len(h, f) + 31) / 32 * 32; }
+  int rc;
+  if ((rc = ensure_xfer(h, need))) return rc;
+  // uploads in the caller's order, mip0 (first read by calc_mip) last: it travels while the momentum
+  // equations are assembled and solved
+  for (int i = 0; i < n_in && !rc; ++i) if (in_fields[i] != CFDL_F_MIP0) rc = st.queue_upload(in_fields[i]);
+  if (!rc && st.in[CFDL_F_MIP0]) rc = st.queue_upload(CFDL_F_MIP0);
+  for (int i = 0; i < n_in && !rc; ++i) if (in_fields[i] != CFDL_F_MIP0) rc = st.land(in_fields[i]);
+  if (!rc && apply_bcs) rc = k_update_boundaries(h);
+  double hs[16];
+  if (!rc) rc = solve_uvwp_impl(h, dt, nit, hs, &st);
+  // what the iteration finishes last (p, gp, gpc, mip, ...) goes out now; u,v,w,gu,gv,gw left during the pc solve
+  for (int i = 0; i < n_out && !rc; ++i) if (!HostStep::early_out(out_fields[i])) rc = st.send(out_fields[i]);
+  // all three streams are drained before the call returns, also on failure
   cudaError_t e1 = cudaStreamSynchronize(h->xfer_in), e2 = cudaStreamSynchronize(h->xfer_out), e3 = cudaStreamSynchronize(h->stream);
   if (rc) return rc;
   if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return fail(CFDL_ERR_CUDA, "cfdl_step_host: %s", cudaGetErrorString(cudaGetLastError()));
-  if (hist) std::memcpy(hist, st, sizeof st);
+  if (hist) std::memcpy(hist, hs, sizeof hs);
   return CFDL_OK;
 }
 

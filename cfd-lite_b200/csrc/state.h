@@ -144,7 +144,7 @@ struct Handle {
   // cfdl_step_host: transfer streams that run beside the compute stream, and a staging area of
   // its own (reference-numbered copies of the late input and the early outputs)
   cudaStream_t xfer_in = nullptr, xfer_out = nullptr;
-  cudaEvent_t xfer_ev[3] = {nullptr, nullptr, nullptr};  // late input landed; u,v,w staged; gu,gv,gw staged
+  std::vector<cudaEvent_t> xfer_evs;  // per field: upload landed in its slot | field permuted into its slot for download
   double* xstage = nullptr;
   size_t xstage_len = 0;
   // multi-GPU (one process per GPU): NCCL communicator and interface buffers

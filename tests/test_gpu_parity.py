@@ -370,6 +370,13 @@ def test_step_host_equals_separate_calls(case, cfdl, solver):
         assert np.array_equal(got_hist2, want_hist)
         for k in outs:
             assert np.array_equal(bufs_out[k].array, want[k]), k
+        # fields outside the usual lists, incl. anb (CSR <-> ELL: the unstaged path)
+        extra = {k: np.zeros(s.field_size(k)) for k in ("anb", "ap", "dc", "bu")}
+        outs3 = {k: bufs_out[k].array for k in outs}
+        outs3.update(extra)
+        s.step_host({k: bufs_in[k].array for k in ins}, outs3, dt=0.01, nit=20)
+        for k in extra:
+            assert np.array_equal(extra[k], s.download(k)), k
         for b in list(bufs_in.values()) + list(bufs_out.values()):
             b.free()
     finally:
