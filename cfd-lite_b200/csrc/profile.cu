@@ -101,6 +101,17 @@ int cfdl_host_alloc(void** ptr, uint64_t bytes) {
   CFDL_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
   return CFDL_OK;
 }
+// page-lock memory the caller owns (e.g. the allocatable arrays of uvwp_t), so that cfdl_step_host's
+// transfers run beside the computation; unregister before the memory is freed
+int cfdl_host_register(void* ptr, uint64_t bytes) {
+  if (!ptr || !bytes) return fail(CFDL_ERR_ARG, "cfdl_host_register: NULL / empty range");
+  CFDL_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return CFDL_OK;
+}
+int cfdl_host_unregister(void* ptr) {
+  if (ptr) CFDL_CUDA(cudaHostUnregister(ptr));
+  return CFDL_OK;
+}
 int cfdl_host_free(void* ptr) {
   if (ptr) CFDL_CUDA(cudaFreeHost(ptr));
   return CFDL_OK;

@@ -90,6 +90,12 @@ module mod_gpu_bridge
       real(c_double) :: hist(4,4)
       integer(c_int) :: ierr
     end function
+    function cfdl_host_register(ptr,bytes) bind(C,name='cfdl_host_register') result(ierr)
+      import :: c_ptr, c_int, c_int64_t
+      type(c_ptr), value :: ptr
+      integer(c_int64_t), value :: bytes
+      integer(c_int) :: ierr
+    end function
     function cfdl_update_time(h) bind(C,name='cfdl_update_time') result(ierr)
       import :: c_ptr,c_int
       type(c_ptr), value :: h
@@ -173,6 +179,21 @@ contains
     do k=1,4
       write(*,"(5x,A16,x,i5,x,15x,es9.3e2,3x,es9.3e2,3x,es9.3e2)") names(k),int(hist(1,k)),hist(2,k),hist(3,k),hist(4,k)
     end do
+  end subroutine
+
+  ! page-lock the state arrays of uvwp_t once (after gpu_construct) so that gpu_step_host's transfers
+  ! overlap the computation; pageable arrays work too, without the overlap
+  subroutine gpu_pin_state(eqn)
+    type(uvwp_t), target :: eqn
+    call pin(eqn%u); call pin(eqn%v); call pin(eqn%w); call pin(eqn%p)
+    call pin(eqn%u0); call pin(eqn%v0); call pin(eqn%w0)
+    call pin(eqn%gu); call pin(eqn%gv); call pin(eqn%gw); call pin(eqn%gp); call pin(eqn%gpc)
+    call pin(eqn%mip); call pin(eqn%mip0)
+  contains
+    subroutine pin(a)
+      real, target :: a(:)
+      call gpu_check(cfdl_host_register(c_loc(a(1)), int(size(a),c_int64_t)*8_c_int64_t),'cfdl_host_register')
+    end subroutine
   end subroutine
 
   ! update_boundaries + solve_uvwp with the HOST arrays of uvwp_t staying authoritative (for drivers

@@ -203,6 +203,15 @@ def default_bcs(raw):
     return np.array(esec, np.int32), np.array(kind, np.int32), np.array(uvw, np.float64)
 
 
+def host_register(arr):
+    """Page-lock a numpy array the caller owns (cfdl_host_register); call host_unregister before it is freed."""
+    _chk(lib().cfdl_host_register(C.c_void_p(arr.ctypes.data), C.c_uint64(arr.nbytes)))
+
+
+def host_unregister(arr):
+    _chk(lib().cfdl_host_unregister(C.c_void_p(arr.ctypes.data)))
+
+
 class PinnedBuffer:
     """Page-locked host array (cudaMallocHost) for the end-to-end path."""
 

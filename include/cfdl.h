@@ -119,6 +119,8 @@ int cfdl_timer_record(cfdl_handle h, int32_t slot);                 /* slot 0..3
 int cfdl_timer_elapsed_ms(cfdl_handle h, int32_t slot_begin, int32_t slot_end, double* ms);
 int cfdl_host_alloc(void** ptr, uint64_t bytes);                    /* page-locked host memory */
 int cfdl_host_free(void* ptr);
+int cfdl_host_register(void* ptr, uint64_t bytes);                  /* page-lock caller-owned memory (Fortran allocatables) */
+int cfdl_host_unregister(void* ptr);
 
 /* ---- host <-> device field sync (for write_vtubin, main.f90:79,89) */
 int cfdl_upload_field(cfdl_handle h, int field, const double* host);

@@ -70,6 +70,9 @@ cudaError_t cudaFree(void* p);
 cudaError_t cuemu_malloc_host(void** p, size_t n);
 template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { return cuemu_malloc_host((void**)p, n); }
 cudaError_t cudaFreeHost(void* p);
+enum { cudaHostRegisterDefault = 0 };
+inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t n, cudaMemcpyKind k);
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind k, cudaStream_t s = nullptr);
 cudaError_t cudaMemset(void* dst, int v, size_t n);
