@@ -215,6 +215,8 @@ int field_id(const Handle* h, const double* p) {
   if (p == h->fld[CFDL_F_W]) return P2P_W;
   if (p == h->fld[CFDL_F_PC]) return P2P_PC;
   if (p == h->rb_work) return P2P_WORK;
+  if (p == h->rb3_work[0]) return P2P_WORK_V;
+  if (p == h->rb3_work[1]) return P2P_WORK_W;
   return -1;
 }
 
@@ -233,12 +235,14 @@ int p2p_alloc_slab(Handle* h) {
   hd.off_flags = off; off += align256(64 * 8);
   hd.off_red_val = off; off += align256(2 * 64 * 2 * 8);
   hd.off_red_seq = off; off += align256(2 * 64 * 8);
+  hd.off_red3_val = off; off += align256(2 * 64 * 6 * 8);
+  hd.off_red3_seq = off; off += align256(2 * 64 * 8);
   const size_t off_ticket = off; off += 256;
   hd.off_xflag = off; off += align256(64 * 8);
   hd.off_mail_val = off; off += align256(2 * 64 * 2 * 8);
   hd.off_mail_seq = off; off += align256(2 * 64 * 8);
   for (int b = 0; b < 2; ++b) { hd.off_stage[b] = (long long)off; off += align256(sizeof(double) * 3 * ((size_t)h->G + 32)); }
-  for (int a = 0; a < 5; ++a) { hd.off_field[a] = (long long)off; off += arr; }
+  for (int a = 0; a < 7; ++a) { hd.off_field[a] = (long long)off; off += arr; }
   for (int i = 0; i < hd.nnbr; ++i) hd.nbr_rank[i] = p.nbr_rank[i];
   for (size_t i = 0; i < p.recv_ptr.size(); ++i) hd.recv_ptr[i] = p.recv_ptr[i];
   CFDL_CUDA(cudaMalloc(&q.slab, off));
@@ -251,6 +255,8 @@ int p2p_alloc_slab(Handle* h) {
   h->fld[CFDL_F_W] = (double*)(q.slab + hd.off_field[P2P_W]);
   h->fld[CFDL_F_PC] = (double*)(q.slab + hd.off_field[P2P_PC]);
   h->rb_work = (double*)(q.slab + hd.off_field[P2P_WORK]);
+  h->rb3_work[0] = (double*)(q.slab + hd.off_field[P2P_WORK_V]);
+  h->rb3_work[1] = (double*)(q.slab + hd.off_field[P2P_WORK_W]);
   q.ticket = (unsigned int*)(q.slab + off_ticket);
   q.xticket = q.ticket + 8;
   return CFDL_OK;
@@ -304,6 +310,19 @@ int p2p_reduce_args(Handle* h, int parity, unsigned long long seq, P2PReduce* ou
   }
   out->my_val = (const double*)(q.slab + q.hdr.off_red_val);
   out->my_seq = (const unsigned long long*)(q.slab + q.hdr.off_red_seq);
+  return CFDL_OK;
+}
+
+int p2p_reduce3_args(Handle* h, int parity, unsigned long long seq, P2PReduce* out) {
+  int rc = p2p_reduce_args(h, parity, seq, out);
+  if (rc) return rc;
+  P2P& q = h->p2p;
+  for (int r = 0; r < h->prep.nranks; ++r) {
+    out->peer_val[r] = (double*)(q.peer_base[r] + q.peer_hdr[r].off_red3_val);
+    out->peer_seq[r] = (unsigned long long*)(q.peer_base[r] + q.peer_hdr[r].off_red3_seq);
+  }
+  out->my_val = (const double*)(q.slab + q.hdr.off_red3_val);
+  out->my_seq = (const unsigned long long*)(q.slab + q.hdr.off_red3_seq);
   return CFDL_OK;
 }
 

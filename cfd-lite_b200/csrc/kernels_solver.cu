@@ -483,7 +483,10 @@ int residual_plain(Handle* h, const double* phi, const double* rhs, bool signed_
 // Both orders give the same bits, so with autotune on the second call of a handle measures both on
 // its own data (u, v, w are put back in between) and later calls use the faster one.
 static bool momentum_fusable(const Handle* h) {
-  return h->K <= 6 && h->prep.nranks == 1 && h->solver_mode != CFDL_SOLVER_PARITY;
+  if (h->K > 6 || h->solver_mode == CFDL_SOLVER_PARITY) return false;
+  if (h->prep.nranks == 1) return true;
+  // partitioned: the fused two-colour passes with the peer-to-peer exchange (slab with the extra value arrays)
+  return h->fused_rb && h->prep.ncolors == 2 && h->p2p.connected && h->use_p2p && h->rb3_work[0] != nullptr;
 }
 static int momentum_run(Handle* h, bool fused, int nit, double* out12) {
   if (fused && h->fused_rb && h->prep.ncolors == 2) return h->K <= 4 ? rb3_solve_t<4>(h, nit, out12) : rb3_solve_t<6>(h, nit, out12);
@@ -529,6 +532,17 @@ int solve_momentum(Handle* h, int nit, double* out12) {
     if (keep) { cudaStreamSynchronize(h->stream); cudaFree(keep); }
     if (rc) return rc;
     if (!ok) { cudaGetLastError(); T.ncand = 0; return momentum_run(h, true, nit, out12); }  // u, v, w may be stale copies: solve again
+    if (h->prep.nranks > 1) {
+      // every rank must take the same decision (the two orders exchange ghosts differently): decide on the slowest rank's times
+      for (int cand = 0; cand < 2; ++cand) {
+        h->scal_host[0] = 0.0; h->scal_host[1] = T.ms[cand];
+        CFDL_CUDA(cudaMemcpyAsync(h->scal + 430, h->scal_host, 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if ((rc = comm_allreduce_sum_max(h, h->scal + 430))) return rc;
+        CFDL_CUDA(cudaMemcpyAsync(h->scal_host, h->scal + 430, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CFDL_CUDA(cudaStreamSynchronize(h->stream));
+        T.ms[cand] = (float)h->scal_host[1];
+      }
+    }
     T.choice = (T.ms[0] >= 0.f && T.ms[0] < T.ms[1]) ? 0 : 1;
     return CFDL_OK;  // the last run (side by side) left u, v, w solved
   }

@@ -40,10 +40,12 @@ struct DevSchedule {
 struct P2PHeader {
   long long magic;
   int rank, nranks, N, Nc, H, ncolors, nnbr, pad;
-  long long off_field[5];  // byte offsets of u, v, w, pc and the second solver array in the slab
+  long long off_field[7];  // byte offsets of u, v, w, pc, the second solver array, and the second arrays of v and w (side-by-side momentum passes)
   long long off_flags;     // unsigned long long flags[64]: flags[r] = last push sequence completed by rank r
   long long off_red_val;   // double red_val[2][64][2]: (sum r^2, max) of rank r, two alternating sets
   long long off_red_seq;   // unsigned long long red_seq[2][64]
+  long long off_red3_val;  // double red3_val[2][64][6]: (sum r^2, max) of u, v, w of rank r (side-by-side momentum passes)
+  long long off_red3_seq;  // unsigned long long red3_seq[2][64]
   long long off_stage[2];  // double stage[G][3]: landing zones for staged ghost exchanges, two alternating
   long long off_xflag;     // unsigned long long xflag[64]: xflag[r] = last staged exchange rank r has delivered
   long long off_mail_val;  // double mail_val[2][64][2]: small all-to-all mailbox (all-reduce / broadcast), alternating sets
@@ -64,7 +66,7 @@ struct P2P {
   unsigned int* ticket = nullptr;
   unsigned int* xticket = nullptr;
 };
-enum { P2P_U = 0, P2P_V = 1, P2P_W = 2, P2P_PC = 3, P2P_WORK = 4 };
+enum { P2P_U = 0, P2P_V = 1, P2P_W = 2, P2P_PC = 3, P2P_WORK = 4, P2P_WORK_V = 5, P2P_WORK_W = 6 };
 
 struct Handle {
   Prep prep;
@@ -265,6 +267,7 @@ struct P2PReduce {
 };
 int p2p_store_args(Handle* h, int color, const double* a, const double* b, unsigned long long seq, P2PStore* out);
 int p2p_reduce_args(Handle* h, int parity, unsigned long long seq, P2PReduce* out);
+int p2p_reduce3_args(Handle* h, int parity, unsigned long long seq, P2PReduce* out);  // slots of 6 doubles (u, v, w)
 int comm_bcast(Handle* h, double* dev, int count, int root);
 void comm_destroy(Handle* h);
 

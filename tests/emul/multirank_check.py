@@ -26,6 +26,10 @@ def main():
     mode = cfdl.SOLVER_PCG if pcg else cfdl.SOLVER_MCSGS
     tol_f, tol_h = (1e-8, 1e-8) if pcg else (1e-12, 1e-10)  # the dot products are summed per rank, then in rank order
     conftest.use_emulated_library()
+    # optional: pin the momentum solves side by side (1) / one by one (0) on the ranks, and a time step large enough for
+    # the momentum equations to need several, different iteration counts
+    fused = os.environ.get("CFDL_TEST_UVW_FUSED")
+    dt = float(os.environ.get("CFDL_TEST_DT", "0.01"))
     raw = cfdl.meshgen(0, n)
     geom = cfdl.mesh_build(raw)
     bcs = cfdl.default_bcs(raw)
@@ -43,11 +47,13 @@ def main():
             else:
                 s = cfdl.Solver(geom, bcs, device=0, cell2rank=c2r, rank=rank, nranks=world)
             s.set_option("solver", mode)
+            if fused is not None:
+                s.set_option("uvw_fused", int(fused))
             handles[rank] = s.ipc_handle()
             bar.wait()
             s.ipc_connect(handles)
             bar.wait()
-            hist = s.run(dt=0.01, nit=100, ntstep=2, ncoef=2)
+            hist = s.run(dt=dt, nit=100, ntstep=2, ncoef=2)
             fields = {}
             for f in fields_wanted:
                 a = np.full(s.field_size(f), np.nan)
@@ -83,7 +89,7 @@ def main():
     assert not errs, errs
     one = cfdl.Solver(geom, bcs, device=0)
     one.set_option("solver", mode)
-    want_hist = one.run(dt=0.01, nit=100, ntstep=2, ncoef=2)
+    want_hist = one.run(dt=dt, nit=100, ntstep=2, ncoef=2)
     for r in range(world):
         hist = out[r][0]
         assert np.array_equal(hist[:, :, 0], want_hist[:, :, 0]), (r, hist[:, :, 0], want_hist[:, :, 0])
@@ -101,8 +107,8 @@ def main():
         assert err < tol_f, (f, err)
         worst = max(worst, err)
     one.close()
-    print("multirank emulation ok: world=%d n=%d structured=%s pcg=%s worst field err %.2e, pc iterations %s"
-          % (world, n, structured, pcg, worst, want_hist[:, 3, 0].astype(int).tolist()))
+    print("multirank emulation ok: world=%d n=%d structured=%s pcg=%s worst field err %.2e, pc iterations %s, momentum iterations %s"
+          % (world, n, structured, pcg, worst, want_hist[:, 3, 0].astype(int).tolist(), want_hist[:, :3, 0].astype(int).tolist()))
 
 
 if __name__ == "__main__":

@@ -19,3 +19,14 @@ def test_partitioned_p2p_run_equals_single_rank_under_emulation(world, n, struct
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "multirank emulation ok" in r.stdout
+
+
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_partitioned_momentum_solves_side_by_side_and_one_by_one(fused):
+    """4 ranks, a time step large enough for different iteration counts of u, v, w: the side-by-side passes with
+    peer-to-peer stores of all three equations (and the one-by-one solves) reproduce the single-rank run."""
+    env = dict(os.environ, CFDL_TEST_UVW_FUSED=fused, CFDL_TEST_DT="5.0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "multirank_check.py"), "4", "12"], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "multirank emulation ok" in r.stdout
