@@ -4,7 +4,8 @@ every rank owns a handle of the emulated library, and the "IPC handle" of a slab
 so the peer-to-peer path of comm.cu / kernels_rb.inc (interface CTAs storing into the neighbours'
 ghost cells, flag words, mailbox all-reduce) runs for real, concurrently, on the host.  The merged
 result must equal the single-rank run like in tests/test_gpu_multi.py.  TEST INFRASTRUCTURE ONLY.
-usage: multirank_check.py <world> <n> [structured|pcg]
+usage: multirank_check.py <world> <n> [structured|pcg|nccl|nccl-tet|nccl-pcg]
+(nccl*: the library's NCCL exchange mode against tests/emul/fake_nccl.cpp instead of the peer-to-peer slabs)
 """
 import os
 import sys
@@ -22,7 +23,11 @@ import conftest  # noqa: E402
 def main():
     world, n = int(sys.argv[1]), int(sys.argv[2])
     structured = len(sys.argv) > 3 and sys.argv[3] == "structured"
-    pcg = len(sys.argv) > 3 and sys.argv[3] == "pcg"  # conjugate gradients for pc: ghost exchange of p + all-reduced dot products
+    pcg = len(sys.argv) > 3 and sys.argv[3] in ("pcg", "nccl-pcg")
+    nccl = len(sys.argv) > 3 and sys.argv[3].startswith("nccl")
+    tet = len(sys.argv) > 3 and sys.argv[3] == "nccl-tet"
+    if nccl:
+        os.environ["CFDL_NCCL_PATH"] = os.path.join(ROOT, "tests", "emul", "_build", "libnccl_emul.so")  # conjugate gradients for pc: ghost exchange of p + all-reduced dot products
     mode = cfdl.SOLVER_PCG if pcg else cfdl.SOLVER_MCSGS
     tol_f, tol_h = (1e-8, 1e-8) if pcg else (1e-12, 1e-10)  # the dot products are summed per rank, then in rank order
     conftest.use_emulated_library()
@@ -30,7 +35,7 @@ def main():
     # the momentum equations to need several, different iteration counts
     fused = os.environ.get("CFDL_TEST_UVW_FUSED")
     dt = float(os.environ.get("CFDL_TEST_DT", "0.01"))
-    raw = cfdl.meshgen(0, n)
+    raw = cfdl.meshgen(1, n, jitter=0.2, shuffle=True) if tet else cfdl.meshgen(0, n)
     geom = cfdl.mesh_build(raw)
     bcs = cfdl.default_bcs(raw)
     c2r, _, _ = cfdl.partition_rcb(geom, world)
@@ -49,9 +54,15 @@ def main():
             s.set_option("solver", mode)
             if fused is not None:
                 s.set_option("uvw_fused", int(fused))
-            handles[rank] = s.ipc_handle()
-            bar.wait()
-            s.ipc_connect(handles)
+            if nccl:
+                if rank == 0:
+                    handles[0] = cfdl.comm_unique_id()
+                bar.wait()
+                s.comm_init(handles[0])
+            else:
+                handles[rank] = s.ipc_handle()
+                bar.wait()
+                s.ipc_connect(handles)
             bar.wait()
             hist = s.run(dt=dt, nit=100, ntstep=2, ncoef=2)
             fields = {}

@@ -21,6 +21,17 @@ def test_partitioned_p2p_run_equals_single_rank_under_emulation(world, n, struct
     assert "multirank emulation ok" in r.stdout
 
 
+@pytest.mark.parametrize("world,n,mode", [(4, 10, "nccl"), (3, 4, "nccl-tet"), (4, 10, "nccl-pcg")])
+def test_partitioned_nccl_mode_equals_single_rank_under_emulation(world, n, mode):
+    """The library's NCCL exchange mode (grouped send/recv of ghost values per colour, all-reduced residual norms and
+    dot products, broadcast of pc(1)) against an in-process stand-in for NCCL (tests/emul/fake_nccl.cpp): hex mesh,
+    tet mesh with more than two colours, conjugate gradients."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "multirank_check.py"), str(world), str(n), mode], cwd=ROOT,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "multirank emulation ok" in r.stdout
+
+
 @pytest.mark.parametrize("fused", ["0", "1"])
 def test_partitioned_momentum_solves_side_by_side_and_one_by_one(fused):
     """4 ranks, a time step large enough for different iteration counts of u, v, w: the side-by-side passes with
