@@ -200,6 +200,7 @@ int create_from_prep(cfdl_handle_s* h, const GeomSource& G, cfdl_handle* out) {
   UP(h->ell_nb, p.ell_nb); UP(h->ell_fs, p.ell_fs); UP(h->nfc, p.nfc); UP(h->ftouch, p.ftouch); UP(h->face_a, p.face_a); UP(h->face_b, p.face_b);
   UP(h->halo_cell, p.halo_cell); UP(h->halo_face, p.halo_face); UP(h->halo_bc, p.halo_bc); UP(h->halo_slot, p.halo_slot);
   UP(h->bc_kind, p.bc_kind); UP(h->bc_uvw, p.bc_uvw); UP(h->c2o, p.c2o); UP(h->f2o, p.f2o); UP(h->row_ptr, p.row_ptr);
+  UP(h->loc_order, p.loc_order);
   UP(h->send_cells, p.send_cells); UP(h->tgt_ptr, p.tgt_ptr); UP(h->tgt_nbr, p.tgt_nbr); UP(h->tgt_pos, p.tgt_pos);
 #undef UP
   {  // global index of every device cell | halo (host transfers), geometry in device numbering

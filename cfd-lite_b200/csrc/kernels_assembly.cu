@@ -325,14 +325,15 @@ int k_calc_coef_uvw(Handle* h, double dt) {
     // same bits from every candidate (tests); 2 = divisions, 3 = reciprocal quotients, 5 = 3 with stored
     // reciprocals, 6/7/8 = 5/3/2 in the paired colour order, 4 = 3 with three CTAs per SM requested
     // 9/10/11/12 = 5/6/(5 with three, four CTAs per SM requested) with fewer live registers
-    static const int cands2[] = {2, 3, 5, 6, 7, 8, 4, 9, 10, 11, 12}, cands[] = {2, 3, 5, 4, 9, 11, 12};
+    // 13/14 = 5/9 in the locality order (any number of colours)
+    static const int cands2[] = {2, 3, 5, 6, 7, 4, 9, 10, 11, 12, 13, 14}, cands[] = {2, 3, 5, 4, 9, 11, 12, 13, 14};
     const bool two = h->prep.ncolors == 2;
-    int rc = autotune_pick(h, h->tune_uvw, two ? cands2 : cands, two ? 11 : 7, [&](int v) { h->uvw_variant = v; return k_calc_coef_uvw_statics(h, dt); });
+    int rc = autotune_pick(h, h->tune_uvw, two ? cands2 : cands, two ? 12 : 9, [&](int v) { h->uvw_variant = v; return k_calc_coef_uvw_statics(h, dt); });
     h->uvw_variant = h->tune_uvw.choice;
     if (rc) return rc;
   }
   prof_begin(h, PROF_COEF_UVW);
-  if (h->uvw_variant >= 2 && h->uvw_variant <= 12 && h->use_statics && h->fs_area) {
+  if (h->uvw_variant >= 2 && h->uvw_variant <= 14 && h->use_statics && h->fs_area) {
     int rc = k_calc_coef_uvw_statics(h, dt);
     if (rc) return rc;
   } else if (h->uvw_variant == 0) {

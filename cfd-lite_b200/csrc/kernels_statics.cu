@@ -80,6 +80,7 @@ int k_face_statics(Handle* h) {
 // ---- calc_coef_uvw on statics (mod_uvwp.f90:161-286) ------------------------------------------
 struct UvwArgsS {
   int N, Nc, Np, ncol0;  // ncol0: cells of the first colour (paired order)
+  const int32_t* order;  // owned cells in spatial order (locality-order variants)
   const int32_t *ell_nb, *ell_fs, *halo_bc, *bc_kind;
   const uint8_t* nfc;
   const double *xc, *yc, *zc, *aip, *vol, *rho, *mu;
@@ -267,6 +268,15 @@ template <int K>
 __global__ void __launch_bounds__(TPB, 4) coef_uvw_statics_lean_occ4_kernel(const UvwArgsS A) {
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.N; c += gridDim.x * blockDim.x) coef_uvw_statics_cell<K, 2, true>(A, c);
 }
+// Locality order (uvw_variant 13 / 14 = stored reciprocals, plain / lean; any number of colours): thread i
+// takes the i-th cell of the base (natural | Morton) order, so the lanes of a warp hold cells of all colours
+// that are neighbours in space — the two cells of a face read its statics in the same instruction or a few
+// instructions apart (L1), where the colour-major sweep reads them a second time from DRAM.  Per-cell
+// arrays are then touched as ncolors contiguous runs per warp instead of one.
+template <int K, bool LEAN>
+__global__ void __launch_bounds__(TPB) coef_uvw_statics_loc_kernel(const UvwArgsS A) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.N; i += gridDim.x * blockDim.x) coef_uvw_statics_cell<K, 2, LEAN>(A, A.order[i]);
+}
 
 // tets (K = 4) and hexes/prisms/pyramids (K = 6) get their own instantiation of every variant
 template <auto K4, auto K6>
@@ -289,6 +299,7 @@ int k_calc_coef_uvw_statics(Handle* h, double dt) {
   A.dt = dt;
   A.S = statics_of(h);
   A.ncol0 = h->prep.ncolors == 2 ? h->prep.color_ptr[1] : h->N;
+  A.order = h->loc_order;
   const int paired_cells = std::max(A.ncol0, h->N - A.ncol0);  // a CTA of the paired order covers TPB cells of each colour
   int v = h->uvw_variant;
   if (h->prep.ncolors != 2) v = (v == 6) ? 5 : (v == 7 ? 3 : (v == 8 ? 2 : (v == 10 ? 9 : v)));  // the paired order needs two colours
@@ -303,6 +314,8 @@ int k_calc_coef_uvw_statics(Handle* h, double dt) {
     case 10: launch_uvw<coef_uvw_statics_lean_paired_kernel<4>, coef_uvw_statics_lean_paired_kernel<6>>(h, A, paired_cells); break;
     case 11: launch_uvw<coef_uvw_statics_lean_occ3_kernel<4>, coef_uvw_statics_lean_occ3_kernel<6>>(h, A, h->N); break;
     case 12: launch_uvw<coef_uvw_statics_lean_occ4_kernel<4>, coef_uvw_statics_lean_occ4_kernel<6>>(h, A, h->N); break;
+    case 13: launch_uvw<coef_uvw_statics_loc_kernel<4, false>, coef_uvw_statics_loc_kernel<6, false>>(h, A, h->N); break;
+    case 14: launch_uvw<coef_uvw_statics_loc_kernel<4, true>, coef_uvw_statics_loc_kernel<6, true>>(h, A, h->N); break;
     default: launch_uvw<coef_uvw_statics_kernel<4, 0>, coef_uvw_statics_kernel<6, 0>>(h, A, h->N); break;
   }
   CFDL_CUDA(cudaGetLastError());
@@ -312,6 +325,7 @@ int k_calc_coef_uvw_statics(Handle* h, double dt) {
 // ---- calc_coef_p on statics (mod_uvwp.f90:289-368) ---------------------------------------------
 struct CoefPArgs {
   int N, Nc, Np, ncol0;
+  const int32_t* order;
   const int32_t *ell_nb, *ell_fs, *halo_bc;
   const uint8_t* nfc;
   const double *rho, *dc, *mip;
@@ -383,6 +397,12 @@ __global__ void __launch_bounds__(TPB) coef_p_statics_paired_kernel(const CoefPA
   }
 }
 
+// coef_p_variant 4 / 5: locality order (see coef_uvw_statics_loc_kernel), division / stored reciprocal
+template <int K, bool FAST>
+__global__ void __launch_bounds__(TPB) coef_p_statics_loc_kernel(const CoefPArgs A) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.N; i += gridDim.x * blockDim.x) coef_p_statics_cell<K, FAST>(A, A.order[i]);
+}
+
 template <auto K4, auto K6>
 static void launch_coef_p(Handle* h, const CoefPArgs& A, int cells) {
   if (h->K <= 4) K4<<<occ_grid<K4>(h, cells, TPB), TPB, 0, S(h)>>>(A);
@@ -392,14 +412,17 @@ static void launch_coef_p(Handle* h, const CoefPArgs& A, int cells) {
 static int coef_p_launch(Handle* h, int variant) {
   CoefPArgs A;
   A.N = h->N; A.Nc = h->Nc; A.Np = h->Np; A.ncol0 = h->prep.ncolors == 2 ? h->prep.color_ptr[1] : h->N;
+  A.order = h->loc_order;
   A.ell_nb = h->ell_nb; A.ell_fs = h->ell_fs; A.halo_bc = h->halo_bc; A.nfc = h->nfc;
   A.rho = h->rho; A.dc = h->fld[CFDL_F_DC]; A.mip = h->fld[CFDL_F_MIP];
   A.ap = h->fld[CFDL_F_AP]; A.anb = h->fld[CFDL_F_ANB]; A.b = h->fld[CFDL_F_B];
   A.S = statics_of(h);
   // 0/1 = linear / paired colour order with the division; 2/3 = the same with the stored reciprocal of dr.n
-  const bool paired = (variant == 1 || variant == 3) && h->prep.ncolors == 2, fast = variant >= 2;
+  const bool paired = (variant == 1 || variant == 3) && h->prep.ncolors == 2, fast = variant == 2 || variant == 3 || variant == 5;
   const int pc = std::max(A.ncol0, h->N - A.ncol0);
-  if (paired && fast) launch_coef_p<coef_p_statics_paired_kernel<4, true>, coef_p_statics_paired_kernel<6, true>>(h, A, pc);
+  if (variant == 4) launch_coef_p<coef_p_statics_loc_kernel<4, false>, coef_p_statics_loc_kernel<6, false>>(h, A, h->N);
+  else if (variant == 5) launch_coef_p<coef_p_statics_loc_kernel<4, true>, coef_p_statics_loc_kernel<6, true>>(h, A, h->N);
+  else if (paired && fast) launch_coef_p<coef_p_statics_paired_kernel<4, true>, coef_p_statics_paired_kernel<6, true>>(h, A, pc);
   else if (paired) launch_coef_p<coef_p_statics_paired_kernel<4, false>, coef_p_statics_paired_kernel<6, false>>(h, A, pc);
   else if (fast) launch_coef_p<coef_p_statics_kernel<4, true>, coef_p_statics_kernel<6, true>>(h, A, h->N);
   else launch_coef_p<coef_p_statics_kernel<4, false>, coef_p_statics_kernel<6, false>>(h, A, h->N);
@@ -409,9 +432,9 @@ static int coef_p_launch(Handle* h, int variant) {
 
 int k_calc_coef_p_statics(Handle* h) {
   if (h->autotune && !h->tune_coef_p.done && h->profile == 0 && h->coef_p_variant < 0) {
-    static const int cands2[] = {0, 1, 2, 3}, cands[] = {0, 2};
+    static const int cands2[] = {0, 1, 2, 3, 4, 5}, cands[] = {0, 2, 4, 5};
     const bool two = h->prep.ncolors == 2;
-    int rc = autotune_pick(h, h->tune_coef_p, two ? cands2 : cands, two ? 4 : 2, [&](int v) { return coef_p_launch(h, v); });
+    int rc = autotune_pick(h, h->tune_coef_p, two ? cands2 : cands, two ? 6 : 4, [&](int v) { return coef_p_launch(h, v); });
     if (rc) return rc;
   }
   return coef_p_launch(h, h->coef_p_variant >= 0 ? h->coef_p_variant : (h->tune_coef_p.ncand ? h->tune_coef_p.choice : 0));

@@ -205,6 +205,8 @@ int prepare_core(Prep& p, const std::vector<int32_t>& o_nb, const std::vector<in
   for (int c = 0; c < ncol; ++c) p.color_ptr[c + 1] += p.color_ptr[c];
   p.o2c.assign(gN, -1);
   p.c2o.resize(N);
+  p.loc_order.clear();
+  p.loc_order.reserve(N);
   p.color_if.assign(ncol, 0);
   {
     // inside a colour the interface cells (those with a neighbour owned by another rank) come
@@ -226,6 +228,7 @@ int prepare_core(Prep& p, const std::vector<int32_t>& o_nb, const std::vector<in
       if (owner(e) != rank) continue;
       int32_t c = (nranks > 1 && is_if[e]) ? cur_if[color[e]]++ : cur_in[color[e]]++;
       p.c2o[c] = e; p.o2c[e] = c;
+      p.loc_order.push_back(c);
     }
   }
   // ---- ghost cells (owned by other ranks, face-adjacent to an owned cell) and interface lists -

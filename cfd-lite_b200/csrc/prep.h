@@ -44,6 +44,7 @@ struct Prep {
   std::vector<int32_t> h2o;        // B: device halo -> original halo (0-based offset from gN)
   std::vector<int32_t> f2o;        // F: device face -> original face (0-based)
   std::vector<int32_t> fown;       // F: 1 when this rank reports the face on download
+  std::vector<int32_t> loc_order;  // N: owned device cells in base (natural | Morton) order — neighbours in space are neighbours here
   std::vector<int32_t> color_ptr;  // ncolors+1 over owned cells (device cells are sorted by colour)
   std::vector<int32_t> color_if;   // per colour: leading cells of the colour that touch another rank (interface cells)
   // per owned device cell c: the peers' ghost slots that mirror it, tgt_nbr/tgt_pos[tgt_ptr[c]..tgt_ptr[c+1])

@@ -81,6 +81,7 @@ struct Handle {
   int32_t *halo_cell = nullptr, *halo_face = nullptr, *halo_bc = nullptr, *bc_kind = nullptr;
   int32_t *c2o = nullptr, *cellmap = nullptr, *f2o = nullptr, *row_ptr = nullptr;  // cellmap: device cell|halo -> global index (size H)
   uint8_t *nfc = nullptr, *halo_slot = nullptr, *ftouch = nullptr;
+  int32_t* loc_order = nullptr;  // owned cells in base (spatial) order: the "locality order" of the assembly kernel variants
   double *bc_uvw = nullptr, *xc = nullptr, *yc = nullptr, *zc = nullptr, *aip = nullptr, *rip = nullptr;
   double *vol = nullptr, *rho = nullptr, *mu = nullptr;
   // fields, indexed by CFDL_F_*

@@ -425,7 +425,7 @@ def test_calc_coef_p_variants_keep_the_bits(case):
     oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)  # provides dc
     oc.calc_coef_p()
     try:
-        for variant in (0, 1, 2, 3):  # 2, 3: the quotient by dr.n through the stored reciprocal (linear, paired)
+        for variant in (0, 1, 2, 3, 4, 5):  # 2, 3: the quotient by dr.n through the stored reciprocal (linear, paired); 4, 5: locality order
             s.set_option("coef_p_variant", variant)
             for f in ("ap", "anb", "b"):
                 s.upload(f, np.full(s.field_size(f), 7.5))  # stale values must be overwritten
