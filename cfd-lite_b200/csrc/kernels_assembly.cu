@@ -575,14 +575,18 @@ __device__ __forceinline__ void matinv3_apply(const double A[6], const double g[
   out[2] = 0.0 + b31 * g[0] + b32 * g[1] + b33 * g[2];
 }
 
+// order != nullptr: locality order (thread i takes cell order[i]: the lanes of a warp hold neighbouring cells of
+// all colours, so the neighbour values a lane gathers are its neighbours' own loads), grad_variant 2 / 3
 template <int K, int NF>
 __global__ void __launch_bounds__(TPB) grad_kernel(int N, int Np, const int32_t* __restrict__ ell_nb, const uint8_t* __restrict__ nfc,
                                                    const double* __restrict__ xc, const double* __restrict__ yc,
                                                    const double* __restrict__ zc, const double* phi0, const double* phi1,
-                                                   const double* phi2, double* g0, double* g1, double* g2) {
+                                                   const double* phi2, double* g0, double* g1, double* g2,
+                                                   const int32_t* __restrict__ order) {
   const double* phis[3] = {phi0, phi1, phi2};
   double* gs[3] = {g0, g1, g2};
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const int c = order ? order[i] : i;
     const int n = nfc[c];
     const double rp[3] = {xc[c], yc[c], zc[c]};
     double pe[NF], g[NF][3], A[6] = {0, 0, 0, 0, 0, 0};
@@ -677,10 +681,12 @@ __global__ void __launch_bounds__(TPB) grad_lsq_kernel(int N, int Np, const int3
                                                        const double* __restrict__ xc, const double* __restrict__ yc,
                                                        const double* __restrict__ zc, const double* __restrict__ binv,
                                                        const double* __restrict__ wslot, const double* phi0, const double* phi1,
-                                                       const double* phi2, double* g0, double* g1, double* g2) {
+                                                       const double* phi2, double* g0, double* g1, double* g2,
+                                                       const int32_t* __restrict__ order) {
   const double* phis[3] = {phi0, phi1, phi2};
   double* gs[3] = {g0, g1, g2};
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const int c = order ? order[i] : i;
     const int n = nfc[c];
     const double rp[3] = {xc[c], yc[c], zc[c]};
     double pe[NF], g[NF][3];
@@ -737,13 +743,15 @@ static void launch_k46(Handle* h, int cells, Args... args) {
   else K6<<<occ_grid<K6>(h, cells, TPB), TPB, 0, S(h)>>>(args...);
 }
 
+// variants: 0 = reference form, 1 = on the LSQ statics, 2 / 3 = 0 / 1 in the locality order
 static int grad1_launch(Handle* h, int variant, const double* phi, double* grad) {
-  if (variant == 1) {
+  const int32_t* order = variant >= 2 ? h->loc_order : nullptr;
+  if (variant == 1 || variant == 3) {
     int rc = ensure_lsq_statics(h);
     if (rc) return rc;
-    launch_k46<grad_lsq_kernel<4, 1>, grad_lsq_kernel<6, 1>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, h->lsq_binv, h->lsq_w, phi, phi, phi, grad, grad, grad);
+    launch_k46<grad_lsq_kernel<4, 1>, grad_lsq_kernel<6, 1>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, h->lsq_binv, h->lsq_w, phi, phi, phi, grad, grad, grad, order);
   } else {
-    launch_k46<grad_kernel<4, 1>, grad_kernel<6, 1>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, phi, phi, phi, grad, grad, grad);
+    launch_k46<grad_kernel<4, 1>, grad_kernel<6, 1>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, phi, phi, phi, grad, grad, grad, order);
   }
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
@@ -751,12 +759,13 @@ static int grad1_launch(Handle* h, int variant, const double* phi, double* grad)
 static int grad3_launch(Handle* h, int variant) {
   const double *u = h->fld[CFDL_F_U], *v = h->fld[CFDL_F_V], *w = h->fld[CFDL_F_W];
   double *gu = h->fld[CFDL_F_GU], *gv = h->fld[CFDL_F_GV], *gw = h->fld[CFDL_F_GW];
-  if (variant == 1) {
+  const int32_t* order = variant >= 2 ? h->loc_order : nullptr;
+  if (variant == 1 || variant == 3) {
     int rc = ensure_lsq_statics(h);
     if (rc) return rc;
-    launch_k46<grad_lsq_kernel<4, 3>, grad_lsq_kernel<6, 3>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, h->lsq_binv, h->lsq_w, u, v, w, gu, gv, gw);
+    launch_k46<grad_lsq_kernel<4, 3>, grad_lsq_kernel<6, 3>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, h->lsq_binv, h->lsq_w, u, v, w, gu, gv, gw, order);
   } else {
-    launch_k46<grad_kernel<4, 3>, grad_kernel<6, 3>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, u, v, w, gu, gv, gw);
+    launch_k46<grad_kernel<4, 3>, grad_kernel<6, 3>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, u, v, w, gu, gv, gw, order);
   }
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
@@ -765,8 +774,8 @@ static int grad3_launch(Handle* h, int variant) {
 int k_calc_grad(Handle* h, const double* phi, double* grad) {
   if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
   if (h->autotune && !h->tune_grad1.done && h->profile == 0 && h->grad_variant < 0) {
-    static const int cands[] = {0, 1};
-    int rc = autotune_pick(h, h->tune_grad1, cands, 2, [&](int v) { return grad1_launch(h, v, phi, grad); });
+    static const int cands[] = {0, 1, 2, 3};
+    int rc = autotune_pick(h, h->tune_grad1, cands, 4, [&](int v) { return grad1_launch(h, v, phi, grad); });
     if (rc) return rc;
   }
   return grad1_launch(h, h->grad_variant >= 0 ? h->grad_variant : (h->tune_grad1.ncand ? h->tune_grad1.choice : 0), phi, grad);
@@ -775,8 +784,8 @@ int k_calc_grad(Handle* h, const double* phi, double* grad) {
 int k_calc_grad3(Handle* h) {  // the three calc_grad calls of mod_uvwp.f90:118-120 in one pass over the mesh
   if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
   if (h->autotune && !h->tune_grad3.done && h->profile == 0 && h->grad_variant < 0) {
-    static const int cands[] = {0, 1};
-    int rc = autotune_pick(h, h->tune_grad3, cands, 2, [&](int v) { return grad3_launch(h, v); });
+    static const int cands[] = {0, 1, 2, 3};
+    int rc = autotune_pick(h, h->tune_grad3, cands, 4, [&](int v) { return grad3_launch(h, v); });
     if (rc) return rc;
   }
   prof_begin(h, PROF_GRAD);

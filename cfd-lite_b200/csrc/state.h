@@ -134,7 +134,7 @@ struct Handle {
   // (9 x Np, entry-major) and the weight 1/|dr|^2 per slot (K x Np)
   double *lsq_binv = nullptr, *lsq_w = nullptr;
   int coef_p_variant = -1;     // calc_coef_p on statics: -1 = chosen by measurement, 0 = linear cell order, 1 = paired colour order
-  int grad_variant = -1;       // calc_grad: -1 = chosen by measurement (0 when autotune is off), 0 = reference form, 1 = on the LSQ statics
+  int grad_variant = -1;       // calc_grad: -1 = chosen by measurement (0 when autotune is off), 0 = reference form, 1 = on the LSQ statics, 2 / 3 = 0 / 1 in the locality order
   double *fs_n[3] = {nullptr, nullptr, nullptr}, *fs_dr[3] = {nullptr, nullptr, nullptr}, *fs_drp[3] = {nullptr, nullptr, nullptr};
   int use_statics = 1;         // 0: recompute face geometry in every kernel (the reference's way)
   // Variant selection by measurement: the first call of a routine times its bit-identical kernel

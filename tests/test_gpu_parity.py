@@ -391,7 +391,7 @@ def test_calc_grad_variants_keep_the_bits(case):
     randomize(oc, s, seed=29)
     got = {}
     try:
-        for variant in (0, 1):
+        for variant in (0, 1, 2, 3):  # 2, 3 = 0, 1 in the locality order
             s.set_option("grad_variant", variant)
             s.calc_grad("p", "gp")
             got[variant, "gp"] = s.download("gp")[:3 * oc.ne]
@@ -400,19 +400,21 @@ def test_calc_grad_variants_keep_the_bits(case):
         want = oc.calc_grad(oc["p"])[:3 * oc.ne]
         check("gp", got[0, "gp"], want)
         for f in ("gp", "gpc"):
-            assert np.array_equal(got[0, f], got[1, f]), f
+            for variant in (1, 2, 3):
+                assert np.array_equal(got[0, f], got[variant, f]), (f, variant)
         # the fused three-field pass runs inside solve_uvwp: two iterations from the same state
         hist = {}
-        for variant in (0, 1):
+        for variant in (0, 1, 2, 3):
             s.set_option("grad_variant", variant)
             randomize(oc, s, seed=31)
             s.update_boundaries()
             hist[variant] = s.solve_uvwp(0.01, 5)
             for f in ("gu", "gv", "gw", "gp", "mip", "p"):
                 got[variant, f] = s.download(f)
-        assert np.array_equal(hist[0], hist[1])
-        for f in ("gu", "gv", "gw", "gp", "mip", "p"):
-            assert np.array_equal(got[0, f], got[1, f]), f
+        for variant in (1, 2, 3):
+            assert np.array_equal(hist[0], hist[variant])
+            for f in ("gu", "gv", "gw", "gp", "mip", "p"):
+                assert np.array_equal(got[0, f], got[variant, f]), (f, variant)
     finally:
         s.set_option("grad_variant", -1)
 
