@@ -23,6 +23,7 @@ def pytest_configure(config):
 
 
 EMUL_LIB = os.path.join(ROOT, "tests", "emul", "_build", "libcfdl_emul.so")
+EMULATED = False  # True when this test process runs against the cuemu build (a few tests then use smaller meshes)
 
 
 def build_emulated_library():
@@ -40,6 +41,8 @@ def use_emulated_library():
     m._lib.cfdl_last_error.restype = ctypes.c_char_p
     assert m._lib.cfdl_emulated() == 1
     m.LIB_PATH = EMUL_LIB
+    global EMULATED
+    EMULATED = True
 
 
 @pytest.fixture(scope="session")
