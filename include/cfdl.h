@@ -111,9 +111,17 @@ int cfdl_get_cell_order(cfdl_handle h, int32_t* c2o, int32_t* color_ptr);
  * set_option keys: "solver", "profile" (0 off; 1: an event pair around every launch of the profiled
  *                  kernels; 2: an event pair around every batch of back-to-back solver passes),
  *                  "reset_counters" (any value); tuning switches: "fused", "pdl", "pdl_rows", "p2p",
- *                  "statics", "uvw_variant", "mip_variant", "occ_grids", "ctas_per_sm".
+ *                  "statics", "mip_variant", "occ_grids", "ctas_per_sm";
+ *                  "autotune" (1 default: bit-identical kernel variants are timed on first use and the
+ *                  fastest kept; 0: round-1 defaults; 2: forget what was measured), and the switches
+ *                  that pin a choice by hand: "uvw_variant" (2..14), "grad_variant" (0..3, -1 measured),
+ *                  "coef_p_variant" (0..5, -1), "mip_fast" (0/1, -1), "correct_fast" (0/1),
+ *                  "uvw_fused" (momentum solves side by side: 0/1, -1 measured), "rb_persistent" (fused
+ *                  passes of a batch in one cooperative launch: 0/1, -1 measured), "pc_sumap" (0/1).
  * get_info keys:   "launches" (kernels launched since reset), "prof_ms_<k>" / "prof_n_<k>" with
  *                  k in sgs, residual, coef_uvw, coef_p, mip, grad, levels, pcg, sgs3 (u,v,w side-by-side passes);
+ *                  "tuned_<r>" (chosen variant, -1 = not measured), "tuned_<r>_n", "tuned_<r>_cand<i>",
+ *                  "tuned_<r>_ms<i>" with r in uvw, grad3, grad1, coef_p, mip, uvw_solve, rb_persistent;
  *                  "ncolors", "morton", "nlevels_natural", "nlevels_blocks", "ell_width", "num_sms". */
 int cfdl_timer_record(cfdl_handle h, int32_t slot);                 /* slot 0..3 */
 int cfdl_timer_elapsed_ms(cfdl_handle h, int32_t slot_begin, int32_t slot_end, double* ms);
