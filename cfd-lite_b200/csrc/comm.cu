@@ -77,12 +77,12 @@ __global__ void __launch_bounds__(256) pack_kernel(double* __restrict__ buf, con
 
 }  // namespace
 
-static int p2p_exchange(Handle* h, double* field, int ncomp);
+static int p2p_exchange(Handle* h, double* field, int ncomp, int color = -1);
 static int p2p_mail(Handle* h, double* dev, int mode, int root);
 
 int comm_exchange(Handle* h, double* field, int ncomp, int color) {
   if (h->prep.nranks == 1 || h->nnbr == 0) return CFDL_OK;
-  if (color < 0 && ncomp <= 3 && h->p2p.connected && h->use_p2p) return p2p_exchange(h, field, ncomp);
+  if (ncomp <= 3 && h->p2p.connected && h->use_p2p) return p2p_exchange(h, field, ncomp, color);  // all colours (-1) or one
   if (!h->comm) return fail(CFDL_ERR_NCCL, "this handle is one partition of %d: call cfdl_comm_init before computing", h->prep.nranks);
   if (ncomp < 1 || ncomp > 9) return fail(CFDL_ERR_ARG, "comm_exchange: ncomp %d", ncomp);
   const Prep& p = h->prep;
@@ -384,6 +384,8 @@ struct StageArgs {
   const double* src;          // field (device numbering, ncomp interleaved)
   double* field;
   int s0[8], cnt[8], d0[8];   // per neighbour: first send cell, count, first ghost slot at the neighbour
+  int g0[8], gcnt[8];         // per neighbour: the ghost range that receives (one colour: a sub-range of the neighbour's ghosts)
+  int whole;                  // 1: all colours — the landing zone is copied as one block
   double* peer_stage[8];
   unsigned long long* peer_flag[8];
   const double* my_stage;
@@ -420,9 +422,16 @@ __global__ void __launch_bounds__(256) stage_exchange_kernel(const __grid_consta
     __threadfence_system();
   }
   __syncthreads();
-  const size_t n = (size_t)A.G * A.ncomp;
   double* ghosts = A.field + (size_t)A.N * A.ncomp;
-  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) ghosts[t] = __ldcg(&A.my_stage[t]);
+  if (A.whole) {
+    const size_t n = (size_t)A.G * A.ncomp;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) ghosts[t] = __ldcg(&A.my_stage[t]);
+    return;
+  }
+  for (int i = 0; i < A.nnbr; ++i) {  // one colour: only the ghost sub-ranges that received
+    const size_t b = (size_t)A.g0[i] * A.ncomp, n = (size_t)A.gcnt[i] * A.ncomp;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) ghosts[b + t] = __ldcg(&A.my_stage[b + t]);
+  }
 }
 
 // small all-to-all through the peers' mailboxes: every rank posts two doubles to every rank,
@@ -466,7 +475,7 @@ __global__ void __launch_bounds__(64) mail_kernel(const __grid_constant__ MailAr
 
 }  // namespace
 
-static int p2p_exchange(Handle* h, double* field, int ncomp) {
+static int p2p_exchange(Handle* h, double* field, int ncomp, int color) {
   P2P& q = h->p2p;
   const Prep& p = h->prep;
   StageArgs A;
@@ -482,10 +491,13 @@ static int p2p_exchange(Handle* h, double* field, int ncomp) {
     int me = -1;
     for (int k = 0; k < ph.nnbr; ++k) if (ph.nbr_rank[k] == p.rank) me = k;
     if (me < 0) return fail(CFDL_ERR_INTERNAL, "p2p_exchange: rank %d does not list rank %d as a neighbour", r, p.rank);
-    A.s0[i] = p.send_ptr[(size_t)i * nc];
-    A.cnt[i] = p.send_ptr[(size_t)(i + 1) * nc] - A.s0[i];
-    if (ph.recv_ptr[(me + 1) * nc] - ph.recv_ptr[me * nc] != A.cnt[i]) return fail(CFDL_ERR_INTERNAL, "p2p_exchange: interface size mismatch with rank %d", r);
-    A.d0[i] = ph.recv_ptr[me * nc];
+    const int c0 = color >= 0 ? color : 0, c1 = color >= 0 ? color + 1 : nc;  // colour slices of a neighbour are adjacent
+    A.s0[i] = p.send_ptr[(size_t)i * nc + c0];
+    A.cnt[i] = p.send_ptr[(size_t)i * nc + c1] - A.s0[i];
+    if (ph.recv_ptr[me * nc + c1] - ph.recv_ptr[me * nc + c0] != A.cnt[i]) return fail(CFDL_ERR_INTERNAL, "p2p_exchange: interface size mismatch with rank %d", r);
+    A.d0[i] = ph.recv_ptr[me * nc + c0];
+    A.g0[i] = p.recv_ptr[(size_t)i * nc + c0];
+    A.gcnt[i] = p.recv_ptr[(size_t)i * nc + c1] - A.g0[i];
     A.peer_stage[i] = (double*)(q.peer_base[r] + ph.off_stage[buf]);
     A.peer_flag[i] = (unsigned long long*)(q.peer_base[r] + ph.off_xflag) + p.rank;
     A.nbr_rank[i] = r;
@@ -493,7 +505,7 @@ static int p2p_exchange(Handle* h, double* field, int ncomp) {
   }
   A.my_stage = (const double*)(q.slab + q.hdr.off_stage[buf]);
   A.my_flags = (const unsigned long long*)(q.slab + q.hdr.off_xflag);
-  A.seq = seq; A.ticket = q.xticket;
+  A.seq = seq; A.ticket = q.xticket; A.whole = color < 0 ? 1 : 0;
   const int ctas = std::max(1, std::min(64, (std::max(total, h->G) * ncomp + 255) / 256));
   stage_exchange_kernel<<<ctas, 256, 0, S(h)>>>(A);
   CFDL_CUDA(cudaGetLastError());

@@ -4,7 +4,7 @@ every rank owns a handle of the emulated library, and the "IPC handle" of a slab
 so the peer-to-peer path of comm.cu / kernels_rb.inc (interface CTAs storing into the neighbours'
 ghost cells, flag words, mailbox all-reduce) runs for real, concurrently, on the host.  The merged
 result must equal the single-rank run like in tests/test_gpu_multi.py.  TEST INFRASTRUCTURE ONLY.
-usage: multirank_check.py <world> <n> [structured|pcg|nccl|nccl-tet|nccl-pcg]
+usage: multirank_check.py <world> <n> [structured|pcg|tet|nccl|nccl-tet|nccl-pcg]
 (nccl*: the library's NCCL exchange mode against tests/emul/fake_nccl.cpp instead of the peer-to-peer slabs)
 """
 import os
@@ -25,7 +25,7 @@ def main():
     structured = len(sys.argv) > 3 and sys.argv[3] == "structured"
     pcg = len(sys.argv) > 3 and sys.argv[3] in ("pcg", "nccl-pcg")
     nccl = len(sys.argv) > 3 and sys.argv[3].startswith("nccl")
-    tet = len(sys.argv) > 3 and sys.argv[3] == "nccl-tet"
+    tet = len(sys.argv) > 3 and sys.argv[3] in ("nccl-tet", "tet")  # "tet": peer-to-peer, one staged exchange per colour
     if nccl:
         os.environ["CFDL_NCCL_PATH"] = os.path.join(ROOT, "tests", "emul", "_build", "libnccl_emul.so")  # conjugate gradients for pc: ghost exchange of p + all-reduced dot products
     mode = cfdl.SOLVER_PCG if pcg else cfdl.SOLVER_MCSGS
