@@ -360,6 +360,9 @@ def main():
             black = (n_owned - n_r) * (row + 8 + 8) + 16 * (n_r + halo_vals)
             per_launch = (red + black) / 2.0
             kname = "rb_red_kernel / rb_black_kernel (fused two-colour SGS pass incl. residual; average of the two)"
+            if tuned.get("rb_persistent", {}).get("chosen") == 1:
+                kname = ("rb_persistent_kernel (the fused two-colour SGS passes of a batch inside one cooperative launch; average pass, "
+                         "red and black; the per-launch 'isolated' figure is the per-pass kernels rb_red_kernel / rb_black_kernel)")
         else:
             # one colour launch updates 1/ncolors of the cells: a full sweep = ncolors launches
             per_launch = ab["sgs_sweep"] / ncol
