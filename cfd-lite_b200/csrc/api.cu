@@ -317,6 +317,7 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "pdl_rows")) { h->pdl_rows = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "pdl")) { h->use_pdl = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "uvw_variant")) { h->uvw_variant = (int)value; h->tune_uvw.done = 1; return CFDL_OK; }  // pinned by hand
+  if (!std::strcmp(key, "rb_keep_mb")) { h->rb_keep_mb = (float)value; return CFDL_OK; }
   if (!std::strcmp(key, "rb_persistent")) { h->rb_persistent = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
   if (!std::strcmp(key, "pc_sumap")) { h->pc_sumap = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "uvw_fused")) { h->uvw_fused = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "state.h"
+#include "device_math.cuh"
 
 namespace cfdl {
 

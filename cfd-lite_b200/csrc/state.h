@@ -109,6 +109,7 @@ struct Handle {
   SolveCtl* ctl3_host = nullptr;  // pinned
   int rb_persistent = -1;         // fused passes of a batch in one cooperative launch: 1 on, 0 off, -1 measured (autotune) else off
   int rbp_refused = 0, pc_solves = 0;
+  float rb_keep_mb = -1.f;        // megabytes of pc coefficients asked to stay in L2 across passes: >= 0 pinned, -1 measured (autotune) else 0
   int pc_sumap = 1;               // fused pc passes rebuild ap as the slot-order sum of anb instead of reading it
   bool pc_sumap_ok = false;       // true while ap/anb on the device are what calc_coef_p wrote (cleared by any other writer)
   int uvw_fused = -1;             // 1: side by side, 0: one after the other as the reference does, -1: measured (autotune) else 1

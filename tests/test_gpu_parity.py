@@ -586,8 +586,9 @@ def test_persistent_passes_keep_the_bits(case, cfdl):
     s.set_option("solver", cfdl.SOLVER_MCSGS)
     try:
         res = {}
-        for flag in (0, 1):
-            s.set_option("rb_persistent", flag)
+        for flag in (0, 1, 2, 3):  # 2, 3 = 0, 1 with the L2 residency hint on the pc coefficient loads (a caching hint: same values)
+            s.set_option("rb_persistent", flag & 1)
+            s.set_option("rb_keep_mb", 35.0 if flag >= 2 else 0.0)
             for sep in (0, 1):  # momentum one by one runs the single-equation passes too
                 s.set_option("uvw_fused", 1 - sep)
                 randomize(oc, s, seed=61)
@@ -597,11 +598,13 @@ def test_persistent_passes_keep_the_bits(case, cfdl):
                     hs.append(s.solve_uvwp(0.01, nit))
                 res[flag, sep] = (np.array(hs), {f: s.download(f) for f in ("u", "v", "w", "p", "pc", "mip")})
         for sep in (0, 1):
-            assert np.array_equal(res[0, sep][0], res[1, sep][0]), (res[0, sep][0], res[1, sep][0])
-            for f, v in res[0, sep][1].items():
-                assert np.array_equal(v, res[1, sep][1][f]), (sep, f)
+            for flag in (1, 2, 3):
+                assert np.array_equal(res[0, sep][0], res[flag, sep][0]), (flag, res[0, sep][0], res[flag, sep][0])
+                for f, v in res[0, sep][1].items():
+                    assert np.array_equal(v, res[flag, sep][1][f]), (flag, sep, f)
     finally:
         s.set_option("rb_persistent", -1)
+        s.set_option("rb_keep_mb", -1.0)
         s.set_option("uvw_fused", -1)
         s.set_option("solver", cfdl.SOLVER_PARITY)
 
