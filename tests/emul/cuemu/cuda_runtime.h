@@ -82,6 +82,7 @@ cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags);
 cudaError_t cudaStreamDestroy(cudaStream_t s);
 cudaError_t cudaStreamSynchronize(cudaStream_t s);
 cudaError_t cudaDeviceSynchronize();
+inline cudaError_t cudaCtxResetPersistingL2Cache() { return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t* e);
 enum { cudaEventDisableTiming = 2 };
 cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned flags);
