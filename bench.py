@@ -355,7 +355,9 @@ def main():
             halo_vals = int(s.get_info("ghost_cells")) + n_local_halos
             # pc passes (nearly all of them: the momentum passes have their own entry when they run side by side) rebuild
             # ap from the row's anb instead of reading it (pc_sumap): 8 + 12K bytes of matrix per row instead of 16 + 12K
-            row = (8 if int(s.get_info("pc_sumap")) else 16) + 12 * K
+            # chosen form of the pc passes (candidate c: persistent = c & 1, L2 hint = (c >> 1) % 3 > 0, 16-bit neighbour offsets = c >= 6)
+            cand = tuned.get("rb_persistent", {}).get("chosen", 0)
+            row = (8 if int(s.get_info("pc_sumap")) else 16) + (10 if cand >= 6 else 12) * K
             red = n_r * (row + 8 + 16) + 8 * (n_owned - n_r + halo_vals)
             black = (n_owned - n_r) * (row + 8 + 8) + 16 * (n_r + halo_vals)
             per_launch = (red + black) / 2.0

@@ -200,7 +200,7 @@ int create_from_prep(cfdl_handle_s* h, const GeomSource& G, cfdl_handle* out) {
   UP(h->ell_nb, p.ell_nb); UP(h->ell_fs, p.ell_fs); UP(h->nfc, p.nfc); UP(h->ftouch, p.ftouch); UP(h->face_a, p.face_a); UP(h->face_b, p.face_b);
   UP(h->halo_cell, p.halo_cell); UP(h->halo_face, p.halo_face); UP(h->halo_bc, p.halo_bc); UP(h->halo_slot, p.halo_slot);
   UP(h->bc_kind, p.bc_kind); UP(h->bc_uvw, p.bc_uvw); UP(h->c2o, p.c2o); UP(h->f2o, p.f2o); UP(h->row_ptr, p.row_ptr);
-  UP(h->loc_order, p.loc_order);
+  UP(h->loc_order, p.loc_order); UP(h->ell_nb16, p.nb16);
   UP(h->send_cells, p.send_cells); UP(h->tgt_ptr, p.tgt_ptr); UP(h->tgt_nbr, p.tgt_nbr); UP(h->tgt_pos, p.tgt_pos);
 #undef UP
   {  // global index of every device cell | halo (host transfers), geometry in device numbering
@@ -317,6 +317,7 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "pdl_rows")) { h->pdl_rows = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "pdl")) { h->use_pdl = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "uvw_variant")) { h->uvw_variant = (int)value; h->tune_uvw.done = 1; return CFDL_OK; }  // pinned by hand
+  if (!std::strcmp(key, "rb_idx16")) { h->rb_idx16 = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
   if (!std::strcmp(key, "rb_keep_mb")) { h->rb_keep_mb = (float)value; return CFDL_OK; }
   if (!std::strcmp(key, "rb_persistent")) { h->rb_persistent = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
   if (!std::strcmp(key, "pc_sumap")) { h->pc_sumap = value != 0.0; return CFDL_OK; }

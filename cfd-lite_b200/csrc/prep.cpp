@@ -368,6 +368,32 @@ int prepare_core(Prep& p, const std::vector<int32_t>& o_nb, const std::vector<in
       p.ell_fs[(size_t)k * Np + c] = (o_fg[idx] > 0) ? (fdev + 1) : -(fdev + 1);
     }
   }
+  // ---- 16-bit neighbour offsets for the pc passes (two colours, one rank) ------------------------
+  p.nb16.clear();
+  p.nb16_ok = false;
+  if (nranks == 1 && ncol == 2) {
+    const int32_t nred = p.color_ptr[1];
+    p.nb16.assign((size_t)K * Np, 0);
+    bool ok = true;
+    for (int32_t c = 0; c < N && ok; ++c) {
+      const bool red = c < nred;
+      const int32_t cl = red ? c : c - nred;
+      int32_t d[8], first = INT32_MIN;
+      for (int k = 0; k < K; ++k) {
+        d[k] = INT32_MIN;
+        const int32_t nb = p.ell_nb[(size_t)k * Np + c];
+        if (k >= p.nfc[c] || nb >= N) continue;          // padding or boundary slot
+        if ((nb < nred) == red) { ok = false; break; }   // a neighbour of the same colour: not a proper two-colouring
+        d[k] = (red ? nb - nred : nb) - cl;
+        if (d[k] < -32768 || d[k] > 32767) { ok = false; break; }
+        if (first == INT32_MIN) first = d[k];
+      }
+      if (first == INT32_MIN) ok = false;                // a cell without cell neighbours
+      for (int k = 0; k < K && ok; ++k) p.nb16[(size_t)k * Np + c] = (int16_t)(d[k] == INT32_MIN ? first : d[k]);
+    }
+    p.nb16_ok = ok;
+    if (!ok) p.nb16.clear();
+  }
   // ---- boundary conditions -------------------------------------------------------------------
   p.bc_kind.assign(bc_kind, bc_kind + nbc);
   p.bc_uvw.assign(bc_uvw, bc_uvw + 3 * (size_t)nbc);

@@ -52,6 +52,11 @@ struct Prep {
   std::vector<int32_t> tgt_ptr, tgt_nbr, tgt_pos;
   std::vector<int32_t> ell_nb;     // K*Np device index of neighbour (cell, ghost or halo), pad = self
   std::vector<int32_t> ell_fs;     // K*Np signed device face id +-(f+1); 0 = padding slot
+  // two colours, one rank: neighbour ids as 16-bit offsets inside the other colour (K*Np; nb16_ok when every
+  // offset fits).  Slot k of red row c points to cell nred + c + nb16, of black row c to (c - nred) + nb16;
+  // boundary and padding slots carry the offset of the row's first cell neighbour (their pc coefficient is zero).
+  std::vector<int16_t> nb16;
+  bool nb16_ok = false;
   std::vector<uint8_t> nfc;        // N faces per cell
   std::vector<uint8_t> ftouch;     // N: bit k set when slot k's cell-cell face is numbered from this cell (its first toucher)
   int32_t touch_end = 0;           // cells [touch_end, N) have ftouch == 0 (two-colour mesh: the whole second colour)

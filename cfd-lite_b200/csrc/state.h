@@ -81,6 +81,7 @@ struct Handle {
   int32_t *halo_cell = nullptr, *halo_face = nullptr, *halo_bc = nullptr, *bc_kind = nullptr;
   int32_t *c2o = nullptr, *cellmap = nullptr, *f2o = nullptr, *row_ptr = nullptr;  // cellmap: device cell|halo -> global index (size H)
   uint8_t *nfc = nullptr, *halo_slot = nullptr, *ftouch = nullptr;
+  int16_t* ell_nb16 = nullptr;   // prep.nb16 on the device (nullptr when the offsets do not fit or the mesh is partitioned)
   int32_t* loc_order = nullptr;  // owned cells in base (spatial) order: the "locality order" of the assembly kernel variants
   double *bc_uvw = nullptr, *xc = nullptr, *yc = nullptr, *zc = nullptr, *aip = nullptr, *rip = nullptr;
   double *vol = nullptr, *rho = nullptr, *mu = nullptr;
@@ -109,6 +110,7 @@ struct Handle {
   SolveCtl* ctl3_host = nullptr;  // pinned
   int rb_persistent = -1;         // fused passes of a batch in one cooperative launch: 1 on, 0 off, -1 measured (autotune) else off
   int rbp_refused = 0, pc_solves = 0;
+  int rb_idx16 = -1;              // pc passes read 16-bit neighbour offsets instead of 32-bit ids: 0/1 pinned, -1 measured (autotune) else 0
   float rb_keep_mb = -1.f;        // megabytes of pc coefficients asked to stay in L2 across passes: >= 0 pinned, -1 measured (autotune) else 0
   int pc_sumap = 1;               // fused pc passes rebuild ap as the slot-order sum of anb instead of reading it
   bool pc_sumap_ok = false;       // true while ap/anb on the device are what calc_coef_p wrote (cleared by any other writer)

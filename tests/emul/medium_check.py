@@ -44,7 +44,7 @@ def main():
         s = cfdl.Solver(geom, bcs, device=0)
         s.set_option("solver", cfdl.SOLVER_MCSGS)
         if not new:
-            for k, v in (("autotune", 0), ("uvw_fused", 0), ("pc_sumap", 0), ("grad_variant", 0), ("coef_p_variant", 0), ("uvw_variant", 2), ("rb_persistent", 0), ("rb_keep_mb", 0)):
+            for k, v in (("autotune", 0), ("uvw_fused", 0), ("pc_sumap", 0), ("grad_variant", 0), ("coef_p_variant", 0), ("uvw_variant", 2), ("rb_persistent", 0), ("rb_keep_mb", 0), ("rb_idx16", 0)):
                 s.set_option(k, v)
         h = s.run(dt=0.5, nit=100, ntstep=2, ncoef=3)
         res[new] = (h, {f: s.download(f) for f in ("u", "v", "w", "p", "gu", "gp", "mip")},

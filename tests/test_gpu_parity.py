@@ -577,35 +577,37 @@ def test_pc_passes_rebuilding_the_diagonal_keep_the_bits(case, cfdl):
 
 
 def test_persistent_passes_keep_the_bits(case, cfdl):
-    """rb_persistent=1 (all fused passes of a batch in one cooperative launch with grid barriers,
-    kernels_rbp.inc) against rb_persistent=0 (one launch per pass): same row-to-thread mapping and
-    reductions, hence identical fields AND identical residual history."""
+    """The forms of the fused two-colour pc solve — one launch per pass / all passes of a batch in one
+    cooperative launch with grid barriers (kernels_rbp.inc), with / without the L2 residency hint on the
+    coefficient loads, 32-bit neighbour ids / 16-bit offsets — use the same row-to-thread mapping and
+    reductions: identical fields AND identical residual history."""
     name, raw, oc, geom, s = case
     if int(s.get_info("ncolors")) != 2:
         pytest.skip("fused two-colour passes only")
     s.set_option("solver", cfdl.SOLVER_MCSGS)
     try:
         res = {}
-        for flag in (0, 1, 2, 3):  # 2, 3 = 0, 1 with the L2 residency hint on the pc coefficient loads (a caching hint: same values)
-            s.set_option("rb_persistent", flag & 1)
-            s.set_option("rb_keep_mb", 35.0 if flag >= 2 else 0.0)
-            for sep in (0, 1):  # momentum one by one runs the single-equation passes too
+        combos = [(p, k, i) for p in (0, 1) for k in (0.0, 35.0) for i in (0, 1)]
+        for combo in combos:
+            s.set_option("rb_persistent", combo[0])
+            s.set_option("rb_keep_mb", combo[1])
+            s.set_option("rb_idx16", combo[2])
+            for sep in ((0, 1) if combo in (combos[0], combos[-1]) else (0,)):  # momentum one by one runs the single-equation passes too
                 s.set_option("uvw_fused", 1 - sep)
                 randomize(oc, s, seed=61)
                 hs = []
                 for nit in (1, 2, 40):
                     s.update_boundaries()
                     hs.append(s.solve_uvwp(0.01, nit))
-                res[flag, sep] = (np.array(hs), {f: s.download(f) for f in ("u", "v", "w", "p", "pc", "mip")})
-        for sep in (0, 1):
-            for flag in (1, 2, 3):
-                assert np.array_equal(res[0, sep][0], res[flag, sep][0]), (flag, res[0, sep][0], res[flag, sep][0])
-                for f, v in res[0, sep][1].items():
-                    assert np.array_equal(v, res[flag, sep][1][f]), (flag, sep, f)
+                res[combo, sep] = (np.array(hs), {f: s.download(f) for f in ("u", "v", "w", "p", "pc", "mip")})
+        for (combo, sep), (hist, fields) in res.items():
+            ref_hist, ref_fields = res[combos[0], sep]
+            assert np.array_equal(hist, ref_hist), (combo, sep, hist, ref_hist)
+            for f, v in fields.items():
+                assert np.array_equal(v, ref_fields[f]), (combo, sep, f)
     finally:
-        s.set_option("rb_persistent", -1)
-        s.set_option("rb_keep_mb", -1.0)
-        s.set_option("uvw_fused", -1)
+        for k in ("rb_persistent", "rb_keep_mb", "rb_idx16", "uvw_fused"):
+            s.set_option(k, -1)
         s.set_option("solver", cfdl.SOLVER_PARITY)
 
 

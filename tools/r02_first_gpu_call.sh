@@ -15,7 +15,7 @@ run r01_kernels --opt autotune=0 --opt uvw_fused=0 --e2e-separate
 run uvw_sep --opt uvw_fused=0 --no-e2e --no-cpu-baseline
 run uvw_fused --opt uvw_fused=1 --no-e2e --no-cpu-baseline
 run pcg --solver pcg --no-e2e --no-cpu-baseline
-for pk in "0 0" "1 0" "0 35" "1 35" "0 60" "1 60"; do set -- $pk; run rb_p$1_k$2 --opt rb_persistent=$1 --opt rb_keep_mb=$2 --steps 12 --no-e2e --no-cpu-baseline; done
+for pk in "0 0" "1 0" "0 35" "1 35" "0 60" "1 60"; do set -- $pk; run rb_p$1_k$2 --opt rb_persistent=$1 --opt rb_keep_mb=$2 --opt rb_idx16=0 --steps 12 --no-e2e --no-cpu-baseline; run rb_p$1_k$2_i16 --opt rb_persistent=$1 --opt rb_keep_mb=$2 --opt rb_idx16=1 --steps 12 --no-e2e --no-cpu-baseline; done
 for v in 2 3 5 6 7 8 4 9 10 11 12; do run uvw_v$v --opt uvw_variant=$v --steps 10 --no-e2e --no-cpu-baseline; done
 for v in 0 1; do run grad_v$v --opt grad_variant=$v --steps 10 --no-e2e --no-cpu-baseline; run coefp_v$v --opt coef_p_variant=$v --steps 10 --no-e2e --no-cpu-baseline; done
 # 3. launch list of one default step + full capture of the assembly kernels and the side-by-side passes
