@@ -317,6 +317,8 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "pdl_rows")) { h->pdl_rows = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "pdl")) { h->use_pdl = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "uvw_variant")) { h->uvw_variant = (int)value; h->tune_uvw.done = 1; return CFDL_OK; }  // pinned by hand
+  if (!std::strcmp(key, "rb_wave")) { h->rb_wave = std::max(0, (int)value); return CFDL_OK; }
+  if (!std::strcmp(key, "rb_wave_block")) { h->rb_wave_block = std::max(1, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "rb_idx16")) { h->rb_idx16 = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
   if (!std::strcmp(key, "rb_keep_mb")) { h->rb_keep_mb = (float)value; return CFDL_OK; }
   if (!std::strcmp(key, "rb_persistent")) { h->rb_persistent = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
@@ -363,6 +365,7 @@ int cfdl_get_info(cfdl_handle h, const char* key, double* value) {
   else if (!std::strcmp(key, "launches")) *value = (double)h->launches;
   else if (!std::strcmp(key, "uvw_variant")) *value = h->uvw_variant;
   else if (!std::strcmp(key, "pc_sumap")) *value = h->pc_sumap;
+  else if (!std::strcmp(key, "color_dist")) *value = h->prep.color_dist;
   else if (!std::strncmp(key, "tuned_", 6)) {
     // "tuned_<routine>" = chosen variant (-1: not tuned); "tuned_<routine>_ms<i>" / "_cand<i>" = the measurements
     const Handle::Tuned* T = nullptr;

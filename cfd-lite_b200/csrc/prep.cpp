@@ -3,6 +3,7 @@
 #include "prep.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 #include "cfdl_common.h"
 
@@ -371,8 +372,21 @@ int prepare_core(Prep& p, const std::vector<int32_t>& o_nb, const std::vector<in
   // ---- 16-bit neighbour offsets for the pc passes (two colours, one rank) ------------------------
   p.nb16.clear();
   p.nb16_ok = false;
+  p.color_dist = -1;
   if (nranks == 1 && ncol == 2) {
     const int32_t nred = p.color_ptr[1];
+    int64_t dist = 0;
+    bool proper = true;
+    for (int32_t c = 0; c < N && proper; ++c) {
+      const bool red = c < nred;
+      for (int k = 0; k < p.nfc[c]; ++k) {
+        const int32_t nb = p.ell_nb[(size_t)k * Np + c];
+        if (nb >= N) continue;
+        if ((nb < nred) == red) { proper = false; break; }
+        dist = std::max<int64_t>(dist, std::llabs((int64_t)(red ? nb - nred : nb) - (red ? c : c - nred)));
+      }
+    }
+    if (proper && dist < INT32_MAX) p.color_dist = (int32_t)dist;
     p.nb16.assign((size_t)K * Np, 0);
     bool ok = true;
     for (int32_t c = 0; c < N && ok; ++c) {

@@ -57,6 +57,7 @@ struct Prep {
   // boundary and padding slots carry the offset of the row's first cell neighbour (their pc coefficient is zero).
   std::vector<int16_t> nb16;
   bool nb16_ok = false;
+  int32_t color_dist = -1;         // two colours, one rank: largest |position of a neighbour in its colour - own position| (-1: unknown)
   std::vector<uint8_t> nfc;        // N faces per cell
   std::vector<uint8_t> ftouch;     // N: bit k set when slot k's cell-cell face is numbered from this cell (its first toucher)
   int32_t touch_end = 0;           // cells [touch_end, N) have ftouch == 0 (two-colour mesh: the whole second colour)

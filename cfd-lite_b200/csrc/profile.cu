@@ -54,7 +54,7 @@ int autotune_pick(Handle* h, Handle::Tuned& T, const int* cands, int n, const st
   }
   float best = 0.f;
   bool have = false;
-  for (int i = 0; i < n && T.ncand < 12; ++i) {
+  for (int i = 0; i < n && T.ncand < 16; ++i) {
     const int c = cands[i];
     float ms = -1.f;
     bool ok = run(c) == CFDL_OK && cudaStreamSynchronize(h->stream) == cudaSuccess;  // warm-up (and a check that it launches)

@@ -110,6 +110,12 @@ struct Handle {
   SolveCtl* ctl3_host = nullptr;  // pinned
   int rb_persistent = -1;         // fused passes of a batch in one cooperative launch: 1 on, 0 off, -1 measured (autotune) else off
   int rbp_refused = 0, pc_solves = 0;
+  int rb_wave = 0;                // pass teams of the temporally blocked pc solve (kernels_rbw.inc); 0 = off (opt-in: not yet run on a GPU)
+  int rb_wave_block = 16;         // iterations per launch of that solve
+  double* wave_keep = nullptr;    // its snapshot of the two value arrays (2H) and residual record
+  double* wave_hist = nullptr;
+  int* wave_prog = nullptr;       // progress / arrival counters
+  int wave_maxch = 0, wave_nq = 0, wave_hist_len = 0;
   int rb_idx16 = -1;              // pc passes read 16-bit neighbour offsets instead of 32-bit ids: 0/1 pinned, -1 measured (autotune) else 0
   float rb_keep_mb = -1.f;        // megabytes of pc coefficients asked to stay in L2 across passes: >= 0 pinned, -1 measured (autotune) else 0
   int pc_sumap = 1;               // fused pc passes rebuild ap as the slot-order sum of anb instead of reading it
@@ -144,7 +150,7 @@ struct Handle {
   // variants on the handle's own data (CUDA events, a few launches each) and keeps the fastest.
   // Setting a *_variant option by hand pins that routine.  autotune = 0 keeps the defaults.
   int autotune = 1;
-  struct Tuned { int done = 0, choice = -1, ncand = 0, cand[12] = {0}; float ms[12] = {0}; };
+  struct Tuned { int done = 0, choice = -1, ncand = 0, cand[16] = {0}; float ms[16] = {0}; };
   Tuned tune_uvw, tune_grad3, tune_grad1, tune_coef_p, tune_mip, tune_uvw_solve, tune_rbp;
   int tune_ctas = 8;           // CTAs per SM for the solver passes (grid = min(need, num_sms * tune_ctas))
   // cfdl_step_host: transfer streams that run beside the compute stream, and a staging area of

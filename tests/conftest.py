@@ -80,3 +80,14 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     scale = max(np.abs(b).max(), 1e-300)
     return np.abs(a - b).max() / scale
+
+
+def same_history(a, b, rtol=1e-12):
+    """Residual histories (it, res_i, res_f, res_max) of two runs that must be the same computation: iteration
+    counts, opening residuals and maxima are exact; the RMS norms are sums whose order depends on the launch
+    geometry of the solver form a handle has chosen by timing, so they agree to rounding only."""
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape
+    assert np.array_equal(a[..., 0], b[..., 0]), (a[..., 0], b[..., 0])
+    assert np.allclose(a[..., 1:], b[..., 1:], rtol=rtol, atol=0.0), np.abs(a[..., 1:] - b[..., 1:]).max()
+    return True
