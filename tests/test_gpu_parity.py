@@ -695,5 +695,5 @@ def test_temporally_blocked_pc_solve_keeps_the_bits(case, cfdl, teams, block):
             assert np.array_equal(v, res[teams][1][f]), f
     finally:
         s.set_option("rb_wave", 0)
-        s.set_option("rb_wave_block", 16)
+        s.set_option("rb_wave_block", 34)
         s.set_option("solver", cfdl.SOLVER_PARITY)
