@@ -318,6 +318,7 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "pdl")) { h->use_pdl = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "uvw_variant")) { h->uvw_variant = (int)value; h->tune_uvw.done = 1; return CFDL_OK; }  // pinned by hand
   if (!std::strcmp(key, "rb_wave")) { h->rb_wave = std::max(0, (int)value); return CFDL_OK; }
+  if (!std::strcmp(key, "rb_wave_rows")) { h->rb_wave_rows = std::max(1, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "rb_wave_block")) { h->rb_wave_block = std::max(1, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "rb_idx16")) { h->rb_idx16 = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
   if (!std::strcmp(key, "rb_keep_mb")) { h->rb_keep_mb = (float)value; return CFDL_OK; }

@@ -111,6 +111,7 @@ struct Handle {
   int rb_persistent = -1;         // fused passes of a batch in one cooperative launch: 1 on, 0 off, -1 measured (autotune) else off
   int rbp_refused = 0, pc_solves = 0;
   int rb_wave = 0;                // pass teams of the temporally blocked pc solve (kernels_rbw.inc); 0 = off (opt-in: not yet run on a GPU)
+  int rb_wave_rows = 1;           // rows per thread per chunk of that solve
   int rb_wave_block = 34;         // iterations per launch of that solve (100-iteration pc solve: three launches)
   double* wave_keep = nullptr;    // its snapshot of the two value arrays (2H) and residual record
   double* wave_hist = nullptr;

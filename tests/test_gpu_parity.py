@@ -683,6 +683,7 @@ def test_temporally_blocked_pc_solve_keeps_the_bits(case, cfdl, teams, block):
             s.set_option("rb_wave", wave)
             s.set_option("rb_wave_block", block)
             s.set_option("rb_idx16", 1 if (wave == 8) else -1)  # the eight-team case also reads 16-bit neighbour offsets
+            s.set_option("rb_wave_rows", 3 if wave == 4 else 1)    # the four-team case takes three rows per thread and chunk
             randomize(oc, s, seed=71)
             hs = []
             for nit in (1, 2, 7, 40, 100):
@@ -697,5 +698,6 @@ def test_temporally_blocked_pc_solve_keeps_the_bits(case, cfdl, teams, block):
     finally:
         s.set_option("rb_wave", 0)
         s.set_option("rb_wave_block", 34)
+        s.set_option("rb_wave_rows", 1)
         s.set_option("rb_idx16", -1)
         s.set_option("solver", cfdl.SOLVER_PARITY)

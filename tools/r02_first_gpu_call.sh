@@ -16,7 +16,9 @@ run uvw_sep --opt uvw_fused=0 --no-e2e --no-cpu-baseline
 run uvw_fused --opt uvw_fused=1 --no-e2e --no-cpu-baseline
 run pcg --solver pcg --no-e2e --no-cpu-baseline
 for pk in "0 0" "1 0" "0 35" "1 35" "0 60" "1 60"; do set -- $pk; run rb_p$1_k$2 --opt rb_persistent=$1 --opt rb_keep_mb=$2 --opt rb_idx16=0 --steps 12 --no-e2e --no-cpu-baseline; run rb_p$1_k$2_i16 --opt rb_persistent=$1 --opt rb_keep_mb=$2 --opt rb_idx16=1 --steps 12 --no-e2e --no-cpu-baseline; done
-for t in 2 4 8 16; do for bl in 8 16 34; do run wave_t${t}_b$bl --opt rb_wave=$t --opt rb_wave_block=$bl --steps 12 --no-e2e --no-cpu-baseline; done; done
+for t in 2 4 8 16; do for r in 1 2 4; do run wave_t${t}_r$r --opt rb_wave=$t --opt rb_wave_rows=$r --steps 12 --no-e2e --no-cpu-baseline; done; done
+run wave_t8_r1_i16 --opt rb_wave=8 --opt rb_idx16=1 --steps 12 --no-e2e --no-cpu-baseline
+run wave_t8_b8 --opt rb_wave=8 --opt rb_wave_block=8 --steps 12 --no-e2e --no-cpu-baseline
 for v in 2 3 5 6 7 8 4 9 10 11 12 13 14; do run uvw_v$v --opt uvw_variant=$v --steps 10 --no-e2e --no-cpu-baseline; done
 for v in 0 1; do run grad_v$v --opt grad_variant=$v --steps 10 --no-e2e --no-cpu-baseline; run coefp_v$v --opt coef_p_variant=$v --steps 10 --no-e2e --no-cpu-baseline; done
 # 3. launch list of one default step + full capture of the assembly kernels and the side-by-side passes
