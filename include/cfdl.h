@@ -120,7 +120,8 @@ int cfdl_get_cell_order(cfdl_handle h, int32_t* c2o, int32_t* color_ptr);
  *                  passes of a batch in one cooperative launch: 0/1, -1 measured), "rb_keep_mb" (megabytes of the pc
  *                  coefficients hinted to stay in L2 across passes: >= 0 pinned, -1 measured), "rb_idx16" (16-bit
  *                  neighbour offsets in the pc passes: 0/1, -1 measured), "rb_wave" (pass teams of the temporally
- *                  blocked pc solve, 0 = not pinned) with "rb_wave_block" (iterations per launch), "pc_sumap" (0/1).
+ *                  blocked pc solve, 0 = not pinned) with "rb_wave_block" (iterations per launch) and "rb_wave_rows"
+ *                  (rows per thread and chunk), "pc_sumap" (0/1).
  * get_info keys:   "launches" (kernels launched since reset), "prof_ms_<k>" / "prof_n_<k>" with
  *                  k in sgs, residual, coef_uvw, coef_p, mip, grad, levels, pcg, sgs3 (u,v,w side-by-side passes);
  *                  "tuned_<r>" (chosen variant, -1 = not measured), "tuned_<r>_n", "tuned_<r>_cand<i>",
