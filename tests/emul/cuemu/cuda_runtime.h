@@ -160,6 +160,7 @@ template <class T> inline T __shfl_sync(unsigned, T v, int src) {
   return all[src & 31];
 }
 inline void __syncwarp(unsigned = 0xffffffffu) { char c = 0, all[32]; cuemu::warp_exchange(&c, all, 1); }
+long long clock64();
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }

@@ -6,6 +6,7 @@
 #include <sys/mman.h>
 #include <ucontext.h>
 #include <unistd.h>
+#include <time.h>
 
 #include <atomic>
 #include <condition_variable>
@@ -361,5 +362,13 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) {
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { std::memset(h, 0, sizeof *h); std::memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
 cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
 cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+
+// "SM clock": MICROseconds of the host's steady clock — the kernels only use it for time limits on their spin
+// waits (a few 1e9 ticks); oversubscribed host threads can wait long, so a tick is deliberately slow here
+long long clock64() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (long long)ts.tv_sec * 1000000ll + ts.tv_nsec / 1000;
+}
 
 extern "C" int cfdl_emulated(void) { return 1; }
