@@ -328,7 +328,9 @@ int k_calc_coef_uvw(Handle* h, double dt) {
     // 13/14 = 5/9 in the locality order (any number of colours)
     static const int cands2[] = {2, 3, 5, 6, 7, 4, 9, 10, 11, 12, 13, 14}, cands[] = {2, 3, 5, 4, 9, 11, 12, 13, 14};
     const bool two = h->prep.ncolors == 2;
-    int rc = autotune_pick(h, h->tune_uvw, two ? cands2 : cands, two ? 12 : 9, [&](int v) { h->uvw_variant = v; return k_calc_coef_uvw_statics(h, dt); });
+    const std::vector<TuneOutput> outs = {{A.ap, (size_t)h->N}, {A.anb, (size_t)h->K * h->Np}, {A.bu, (size_t)h->N}, {A.bv, (size_t)h->N},
+                                          {A.bw, (size_t)h->N}, {A.d, (size_t)h->N}, {A.dc, (size_t)h->N}};
+    int rc = autotune_pick(h, h->tune_uvw, two ? cands2 : cands, two ? 12 : 9, [&](int v) { h->uvw_variant = v; return k_calc_coef_uvw_statics(h, dt); }, 3, outs);
     h->uvw_variant = h->tune_uvw.choice;
     if (rc) return rc;
   }
@@ -775,7 +777,7 @@ int k_calc_grad(Handle* h, const double* phi, double* grad) {
   if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
   if (h->autotune && !h->tune_grad1.done && h->profile == 0 && h->grad_variant < 0) {
     static const int cands[] = {0, 1, 2, 3};
-    int rc = autotune_pick(h, h->tune_grad1, cands, 4, [&](int v) { return grad1_launch(h, v, phi, grad); });
+    int rc = autotune_pick(h, h->tune_grad1, cands, 4, [&](int v) { return grad1_launch(h, v, phi, grad); }, 3, {{grad, 3 * (size_t)h->N}});
     if (rc) return rc;
   }
   return grad1_launch(h, h->grad_variant >= 0 ? h->grad_variant : (h->tune_grad1.ncand ? h->tune_grad1.choice : 0), phi, grad);
@@ -785,7 +787,8 @@ int k_calc_grad3(Handle* h) {  // the three calc_grad calls of mod_uvwp.f90:118-
   if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
   if (h->autotune && !h->tune_grad3.done && h->profile == 0 && h->grad_variant < 0) {
     static const int cands[] = {0, 1, 2, 3};
-    int rc = autotune_pick(h, h->tune_grad3, cands, 4, [&](int v) { return grad3_launch(h, v); });
+    int rc = autotune_pick(h, h->tune_grad3, cands, 4, [&](int v) { return grad3_launch(h, v); }, 3,
+                           {{h->fld[CFDL_F_GU], 3 * (size_t)h->N}, {h->fld[CFDL_F_GV], 3 * (size_t)h->N}, {h->fld[CFDL_F_GW], 3 * (size_t)h->N}});
     if (rc) return rc;
   }
   prof_begin(h, PROF_GRAD);

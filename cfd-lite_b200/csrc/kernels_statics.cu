@@ -434,7 +434,8 @@ int k_calc_coef_p_statics(Handle* h) {
   if (h->autotune && !h->tune_coef_p.done && h->profile == 0 && h->coef_p_variant < 0) {
     static const int cands2[] = {0, 1, 2, 3, 4, 5}, cands[] = {0, 2, 4, 5};
     const bool two = h->prep.ncolors == 2;
-    int rc = autotune_pick(h, h->tune_coef_p, two ? cands2 : cands, two ? 6 : 4, [&](int v) { return coef_p_launch(h, v); });
+    int rc = autotune_pick(h, h->tune_coef_p, two ? cands2 : cands, two ? 6 : 4, [&](int v) { return coef_p_launch(h, v); }, 3,
+                           {{h->fld[CFDL_F_AP], (size_t)h->N}, {h->fld[CFDL_F_ANB], (size_t)h->K * h->Np}, {h->fld[CFDL_F_B], (size_t)h->N}});
     if (rc) return rc;
   }
   return coef_p_launch(h, h->coef_p_variant >= 0 ? h->coef_p_variant : (h->tune_coef_p.ncand ? h->tune_coef_p.choice : 0));
@@ -570,7 +571,7 @@ int k_calc_mip_statics(Handle* h, bool rhie_chow, double dt) {
     // mip_fast: -1 = measured on first use (a Rhie-Chow call: the plain interpolation has no quotient), 0 = divisions, 1 = reciprocals
     if (h->autotune && !h->tune_mip.done && h->profile == 0 && h->mip_fast < 0 && rhie_chow) {
       static const int cands[] = {0, 1};
-      int rc = autotune_pick(h, h->tune_mip, cands, 2, go);
+      int rc = autotune_pick(h, h->tune_mip, cands, 2, go, 3, {{A.mip, (size_t)h->Fi}});
       if (rc) return rc;
     }
     return go(h->mip_fast >= 0 ? h->mip_fast : (h->tune_mip.ncand ? h->tune_mip.choice : 0));

@@ -189,7 +189,11 @@ int prof_end(Handle* h, int count = 1, int level = 1);
 int prof_collect(Handle* h);  // after a stream sync: fold finished event pairs into prof_ms / prof_n
 // times run(cand) for every candidate (one warm-up launch, then `reps` timed ones between two events on
 // the handle's stream) and records the fastest in T; a candidate whose launch fails is skipped
-int autotune_pick(Handle* h, Handle::Tuned& T, const int* cands, int n, const std::function<int(int)>& run, int reps = 3);
+// `outputs` (pointer, length) lists what a candidate writes: every candidate's outputs must carry the values of the
+// first candidate's (a checksum over the bit patterns, zeros of either sign alike), or it is discarded (ms = -2)
+struct TuneOutput { const double* p; size_t n; };
+int autotune_pick(Handle* h, Handle::Tuned& T, const int* cands, int n, const std::function<int(int)>& run, int reps = 3,
+                  const std::vector<TuneOutput>& outputs = std::vector<TuneOutput>());
 
 // launch geometry helper: grids are sized as a multiple of the SM count (B200: 148)
 inline int grid_for(const Handle* h, int64_t n, int threads, int ctas_per_sm = 8) {

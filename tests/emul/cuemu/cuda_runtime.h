@@ -161,6 +161,7 @@ template <class T> inline T __shfl_sync(unsigned, T v, int src) {
 }
 inline void __syncwarp(unsigned = 0xffffffffu) { char c = 0, all[32]; cuemu::warp_exchange(&c, all, 1); }
 long long clock64();
+inline long long __double_as_longlong(double v) { long long r; std::memcpy(&r, &v, sizeof r); return r; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
