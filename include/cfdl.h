@@ -38,7 +38,13 @@ enum {
 enum {
   CFDL_BC_WALL = 0,     /* dirichlet0: u=v=w=0, bc_type 'dirichlet' */
   CFDL_BC_LID = 1,      /* lid: (u,v,w)=bc_uvw (reference: 1,0,0), 'dirichlet' */
-  CFDL_BC_SYMMETRY = 2  /* symmetry: mirrored velocity, 'zero_flux' */
+  CFDL_BC_SYMMETRY = 2  /* symmetry: mirrored velocity, 'zero_flux' (mod_uvwp.f90:517-546; assembly :266-268) */
+  /* NOT offered: the reference's `inlet` / `outlet` callbacks (mod_uvwp.f90:571-606).  They set bc_type 'inlet' /
+     'outlet_p', which neither `select case` of the assembly handles (calc_coef_uvw :254-269 knows 'dirichlet' and
+     'zero_flux' only, calc_coef_p :355-360 likewise): a boundary face of such a section adds the values `d`, `f`
+     left over from whatever face was processed before it — undefined behaviour in the reference itself, no BC the
+     reference binds uses them (construct_uvwp :73-78), so there is nothing to be faithful to.  cfdl_create rejects
+     any other kind with CFDL_ERR_UNSUPPORTED. */
 };
 
 /* linear-solver modes */

@@ -137,6 +137,7 @@ int orc_set_param(void* h, const char* key, double v) {
   Case* c = (Case*)h;
   if (!std::strcmp(key, "dt")) c->dt = v;
   else if (!std::strcmp(key, "nit")) c->nit = (int)v;
+  else if (!std::strcmp(key, "pref_cell")) c->pref_cell = (int)v;
   else return 1;
   return 0;
 }

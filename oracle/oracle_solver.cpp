@@ -603,7 +603,7 @@ void solve_uvwp(Case& c, SolveStat st[4]) {  // :95-134
   calc_coef_p(c);
   std::fill(c.phic.d.begin(), c.phic.d.end(), 0.0);  // set_a_0
   st[3] = solve(c, true, c.ap.data(), c.anb.data(), c.b.data(), c.phic.data(), c.nit);
-  double pref = c.phic(1);
+  double pref = c.phic(c.pref_cell);  // phic(1) in the reference (:129)
   adjust_pc(c, pref);
   calc_grad(c.phic.data(), c.gpc.data(), g.xc.data(), g.yc.data(), g.zc.data(), g.ef2nb_idx.data(), g.ef2nb1.data(), g.ne);
   update_uvwp(c);

@@ -36,6 +36,7 @@ struct Case {
   Mesh m;
   // phys_t, mod_physics.f90:13-35
   double dt = 0.01;
+  int pref_cell = 1;  // reference: pref = phic(1), mod_uvwp.f90:129; tests of renumbered meshes point it at the cell that was cell 1
   int ntstep = 10, ncoef = 3, nit = 100, n_subdomains = 4;
   A1<double> ap, anb, b, phic;
   std::vector<Subdomain> subdomain;

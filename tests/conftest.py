@@ -58,10 +58,13 @@ def oracle():
     return m
 
 
-def make_case(cfdl, oracle, kind, n, jitter=0.0, shuffle=False, n_subdomains=1, seed=12345):
-    """Synthetic mesh -> (raw, oracle case, geometry dict in the reference's array format)."""
+def make_case(cfdl, oracle, kind, n, jitter=0.0, shuffle=False, n_subdomains=1, seed=12345, symmetry=()):
+    """Synthetic mesh -> (raw, oracle case, geometry dict in the reference's array format).
+    symmetry: indices (2-D section order) of the BCs that become `symmetry` (mod_uvwp.f90:517-546) instead of walls."""
     raw = cfdl.meshgen(kind, n, jitter=jitter, shuffle=shuffle, seed=seed)
     oc = oracle.OracleCase(raw, n_subdomains=n_subdomains)
+    for i in symmetry:
+        oc.set_bc(i, 2)  # BC_SYMMETRY: mirrored halo velocity, bc_type 'zero_flux'
     geom = dict(ne=oc.ne, nf=oc.nf, nbf=oc.nbf)
     for k in ("ef2nb_idx", "ef2nb_nb", "ef2nb_fg", "s2g", "bs", "xc", "yc", "zc", "aip", "rip", "vol"):
         geom[k] = oc[k].copy()

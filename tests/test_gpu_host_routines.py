@@ -3,15 +3,14 @@ _adjust_pc, _update_uvwp): the flattened form of the reference's derived-type si
 (SURVEY §8b).  Each is upload -> the routine tested in test_gpu_parity.py -> download, so the
 results must again equal the oracle's bit for bit.
 
-These entry points were added after the round's GPU budget was spent: they pass on the host
-emulation of the CUDA sources (tests/emul, `pytest -m gpu --emul`); on the GPU the expectation is
-recorded as non-strict xfail until a run has confirmed it (an XPASS is the confirmation)."""
+Confirmed on a B200 in round 2 (profiles/r02_call1_pytest_gpu.log: the four former non-strict xfails XPASSed),
+since then plain tests."""
 import numpy as np
 import pytest
 
 from conftest import make_case, make_solver, rel_err
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="not yet run on a GPU (added after the round's GPU budget was spent)")]
+pytestmark = pytest.mark.gpu
 
 STATE = ("u", "v", "w", "p", "u0", "v0", "w0", "gu", "gv", "gw", "gp", "mip", "mip0")
 

@@ -22,6 +22,10 @@ CASES = {
     "hex6_jitter": dict(kind=0, n=6, jitter=0.25, n_subdomains=1),
     "tet4_shuffled": dict(kind=1, n=4, jitter=0.2, shuffle=True, n_subdomains=1),
     "tet3_sub2": dict(kind=1, n=3, jitter=0.2, shuffle=True, n_subdomains=2),
+    # symmetry planes (mod_uvwp.f90:517-546, bc_type 'zero_flux' in calc_coef_uvw :266-268) on two opposite and one
+    # adjacent side of a jittered mesh (non-axis-aligned normals), walls + lid elsewhere
+    "hex6_symmetry": dict(kind=0, n=6, jitter=0.2, n_subdomains=1, symmetry=(2, 3, 4)),
+    "tet3_symmetry": dict(kind=1, n=3, jitter=0.2, shuffle=True, n_subdomains=1, symmetry=(0, 5)),
 }
 
 
