@@ -276,16 +276,6 @@ def main():
         step(i)
         dbg("warmup step", i)
     hist_last = None
-    # kernel variants chosen by measurement during the first warm-up step (bit-identical candidates)
-    tuned = {}
-    for r in ("uvw", "grad3", "grad1", "coef_p", "mip", "uvw_solve", "rb_persistent"):
-        try:
-            n_c = int(s.get_info("tuned_%s_n" % r))
-            if n_c > 0:
-                tuned[r] = {"chosen": int(s.get_info("tuned_" + r)),
-                            "ms": {str(int(s.get_info("tuned_%s_cand%d" % (r, i)))): round(s.get_info("tuned_%s_ms%d" % (r, i)), 4) for i in range(n_c)}}
-        except cfdl.CfdlError as ex:
-            dbg("tuning info unavailable:", ex)
     barrier()
     s.set_option("reset_counters", 1)
     s.timer_record(0)
@@ -356,15 +346,16 @@ def main():
             # pc passes (nearly all of them: the momentum passes have their own entry when they run side by side) rebuild
             # ap from the row's anb instead of reading it (pc_sumap): 8 + 12K bytes of matrix per row instead of 16 + 12K
             # chosen form of the pc passes (candidate c: persistent = c & 1, L2 hint = (c >> 1) % 3 > 0, 16-bit neighbour offsets = c >= 6)
-            cand = tuned.get("rb_persistent", {}).get("chosen", 0)
-            row = (8 if int(s.get_info("pc_sumap")) else 16) + (10 if cand >= 6 else 12) * K
+            rbq = int(s.get_info("rbq_active")) == 1
+            i16 = int(s.get_info("rb_idx16")) == 1
+            row = (8 if int(s.get_info("pc_sumap")) else 16) + (10 if i16 else 12) * K
             red = n_r * (row + 8 + 16) + 8 * (n_owned - n_r + halo_vals)
             black = (n_owned - n_r) * (row + 8 + 8) + 16 * (n_r + halo_vals)
             per_launch = (red + black) / 2.0
             kname = "rb_red_kernel / rb_black_kernel (fused two-colour SGS pass incl. residual; average of the two)"
-            if tuned.get("rb_persistent", {}).get("chosen") == 1:
-                kname = ("rb_persistent_kernel (the fused two-colour SGS passes of a batch inside one cooperative launch; average pass, "
-                         "red and black; the per-launch 'isolated' figure is the per-pass kernels rb_red_kernel / rb_black_kernel)")
+            if rbq:
+                kname = ("rbq_kernel (all red/black passes of a pc solve in one persistent launch, neighbour-only synchronisation; "
+                         "launch time / passes; the 'isolated' figure is the pass-by-pass kernels rb_red_kernel / rb_black_kernel, one event pair per launch)")
         else:
             # one colour launch updates 1/ncolors of the cells: a full sweep = ncolors launches
             per_launch = ab["sgs_sweep"] / ncol
@@ -501,7 +492,7 @@ def main():
         line = {"metric": "cell-iterations/s (SIMPLE)", "value": value, "unit": "cell-iterations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args.mesh, n_global, ne), "solver": args.solver, "ncolors": ncol, "options": args.opt, "mesh_source": "structured per-rank generator" if structured else "reference-format arrays", "fused_two_colour_passes": bool(fused), "kernel_variants_chosen_by_timing": tuned, "timed_loop": loop, "programmatic_dependent_launch": bool(fused and not args.no_pdl),
+                "config": {"workload": workload_name(args.mesh, n_global, ne), "solver": args.solver, "ncolors": ncol, "options": args.opt, "mesh_source": "structured per-rank generator" if structured else "reference-format arrays", "fused_two_colour_passes": bool(fused), "timed_loop": loop, "programmatic_dependent_launch": bool(fused and not args.no_pdl),
                            "cells_per_gpu": ne // world, "setup_seconds": round(setup_s, 1), "l2": "working set (>1 GB per GPU) exceeds the 126 MB L2; no flush needed" if ne // world > 1000000 else
                            "working set may fit L2",
                            "parallelism": "1 GPU" if world == 1 else

@@ -312,32 +312,15 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   }
   if (!std::strcmp(key, "fused")) { h->fused_rb = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "p2p")) { h->use_p2p = value != 0.0; return CFDL_OK; }
-  if (!std::strcmp(key, "mip_variant")) { h->mip_variant = (int)value; return CFDL_OK; }
   if (!std::strcmp(key, "occ_grids")) { h->occ_grids = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "pdl_rows")) { h->pdl_rows = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "pdl")) { h->use_pdl = value != 0.0; return CFDL_OK; }
-  if (!std::strcmp(key, "uvw_variant")) { h->uvw_variant = (int)value; h->tune_uvw.done = 1; return CFDL_OK; }  // pinned by hand
-  if (!std::strcmp(key, "rb_wave")) { h->rb_wave = std::max(0, (int)value); return CFDL_OK; }
-  if (!std::strcmp(key, "rb_wave_rows")) { h->rb_wave_rows = std::max(1, (int)value); return CFDL_OK; }
-  if (!std::strcmp(key, "rb_wave_block")) { h->rb_wave_block = std::max(1, (int)value); return CFDL_OK; }
-  if (!std::strcmp(key, "rb_idx16")) { h->rb_idx16 = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
-  if (!std::strcmp(key, "rb_keep_mb")) { h->rb_keep_mb = (float)value; return CFDL_OK; }
-  if (!std::strcmp(key, "rb_persistent")) { h->rb_persistent = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
+  if (!std::strcmp(key, "rb_idx16")) { h->rb_idx16 = value != 0.0; return CFDL_OK; }
+  if (!std::strcmp(key, "rbq")) { h->rbq = value != 0.0; if (value == 2.0) h->rbq_refused = 0; return CFDL_OK; }
+  if (!std::strcmp(key, "rbq_ctas")) { h->rbq_ctas_per_sm = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "pc_sumap")) { h->pc_sumap = value != 0.0; return CFDL_OK; }
-  if (!std::strcmp(key, "uvw_fused")) { h->uvw_fused = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
-  if (!std::strcmp(key, "grad_variant")) { h->grad_variant = (int)value; return CFDL_OK; }
-  if (!std::strcmp(key, "coef_p_variant")) { h->coef_p_variant = (int)value; return CFDL_OK; }
-  if (!std::strcmp(key, "mip_fast")) { h->mip_fast = value < 0.0 ? -1 : (value != 0.0); return CFDL_OK; }
-  if (!std::strcmp(key, "correct_fast")) { h->correct_fast = value != 0.0; return CFDL_OK; }
-  if (!std::strcmp(key, "autotune")) {
-    h->autotune = value != 0.0;
-    if (value == 2.0) {
-      h->tune_uvw = Handle::Tuned(); h->tune_grad3 = Handle::Tuned(); h->tune_grad1 = Handle::Tuned(); h->tune_coef_p = Handle::Tuned();
-      h->tune_mip = Handle::Tuned(); h->tune_uvw_solve = Handle::Tuned(); h->momentum_calls = 0;
-      h->tune_rbp = Handle::Tuned(); h->pc_solves = 0;
-    }
-    return CFDL_OK;
-  }
+  if (!std::strcmp(key, "uvw_fused")) { h->uvw_fused = value != 0.0; return CFDL_OK; }
+  if (!std::strcmp(key, "grad_variant")) { h->grad_variant = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "statics")) { h->use_statics = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "ctas_per_sm")) { h->tune_ctas = std::max(1, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "profile")) {
@@ -364,35 +347,20 @@ int cfdl_get_info(cfdl_handle h, const char* key, double* value) {
   else if (!std::strcmp(key, "num_sms")) *value = h->num_sms;
   else if (!std::strcmp(key, "solver")) *value = h->solver_mode;
   else if (!std::strcmp(key, "launches")) *value = (double)h->launches;
-  else if (!std::strcmp(key, "uvw_variant")) *value = h->uvw_variant;
   else if (!std::strcmp(key, "pc_sumap")) *value = h->pc_sumap;
   else if (!std::strcmp(key, "color_dist")) *value = h->prep.color_dist;
-  else if (!std::strncmp(key, "tuned_", 6)) {
-    // "tuned_<routine>" = chosen variant (-1: not tuned); "tuned_<routine>_ms<i>" / "_cand<i>" = the measurements
-    const Handle::Tuned* T = nullptr;
-    const char* r = key + 6;
-    size_t len = 0;
-    static const char* names[7] = {"uvw", "grad3", "grad1", "coef_p", "mip", "uvw_solve", "rb_persistent"};
-    const Handle::Tuned* all[7] = {&h->tune_uvw, &h->tune_grad3, &h->tune_grad1, &h->tune_coef_p, &h->tune_mip, &h->tune_uvw_solve, &h->tune_rbp};
-    for (int i = 0; i < 7; ++i) {
-      const size_t l = std::strlen(names[i]);
-      if (!std::strncmp(r, names[i], l) && (r[l] == 0 || r[l] == '_') && l > len) { T = all[i]; len = l; }
-    }
-    if (!T) return fail(CFDL_ERR_ARG, "cfdl_get_info: unknown key '%s'", key);
-    r += len;
-    if (*r == 0) *value = T->ncand ? T->choice : -1;
-    else if (!std::strncmp(r, "_ms", 3)) { const int i = std::atoi(r + 3); *value = (i >= 0 && i < T->ncand) ? T->ms[i] : -1; }
-    else if (!std::strncmp(r, "_cand", 5)) { const int i = std::atoi(r + 5); *value = (i >= 0 && i < T->ncand) ? T->cand[i] : -1; }
-    else if (!std::strcmp(r, "_n")) *value = T->ncand;
-    else return fail(CFDL_ERR_ARG, "cfdl_get_info: unknown key '%s'", key);
-  }
+  else if (!std::strcmp(key, "rbq_active")) *value = (h->rbq && !h->rbq_refused && h->rbq_occ > 0) ? 1 : 0;
+  else if (!std::strcmp(key, "rbq_refused")) *value = h->rbq_refused;
+  else if (!std::strcmp(key, "rbq_occ")) *value = h->rbq_occ;
+  else if (!std::strcmp(key, "rb_idx16")) *value = (h->rb_idx16 && h->ell_nb16) ? 1 : 0;
+  else if (!std::strcmp(key, "rbq_extra_passes")) *value = (double)h->prof_extra_passes;
   else if (!std::strcmp(key, "owned_cells")) *value = h->N;
   else if (!std::strcmp(key, "ghost_cells")) *value = h->G;
   else if (!std::strcmp(key, "local_halos")) *value = h->B;
   else if (!std::strcmp(key, "local_faces")) *value = h->F;
   else if (!std::strcmp(key, "neighbour_ranks")) *value = h->nnbr;
   else if (!std::strncmp(key, "prof_ms_", 8) || !std::strncmp(key, "prof_n_", 7)) {
-    static const char* names[PROF_KINDS] = {"sgs", "residual", "coef_uvw", "coef_p", "mip", "grad", "levels", "pcg", "sgs3"};
+    static const char* names[PROF_KINDS] = {"sgs", "residual", "coef_uvw", "coef_p", "mip", "grad", "levels", "pcg", "sgs3", "residual3", "grad1"};
     const bool is_ms = key[5] == 'm';
     const char* nm = key + (is_ms ? 8 : 7);
     int rc = prof_collect(h);

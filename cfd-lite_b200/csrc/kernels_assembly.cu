@@ -178,133 +178,6 @@ __global__ void __launch_bounds__(TPB) coef_uvw_kernel(const UvwArgs A) {
   }
 }
 
-// Slot-parallel form of the same routine: one thread per (cell, face slot) evaluates the face
-// terms (the ~19 FP64 divisions / square roots per face that made the one-thread-per-cell kernel
-// latency bound at 12 % occupancy), the per-slot results go through shared memory, and one thread
-// per cell adds them up in the reference's slot order, applies the boundary faces and writes the
-// row.  Same operations in the same order => same bits as coef_uvw_kernel.
-#define UVW_CELLS 64
-template <int K>
-__global__ void __launch_bounds__(UVW_CELLS* K, 2) coef_uvw_slots_kernel(const UvwArgs A) {
-  // per slot: d, fnb, f_in, ss[3], defc[3]
-  __shared__ double sh[9][K][UVW_CELLS];
-  const int N = A.N, Nc = A.Nc, Np = A.Np;
-  const int k = threadIdx.x / UVW_CELLS, cl = threadIdx.x % UVW_CELLS;
-  for (int base = blockIdx.x * UVW_CELLS; base < N; base += gridDim.x * UVW_CELLS) {
-    const int c = base + cl;
-    double d = 0.0, fnb = 0.0, f_in = 0.0, ss[3] = {0, 0, 0}, dfc[3] = {0, 0, 0};
-    if (c < N && k < A.nfc[c]) {
-      const int nb = A.ell_nb[(size_t)k * Np + c];
-      if (nb < Nc) {  // lfnb > 0 (owned or ghost cell)
-        const int fs = A.ell_fs[(size_t)k * Np + c];
-        const int f = abs(fs) - 1;
-        const double sg = fs > 0 ? 1.0 : -1.0;
-        const double rp[3] = {A.xc[c], A.yc[c], A.zc[c]};
-        double a[3], rip[3];
-        load3(A.aip, f, a); load3(A.rip, f, rip);
-        const double area = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-        const double norm[3] = {sg * a[0] / area, sg * a[1] / area, sg * a[2] / area};
-        const double rpnb[3] = {A.xc[nb], A.yc[nb], A.zc[nb]};
-        const double dr[3] = {rpnb[0] - rp[0], rpnb[1] - rp[1], rpnb[2] - rp[2]};
-        const double ds = sqrt(dot3(dr, dr));
-        const double wt = vec_weight(rip, rp, rpnb);
-        double drip[3] = {rip[0] - rp[0], rip[1] - rp[1], rip[2] - rp[2]};
-        double t = dot3(drip, norm);
-        const double rp_p[3] = {rip[0] - t * norm[0], rip[1] - t * norm[1], rip[2] - t * norm[2]};
-        drip[0] = rip[0] - rpnb[0]; drip[1] = rip[1] - rpnb[1]; drip[2] = rip[2] - rpnb[2];
-        t = dot3(drip, norm);
-        const double rpnb_p[3] = {rip[0] - t * norm[0], rip[1] - t * norm[1], rip[2] - t * norm[2]};
-        const double dr_p[3] = {rpnb_p[0] - rp_p[0], rpnb_p[1] - rp_p[1], rpnb_p[2] - rp_p[2]};
-        const double ds_p = sqrt(dot3(dr_p, dr_p));
-        f_in = -sg * A.mip[f];
-        fnb = fmax(f_in, 0.0);
-        const double muip = (1.0 - wt) * A.mu[c] + wt * A.mu[nb];
-        d = muip * area / ds;
-        double gue[3], gve[3], gwe[3], gun[3], gvn[3], gwn[3];
-        load3(A.gu, c, gue); load3(A.gv, c, gve); load3(A.gw, c, gwe);
-        load3(A.gu, nb, gun); load3(A.gv, nb, gvn); load3(A.gw, nb, gwn);
-        const double w1 = 1.0 - wt;
-#pragma unroll
-        for (int m = 0; m < 3; ++m) {
-          const double gip[3] = {w1 * gue[m] + wt * gun[m], w1 * gve[m] + wt * gvn[m], w1 * gwe[m] + wt * gwn[m]};
-          ss[m] = muip * area * dot3(gip, dr) / ds;
-        }
-        double gip[3] = {w1 * gue[0] + wt * gun[0], w1 * gue[1] + wt * gun[1], w1 * gue[2] + wt * gun[2]};
-        dfc[0] = muip * area * (dot3(gip, dr_p) / ds_p - dot3(gip, dr) / ds);
-        gip[0] = w1 * gve[0] + wt * gvn[0]; gip[1] = w1 * gve[1] + wt * gvn[1]; gip[2] = w1 * gve[2] + wt * gvn[2];
-        dfc[1] = muip * area * (dot3(gip, dr_p) / ds_p - dot3(gip, dr) / ds);
-        gip[0] = w1 * gwe[0] + wt * gwn[0]; gip[1] = w1 * gwe[1] + wt * gwn[1]; gip[2] = w1 * gwe[2] + wt * gwn[2];
-        dfc[2] = muip * area * (dot3(gip, dr_p) / ds_p - dot3(gip, dr) / ds);
-      }
-    }
-    sh[0][k][cl] = d; sh[1][k][cl] = fnb; sh[2][k][cl] = f_in;
-    sh[3][k][cl] = ss[0]; sh[4][k][cl] = ss[1]; sh[5][k][cl] = ss[2];
-    sh[6][k][cl] = dfc[0]; sh[7][k][cl] = dfc[1]; sh[8][k][cl] = dfc[2];
-    __syncthreads();
-    if (k == 0 && c < N) {  // one thread per cell: sums in slot order, boundary faces, row output
-      const int n = A.nfc[c];
-      double ap = 0.0, sumf = 0.0, sumss[3] = {0, 0, 0}, sumdefc[3] = {0, 0, 0};
-      for (int kk = 0; kk < n; ++kk) {
-        sumf = sumf + sh[2][kk][cl];
-        sumss[0] = sumss[0] + sh[3][kk][cl]; sumss[1] = sumss[1] + sh[4][kk][cl]; sumss[2] = sumss[2] + sh[5][kk][cl];
-        sumdefc[0] = sumdefc[0] + sh[6][kk][cl]; sumdefc[1] = sumdefc[1] + sh[7][kk][cl]; sumdefc[2] = sumdefc[2] + sh[8][kk][cl];
-        ap = ap + sh[0][kk][cl] + sh[1][kk][cl];
-      }
-      const double vol = A.vol[c];
-      const double ap0 = A.rho[c] * vol / A.dt;
-      ap = ap + ap0;
-      const double ue = A.u[c], ve = A.v[c], we = A.w[c];
-      double bu = ap0 * A.u0[c] + sumf * ue - vol * A.gp[3 * (size_t)c] + sumss[0] + sumdefc[0];
-      double bv = ap0 * A.v0[c] + sumf * ve - vol * A.gp[3 * (size_t)c + 1] + sumss[1] + sumdefc[1];
-      double bw = ap0 * A.w0[c] + sumf * we - vol * A.gp[3 * (size_t)c + 2] + sumss[2] + sumdefc[2];
-      int last = -1;  // boundary faces in halo order, like the reference's BC loop (:243-273)
-      for (int tt = 0; tt < n; ++tt) {
-        int best = 0x7fffffff, bk = -1;
-        for (int kk = 0; kk < n; ++kk) {
-          const int nbk = A.ell_nb[(size_t)kk * Np + c];
-          if (nbk >= Nc && nbk > last && nbk < best) { best = nbk; bk = kk; }
-        }
-        if (bk < 0) break;
-        last = best;
-        const int bc = A.halo_bc[best - Nc];
-        if (bc < 0) continue;
-        const int f = A.ell_fs[(size_t)bk * Np + c] - 1;
-        double a[3];
-        load3(A.aip, f, a);
-        const double area = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-        const double norm[3] = {a[0] / area, a[1] / area, a[2] / area};
-        const double dr[3] = {A.xc[best] - A.xc[c], A.yc[best] - A.yc[c], A.zc[best] - A.zc[c]};
-        const double ds = sqrt(dot3(dr, dr));
-        const double db = A.mu[c] * area / ds;
-        if (A.bc_kind[bc] != CFDL_BC_SYMMETRY) {  // 'dirichlet'
-          const double vbnc[3] = {A.u[best], A.v[best], A.w[best]};
-          double vrel[3] = {ue, ve, we};
-          const double vn = dot3(vrel, norm);
-          vrel[0] = vrel[0] - vn * norm[0]; vrel[1] = vrel[1] - vn * norm[1]; vrel[2] = vrel[2] - vn * norm[2];
-          vrel[0] = vbnc[0] - vrel[0]; vrel[1] = vbnc[1] - vrel[1]; vrel[2] = vbnc[2] - vrel[2];
-          bu = bu + db * vrel[0] - db * ue;
-          bv = bv + db * vrel[1] - db * ve;
-          bw = bw + db * vrel[2] - db * we;
-        }
-        ap = ap + db;
-        sh[0][bk][cl] = sh[0][bk][cl] + sh[1][bk][cl] + db;  // anb(idx) = anb(idx) + d + f with anb(idx) = 0 + 0
-        sh[1][bk][cl] = 0.0;
-      }
-      double dcv = ap;
-      for (int kk = 0; kk < n; ++kk) {
-        const double anbk = sh[0][kk][cl] + sh[1][kk][cl];
-        dcv = dcv - anbk;
-        A.anb[(size_t)kk * Np + c] = anbk;
-      }
-      A.ap[c] = ap;
-      A.bu[c] = bu; A.bv[c] = bv; A.bw[c] = bw;
-      A.d[c] = vol / ap;
-      A.dc[c] = vol / dcv;
-    }
-    __syncthreads();
-  }
-}
-
 int k_calc_coef_uvw(Handle* h, double dt) {
   UvwArgs A;
   A.N = h->N; A.Nc = h->Nc; A.Np = h->Np;
@@ -318,32 +191,15 @@ int k_calc_coef_uvw(Handle* h, double dt) {
   A.bw = h->fld[CFDL_F_BW]; A.d = h->fld[CFDL_F_D]; A.dc = h->fld[CFDL_F_DC];
   A.dt = dt;
   const int g = grid_for(h, h->N, TPB);
-  const int gs = grid_for(h, h->N, UVW_CELLS, 16);
   if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
   h->pc_sumap_ok = false;  // ap, anb become the momentum matrix
-  if (h->autotune && !h->tune_uvw.done && h->profile == 0 && h->uvw_variant == 2 && h->use_statics && h->fs_area) {
-    // same bits from every candidate (tests); 2 = divisions, 3 = reciprocal quotients, 5 = 3 with stored
-    // reciprocals, 6/7/8 = 5/3/2 in the paired colour order, 4 = 3 with three CTAs per SM requested
-    // 9/10/11/12 = 5/6/(5 with three, four CTAs per SM requested) with fewer live registers
-    // 13/14 = 5/9 in the locality order (any number of colours)
-    static const int cands2[] = {2, 3, 5, 6, 7, 4, 9, 10, 11, 12, 13, 14}, cands[] = {2, 3, 5, 4, 9, 11, 12, 13, 14};
-    const bool two = h->prep.ncolors == 2;
-    const std::vector<TuneOutput> outs = {{A.ap, (size_t)h->N}, {A.anb, (size_t)h->K * h->Np}, {A.bu, (size_t)h->N}, {A.bv, (size_t)h->N},
-                                          {A.bw, (size_t)h->N}, {A.d, (size_t)h->N}, {A.dc, (size_t)h->N}};
-    int rc = autotune_pick(h, h->tune_uvw, two ? cands2 : cands, two ? 12 : 9, [&](int v) { h->uvw_variant = v; return k_calc_coef_uvw_statics(h, dt); }, 3, outs);
-    h->uvw_variant = h->tune_uvw.choice;
-    if (rc) return rc;
-  }
   prof_begin(h, PROF_COEF_UVW);
-  if (h->uvw_variant >= 2 && h->uvw_variant <= 14 && h->use_statics && h->fs_area) {
+  if (h->use_statics && h->fs_area) {  // on precomputed face statics (kernels_statics.cu)
     int rc = k_calc_coef_uvw_statics(h, dt);
     if (rc) return rc;
-  } else if (h->uvw_variant == 0) {
+  } else {                             // statics = 0: the reference's form, geometry recomputed per face
     if (h->K <= 4) coef_uvw_kernel<4><<<g, TPB, 0, S(h)>>>(A);
     else coef_uvw_kernel<6><<<g, TPB, 0, S(h)>>>(A);
-  } else {
-    if (h->K <= 4) coef_uvw_slots_kernel<4><<<gs, UVW_CELLS * 4, 0, S(h)>>>(A);
-    else coef_uvw_slots_kernel<6><<<gs, UVW_CELLS * 6, 0, S(h)>>>(A);
   }
   prof_end(h);
   CFDL_CUDA(cudaGetLastError());
@@ -577,18 +433,15 @@ __device__ __forceinline__ void matinv3_apply(const double A[6], const double g[
   out[2] = 0.0 + b31 * g[0] + b32 * g[1] + b33 * g[2];
 }
 
-// order != nullptr: locality order (thread i takes cell order[i]: the lanes of a warp hold neighbouring cells of
-// all colours, so the neighbour values a lane gathers are its neighbours' own loads), grad_variant 2 / 3
+// grad_variant 0: the reference's form (weights and the 3x3 inverse rebuilt per call)
 template <int K, int NF>
 __global__ void __launch_bounds__(TPB) grad_kernel(int N, int Np, const int32_t* __restrict__ ell_nb, const uint8_t* __restrict__ nfc,
                                                    const double* __restrict__ xc, const double* __restrict__ yc,
                                                    const double* __restrict__ zc, const double* phi0, const double* phi1,
-                                                   const double* phi2, double* g0, double* g1, double* g2,
-                                                   const int32_t* __restrict__ order) {
+                                                   const double* phi2, double* g0, double* g1, double* g2) {
   const double* phis[3] = {phi0, phi1, phi2};
   double* gs[3] = {g0, g1, g2};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-    const int c = order ? order[i] : i;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
     const int n = nfc[c];
     const double rp[3] = {xc[c], yc[c], zc[c]};
     double pe[NF], g[NF][3], A[6] = {0, 0, 0, 0, 0, 0};
@@ -683,12 +536,10 @@ __global__ void __launch_bounds__(TPB) grad_lsq_kernel(int N, int Np, const int3
                                                        const double* __restrict__ xc, const double* __restrict__ yc,
                                                        const double* __restrict__ zc, const double* __restrict__ binv,
                                                        const double* __restrict__ wslot, const double* phi0, const double* phi1,
-                                                       const double* phi2, double* g0, double* g1, double* g2,
-                                                       const int32_t* __restrict__ order) {
+                                                       const double* phi2, double* g0, double* g1, double* g2) {
   const double* phis[3] = {phi0, phi1, phi2};
   double* gs[3] = {g0, g1, g2};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-    const int c = order ? order[i] : i;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < N; c += gridDim.x * blockDim.x) {
     const int n = nfc[c];
     const double rp[3] = {xc[c], yc[c], zc[c]};
     double pe[NF], g[NF][3];
@@ -745,29 +596,28 @@ static void launch_k46(Handle* h, int cells, Args... args) {
   else K6<<<occ_grid<K6>(h, cells, TPB), TPB, 0, S(h)>>>(args...);
 }
 
-// variants: 0 = reference form, 1 = on the LSQ statics, 2 / 3 = 0 / 1 in the locality order
-static int grad1_launch(Handle* h, int variant, const double* phi, double* grad) {
-  const int32_t* order = variant >= 2 ? h->loc_order : nullptr;
-  if (variant == 1 || variant == 3) {
+// grad_variant 1 (default; B200, 128^3: 0.134 against 0.156 ms for u,v,w, 0.090 against 0.108 for one field; the
+// locality order measured slower for both) = on the LSQ statics, 0 = the reference's form
+static int grad1_launch(Handle* h, const double* phi, double* grad) {
+  if (h->grad_variant != 0) {
     int rc = ensure_lsq_statics(h);
     if (rc) return rc;
-    launch_k46<grad_lsq_kernel<4, 1>, grad_lsq_kernel<6, 1>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, h->lsq_binv, h->lsq_w, phi, phi, phi, grad, grad, grad, order);
+    launch_k46<grad_lsq_kernel<4, 1>, grad_lsq_kernel<6, 1>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, h->lsq_binv, h->lsq_w, phi, phi, phi, grad, grad, grad);
   } else {
-    launch_k46<grad_kernel<4, 1>, grad_kernel<6, 1>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, phi, phi, phi, grad, grad, grad, order);
+    launch_k46<grad_kernel<4, 1>, grad_kernel<6, 1>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, phi, phi, phi, grad, grad, grad);
   }
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
-static int grad3_launch(Handle* h, int variant) {
+static int grad3_launch(Handle* h) {
   const double *u = h->fld[CFDL_F_U], *v = h->fld[CFDL_F_V], *w = h->fld[CFDL_F_W];
   double *gu = h->fld[CFDL_F_GU], *gv = h->fld[CFDL_F_GV], *gw = h->fld[CFDL_F_GW];
-  const int32_t* order = variant >= 2 ? h->loc_order : nullptr;
-  if (variant == 1 || variant == 3) {
+  if (h->grad_variant != 0) {
     int rc = ensure_lsq_statics(h);
     if (rc) return rc;
-    launch_k46<grad_lsq_kernel<4, 3>, grad_lsq_kernel<6, 3>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, h->lsq_binv, h->lsq_w, u, v, w, gu, gv, gw, order);
+    launch_k46<grad_lsq_kernel<4, 3>, grad_lsq_kernel<6, 3>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, h->lsq_binv, h->lsq_w, u, v, w, gu, gv, gw);
   } else {
-    launch_k46<grad_kernel<4, 3>, grad_kernel<6, 3>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, u, v, w, gu, gv, gw, order);
+    launch_k46<grad_kernel<4, 3>, grad_kernel<6, 3>>(h, h->N, h->N, h->Np, h->ell_nb, h->nfc, h->xc, h->yc, h->zc, u, v, w, gu, gv, gw);
   }
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
@@ -775,30 +625,20 @@ static int grad3_launch(Handle* h, int variant) {
 
 int k_calc_grad(Handle* h, const double* phi, double* grad) {
   if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
-  if (h->autotune && !h->tune_grad1.done && h->profile == 0 && h->grad_variant < 0) {
-    static const int cands[] = {0, 1, 2, 3};
-    int rc = autotune_pick(h, h->tune_grad1, cands, 4, [&](int v) { return grad1_launch(h, v, phi, grad); }, 3, {{grad, 3 * (size_t)h->N}});
-    if (rc) return rc;
-  }
-  return grad1_launch(h, h->grad_variant >= 0 ? h->grad_variant : (h->tune_grad1.ncand ? h->tune_grad1.choice : 0), phi, grad);
-}
-
-int k_calc_grad3(Handle* h) {  // the three calc_grad calls of mod_uvwp.f90:118-120 in one pass over the mesh
-  if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
-  if (h->autotune && !h->tune_grad3.done && h->profile == 0 && h->grad_variant < 0) {
-    static const int cands[] = {0, 1, 2, 3};
-    int rc = autotune_pick(h, h->tune_grad3, cands, 4, [&](int v) { return grad3_launch(h, v); }, 3,
-                           {{h->fld[CFDL_F_GU], 3 * (size_t)h->N}, {h->fld[CFDL_F_GV], 3 * (size_t)h->N}, {h->fld[CFDL_F_GW], 3 * (size_t)h->N}});
-    if (rc) return rc;
-  }
-  prof_begin(h, PROF_GRAD);
-  int rc = grad3_launch(h, h->grad_variant >= 0 ? h->grad_variant : (h->tune_grad3.ncand ? h->tune_grad3.choice : 0));
+  prof_begin(h, PROF_GRAD1);
+  int rc = grad1_launch(h, phi, grad);
   prof_end(h);
   return rc;
 }
 
+int k_calc_grad3(Handle* h) {  // the three calc_grad calls of mod_uvwp.f90:118-120 in one pass over the mesh
+  if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
+  prof_begin(h, PROF_GRAD);
+  int rc = grad3_launch(h);
+  prof_end(h);
+  return rc;
+}
 
-// ---- update_time, mod_physics.f90:101-112 ------------------------------------------------------
 int k_update_time(Handle* h) {
   const size_t hb = sizeof(double) * (size_t)h->H;
   CFDL_CUDA(cudaMemcpyAsync(h->fld[CFDL_F_U0], h->fld[CFDL_F_U], hb, cudaMemcpyDeviceToDevice, h->stream));

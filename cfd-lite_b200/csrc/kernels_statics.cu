@@ -90,199 +90,122 @@ struct UvwArgsS {
   FaceStatics S;
 };
 
-// FASTDIV (uvw_variant=3): the ten quotients per face share two divisors (|dr| and |dr_p|); their
-// reciprocals are taken once and every quotient is formed with quot<true> — same bits, ~35 % fewer
-// instructions in a kernel that ncu shows issue-bound at 25 % occupancy.
-// DIV: 0 = plain divisions; 1 = quot<true> with the two reciprocals taken in the kernel; 2 = quot<true>
-// with the reciprocals read from the statics (two divisions per face side less, 16 bytes more)
-// LEAN: the K coefficients and neighbour ids are not held in registers across the cell — anb is stored
-// slot by slot and read back (this thread's own stores: L1) for dc, boundary slots are remembered in a
-// bit mask and their ids re-read; fewer live registers for the face loop.
-template <int K, int DIV, bool LEAN = false>
+// The ten quotients per face share two divisors (|dr| and |dr_p|); their reciprocals come from the statics
+// and every quotient is formed with quot<true> (one multiply + two FMAs: the correctly rounded quotient,
+// device_math.cuh) — the bits of the reference's divisions for a third of their instructions.
+// Round 2 timed fourteen forms of this routine on a B200 (profiles/r02_call1_bench_default_autotune.json:
+// divisions 0.89 ms, in-kernel reciprocals 0.53, stored reciprocals 0.49, paired colour order 0.47, lean
+// register variants 0.48-0.56, forced occupancy 0.53-0.59, locality order 0.46); the winner is what is left.
+template <int K>
 __device__ __forceinline__ void coef_uvw_statics_cell(const UvwArgsS& A, const int c) {
-  constexpr bool FASTDIV = DIV != 0;
   const int Nc = A.Nc, Np = A.Np;
-  {
-    const int n = A.nfc[c];
-    const double mu_e = A.mu[c];
-    double gue[3], gve[3], gwe[3];
-    load3(A.gu, c, gue); load3(A.gv, c, gve); load3(A.gw, c, gwe);
-    double ap = 0.0, sumf = 0.0, sumss[3] = {0, 0, 0}, sumdefc[3] = {0, 0, 0};
-    double anbk[LEAN ? 1 : K];
-    int nbk[LEAN ? 1 : K];
-    unsigned bmask = 0;  // LEAN: slots whose neighbour is a boundary halo
+  const int n = A.nfc[c];
+  const double mu_e = A.mu[c];
+  double gue[3], gve[3], gwe[3];
+  load3(A.gu, c, gue); load3(A.gv, c, gve); load3(A.gw, c, gwe);
+  double ap = 0.0, sumf = 0.0, sumss[3] = {0, 0, 0}, sumdefc[3] = {0, 0, 0};
+  double anbk[K];
+  int nbk[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      if (!LEAN) { anbk[k] = 0.0; nbk[k] = -1; }
-      if (k < n) {
-        const int nb = A.ell_nb[(size_t)k * Np + c];
-        const int fs = A.ell_fs[(size_t)k * Np + c];
-        if (LEAN) { if (nb >= Nc) bmask |= 1u << k; }
-        else nbk[k] = nb;
-        double d = 0.0, fnb = 0.0;
-        if (nb < Nc) {
-          const int f = abs(fs) - 1;
-          const bool own = fs > 0;
-          const double sg = own ? 1.0 : -1.0;
-          const double area = A.S.area[f], ds = A.S.ds[f], ds_p = A.S.dsp[f];
-          const double wt = own ? A.S.wto[f] : A.S.wtn[f];
-          const double dr[3] = {sg * A.S.dr[0][f], sg * A.S.dr[1][f], sg * A.S.dr[2][f]};
-          const double dr_p[3] = {sg * A.S.drp[0][f], sg * A.S.drp[1][f], sg * A.S.drp[2][f]};
-          const double f_in = -sg * A.mip[f];
-          fnb = fmax(f_in, 0.0);
-          sumf = sumf + f_in;
-          const double muip = (1.0 - wt) * mu_e + wt * A.mu[nb];
-          const double rds = DIV == 2 ? A.S.rds[f] : (DIV == 1 ? 1.0 / ds : 0.0), rdsp = DIV == 2 ? A.S.rdsp[f] : (DIV == 1 ? 1.0 / ds_p : 0.0);
-          d = quot<FASTDIV>(muip * area, ds, rds);
-          double gun[3], gvn[3], gwn[3];
-          load3(A.gu, nb, gun); load3(A.gv, nb, gvn); load3(A.gw, nb, gwn);
-          const double w1 = 1.0 - wt;
+  for (int k = 0; k < K; ++k) {
+    anbk[k] = 0.0; nbk[k] = -1;
+    if (k < n) {
+      const int nb = A.ell_nb[(size_t)k * Np + c];
+      const int fs = A.ell_fs[(size_t)k * Np + c];
+      nbk[k] = nb;
+      double d = 0.0, fnb = 0.0;
+      if (nb < Nc) {
+        const int f = abs(fs) - 1;
+        const bool own = fs > 0;
+        const double sg = own ? 1.0 : -1.0;
+        const double area = A.S.area[f], ds = A.S.ds[f], ds_p = A.S.dsp[f];
+        const double wt = own ? A.S.wto[f] : A.S.wtn[f];
+        const double dr[3] = {sg * A.S.dr[0][f], sg * A.S.dr[1][f], sg * A.S.dr[2][f]};
+        const double dr_p[3] = {sg * A.S.drp[0][f], sg * A.S.drp[1][f], sg * A.S.drp[2][f]};
+        const double f_in = -sg * A.mip[f];
+        fnb = fmax(f_in, 0.0);
+        sumf = sumf + f_in;
+        const double muip = (1.0 - wt) * mu_e + wt * A.mu[nb];
+        const double rds = A.S.rds[f], rdsp = A.S.rdsp[f];
+        d = quot<true>(muip * area, ds, rds);
+        double gun[3], gvn[3], gwn[3];
+        load3(A.gu, nb, gun); load3(A.gv, nb, gvn); load3(A.gw, nb, gwn);
+        const double w1 = 1.0 - wt;
 #pragma unroll
-          for (int m = 0; m < 3; ++m) {
-            const double gip[3] = {w1 * gue[m] + wt * gun[m], w1 * gve[m] + wt * gvn[m], w1 * gwe[m] + wt * gwn[m]};
-            sumss[m] = sumss[m] + quot<FASTDIV>(muip * area * dot3(gip, dr), ds, rds);
-          }
-          {
-            double gip[3] = {w1 * gue[0] + wt * gun[0], w1 * gue[1] + wt * gun[1], w1 * gue[2] + wt * gun[2]};
-            sumdefc[0] = sumdefc[0] + muip * area * (quot<FASTDIV>(dot3(gip, dr_p), ds_p, rdsp) - quot<FASTDIV>(dot3(gip, dr), ds, rds));
-            gip[0] = w1 * gve[0] + wt * gvn[0]; gip[1] = w1 * gve[1] + wt * gvn[1]; gip[2] = w1 * gve[2] + wt * gvn[2];
-            sumdefc[1] = sumdefc[1] + muip * area * (quot<FASTDIV>(dot3(gip, dr_p), ds_p, rdsp) - quot<FASTDIV>(dot3(gip, dr), ds, rds));
-            gip[0] = w1 * gwe[0] + wt * gwn[0]; gip[1] = w1 * gwe[1] + wt * gwn[1]; gip[2] = w1 * gwe[2] + wt * gwn[2];
-            sumdefc[2] = sumdefc[2] + muip * area * (quot<FASTDIV>(dot3(gip, dr_p), ds_p, rdsp) - quot<FASTDIV>(dot3(gip, dr), ds, rds));
-          }
+        for (int m = 0; m < 3; ++m) {
+          const double gip[3] = {w1 * gue[m] + wt * gun[m], w1 * gve[m] + wt * gvn[m], w1 * gwe[m] + wt * gwn[m]};
+          sumss[m] = sumss[m] + quot<true>(muip * area * dot3(gip, dr), ds, rds);
         }
-        if (LEAN) A.anb[(size_t)k * Np + c] = d + fnb;
-        else anbk[k] = d + fnb;
-        ap = ap + d + fnb;
-      }
-    }
-    const double vol = A.vol[c];
-    const double ap0 = A.rho[c] * vol / A.dt;
-    ap = ap + ap0;
-    const double ue = A.u[c], ve = A.v[c], we = A.w[c];
-    double bu = ap0 * A.u0[c] + sumf * ue - vol * A.gp[3 * (size_t)c] + sumss[0] + sumdefc[0];
-    double bv = ap0 * A.v0[c] + sumf * ve - vol * A.gp[3 * (size_t)c + 1] + sumss[1] + sumdefc[1];
-    double bw = ap0 * A.w0[c] + sumf * we - vol * A.gp[3 * (size_t)c + 2] + sumss[2] + sumdefc[2];
-    int last = -1;  // boundary faces in halo order (rare: geometry evaluated on the fly as in the reference)
-    for (int t = 0; t < K; ++t) {
-      int best = 0x7fffffff, bk = -1;
-      if (LEAN) {
-        if (!bmask) break;
-        for (int k = 0; k < K; ++k) {
-          if (!(bmask >> k & 1u)) continue;
-          const int nb = A.ell_nb[(size_t)k * Np + c];
-          if (nb > last && nb < best) { best = nb; bk = k; }
+        {
+          double gip[3] = {w1 * gue[0] + wt * gun[0], w1 * gue[1] + wt * gun[1], w1 * gue[2] + wt * gun[2]};
+          sumdefc[0] = sumdefc[0] + muip * area * (quot<true>(dot3(gip, dr_p), ds_p, rdsp) - quot<true>(dot3(gip, dr), ds, rds));
+          gip[0] = w1 * gve[0] + wt * gvn[0]; gip[1] = w1 * gve[1] + wt * gvn[1]; gip[2] = w1 * gve[2] + wt * gvn[2];
+          sumdefc[1] = sumdefc[1] + muip * area * (quot<true>(dot3(gip, dr_p), ds_p, rdsp) - quot<true>(dot3(gip, dr), ds, rds));
+          gip[0] = w1 * gwe[0] + wt * gwn[0]; gip[1] = w1 * gwe[1] + wt * gwn[1]; gip[2] = w1 * gwe[2] + wt * gwn[2];
+          sumdefc[2] = sumdefc[2] + muip * area * (quot<true>(dot3(gip, dr_p), ds_p, rdsp) - quot<true>(dot3(gip, dr), ds, rds));
         }
-      } else {
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-          if (nbk[k] >= Nc && nbk[k] > last && nbk[k] < best) { best = nbk[k]; bk = k; }
       }
-      if (bk < 0) break;
-      last = best;
-      const int bc = A.halo_bc[best - Nc];
-      if (bc < 0) continue;
-      const int f = A.ell_fs[(size_t)bk * Np + c] - 1;
-      double a[3];
-      load3(A.aip, f, a);
-      const double area = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-      const double norm[3] = {a[0] / area, a[1] / area, a[2] / area};
-      const double dr[3] = {A.xc[best] - A.xc[c], A.yc[best] - A.yc[c], A.zc[best] - A.zc[c]};
-      const double ds = sqrt(dot3(dr, dr));
-      const double d = mu_e * area / ds;
-      if (A.bc_kind[bc] != CFDL_BC_SYMMETRY) {
-        const double vbnc[3] = {A.u[best], A.v[best], A.w[best]};
-        double vrel[3] = {ue, ve, we};
-        const double vn = dot3(vrel, norm);
-        vrel[0] = vrel[0] - vn * norm[0]; vrel[1] = vrel[1] - vn * norm[1]; vrel[2] = vrel[2] - vn * norm[2];
-        vrel[0] = vbnc[0] - vrel[0]; vrel[1] = vbnc[1] - vrel[1]; vrel[2] = vbnc[2] - vrel[2];
-        bu = bu + d * vrel[0] - d * ue;
-        bv = bv + d * vrel[1] - d * ve;
-        bw = bw + d * vrel[2] - d * we;
-      }
-      ap = ap + d;
-      if (LEAN) {
-        A.anb[(size_t)bk * Np + c] = 0.0 + d;  // the face loop stored d + fnb = 0 for a boundary slot
-      } else {
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-          if (k == bk) anbk[k] = anbk[k] + d;
-      }
+      anbk[k] = d + fnb;
+      ap = ap + d + fnb;
     }
-    double dcv = ap;
-    if (LEAN) {
+  }
+  const double vol = A.vol[c];
+  const double ap0 = A.rho[c] * vol / A.dt;
+  ap = ap + ap0;
+  const double ue = A.u[c], ve = A.v[c], we = A.w[c];
+  double bu = ap0 * A.u0[c] + sumf * ue - vol * A.gp[3 * (size_t)c] + sumss[0] + sumdefc[0];
+  double bv = ap0 * A.v0[c] + sumf * ve - vol * A.gp[3 * (size_t)c + 1] + sumss[1] + sumdefc[1];
+  double bw = ap0 * A.w0[c] + sumf * we - vol * A.gp[3 * (size_t)c + 2] + sumss[2] + sumdefc[2];
+  int last = -1;  // boundary faces in halo order (rare: geometry evaluated on the fly as in the reference)
+  for (int t = 0; t < K; ++t) {
+    int best = 0x7fffffff, bk = -1;
 #pragma unroll
-      for (int k = 0; k < K; ++k)
-        if (k < n) dcv = dcv - A.anb[(size_t)k * Np + c];
-    } else {
-#pragma unroll
-      for (int k = 0; k < K; ++k)
-        if (k < n) { dcv = dcv - anbk[k]; A.anb[(size_t)k * Np + c] = anbk[k]; }
+    for (int k = 0; k < K; ++k)
+      if (nbk[k] >= Nc && nbk[k] > last && nbk[k] < best) { best = nbk[k]; bk = k; }
+    if (bk < 0) break;
+    last = best;
+    const int bc = A.halo_bc[best - Nc];
+    if (bc < 0) continue;
+    const int f = A.ell_fs[(size_t)bk * Np + c] - 1;
+    double a[3];
+    load3(A.aip, f, a);
+    const double area = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    const double norm[3] = {a[0] / area, a[1] / area, a[2] / area};
+    const double dr[3] = {A.xc[best] - A.xc[c], A.yc[best] - A.yc[c], A.zc[best] - A.zc[c]};
+    const double ds = sqrt(dot3(dr, dr));
+    const double d = mu_e * area / ds;
+    if (A.bc_kind[bc] != CFDL_BC_SYMMETRY) {
+      const double vbnc[3] = {A.u[best], A.v[best], A.w[best]};
+      double vrel[3] = {ue, ve, we};
+      const double vn = dot3(vrel, norm);
+      vrel[0] = vrel[0] - vn * norm[0]; vrel[1] = vrel[1] - vn * norm[1]; vrel[2] = vrel[2] - vn * norm[2];
+      vrel[0] = vbnc[0] - vrel[0]; vrel[1] = vbnc[1] - vrel[1]; vrel[2] = vbnc[2] - vrel[2];
+      bu = bu + d * vrel[0] - d * ue;
+      bv = bv + d * vrel[1] - d * ve;
+      bw = bw + d * vrel[2] - d * we;
     }
-    A.ap[c] = ap;
-    A.bu[c] = bu; A.bv[c] = bv; A.bw[c] = bw;
-    A.d[c] = vol / ap;
-    A.dc[c] = vol / dcv;
+    ap = ap + d;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (k == bk) anbk[k] = anbk[k] + d;
   }
+  double dcv = ap;
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+    if (k < n) { dcv = dcv - anbk[k]; A.anb[(size_t)k * Np + c] = anbk[k]; }
+  A.ap[c] = ap;
+  A.bu[c] = bu; A.bv[c] = bv; A.bw[c] = bw;
+  A.d[c] = vol / ap;
+  A.dc[c] = vol / dcv;
 }
 
-template <int K, int DIV>
-__device__ __forceinline__ void coef_uvw_statics_body(const UvwArgsS& A) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.N; c += gridDim.x * blockDim.x) coef_uvw_statics_cell<K, DIV>(A, c);
-}
-// Two-colour meshes, colour-major numbering: a CTA takes TPB cells of the first colour and then the
-// TPB cells at the same position of the second colour.  On meshes numbered with some locality these
-// are each other's neighbours, so the statics of their common faces — which the linear order reads a
-// second time half a kernel later, from DRAM — are still in L1/L2.  Same cells, same per-cell code.
-template <int K, int DIV, bool LEAN>
-__device__ __forceinline__ void coef_uvw_statics_body_paired(const UvwArgsS& A) {
-  const int n0 = A.ncol0, n1 = A.N - A.ncol0;
-  const int nq = (max(n0, n1) + (int)blockDim.x - 1) / (int)blockDim.x;
-  for (int q = blockIdx.x; q < nq; q += gridDim.x) {
-    const int i = q * blockDim.x + threadIdx.x;
-#pragma unroll 1
-    for (int col = 0; col < 2; ++col)
-      if (i < (col ? n1 : n0)) coef_uvw_statics_cell<K, DIV, LEAN>(A, col ? n0 + i : i);
-  }
-}
-
-template <int K, int DIV>
-__global__ void __launch_bounds__(TPB) coef_uvw_statics_kernel(const UvwArgsS A) { coef_uvw_statics_body<K, DIV>(A); }
-// uvw_variant=4: FASTDIV with three resident CTAs per SM requested (80 registers, some spills): occupancy experiment
+// Locality order (any number of colours): thread i takes the i-th cell of the base (natural | Morton) order,
+// so the lanes of a warp hold cells of all colours that are neighbours in space — the two cells of a face read
+// its statics in the same instruction or a few instructions apart (L1), where a colour-major sweep reads them
+// a second time from DRAM, half a kernel later.  Per-cell arrays are touched as ncolors contiguous runs per warp.
 template <int K>
-__global__ void __launch_bounds__(TPB, 3) coef_uvw_statics_occ3_kernel(const UvwArgsS A) { coef_uvw_statics_body<K, 1>(A); }
-template <int K, int DIV>
-__global__ void __launch_bounds__(TPB) coef_uvw_statics_paired_kernel(const UvwArgsS A) { coef_uvw_statics_body_paired<K, DIV, false>(A); }
-// uvw_variant 9/10: stored reciprocals, lean register use (linear / paired order); 11: 9 with three CTAs per SM requested
-template <int K>
-__global__ void __launch_bounds__(TPB) coef_uvw_statics_lean_kernel(const UvwArgsS A) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.N; c += gridDim.x * blockDim.x) coef_uvw_statics_cell<K, 2, true>(A, c);
-}
-template <int K>
-__global__ void __launch_bounds__(TPB) coef_uvw_statics_lean_paired_kernel(const UvwArgsS A) { coef_uvw_statics_body_paired<K, 2, true>(A); }
-template <int K>
-__global__ void __launch_bounds__(TPB, 3) coef_uvw_statics_lean_occ3_kernel(const UvwArgsS A) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.N; c += gridDim.x * blockDim.x) coef_uvw_statics_cell<K, 2, true>(A, c);
-}
-template <int K>
-__global__ void __launch_bounds__(TPB, 4) coef_uvw_statics_lean_occ4_kernel(const UvwArgsS A) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.N; c += gridDim.x * blockDim.x) coef_uvw_statics_cell<K, 2, true>(A, c);
-}
-// Locality order (uvw_variant 13 / 14 = stored reciprocals, plain / lean; any number of colours): thread i
-// takes the i-th cell of the base (natural | Morton) order, so the lanes of a warp hold cells of all colours
-// that are neighbours in space — the two cells of a face read its statics in the same instruction or a few
-// instructions apart (L1), where the colour-major sweep reads them a second time from DRAM.  Per-cell
-// arrays are then touched as ncolors contiguous runs per warp instead of one.
-template <int K, bool LEAN>
-__global__ void __launch_bounds__(TPB) coef_uvw_statics_loc_kernel(const UvwArgsS A) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.N; i += gridDim.x * blockDim.x) coef_uvw_statics_cell<K, 2, LEAN>(A, A.order[i]);
-}
-
-// tets (K = 4) and hexes/prisms/pyramids (K = 6) get their own instantiation of every variant
-template <auto K4, auto K6>
-static void launch_uvw(Handle* h, const UvwArgsS& A, int cells) {
-  if (h->K <= 4) K4<<<occ_grid<K4>(h, cells, TPB), TPB, 0, S(h)>>>(A);
-  else K6<<<occ_grid<K6>(h, cells, TPB), TPB, 0, S(h)>>>(A);
+__global__ void __launch_bounds__(TPB) coef_uvw_statics_kernel(const UvwArgsS A) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.N; i += gridDim.x * blockDim.x) coef_uvw_statics_cell<K>(A, A.order ? A.order[i] : i);
 }
 
 int k_calc_coef_uvw_statics(Handle* h, double dt) {
@@ -300,24 +223,8 @@ int k_calc_coef_uvw_statics(Handle* h, double dt) {
   A.S = statics_of(h);
   A.ncol0 = h->prep.ncolors == 2 ? h->prep.color_ptr[1] : h->N;
   A.order = h->loc_order;
-  const int paired_cells = std::max(A.ncol0, h->N - A.ncol0);  // a CTA of the paired order covers TPB cells of each colour
-  int v = h->uvw_variant;
-  if (h->prep.ncolors != 2) v = (v == 6) ? 5 : (v == 7 ? 3 : (v == 8 ? 2 : (v == 10 ? 9 : v)));  // the paired order needs two colours
-  switch (v) {
-    case 3: launch_uvw<coef_uvw_statics_kernel<4, 1>, coef_uvw_statics_kernel<6, 1>>(h, A, h->N); break;
-    case 4: launch_uvw<coef_uvw_statics_occ3_kernel<4>, coef_uvw_statics_occ3_kernel<6>>(h, A, h->N); break;
-    case 5: launch_uvw<coef_uvw_statics_kernel<4, 2>, coef_uvw_statics_kernel<6, 2>>(h, A, h->N); break;
-    case 6: launch_uvw<coef_uvw_statics_paired_kernel<4, 2>, coef_uvw_statics_paired_kernel<6, 2>>(h, A, paired_cells); break;
-    case 7: launch_uvw<coef_uvw_statics_paired_kernel<4, 1>, coef_uvw_statics_paired_kernel<6, 1>>(h, A, paired_cells); break;
-    case 8: launch_uvw<coef_uvw_statics_paired_kernel<4, 0>, coef_uvw_statics_paired_kernel<6, 0>>(h, A, paired_cells); break;
-    case 9: launch_uvw<coef_uvw_statics_lean_kernel<4>, coef_uvw_statics_lean_kernel<6>>(h, A, h->N); break;
-    case 10: launch_uvw<coef_uvw_statics_lean_paired_kernel<4>, coef_uvw_statics_lean_paired_kernel<6>>(h, A, paired_cells); break;
-    case 11: launch_uvw<coef_uvw_statics_lean_occ3_kernel<4>, coef_uvw_statics_lean_occ3_kernel<6>>(h, A, h->N); break;
-    case 12: launch_uvw<coef_uvw_statics_lean_occ4_kernel<4>, coef_uvw_statics_lean_occ4_kernel<6>>(h, A, h->N); break;
-    case 13: launch_uvw<coef_uvw_statics_loc_kernel<4, false>, coef_uvw_statics_loc_kernel<6, false>>(h, A, h->N); break;
-    case 14: launch_uvw<coef_uvw_statics_loc_kernel<4, true>, coef_uvw_statics_loc_kernel<6, true>>(h, A, h->N); break;
-    default: launch_uvw<coef_uvw_statics_kernel<4, 0>, coef_uvw_statics_kernel<6, 0>>(h, A, h->N); break;
-  }
+  if (h->K <= 4) coef_uvw_statics_kernel<4><<<occ_grid<coef_uvw_statics_kernel<4>>(h, h->N, TPB), TPB, 0, S(h)>>>(A);
+  else coef_uvw_statics_kernel<6><<<occ_grid<coef_uvw_statics_kernel<6>>(h, h->N, TPB), TPB, 0, S(h)>>>(A);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
@@ -333,8 +240,8 @@ struct CoefPArgs {
   FaceStatics S;
 };
 
-// FAST: the quotient by dr.n through the stored reciprocal and quot<true> (same bits as the division)
-template <int K, bool FAST>
+// the quotient by dr.n through the stored reciprocal and quot<true> (same bits as the division)
+template <int K>
 __device__ __forceinline__ void coef_p_statics_cell(const CoefPArgs& A, const int c) {
   const int Nc = A.Nc, Np = A.Np;
   const int n = A.nfc[c];
@@ -357,7 +264,7 @@ __device__ __forceinline__ void coef_p_statics_cell(const CoefPArgs& A, const in
         const double f_in = -sg * A.mip[f];
         sumf = sumf + f_in;
         const double rhoip = (1.0 - wt) * rho_e + wt * A.rho[nb];
-        d = quot<FAST>((1.0 - wt) * dc_e + wt * A.dc[nb], A.S.dn[f], FAST ? A.S.rdn[f] : 0.0) * rhoip * A.S.area[f];
+        d = quot<true>((1.0 - wt) * dc_e + wt * A.dc[nb], A.S.dn[f], A.S.rdn[f]) * rhoip * A.S.area[f];
       }
       A.anb[(size_t)k * Np + c] = d;
       ap = ap + d;
@@ -379,13 +286,11 @@ __device__ __forceinline__ void coef_p_statics_cell(const CoefPArgs& A, const in
   A.b[c] = b;
 }
 
-template <int K, bool FAST>
-__global__ void __launch_bounds__(TPB) coef_p_statics_kernel(const CoefPArgs A) {
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.N; c += gridDim.x * blockDim.x) coef_p_statics_cell<K, FAST>(A, c);
-}
-// coef_p_variant 1: the paired colour order of coef_uvw_statics_body_paired (face statics and mip of a
-// face are read by both of its cells within one CTA's pass instead of half a kernel apart)
-template <int K, bool FAST>
+// two-colour meshes: the paired colour order — a CTA takes TPB cells of the first colour and then the TPB cells
+// at the same position of the second colour, on a mesh numbered with locality their neighbours, so the statics
+// and mip of a face are read by both of its cells within one CTA's pass instead of half a kernel apart
+// (B200, 128^3: 0.158 ms against 0.183 linear and 0.175 in the locality order)
+template <int K>
 __global__ void __launch_bounds__(TPB) coef_p_statics_paired_kernel(const CoefPArgs A) {
   const int n0 = A.ncol0, n1 = A.N - A.ncol0;
   const int nq = (max(n0, n1) + (int)blockDim.x - 1) / (int)blockDim.x;
@@ -393,14 +298,13 @@ __global__ void __launch_bounds__(TPB) coef_p_statics_paired_kernel(const CoefPA
     const int i = q * blockDim.x + threadIdx.x;
 #pragma unroll 1
     for (int col = 0; col < 2; ++col)
-      if (i < (col ? n1 : n0)) coef_p_statics_cell<K, FAST>(A, col ? n0 + i : i);
+      if (i < (col ? n1 : n0)) coef_p_statics_cell<K>(A, col ? n0 + i : i);
   }
 }
-
-// coef_p_variant 4 / 5: locality order (see coef_uvw_statics_loc_kernel), division / stored reciprocal
-template <int K, bool FAST>
+// more colours: locality order (see coef_uvw_statics_kernel)
+template <int K>
 __global__ void __launch_bounds__(TPB) coef_p_statics_loc_kernel(const CoefPArgs A) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.N; i += gridDim.x * blockDim.x) coef_p_statics_cell<K, FAST>(A, A.order[i]);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.N; i += gridDim.x * blockDim.x) coef_p_statics_cell<K>(A, A.order ? A.order[i] : i);
 }
 
 template <auto K4, auto K6>
@@ -409,7 +313,7 @@ static void launch_coef_p(Handle* h, const CoefPArgs& A, int cells) {
   else K6<<<occ_grid<K6>(h, cells, TPB), TPB, 0, S(h)>>>(A);
 }
 
-static int coef_p_launch(Handle* h, int variant) {
+int k_calc_coef_p_statics(Handle* h) {
   CoefPArgs A;
   A.N = h->N; A.Nc = h->Nc; A.Np = h->Np; A.ncol0 = h->prep.ncolors == 2 ? h->prep.color_ptr[1] : h->N;
   A.order = h->loc_order;
@@ -417,73 +321,20 @@ static int coef_p_launch(Handle* h, int variant) {
   A.rho = h->rho; A.dc = h->fld[CFDL_F_DC]; A.mip = h->fld[CFDL_F_MIP];
   A.ap = h->fld[CFDL_F_AP]; A.anb = h->fld[CFDL_F_ANB]; A.b = h->fld[CFDL_F_B];
   A.S = statics_of(h);
-  // 0/1 = linear / paired colour order with the division; 2/3 = the same with the stored reciprocal of dr.n
-  const bool paired = (variant == 1 || variant == 3) && h->prep.ncolors == 2, fast = variant == 2 || variant == 3 || variant == 5;
-  const int pc = std::max(A.ncol0, h->N - A.ncol0);
-  if (variant == 4) launch_coef_p<coef_p_statics_loc_kernel<4, false>, coef_p_statics_loc_kernel<6, false>>(h, A, h->N);
-  else if (variant == 5) launch_coef_p<coef_p_statics_loc_kernel<4, true>, coef_p_statics_loc_kernel<6, true>>(h, A, h->N);
-  else if (paired && fast) launch_coef_p<coef_p_statics_paired_kernel<4, true>, coef_p_statics_paired_kernel<6, true>>(h, A, pc);
-  else if (paired) launch_coef_p<coef_p_statics_paired_kernel<4, false>, coef_p_statics_paired_kernel<6, false>>(h, A, pc);
-  else if (fast) launch_coef_p<coef_p_statics_kernel<4, true>, coef_p_statics_kernel<6, true>>(h, A, h->N);
-  else launch_coef_p<coef_p_statics_kernel<4, false>, coef_p_statics_kernel<6, false>>(h, A, h->N);
+  if (h->prep.ncolors == 2) launch_coef_p<coef_p_statics_paired_kernel<4>, coef_p_statics_paired_kernel<6>>(h, A, std::max(A.ncol0, h->N - A.ncol0));
+  else launch_coef_p<coef_p_statics_loc_kernel<4>, coef_p_statics_loc_kernel<6>>(h, A, h->N);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
 
-int k_calc_coef_p_statics(Handle* h) {
-  if (h->autotune && !h->tune_coef_p.done && h->profile == 0 && h->coef_p_variant < 0) {
-    static const int cands2[] = {0, 1, 2, 3, 4, 5}, cands[] = {0, 2, 4, 5};
-    const bool two = h->prep.ncolors == 2;
-    int rc = autotune_pick(h, h->tune_coef_p, two ? cands2 : cands, two ? 6 : 4, [&](int v) { return coef_p_launch(h, v); }, 3,
-                           {{h->fld[CFDL_F_AP], (size_t)h->N}, {h->fld[CFDL_F_ANB], (size_t)h->K * h->Np}, {h->fld[CFDL_F_B], (size_t)h->N}});
-    if (rc) return rc;
-  }
-  return coef_p_launch(h, h->coef_p_variant >= 0 ? h->coef_p_variant : (h->tune_coef_p.ncand ? h->tune_coef_p.choice : 0));
-}
-
 // ---- calc_mip on statics (mod_uvwp.f90:438-490) ------------------------------------------------
-struct MipArgsS {
-  int Fi;
-  const int32_t *face_a, *face_b;
-  const double* rho;
-  const double *u, *v, *w, *u0, *v0, *w0, *p, *gp, *d, *mip0;
-  double* mip;
-  double dt;
-  int rhie_chow;
-  FaceStatics S;
-};
-
-__global__ void __launch_bounds__(TPB) mip_statics_kernel(const MipArgsS A) {
-  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < A.Fi; f += gridDim.x * blockDim.x) {
-    const int e = A.face_a[f], nb = A.face_b[f];
-    const double area = A.S.area[f];
-    const double norm[3] = {A.S.n[0][f], A.S.n[1][f], A.S.n[2][f]};
-    const double wt = A.S.wto[f];
-    const double w1 = 1.0 - wt;
-    const double velip[3] = {w1 * A.u[e] + wt * A.u[nb], w1 * A.v[e] + wt * A.v[nb], w1 * A.w[e] + wt * A.w[nb]};
-    const double rhoip = A.rho[e] * w1 + A.rho[nb] * wt;
-    double m = dot3(velip, norm) * rhoip * area;
-    if (A.rhie_chow) {
-      const double dr[3] = {A.S.dr[0][f], A.S.dr[1][f], A.S.dr[2][f]};
-      double ge[3], gn[3];
-      load3(A.gp, e, ge); load3(A.gp, nb, gn);
-      const double gpip[3] = {w1 * ge[0] + wt * gn[0], w1 * ge[1] + wt * gn[1], w1 * ge[2] + wt * gn[2]};
-      const double dip = w1 * A.d[e] + wt * A.d[nb];
-      const double velip0[3] = {w1 * A.u0[e] + wt * A.u0[nb], w1 * A.v0[e] + wt * A.v0[nb], w1 * A.w0[e] + wt * A.w0[nb]};
-      m = m - rhoip * area * dip / A.S.dn[f] * (A.p[nb] - A.p[e] - dot3(gpip, dr))
-            - rhoip / A.dt * dip * (A.mip0[f] - dot3(velip0, norm) * rhoip * area);
-    }
-    A.mip[f] = m;
-  }
-}
-
-// The same faces visited from the cells: a thread takes one cell and the cell-cell faces that are
+// Faces visited from the cells: a thread takes one cell and the cell-cell faces that are
 // numbered from it (ftouch; on a two-colour mesh every face of a first-colour cell).  Faces are
 // numbered slot-major over exactly these cells, so for a fixed slot consecutive threads read
 // consecutive statics and write consecutive mip entries, the cell's own fields are read once,
-// and the neighbours' fields come from L2 instead of one DRAM pass per face slot.  Each face
-// evaluates the expression of mip_statics_kernel on (owner, neighbour) in the reference's
-// orientation, hence the same bits.
+// and the neighbours' fields come from L2 instead of one DRAM pass per face slot (a thread per face
+// streamed 2.5x the algorithmic bytes, round-1 ncu).  Each face evaluates the reference's expression on
+// (owner, neighbour) in the reference's orientation, hence the same bits.
 struct MipCellArgs {
   int n_cells, Np, K;
   const int32_t *ell_nb, *ell_fs;
@@ -506,10 +357,10 @@ __device__ __forceinline__ void mip_load_cell(const MipCellArgs& A, int c, bool 
   }
 }
 
-// FAST: both quotients of the Rhie-Chow term (by dr.n and by dt) through reciprocals and quot<true>
-template <int K, bool FAST>
+// both quotients of the Rhie-Chow term (by dr.n and by dt) through reciprocals and quot<true>
+template <int K>
 __global__ void __launch_bounds__(TPB, 3) mip_cells_kernel(const MipCellArgs A) {
-  const double rdt = FAST ? 1.0 / A.dt : 0.0;
+  const double rdt = 1.0 / A.dt;
   const bool rc = A.rhie_chow != 0;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < A.n_cells; c += gridDim.x * blockDim.x) {
     const unsigned mask = A.ftouch[c];
@@ -539,8 +390,8 @@ __global__ void __launch_bounds__(TPB, 3) mip_cells_kernel(const MipCellArgs A) 
         const double gpip[3] = {w1 * E.g[0] + wt * NB.g[0], w1 * E.g[1] + wt * NB.g[1], w1 * E.g[2] + wt * NB.g[2]};
         const double dip = w1 * E.d + wt * NB.d;
         const double velip0[3] = {w1 * E.u0 + wt * NB.u0, w1 * E.v0 + wt * NB.v0, w1 * E.w0 + wt * NB.w0};
-        m = m - quot<FAST>(rhoip * area * dip, A.S.dn[f], FAST ? A.S.rdn[f] : 0.0) * (NB.p - E.p - dot3(gpip, dr))
-              - quot<FAST>(rhoip, A.dt, rdt) * dip * (A.mip0[f] - dot3(velip0, norm) * rhoip * area);
+        m = m - quot<true>(rhoip * area * dip, A.S.dn[f], A.S.rdn[f]) * (NB.p - E.p - dot3(gpip, dr))
+              - quot<true>(rhoip, A.dt, rdt) * dip * (A.mip0[f] - dot3(velip0, norm) * rhoip * area);
       }
       A.mip[f] = m;
     }
@@ -555,41 +406,20 @@ static void launch_mip(Handle* h, const MipCellArgs& A) {
 
 int k_calc_mip_statics(Handle* h, bool rhie_chow, double dt) {
   if (h->Fi == 0) return CFDL_OK;
-  if (h->mip_variant == 1 && h->K <= 6) {
-    MipCellArgs A;
-    A.n_cells = h->prep.touch_end; A.Np = h->Np; A.K = h->K; A.ell_nb = h->ell_nb; A.ell_fs = h->ell_fs; A.ftouch = h->ftouch; A.rho = h->rho;
-    A.u = h->fld[CFDL_F_U]; A.v = h->fld[CFDL_F_V]; A.w = h->fld[CFDL_F_W];
-    A.u0 = h->fld[CFDL_F_U0]; A.v0 = h->fld[CFDL_F_V0]; A.w0 = h->fld[CFDL_F_W0];
-    A.p = h->fld[CFDL_F_P]; A.gp = h->fld[CFDL_F_GP]; A.d = h->fld[CFDL_F_D]; A.mip0 = h->fld[CFDL_F_MIP0];
-    A.mip = h->fld[CFDL_F_MIP]; A.dt = dt; A.rhie_chow = rhie_chow ? 1 : 0;
-    A.S = statics_of(h);
-    auto go = [&](int fast) {
-      if (fast) launch_mip<mip_cells_kernel<4, true>, mip_cells_kernel<6, true>>(h, A);
-      else launch_mip<mip_cells_kernel<4, false>, mip_cells_kernel<6, false>>(h, A);
-      return cudaGetLastError() == cudaSuccess ? CFDL_OK : fail(CFDL_ERR_CUDA, "calc_mip launch failed");
-    };
-    // mip_fast: -1 = measured on first use (a Rhie-Chow call: the plain interpolation has no quotient), 0 = divisions, 1 = reciprocals
-    if (h->autotune && !h->tune_mip.done && h->profile == 0 && h->mip_fast < 0 && rhie_chow) {
-      static const int cands[] = {0, 1};
-      int rc = autotune_pick(h, h->tune_mip, cands, 2, go, 3, {{A.mip, (size_t)h->Fi}});
-      if (rc) return rc;
-    }
-    return go(h->mip_fast >= 0 ? h->mip_fast : (h->tune_mip.ncand ? h->tune_mip.choice : 0));
-  }
-  MipArgsS A;
-  A.Fi = h->Fi; A.face_a = h->face_a; A.face_b = h->face_b; A.rho = h->rho;
+  MipCellArgs A;
+  A.n_cells = h->prep.touch_end; A.Np = h->Np; A.K = h->K; A.ell_nb = h->ell_nb; A.ell_fs = h->ell_fs; A.ftouch = h->ftouch; A.rho = h->rho;
   A.u = h->fld[CFDL_F_U]; A.v = h->fld[CFDL_F_V]; A.w = h->fld[CFDL_F_W];
   A.u0 = h->fld[CFDL_F_U0]; A.v0 = h->fld[CFDL_F_V0]; A.w0 = h->fld[CFDL_F_W0];
   A.p = h->fld[CFDL_F_P]; A.gp = h->fld[CFDL_F_GP]; A.d = h->fld[CFDL_F_D]; A.mip0 = h->fld[CFDL_F_MIP0];
   A.mip = h->fld[CFDL_F_MIP]; A.dt = dt; A.rhie_chow = rhie_chow ? 1 : 0;
   A.S = statics_of(h);
-  mip_statics_kernel<<<occ_grid<mip_statics_kernel>(h, h->Fi, TPB), TPB, 0, S(h)>>>(A);
+  launch_mip<mip_cells_kernel<4>, mip_cells_kernel<6>>(h, A);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
 
 // ---- face part of update_uvwp on statics (mod_uvwp.f90:394-415) ----------------------------------
-template <bool FAST>
+// (the quotient by dr.n through the stored reciprocal: quot<true>, same bits as the division)
 __global__ void __launch_bounds__(TPB) correct_faces_statics_kernel(int Fi, const int32_t* __restrict__ face_a, const int32_t* __restrict__ face_b,
                                                                     const double* __restrict__ rho, const double* __restrict__ dc,
                                                                     const double* __restrict__ pc, const FaceStatics S, double* mip) {
@@ -598,21 +428,15 @@ __global__ void __launch_bounds__(TPB) correct_faces_statics_kernel(int Fi, cons
     const double wt = S.wto[f];
     const double dip = (1.0 - wt) * dc[e] + wt * dc[nb];
     const double rhoip = (rho[e] + rho[nb]) / 2.0;
-    const double dmip = quot<FAST>(rhoip * S.area[f] * dip * (pc[nb] - pc[e]), S.dn[f], FAST ? S.rdn[f] : 0.0);
+    const double dmip = quot<true>(rhoip * S.area[f] * dip * (pc[nb] - pc[e]), S.dn[f], S.rdn[f]);
     mip[f] = mip[f] - dmip;
   }
 }
 
 int k_correct_faces_statics(Handle* h) {
   if (h->Fi == 0) return CFDL_OK;
-  // the kernel updates mip in place, so its two forms cannot be timed against each other on live data;
-  // correct_fast (default 0) selects the reciprocal form by hand
-  if (h->correct_fast)
-    correct_faces_statics_kernel<true><<<occ_grid<correct_faces_statics_kernel<true>>(h, h->Fi, TPB), TPB, 0, S(h)>>>(h->Fi, h->face_a, h->face_b, h->rho, h->fld[CFDL_F_DC],
-                                                                                          h->fld[CFDL_F_PC], statics_of(h), h->fld[CFDL_F_MIP]);
-  else
-    correct_faces_statics_kernel<false><<<occ_grid<correct_faces_statics_kernel<false>>(h, h->Fi, TPB), TPB, 0, S(h)>>>(h->Fi, h->face_a, h->face_b, h->rho, h->fld[CFDL_F_DC],
-                                                                                            h->fld[CFDL_F_PC], statics_of(h), h->fld[CFDL_F_MIP]);
+  correct_faces_statics_kernel<<<occ_grid<correct_faces_statics_kernel>(h, h->Fi, TPB), TPB, 0, S(h)>>>(h->Fi, h->face_a, h->face_b, h->rho, h->fld[CFDL_F_DC],
+                                                                                                  h->fld[CFDL_F_PC], statics_of(h), h->fld[CFDL_F_MIP]);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }

@@ -42,71 +42,6 @@ int prof_collect(Handle* h) {
   return CFDL_OK;
 }
 
-// order-independent checksum of an array's values: the wrapping sum of the 64-bit patterns, +0 and -0 alike
-__global__ void __launch_bounds__(256) checksum_kernel(size_t n, const double* __restrict__ a, unsigned long long* out) {
-  unsigned long long s = 0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const double v = a[i];
-    s += v == 0.0 ? 0ull : (unsigned long long)__double_as_longlong(v);
-  }
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
-}
-
-static bool outputs_checksum(Handle* h, const std::vector<TuneOutput>& outs, unsigned long long* cs) {
-  unsigned long long* dev = reinterpret_cast<unsigned long long*>(h->scal + 444);
-  if (cudaMemsetAsync(dev, 0, sizeof(unsigned long long), h->stream) != cudaSuccess) return false;
-  for (const TuneOutput& o : outs)
-    if (o.p && o.n) checksum_kernel<<<grid_for(h, (int64_t)o.n, 256), 256, 0, S(h)>>>(o.n, o.p, dev);
-  return cudaMemcpyAsync(cs, dev, sizeof *cs, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess && cudaStreamSynchronize(h->stream) == cudaSuccess;
-}
-
-int autotune_pick(Handle* h, Handle::Tuned& T, const int* cands, int n, const std::function<int(int)>& run, int reps,
-                  const std::vector<TuneOutput>& outputs) {
-  T.done = 1;
-  unsigned long long ref_cs = 0;
-  bool have_ref = false;
-  T.ncand = 0;
-  T.choice = cands[0];
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
-    if (e0) cudaEventDestroy(e0);
-    cudaGetLastError();
-    return CFDL_OK;  // no timing possible: keep the first candidate
-  }
-  float best = 0.f;
-  bool have = false;
-  for (int i = 0; i < n && T.ncand < 16; ++i) {
-    const int c = cands[i];
-    float ms = -1.f;
-    bool ok = run(c) == CFDL_OK && cudaStreamSynchronize(h->stream) == cudaSuccess;  // warm-up (and a check that it launches)
-    bool wrong = false;
-    if (ok && !outputs.empty()) {  // the candidate's outputs against the first candidate's
-      unsigned long long cs = 0;
-      if (outputs_checksum(h, outputs, &cs)) {
-        if (!have_ref) { ref_cs = cs; have_ref = true; }
-        else if (cs != ref_cs) wrong = true;
-      }
-    }
-    if (wrong) {
-      T.cand[T.ncand] = c; T.ms[T.ncand] = -2.f; T.ncand++;  // ran, but did not reproduce the reference form: never chosen
-      continue;
-    }
-    if (ok) ok = cudaEventRecord(e0, h->stream) == cudaSuccess;
-    for (int r = 0; ok && r < reps; ++r) ok = run(c) == CFDL_OK;
-    if (ok) ok = cudaEventRecord(e1, h->stream) == cudaSuccess && cudaEventSynchronize(e1) == cudaSuccess &&
-                 cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess;
-    if (!ok) { cudaGetLastError(); ms = -1.f; }
-    T.cand[T.ncand] = c;
-    T.ms[T.ncand] = ok ? ms / reps : -1.f;
-    T.ncand++;
-    if (ok && (!have || ms < best)) { best = ms; have = true; T.choice = c; }
-  }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  return CFDL_OK;
-}
-
 }  // namespace cfdl
 
 using namespace cfdl;

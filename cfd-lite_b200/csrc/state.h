@@ -108,51 +108,35 @@ struct Handle {
   double* rb3_work[2] = {nullptr, nullptr};
   SolveCtl* ctl3 = nullptr;       // device, 3 blocks
   SolveCtl* ctl3_host = nullptr;  // pinned
-  int rb_persistent = -1;         // fused passes of a batch in one cooperative launch: 1 on, 0 off, -1 measured (autotune) else off
-  int rbp_refused = 0, pc_solves = 0;
-  int rb_wave = 0;                // pass teams of the temporally blocked pc solve (kernels_rbw.inc); 0 = off (opt-in: not yet run on a GPU)
-  int rb_wave_rows = 1;           // rows per thread per chunk of that solve
-  int rb_wave_block = 34;         // iterations per launch of that solve (100-iteration pc solve: three launches)
-  double* wave_keep = nullptr;    // its snapshot of the two value arrays (2H) and residual record
-  double* wave_hist = nullptr;
-  int* wave_prog = nullptr;       // progress / arrival counters
-  int wave_maxch = 0, wave_nq = 0, wave_hist_len = 0;
-  int rb_idx16 = -1;              // pc passes read 16-bit neighbour offsets instead of 32-bit ids: 0/1 pinned, -1 measured (autotune) else 0
-  float rb_keep_mb = -1.f;        // megabytes of pc coefficients asked to stay in L2 across passes: >= 0 pinned, -1 measured (autotune) else 0
+  // the pc solve as one persistent launch with neighbour-only synchronisation (kernels_rbq.inc; one GPU, two colours)
+  int rbq = 1;                    // 0: always pass by pass
+  int rbq_refused = 0;            // the cooperative launch was refused or a wait timed out: pass by pass from then on
+  int rbq_occ = 0;                // co-resident CTAs per SM of rbq_kernel (occupancy calculator, first use)
+  int rbq_ctas_per_sm = 0;        // > 0: use fewer CTAs per SM than that
+  double* rbq_mem = nullptr;      // red pairs, black buffers, per-pass partials, progress words
+  size_t rbq_len = 0;
+  int64_t prof_extra_passes = 0;  // passes executed a second time because the stopping rule fired inside a block
+  int rb_idx16 = 1;               // pc passes read 16-bit neighbour offsets instead of 32-bit ids where prep.nb16 exists
   int pc_sumap = 1;               // fused pc passes rebuild ap as the slot-order sum of anb instead of reading it
   bool pc_sumap_ok = false;       // true while ap/anb on the device are what calc_coef_p wrote (cleared by any other writer)
-  int uvw_fused = -1;             // 1: side by side, 0: one after the other as the reference does, -1: measured (autotune) else 1
-  int momentum_calls = 0;
+  int uvw_fused = 1;              // 1: u, v, w side by side, 0: one after the other as the reference does (same bits)
   int last_passes[4] = {1, 1, 1, 1};  // per equation: passes the previous solve needed (first-batch size estimate)
   int fused_rb = 1;            // 0: always use one launch per colour + residual pass
   int use_p2p = 1;             // 0: NCCL send/recv even when peer slabs are connected
-  int mip_variant = 1;         // calc_mip on statics: 1 = from the cells that number the faces, 0 = one thread per face
   int occ_grids = 1;           // assembly kernels: grid = resident CTAs (occupancy API) instead of 8 per SM
   int pdl_rows = 1;            // rows per thread prefetched to L2 ahead of the dependency wait
   int use_pdl = 1;             // fused passes: programmatic dependent launch (a pass loads its first matrix rows while the previous one drains)
-  int uvw_variant = 2;         // calc_coef_uvw: 0 = one thread per cell, 1 = one thread per (cell, face slot),
-                               // 2 = one thread per cell on precomputed face statics, 3 = as 2 with the ten quotients
-                               // per face formed from two reciprocals + FMA corrections (same bits; not yet timed)
   // per cell-cell face, owner orientation, computed once with the very expressions the reference
   // evaluates every iteration (area, unit normal, |dr|, projected |dr_p|, dr.n, both distance
   // weights, dr, dr_p): the assembly kernels then need 10 instead of 19 FP64 div/sqrt per face
   double *fs_area = nullptr, *fs_ds = nullptr, *fs_dsp = nullptr, *fs_dn = nullptr, *fs_wto = nullptr, *fs_wtn = nullptr;
   double *fs_rds = nullptr, *fs_rdsp = nullptr, *fs_rdn = nullptr;  // RN(1/ds), RN(1/dsp), RN(1/dn)
-  int mip_fast = -1;           // calc_mip from the cells: quotients by division (0), by reciprocals (1), measured (-1)
-  int correct_fast = 0;        // face correction: quotient by dr.n through the stored reciprocal
   // least-squares gradient statics (filled on first use by grad_variant 1): inverse LSQ matrix per cell
   // (9 x Np, entry-major) and the weight 1/|dr|^2 per slot (K x Np)
   double *lsq_binv = nullptr, *lsq_w = nullptr;
-  int coef_p_variant = -1;     // calc_coef_p on statics: -1 = chosen by measurement, 0 = linear cell order, 1 = paired colour order
-  int grad_variant = -1;       // calc_grad: -1 = chosen by measurement (0 when autotune is off), 0 = reference form, 1 = on the LSQ statics, 2 / 3 = 0 / 1 in the locality order
+  int grad_variant = 1;        // calc_grad: 1 = on the LSQ statics (inverse matrix and weights precomputed), 0 = the reference's form
   double *fs_n[3] = {nullptr, nullptr, nullptr}, *fs_dr[3] = {nullptr, nullptr, nullptr}, *fs_drp[3] = {nullptr, nullptr, nullptr};
   int use_statics = 1;         // 0: recompute face geometry in every kernel (the reference's way)
-  // Variant selection by measurement: the first call of a routine times its bit-identical kernel
-  // variants on the handle's own data (CUDA events, a few launches each) and keeps the fastest.
-  // Setting a *_variant option by hand pins that routine.  autotune = 0 keeps the defaults.
-  int autotune = 1;
-  struct Tuned { int done = 0, choice = -1, ncand = 0, cand[16] = {0}; float ms[16] = {0}; };
-  Tuned tune_uvw, tune_grad3, tune_grad1, tune_coef_p, tune_mip, tune_uvw_solve, tune_rbp;
   int tune_ctas = 8;           // CTAs per SM for the solver passes (grid = min(need, num_sms * tune_ctas))
   // cfdl_step_host: transfer streams that run beside the compute stream, and a staging area of
   // its own (reference-numbered copies of the late input and the early outputs)
@@ -174,8 +158,8 @@ struct Handle {
   std::vector<cudaEvent_t> prof_ev;  // pairs (begin, end)
   std::vector<int> prof_kind, prof_cnt;  // per pair: kernel kind, launches it covers
   size_t prof_used = 0;
-  double prof_ms[10] = {0};
-  int64_t prof_n[10] = {0};
+  double prof_ms[12] = {0};
+  int64_t prof_n[12] = {0};
   cudaEvent_t timer_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -183,18 +167,13 @@ struct Handle {
 inline cudaStream_t S(Handle* h) { h->launches++; return h->stream; }
 
 // profiled kernel kinds (per-launch CUDA-event timing when h->profile is on)
-enum { PROF_SGS_SWEEP = 0, PROF_RESIDUAL = 1, PROF_COEF_UVW = 2, PROF_COEF_P = 3, PROF_MIP = 4, PROF_GRAD = 5, PROF_LEVELS = 6, PROF_PCG = 7, PROF_SGS3 = 8, PROF_KINDS = 9 };
+// PROF_RESIDUAL: residual_kernel (one right-hand side); PROF_RESIDUAL3: residual3_kernel (u, v, w) incl. its cross-rank reduction;
+// PROF_GRAD: the fused u,v,w gradient pass; PROF_GRAD1: the single-field gradient (gpc)
+enum { PROF_SGS_SWEEP = 0, PROF_RESIDUAL = 1, PROF_COEF_UVW = 2, PROF_COEF_P = 3, PROF_MIP = 4, PROF_GRAD = 5, PROF_LEVELS = 6, PROF_PCG = 7, PROF_SGS3 = 8,
+       PROF_RESIDUAL3 = 9, PROF_GRAD1 = 10, PROF_KINDS = 11 };
 int prof_begin(Handle* h, int kind, int level = 1);
 int prof_end(Handle* h, int count = 1, int level = 1);
 int prof_collect(Handle* h);  // after a stream sync: fold finished event pairs into prof_ms / prof_n
-// times run(cand) for every candidate (one warm-up launch, then `reps` timed ones between two events on
-// the handle's stream) and records the fastest in T; a candidate whose launch fails is skipped
-// `outputs` (pointer, length) lists what a candidate writes: every candidate's outputs must carry the values of the
-// first candidate's (a checksum over the bit patterns, zeros of either sign alike), or it is discarded (ms = -2)
-struct TuneOutput { const double* p; size_t n; };
-int autotune_pick(Handle* h, Handle::Tuned& T, const int* cands, int n, const std::function<int(int)>& run, int reps = 3,
-                  const std::vector<TuneOutput>& outputs = std::vector<TuneOutput>());
-
 // launch geometry helper: grids are sized as a multiple of the SM count (B200: 148)
 inline int grid_for(const Handle* h, int64_t n, int threads, int ctas_per_sm = 8) {
   int64_t need = (n + threads - 1) / threads;

@@ -38,6 +38,8 @@ using std::max;
 using std::min;
 
 struct uint3 { unsigned x, y, z; };
+struct alignas(16) double2 { double x, y; };
+struct alignas(8) int2 { int x, y; };
 struct dim3 {
   unsigned x, y, z;
   constexpr dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
@@ -130,6 +132,15 @@ inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* c, void (*kern)(
 
 // ---- device intrinsics --------------------------------------------------------------------------
 inline void __syncthreads() { cuemu::sync_threads(); }
+inline int __syncthreads_or(int pred) {
+  __shared__ int acc;
+  cuemu::sync_threads();
+  if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) acc = 0;
+  cuemu::sync_threads();
+  if (pred) acc = 1;
+  cuemu::sync_threads();
+  return acc;
+}
 inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }

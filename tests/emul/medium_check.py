@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """Medium-size runs on the cuemu build (grids of tens of CTAs, several rows per thread — the unit
 tests' meshes fit in one or two CTAs): (1) exact mode against the oracle on an n^3 hex cavity,
-(2) the throughput mode with every post-round-1 path switched on and the kernel variants drawn at
-random (CUEMU_RANDOM_TIMES) against the same mode with all of them off: identical bits.
+(2) the throughput mode as shipped (face statics, side-by-side momentum passes, persistent pc solve, 16-bit
+offsets, dependent launches) against the same mode with all of that off (the reference's forms): identical bits.
 TEST INFRASTRUCTURE ONLY.   usage: medium_check.py <n>"""
 import os
 import sys
@@ -38,23 +38,24 @@ def main():
         worst = max(worst, np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
     assert worst <= 1e-10, worst
     s.close()
-    # (2) throughput mode: new paths on (variants by "timing") vs off
+    # (2) throughput mode: shipped paths vs all of them off
     res = {}
     for new in (0, 1):
         s = cfdl.Solver(geom, bcs, device=0)
         s.set_option("solver", cfdl.SOLVER_MCSGS)
         if not new:
-            for k, v in (("autotune", 0), ("uvw_fused", 0), ("pc_sumap", 0), ("grad_variant", 0), ("coef_p_variant", 0), ("uvw_variant", 2), ("rb_persistent", 0), ("rb_keep_mb", 0), ("rb_idx16", 0)):
+            for k, v in (("uvw_fused", 0), ("pc_sumap", 0), ("grad_variant", 0), ("statics", 0), ("rbq", 0), ("rb_idx16", 0), ("pdl", 0)):
                 s.set_option(k, v)
         h = s.run(dt=0.5, nit=100, ntstep=2, ncoef=3)
         res[new] = (h, {f: s.download(f) for f in ("u", "v", "w", "p", "gu", "gp", "mip")},
-                    [int(s.get_info("tuned_" + r)) for r in ("uvw", "grad3", "grad1", "coef_p", "uvw_solve", "rb_persistent")])
+                    [int(s.get_info("rbq_active"))])
         s.close()
     assert np.array_equal(res[0][0][:, :, 0], res[1][0][:, :, 0])
     assert np.allclose(res[0][0], res[1][0], rtol=1e-12, atol=0.0)
     for f, v in res[0][1].items():
         assert np.array_equal(v, res[1][1][f]), f
-    print("medium emulation ok: n=%d exact-mode err %.1e; variants chosen (uvw, grad3, grad1, coef_p, uvw_solve, rb_persistent) = %s; momentum its %s"
+    assert res[1][2] == [1] and res[0][2] == [0]
+    print("medium emulation ok: n=%d exact-mode err %.1e; persistent pc solve active = %s; momentum its %s"
           % (n, worst, res[1][2], res[1][0][-1, :3, 0].astype(int).tolist()))
 
 

@@ -41,8 +41,7 @@ def test_bench_script_runs_under_emulation():
 
 def test_medium_mesh_runs_under_emulation():
     """Grids of tens of CTAs with several rows per thread (tests/emul/medium_check.py): exact mode equals the
-    oracle; the throughput mode with randomly drawn kernel variants and every post-round-1 path on equals
-    the same mode with all of them off, bit for bit."""
+    oracle; the throughput mode as shipped equals the same mode with every optimised path switched off, bit for bit."""
     import os as _os
     for seed in ("3",):
         env = dict(_os.environ, CUEMU_RANDOM_TIMES=seed)

@@ -57,19 +57,18 @@ def test_host_assembly_chain(case):
     assert np.array_equal(mip2, oc["mip"])
 
 
-def test_coef_uvw_reciprocal_variants_keep_the_bits(case):
-    """uvw_variant 3 (quotients from two reciprocals + FMA corrections), 4 (the same with three resident
-    CTAs per SM), 5 (reciprocals read from the face statics) 6/7/8 (5/3/2 in the paired colour order) and 9/10/11/12 (lean register use), 13/14 (locality order)
-    against the oracle: same bits as the dividing kernel."""
+def test_coef_uvw_on_statics_keeps_the_bits(case):
+    """calc_coef_uvw on the face statics (ten quotients per face from two stored reciprocals + FMA corrections,
+    locality order) and in the reference's form (statics = 0) against the oracle: same bits."""
     oc, s = case
     for name in STATE:
         s.upload(name, oc[name])
     oc.calc_coef_uvw()
     try:
-        for variant in (3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14):
-            s.set_option("uvw_variant", variant)
+        for statics in (1, 0):
+            s.set_option("statics", statics)
             s.calc_coef_uvw(dt=0.01)
             for f in ("ap", "anb", "bu", "bv", "bw", "d", "dc"):
-                assert np.array_equal(s.download(f), oc[f]), (variant, f)
+                assert np.array_equal(s.download(f), oc[f]), (statics, f)
     finally:
-        s.set_option("uvw_variant", 2)
+        s.set_option("statics", 1)

@@ -73,15 +73,17 @@ def test_calc_coef_uvw(case):
     oc.update_boundaries(); s.update_boundaries()
     oc.calc_coef_uvw()
     try:
-        for variant in (2, 1, 0):  # 2: precomputed face statics; 1: thread per (cell, slot); 0: thread per cell — same bits
-            s.set_option("uvw_variant", variant)
+        for statics in (1, 0):  # 1: precomputed face statics + reciprocal quotients, locality order; 0: the reference's form — same bits
+            s.set_option("statics", statics)
+            for f in ("ap", "anb", "bu", "bv", "bw", "d", "dc"):
+                s.upload(f, np.full(s.field_size(f), 7.5))  # stale values must be overwritten
             s.calc_coef_uvw(dt=0.01)
             for f in ("ap", "anb", "bu", "bv", "bw", "d", "dc"):
                 got = s.download(f)
                 check(f, got, oc[f])
-                assert np.array_equal(got, oc[f]), "%s (variant %d) is not bit-identical: %.3e" % (f, variant, rel_err(got, oc[f]))
+                assert np.array_equal(got, oc[f]), "%s (statics %d) is not bit-identical: %.3e" % (f, statics, rel_err(got, oc[f]))
     finally:
-        s.set_option("uvw_variant", 2)
+        s.set_option("statics", 1)
 
 
 def test_calc_grad(case):
@@ -114,20 +116,17 @@ def test_calc_mip(case, rhie_chow):
     mip_in = oc["mip"].copy()
     oc.calc_mip(rhie_chow)
     try:
-        # precomputed face geometry (visited from the cells that number the faces, or one thread per
-        # face) vs geometry recomputed in the kernel: same bits
-        for statics, variant in ((1, 1), (1, 0), (0, 0)):
+        # precomputed face geometry (faces visited from the cells that number them, reciprocal quotients)
+        # vs geometry recomputed in a per-face kernel as the reference does: same bits
+        for statics in (1, 0):
             s.set_option("statics", statics)
-            s.set_option("mip_variant", variant)
             s.upload("mip", mip_in)  # every variant starts from the same faces (boundary ones are not written)
             s.calc_mip(rhie_chow, dt=0.01)
             got = s.download("mip")
             check("mip", got, oc["mip"])
-            assert np.array_equal(got, oc["mip"]), "mip (statics=%d, variant=%d) not bit-identical: %.3e" % (
-                statics, variant, rel_err(got, oc["mip"]))
+            assert np.array_equal(got, oc["mip"]), "mip (statics=%d) not bit-identical: %.3e" % (statics, rel_err(got, oc["mip"]))
     finally:
         s.set_option("statics", 1)
-        s.set_option("mip_variant", 1)
 
 
 def test_calc_coef_p(case):
@@ -329,7 +328,7 @@ def test_overlapped_passes_equal_serialised_passes(cfdl):
     raw = cfdl.meshgen(cfdl.MESH_HEX, 28 if conftest.EMULATED else 64)  # (launch overlap does not exist under emulation)
     geom = cfdl.mesh_build(raw)
     out = []
-    for opts in ({"pdl": 1}, {"pdl": 0}, {"fused": 0}):
+    for opts in ({"pdl": 1}, {"pdl": 0, "rbq": 0}, {"pdl": 1, "rbq": 0}, {"fused": 0}):
         s = cfdl.Solver(geom, cfdl.default_bcs(raw))
         s.set_option("solver", cfdl.SOLVER_MCSGS)
         for k, v in opts.items():
@@ -397,7 +396,7 @@ def test_calc_grad_variants_keep_the_bits(case):
     randomize(oc, s, seed=29)
     got = {}
     try:
-        for variant in (0, 1, 2, 3):  # 2, 3 = 0, 1 in the locality order
+        for variant in (0, 1):
             s.set_option("grad_variant", variant)
             s.calc_grad("p", "gp")
             got[variant, "gp"] = s.download("gp")[:3 * oc.ne]
@@ -406,42 +405,44 @@ def test_calc_grad_variants_keep_the_bits(case):
         want = oc.calc_grad(oc["p"])[:3 * oc.ne]
         check("gp", got[0, "gp"], want)
         for f in ("gp", "gpc"):
-            for variant in (1, 2, 3):
+            for variant in (1,):
                 assert np.array_equal(got[0, f], got[variant, f]), (f, variant)
         # the fused three-field pass runs inside solve_uvwp: two iterations from the same state
         hist = {}
-        for variant in (0, 1, 2, 3):
+        for variant in (0, 1):
             s.set_option("grad_variant", variant)
             randomize(oc, s, seed=31)
             s.update_boundaries()
             hist[variant] = s.solve_uvwp(0.01, 5)
             for f in ("gu", "gv", "gw", "gp", "mip", "p"):
                 got[variant, f] = s.download(f)
-        for variant in (1, 2, 3):
+        for variant in (1,):
             assert same_history(hist[0], hist[variant])
             for f in ("gu", "gv", "gw", "gp", "mip", "p"):
                 assert np.array_equal(got[0, f], got[variant, f]), (f, variant)
     finally:
-        s.set_option("grad_variant", -1)
+        s.set_option("grad_variant", 1)
 
 
-def test_calc_coef_p_variants_keep_the_bits(case):
-    """coef_p_variant 1 (paired colour order), 2 and 3 (reciprocal quotients) against the oracle: same bits."""
+def test_calc_coef_p_overwrites_stale_values(case):
+    """calc_coef_p on the face statics (paired colour order on two-colour meshes, locality order otherwise,
+    quotient by dr.n through the stored reciprocal) and in the reference's form: every entry of ap, anb, b is
+    rewritten and equals the oracle's bits."""
     _, raw, oc, geom, s = case
     randomize(oc, s, seed=37)
     oc.update_boundaries(); s.update_boundaries()
     oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)  # provides dc
     oc.calc_coef_p()
     try:
-        for variant in (0, 1, 2, 3, 4, 5):  # 2, 3: the quotient by dr.n through the stored reciprocal (linear, paired); 4, 5: locality order
-            s.set_option("coef_p_variant", variant)
+        for statics in (1, 0):
+            s.set_option("statics", statics)
             for f in ("ap", "anb", "b"):
                 s.upload(f, np.full(s.field_size(f), 7.5))  # stale values must be overwritten
             s.calc_coef_p()
             for f in ("ap", "anb", "b"):
-                assert np.array_equal(s.download(f), oc[f]), (variant, f)
+                assert np.array_equal(s.download(f), oc[f]), (statics, f)
     finally:
-        s.set_option("coef_p_variant", -1)
+        s.set_option("statics", 1)
 
 
 def _numpy_pcg(ne, idx, nb_packed, ap, anb, b, phi0, nit):
@@ -539,7 +540,7 @@ def test_momentum_solves_side_by_side_keep_the_bits(case, cfdl):
             for f, v in res[0][2].items():
                 assert np.array_equal(v, res[1][2][f]), (seed, nit, f)
     finally:
-        s.set_option("uvw_fused", -1)
+        s.set_option("uvw_fused", 1)
         s.set_option("solver", cfdl.SOLVER_PARITY)
 
 
@@ -580,38 +581,40 @@ def test_pc_passes_rebuilding_the_diagonal_keep_the_bits(case, cfdl):
         s.set_option("solver", cfdl.SOLVER_PARITY)
 
 
-def test_persistent_passes_keep_the_bits(case, cfdl):
-    """The forms of the fused two-colour pc solve — one launch per pass / all passes of a batch in one
-    cooperative launch with grid barriers (kernels_rbp.inc), with / without the L2 residency hint on the
-    coefficient loads, 32-bit neighbour ids / 16-bit offsets — use the same row-to-thread mapping and
-    reductions: identical fields AND identical residual history."""
+def test_persistent_pc_solve_keeps_the_bits(case, cfdl):
+    """The pc solve as ONE persistent launch with neighbour-only synchronisation (kernels_rbq.inc: red values as
+    {newest, mid} pairs, two rows per thread, 128-bit loads, a fixed block of iterations per launch with the
+    stopping rule applied to the recorded residuals, a block redone when the rule fired inside it) against the
+    pass-by-pass kernels, with 16-bit neighbour offsets and with 32-bit ids: same fields, same iteration
+    counts; the RMS norms are summed per chunk instead of per grid-stride CTA and agree to rounding.  The
+    iteration caps 1, 2, 7 exercise the estimate-too-short / rule-fires-inside-the-block paths, 40 and 100 the
+    long solves; several CTAs per SM are forced so that even the small meshes are cut into many chunks."""
     name, raw, oc, geom, s = case
     if int(s.get_info("ncolors")) != 2:
         pytest.skip("fused two-colour passes only")
     s.set_option("solver", cfdl.SOLVER_MCSGS)
     try:
         res = {}
-        combos = [(p, k, i) for p in (0, 1) for k in (0.0, 35.0) for i in (0, 1)]
+        combos = [(0, 1), (1, 1), (1, 0), (0, 0)]
         for combo in combos:
-            s.set_option("rb_persistent", combo[0])
-            s.set_option("rb_keep_mb", combo[1])
-            s.set_option("rb_idx16", combo[2])
-            for sep in ((0, 1) if combo in (combos[0], combos[-1]) else (0,)):  # momentum one by one runs the single-equation passes too
-                s.set_option("uvw_fused", 1 - sep)
-                randomize(oc, s, seed=61)
-                hs = []
-                for nit in (1, 2, 40):
-                    s.update_boundaries()
-                    hs.append(s.solve_uvwp(0.01, nit))
-                res[combo, sep] = (np.array(hs), {f: s.download(f) for f in ("u", "v", "w", "p", "pc", "mip")})
-        for (combo, sep), (hist, fields) in res.items():
-            ref_hist, ref_fields = res[combos[0], sep]
-            assert np.array_equal(hist, ref_hist), (combo, sep, hist, ref_hist)
+            s.set_option("rbq", combo[0])
+            s.set_option("rb_idx16", combo[1])
+            randomize(oc, s, seed=61)
+            hs = []
+            for nit in (1, 2, 7, 40, 100, 3):
+                s.update_boundaries()
+                hs.append(s.solve_uvwp(0.01, nit))
+            res[combo] = (np.array(hs), {f: s.download(f) for f in ("u", "v", "w", "p", "pc", "mip")})
+            if combo[0]:
+                assert int(s.get_info("rbq_active")) == 1 and int(s.get_info("rbq_refused")) == 0
+        ref_hist, ref_fields = res[combos[0]]
+        for combo, (hist, fields) in res.items():
+            assert same_history(hist, ref_hist), (combo, hist, ref_hist)
             for f, v in fields.items():
-                assert np.array_equal(v, ref_fields[f]), (combo, sep, f)
+                assert np.array_equal(v, ref_fields[f]), (combo, f)
     finally:
-        for k in ("rb_persistent", "rb_keep_mb", "rb_idx16", "uvw_fused"):
-            s.set_option(k, -1)
+        s.set_option("rbq", 1)
+        s.set_option("rb_idx16", 1)
         s.set_option("solver", cfdl.SOLVER_PARITY)
 
 
@@ -640,68 +643,3 @@ def test_restart_from_checkpoint_reproduces_the_run(case, cfdl, tmp_path, solver
             b.checkpoint_read(path)
     finally:
         a.close(); b.close()
-
-
-def test_reciprocal_quotients_in_mip_and_face_correction_keep_the_bits(case):
-    """mip_fast=1 / correct_fast=1: the quotients by dr.n and dt formed from reciprocals + FMA correction
-    (quot<true>, device_math.cuh) in calc_mip and in the face correction of update_uvwp — same bits as
-    the divisions, checked against the oracle."""
-    _, raw, oc, geom, s = case
-    randomize(oc, s, seed=67)
-    oc.update_boundaries(); s.update_boundaries()
-    oc.calc_coef_uvw(); s.calc_coef_uvw(dt=0.01)  # d, dc
-    mip_in = oc["mip"].copy()
-    oc.calc_mip(True)
-    try:
-        for fast in (0, 1):
-            s.set_option("mip_fast", fast)
-            s.upload("mip", mip_in)
-            s.calc_mip(True, dt=0.01)
-            assert np.array_equal(s.download("mip"), oc["mip"]), fast
-        oc.adjust_pc(); oc["gpc"][:] = oc.calc_grad(oc["phic"])
-        mip_before, p_before, gp_before = oc["mip"].copy(), oc["p"].copy(), oc["gp"].copy()
-        oc.update_uvwp()
-        for fast in (0, 1):
-            s.set_option("correct_fast", fast)
-            s.upload("mip", mip_before); s.upload("p", p_before); s.upload("gp", gp_before); s.upload("pc", oc["phic"]); s.upload("gpc", oc["gpc"])
-            s.update_uvwp()
-            assert np.array_equal(s.download("mip"), oc["mip"]), fast
-    finally:
-        s.set_option("mip_fast", -1)
-        s.set_option("correct_fast", 0)
-
-
-@pytest.mark.parametrize("teams,block", [(2, 3), (4, 16), (8, 5)])
-def test_temporally_blocked_pc_solve_keeps_the_bits(case, cfdl, teams, block):
-    """rb_wave = T (kernels_rbw.inc: T pass teams in one cooperative launch, a pass starts a chunk as soon as
-    the previous pass is far enough ahead; blocks of rb_wave_block iterations, redone from a snapshot when
-    the stopping rule fired inside a block) against the pass-by-pass solve: same fields, same iteration
-    counts, residual norms up to summation order."""
-    name, raw, oc, geom, s = case
-    if int(s.get_info("ncolors")) != 2:
-        pytest.skip("fused two-colour passes only")
-    s.set_option("solver", cfdl.SOLVER_MCSGS)
-    try:
-        res = {}
-        for wave in (0, teams):
-            s.set_option("rb_wave", wave)
-            s.set_option("rb_wave_block", block)
-            s.set_option("rb_idx16", 1 if (wave == 8) else -1)  # the eight-team case also reads 16-bit neighbour offsets
-            s.set_option("rb_wave_rows", 3 if wave == 4 else 1)    # the four-team case takes three rows per thread and chunk
-            randomize(oc, s, seed=71)
-            hs = []
-            for nit in (1, 2, 7, 40, 100):
-                s.update_boundaries()
-                hs.append(s.solve_uvwp(0.01, nit))
-            res[wave] = (np.array(hs), {f: s.download(f) for f in ("u", "v", "w", "p", "pc", "mip")})
-        a, b = res[0][0], res[teams][0]
-        assert np.array_equal(a[:, :, 0], b[:, :, 0]), (a[:, :, 0], b[:, :, 0])
-        assert np.allclose(a[:, :, 1:], b[:, :, 1:], rtol=1e-12, atol=0.0)
-        for f, v in res[0][1].items():
-            assert np.array_equal(v, res[teams][1][f]), f
-    finally:
-        s.set_option("rb_wave", 0)
-        s.set_option("rb_wave_block", 34)
-        s.set_option("rb_wave_rows", 1)
-        s.set_option("rb_idx16", -1)
-        s.set_option("solver", cfdl.SOLVER_PARITY)
