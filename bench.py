@@ -28,10 +28,12 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "cfd-lite_b200", "python"))
-# NCCL's "NCCL version ..." banner goes to stdout by default; stdout carries exactly one JSON line
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-if not os.environ.get("CFDL_KEEP_NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = "NONE"  # any level >= VERSION prints the banner with printf
+# stdout carries exactly one JSON line, but native libraries print there too (NCCL's version banner and, with
+# NCCL_DEBUG=INFO, its whole log).  NCCL_DEBUG is left as the caller set it; instead file descriptor 1 is pointed at
+# stderr for the life of the process and the JSON line goes to a private duplicate of the original stdout.
+sys.stdout.flush()
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 SOLVERS = {"parity": 0, "mcsgs": 1, "pcg": 2}
 DT, NIT, NCOEF = 0.01, 100, 3  # reference defaults, src/modules/mod_physics.f90:15-18
@@ -92,16 +94,15 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def ncu_traffic(fused, args, world):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
-    (profiles/r01_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum, `ncu --set full`);
-    only quoted for the configuration that capture was taken on, else null."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if not (fused and world == 1 and args.mesh == "hex" and args.n == 128 and os.path.exists(p)):
+def ncu_traffic(kernel_key, args, world):
+    """DRAM bytes per pass of the dominant kernel from the committed ncu capture (profiles/r02_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch, divided by the passes the launch
+    executes); only quoted for the kernel and the configuration that capture was taken on, else null."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not (world == 1 and args.mesh == "hex" and args.n == 128 and os.path.exists(p)):
         return None
     try:
-        t = json.load(open(p))["dram_bytes_per_launch"]
-        return 0.5 * (t["rb_red_kernel<6>"] + t["rb_black_kernel<6>"])
+        return float(json.load(open(p))["dram_bytes_per_pass"][kernel_key])
     except Exception:
         return None
 
@@ -158,7 +159,7 @@ def run_reference(args, rank):
                                        "(g++ -O3 -ffp-contract=off, 1 thread: the reference is serial and has no OpenMP)" % (args.steps, args.warmup)},
             "e2e": {"value": value, "unit": "cell-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def dbg(*a):
@@ -313,7 +314,7 @@ def main():
     nprof = min(args.steps, 6)
     for i in range(nprof):
         step(args.warmup + args.steps + i)
-    kinds = ("sgs", "residual", "levels", "coef_uvw", "coef_p", "mip", "grad", "pcg", "sgs3")
+    kinds = ("sgs", "residual", "residual3", "levels", "coef_uvw", "coef_p", "mip", "grad", "grad1", "pcg", "sgs3")
     prof = {k: (s.get_info("prof_ms_" + k), int(s.get_info("prof_n_" + k))) for k in kinds}
     s.set_option("profile", 0)
     # fused passes are launched back to back and overlap head/tail (programmatic dependent launch);
@@ -353,13 +354,16 @@ def main():
             black = (n_owned - n_r) * (row + 8 + 8) + 16 * (n_r + halo_vals)
             per_launch = (red + black) / 2.0
             kname = "rb_red_kernel / rb_black_kernel (fused two-colour SGS pass incl. residual; average of the two)"
+            kkey = "rb_pass_i16" if i16 else "rb_pass_i32"
             if rbq:
+                kkey = "rbq_i16" if i16 else "rbq_i32"
                 kname = ("rbq_kernel (all red/black passes of a pc solve in one persistent launch, neighbour-only synchronisation; "
                          "launch time / passes; the 'isolated' figure is the pass-by-pass kernels rb_red_kernel / rb_black_kernel, one event pair per launch)")
         else:
             # one colour launch updates 1/ncolors of the cells: a full sweep = ncolors launches
             per_launch = ab["sgs_sweep"] / ncol
             kname = "sgs_range_kernel (one colour of a Gauss-Seidel sweep)"
+            kkey = "sgs_range"
         iso_ms = prof["sgs"][0] / prof["sgs"][1]
         iso = per_launch / (iso_ms * 1e-3) / 1e9
         if fused and batch:  # average duration of a pass inside its batch, as it runs in the timed steps
@@ -368,15 +372,37 @@ def main():
             avg_ms, timed, how = iso_ms, prof["sgs"][1], "one CUDA-event pair per launch"
         ach = per_launch / (avg_ms * 1e-3) / 1e9
         roof = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic(fused, args, world), "peak_source": peak_src,
+                "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic(kkey, args, world), "peak_source": peak_src,
                 "bytes_per_launch": per_launch, "avg_launch_ms": avg_ms, "launches_timed": timed, "timing": how,
                 "isolated": {"achieved": iso, "frac": iso / peak, "avg_launch_ms": iso_ms, "launches_timed": prof["sgs"][1],
                              "timing": "one CUDA-event pair per launch (launches serialised, no overlap)"}}
     if prof["residual"][1] > 0:
+        # residual_kernel only (one right-hand side: 20N + 12Z + 8H); the three-RHS residual3_kernel of the
+        # side-by-side momentum solves and its cross-rank reduction are timed under their own kind (residual3)
         avg_ms = prof["residual"][0] / prof["residual"][1]
         ach = ab["residual"] / (avg_ms * 1e-3) / 1e9
-        extra_roof["residual_spmv"] = {"achieved": ach, "frac": ach / peak, "unit": "GB/s", "bytes_per_launch": ab["residual"],
-                                       "avg_launch_ms": avg_ms, "launches_timed": prof["residual"][1]}
+        extra_roof["residual_spmv"] = {"kernel": "residual_kernel (SpMV + norm, one right-hand side)", "achieved": ach, "frac": ach / peak, "unit": "GB/s",
+                                       "bytes_per_launch": ab["residual"], "avg_launch_ms": avg_ms, "launches_timed": prof["residual"][1]}
+    if prof["residual3"][1] > 0 and world == 1:
+        # residual3_kernel: the matrix row once (16 + 12K B), per equation b + own value (16 B) and the gathered values (8 B per cell or halo)
+        per3r = n_owned * (16 + 12 * K + 3 * 16) + 3 * 8 * (n_owned + n_local_halos)
+        avg_ms = prof["residual3"][0] / prof["residual3"][1]
+        ach = per3r / (avg_ms * 1e-3) / 1e9
+        extra_roof["residual3_spmv"] = {"kernel": "residual3_kernel (SpMV + norm for u, v, w in one pass over the matrix)", "achieved": ach, "frac": ach / peak,
+                                        "unit": "GB/s", "bytes_per_launch": per3r, "avg_launch_ms": avg_ms, "launches_timed": prof["residual3"][1]}
+    # assembly kernels against SURVEY 8(d)'s algorithmic bytes (reference layout: every distinct input element once, every output once)
+    Fl, Hl, Zl = n_local_faces, n_owned + int(s.get_info("ghost_cells")) + n_local_halos, K * n_owned
+    asm_bytes = {"coef_uvw": ("calc_coef_uvw", 196 * n_owned + 16 * Zl + 56 * Fl + 48 * Hl),
+                 "coef_p": ("calc_coef_p", 36 * n_owned + 16 * Zl + 56 * Fl + 24 * Hl),
+                 "mip": ("calc_mip", 124 * n_owned + 72 * Fl),
+                 "grad": ("calc_grad x3 in one pass (geometry and connectivity once: 3(28N+4Z+32H) - 2(4Z+24H))", 3 * (28 * n_owned + 4 * Zl + 32 * Hl) - 2 * (4 * Zl + 24 * Hl)),
+                 "grad1": ("calc_grad", 28 * n_owned + 4 * Zl + 32 * Hl)}
+    for kk, (nm, nbytes) in asm_bytes.items():
+        if prof[kk][1] > 0:
+            avg_ms = prof[kk][0] / prof[kk][1]
+            ach = nbytes / (avg_ms * 1e-3) / 1e9
+            extra_roof[kk] = {"kernel": nm, "achieved": ach, "frac": ach / peak, "unit": "GB/s", "bytes_per_launch": nbytes,
+                              "avg_launch_ms": avg_ms, "launches_timed": prof[kk][1]}
     if prof["sgs3"][1] > 0:
         # u, v, w side by side (kernels_rb3.inc): a pass reads a row's ap, anb, ids once (16+12K B) and per equation
         # b + own value (16 B), writes 8 B (red passes 16 B) and gathers the other colour's values (8 B per cell, 16 in black passes)
@@ -395,7 +421,12 @@ def main():
         roof = {"kernel": "level_sgs_kernel (persistent level-scheduled exact SGS, latency-bound by design)", "bound": "hbm",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                 "bytes_per_launch": per_launch, "avg_launch_ms": avg_ms, "launches_timed": prof["levels"][1]}
+    # per-phase time of a step: kernels bracketed one by one (profile = 1), except the two-colour passes, which are taken from
+    # the batch timing (they overlap / run inside one persistent launch in production; one event pair per launch would serialise them)
     phase_ms = {k: prof[k][0] / nprof for k in kinds if prof[k][1] > 0}
+    if fused and batch:
+        phase_ms["sgs"] = batch[0] / nprof
+    phase_ms["sum_of_phases"] = sum(phase_ms.values())
 
     # ---- e2e: same steps through the C ABI with host buffers inside the timed region ----------
     e2e = None
@@ -497,10 +528,11 @@ def main():
                            "working set may fit L2",
                            "parallelism": "1 GPU" if world == 1 else
                            "%d GPUs, one RCB block of the global mesh per GPU; ghost-cell exchange: %s" % (world, exchange),
+                           "solver_iterations_last_step(u,v,w,pc)": [int(x) for x in hist_last[:, 0]] if hist_last is not None else None,
                            "last_step_history(it,res_i,res_f,res_max)": hist_last.tolist() if hist_last is not None else None},
                 "roofline": roof, "roofline_other": extra_roof, "phase_ms_per_step": phase_ms, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": launches, "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     s.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -96,6 +96,9 @@ struct UvwArgsS {
 // Round 2 timed fourteen forms of this routine on a B200 (profiles/r02_call1_bench_default_autotune.json:
 // divisions 0.89 ms, in-kernel reciprocals 0.53, stored reciprocals 0.49, paired colour order 0.47, lean
 // register variants 0.48-0.56, forced occupancy 0.53-0.59, locality order 0.46); the winner is what is left.
+// A slot-parallel form on the statics (one thread per (cell, face slot), terms handed over in shared memory, one
+// thread per cell summing in slot order; 56-80 registers, 37-56 % occupancy) was measured too: 0.91-1.16 ms — more
+// than half of its stall cycles sit at the hand-over barrier (profiles/r02_ncu_assembly.md) — and was dropped.
 template <int K>
 __device__ __forceinline__ void coef_uvw_statics_cell(const UvwArgsS& A, const int c) {
   const int Nc = A.Nc, Np = A.Np;

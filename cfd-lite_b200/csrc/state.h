@@ -111,7 +111,7 @@ struct Handle {
   // the pc solve as one persistent launch with neighbour-only synchronisation (kernels_rbq.inc; one GPU, two colours)
   int rbq = 1;                    // 0: always pass by pass
   int rbq_refused = 0;            // the cooperative launch was refused or a wait timed out: pass by pass from then on
-  int rbq_occ = 0;                // co-resident CTAs per SM of rbq_kernel (occupancy calculator, first use)
+  int rbq_occ = 0, rbq_occ_for = -1;  // co-resident CTAs per SM of the rbq_kernel instantiation in use (occupancy calculator)
   int rbq_ctas_per_sm = 0;        // > 0: use fewer CTAs per SM than that
   double* rbq_mem = nullptr;      // red pairs, black buffers, per-pass partials, progress words
   size_t rbq_len = 0;

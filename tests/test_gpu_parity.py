@@ -73,7 +73,8 @@ def test_calc_coef_uvw(case):
     oc.update_boundaries(); s.update_boundaries()
     oc.calc_coef_uvw()
     try:
-        for statics in (1, 0):  # 1: precomputed face statics + reciprocal quotients, locality order; 0: the reference's form — same bits
+        # statics 1: precomputed face statics + reciprocal quotients, locality order; statics 0: the reference's form — same bits
+        for statics in (1, 0):
             s.set_option("statics", statics)
             for f in ("ap", "anb", "bu", "bv", "bw", "d", "dc"):
                 s.upload(f, np.full(s.field_size(f), 7.5))  # stale values must be overwritten
