@@ -114,7 +114,10 @@ def build_mesh(cfdl, kind, n):
     return raw, geom
 
 
-def workload_name(kind, n, ne):
+def workload_name(kind, n, ne, nz=None):
+    if nz and nz != n:
+        return ("lid-driven cavity of depth %d, synthetic %dx%dx%d hex mesh = %d stacked %d^3 blocks of cell edge 1/%d (%d cells), lid on the top z face, "
+                "rho=5 mu=0.01 dt=0.01 nit=100" % (nz // n, n, n, nz, nz // n, n, n, ne))
     return "lid-driven cavity, synthetic %s mesh n=%d (%d cells), rho=5 mu=0.01 dt=0.01 nit=100" % (
         "%d^3 hex" % n if kind == "hex" else "Kuhn-tet (jitter 0.2h, shuffled ids)", n, ne)
 
@@ -181,6 +184,11 @@ def main():
     ap.add_argument("--global-size", type=int, default=None, help="cells per edge of the WHOLE cube (overrides the weak-scaling rule), e.g. 512 with --gpus 8")
     ap.add_argument("--structured", action="store_true",
                     help="hex cavity generated per rank without the reference's packed int32 arrays (automatic beyond their 2^26 limit)")
+    ap.add_argument("--partition", default=None, choices=["slabs", "rcb"],
+                    help="several GPUs, hex: slabs along z (default; the persistent pc solve synchronises chunk to chunk across ranks) or the "
+                         "reference's recursive bisection (x, y, z in turn; pc solve pass by pass)")
+    ap.add_argument("--weak-cubes", action="store_true", help="weak-scaling series of cubes n = size * N^(1/3) (round 1) instead of N stacked size^3 blocks")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--no-pdl", action="store_true", help="fused passes fully serialised (no programmatic dependent launch)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="cfdl_set_option(KEY, VALUE) after creation (tuning experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -216,37 +224,65 @@ def main():
 
     # weak scaling: the global cube grows with the GPU count so that every GPU keeps ~n^3 cells;
     # the mesh is split by the reference's own RCB (x-slabs, columns, octants on a cube)
+    # Several GPUs, hex (default): N blocks of size^3 cells stacked along z — a cavity of depth N with the lid on top, cut into
+    # one slab per GPU: every GPU keeps exactly the N=1 work (same cells, same cell size), so the series is a weak-scaling
+    # series by construction.  --global-size G: the G^3 cube on N GPUs (strong series of BASELINE.json configs 3 and 5).
+    # --weak-cubes: round 1's cubes of edge size * N^(1/3).
     exchange = "NCCL send/recv after every pass, residual norms by NCCL all-reduce"
-    n_global = args.global_size or (args.n if world == 1 else int(round(args.n * world ** (1.0 / 3.0))))
-    structured = args.mesh == "hex" and (args.structured or n_global ** 3 + 6 * n_global ** 2 >= 2 ** 26)
+    partition = args.partition or ("slabs" if args.mesh == "hex" else "rcb")
+    nz_global = None
+    if args.global_size:
+        n_global = args.global_size
+    elif world == 1 or args.mesh != "hex":
+        n_global = args.n if world == 1 else int(round(args.n * world ** (1.0 / 3.0)))
+    elif args.weak_cubes or partition != "slabs":
+        n_global = int(round(args.n * world ** (1.0 / 3.0)))
+    else:
+        n_global, nz_global = args.n, args.n * world
+    cells_global = n_global * n_global * (nz_global or n_global)
+    structured = args.mesh == "hex" and (args.structured or nz_global is not None or cells_global + 6 * n_global ** 2 >= 2 ** 26)
     if world > 1 and args.solver == "parity":
         raise SystemExit("bench.py: the exact natural-order solver is single-GPU; use --solver mcsgs with --gpus > 1")
     raw = geom = None
     t_setup = time.perf_counter()
-    if structured:  # same mesh, same numbering, generated analytically on every rank (cfdl_create_structured_hex)
-        s = cfdl.Solver.structured_hex(n_global, device=local_rank, rank=rank, nranks=world)
-    else:
-        raw, geom = build_mesh(cfdl, args.mesh, n_global)
-        if world == 1:
-            s = cfdl.Solver(geom, cfdl.default_bcs(raw), device=local_rank)
+
+    def make_solver(n, nz, use_structured, nranks, rk):
+        """One handle of the mesh n x n x (nz or n) (rank rk of nranks), connected to its peers."""
+        r = g = None
+        if use_structured:  # same mesh, same numbering, generated analytically on every rank (cfdl_create_structured_hex[_slabs])
+            sv = cfdl.Solver.structured_hex(n, device=local_rank, rank=rk, nranks=nranks, slabs=(partition == "slabs"), nz=nz)
         else:
-            c2r, _, _ = cfdl.partition_rcb(geom, world, want_order=False)
-            s = cfdl.Solver(geom, cfdl.default_bcs(raw), device=local_rank, cell2rank=c2r, rank=rank, nranks=world)
-    if world == 1:
-        s.set_option("solver", SOLVERS[args.solver])
-    else:
-        ids = [cfdl.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        s.comm_init(ids[0])
-        s.set_option("solver", SOLVERS[args.solver])
-        if not args.no_p2p:
+            r, g = build_mesh(cfdl, args.mesh, n)
+            if nranks == 1:
+                sv = cfdl.Solver(g, cfdl.default_bcs(r), device=local_rank)
+            else:
+                if partition == "slabs" and args.mesh == "hex":  # cell id = i + n (j + n k)
+                    kk = np.arange(n ** 3) // (n * n)
+                    c2r = np.zeros(n ** 3, np.int32)
+                    for q in range(nranks):
+                        c2r[(kk >= n * q // nranks) & (kk < n * (q + 1) // nranks)] = q + 1
+                else:
+                    c2r, _, _ = cfdl.partition_rcb(g, nranks, want_order=False)
+                sv = cfdl.Solver(g, cfdl.default_bcs(r), device=local_rank, cell2rank=c2r, rank=rk, nranks=nranks)
+        how = None
+        if nranks > 1:
+            ids = [cfdl.comm_unique_id() if rk == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            sv.comm_init(ids[0])
+        sv.set_option("solver", SOLVERS[args.solver])
+        if nranks > 1 and not args.no_p2p:
             try:  # peer-to-peer ghost exchange over NVLink (CUDA IPC); NCCL send/recv stays the fallback
-                handles = [None] * world
-                dist.all_gather_object(handles, s.ipc_handle())
-                s.ipc_connect(handles)
-                exchange = "peer-to-peer stores into the neighbours' ghost cells + flag words (CUDA IPC over NVLink), residual norms through peer slots"
+                handles = [None] * nranks
+                dist.all_gather_object(handles, sv.ipc_handle())
+                sv.ipc_connect(handles)
+                how = "peer-to-peer stores into the neighbours' ghost cells + flag words (CUDA IPC over NVLink), residual norms through peer slots"
             except cfdl.CfdlError as ex:
                 dbg("p2p unavailable:", ex)
+        return sv, r, g, how
+
+    s, raw, geom, how = make_solver(n_global, nz_global, structured, world, rank)
+    if how:
+        exchange = how
     if args.unfused:
         s.set_option("fused", 0)
     if args.no_pdl:
@@ -332,6 +368,8 @@ def main():
     except cfdl.CfdlError as ex:
         dbg("batch profiling unavailable:", ex)
     s.set_option("profile", 0)
+    rbq_dist = int(s.get_info("rbq_dist")) if world > 1 else 0
+    passes_per_step = (batch[1] / nprof) if batch else None  # two-colour passes that did work, per SIMPLE iteration (pc + momentum one-by-one)
     K = int(s.get_info("ell_width"))  # faces per cell (hex 6, tet 4: no ELL padding)
     ab = algorithmic_bytes(n_owned, K * n_owned, n_owned + int(s.get_info("ghost_cells")) + n_local_halos)  # this rank's partition
     ncol = int(s.get_info("ncolors"))
@@ -347,8 +385,8 @@ def main():
             # pc passes (nearly all of them: the momentum passes have their own entry when they run side by side) rebuild
             # ap from the row's anb instead of reading it (pc_sumap): 8 + 12K bytes of matrix per row instead of 16 + 12K
             # chosen form of the pc passes (candidate c: persistent = c & 1, L2 hint = (c >> 1) % 3 > 0, 16-bit neighbour offsets = c >= 6)
-            rbq = int(s.get_info("rbq_active")) == 1
-            i16 = int(s.get_info("rb_idx16")) == 1
+            rbq = int(s.get_info("rbq_active")) == 1 if world == 1 else rbq_dist == 1
+            i16 = int(s.get_info("rb_idx16")) == 1 and not (world > 1 and rbq_dist == 1)  # the partitioned persistent form reads 32-bit positions
             row = (8 if int(s.get_info("pc_sumap")) else 16) + (10 if i16 else 12) * K
             red = n_r * (row + 8 + 16) + 8 * (n_owned - n_r + halo_vals)
             black = (n_owned - n_r) * (row + 8 + 8) + 16 * (n_r + halo_vals)
@@ -503,6 +541,54 @@ def main():
         for b in bufs.values():
             b.free()
 
+    # ---- parity_check (several GPUs): the partitioned run against a single-GPU run of the same mesh ------------------------------
+    # fresh handles, ncoef = 3 SIMPLE iterations + update_time from the initial state; every rank reports the cells it owns, rank 0
+    # runs the whole mesh on its own GPU and compares u, v, w, p and the solver iteration counts.  The bench mesh itself up to
+    # 5 M cells, beyond that the same shape with 64^2 cells per plane (same code paths: partition, exchange mode, persistent solve).
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        import torch
+        try:
+            pn, pnz = n_global, nz_global
+            if cells_global > 5000000:
+                pn, pnz = 64, (64 * world if nz_global else None)
+            sp, _, _, _ = make_solver(pn, pnz, structured or pnz is not None, world, rank)
+            for kv in args.opt:
+                k, v = kv.split("=")
+                sp.set_option(k, float(v))
+            hist_p = sp.run(dt=DT, nit=NIT, ntstep=1, ncoef=NCOEF)
+            mine = {}
+            for f in ("u", "v", "w", "p"):
+                a = np.full(sp.field_size(f), np.nan)
+                sp.download_into(f, a)  # writes only the entries this rank owns
+                own = ~np.isnan(a)
+                t = torch.from_numpy(np.where(own, a, 0.0)).cuda()
+                c = torch.from_numpy(own.astype(np.float64)).cuda()
+                dist.all_reduce(t); dist.all_reduce(c)  # every entry is owned by exactly one rank: x + 0 + ... + 0 = x
+                mine[f] = (t.cpu().numpy(), c.cpu().numpy())
+            rbq_dist_par = int(sp.get_info("rbq_dist"))
+            sp.close()
+            if rank == 0:
+                one, _, _, _ = make_solver(pn, pnz, structured or pnz is not None, 1, 0)
+                for kv in args.opt:
+                    k, v = kv.split("=")
+                    one.set_option(k, float(v))
+                hist_1 = one.run(dt=DT, nit=NIT, ntstep=1, ncoef=NCOEF)
+                worst, owned_once = 0.0, True
+                for f in ("u", "v", "w", "p"):
+                    w = one.download(f)
+                    owned_once = owned_once and bool(np.all(mine[f][1] == 1.0))
+                    worst = max(worst, float(np.abs(mine[f][0] - w).max() / max(np.abs(w).max(), 1e-300)))
+                one.close()
+                same_it = bool(np.array_equal(hist_p[:, :, 0], hist_1[:, :, 0]))
+                parity = {"result": "ok" if (worst <= 1e-12 and same_it and owned_once) else "fail", "max_rel_err(u,v,w,p)": worst,
+                          "iteration_counts_equal": same_it, "every_cell_reported_once": owned_once, "tolerance": 1e-12,
+                          "mesh": "%dx%dx%d" % (pn, pn, pnz or pn), "steps": NCOEF, "persistent_partitioned_pc_solve": rbq_dist_par == 1,
+                          "what": "%d-GPU run vs a single-GPU run of the same mesh on rank 0 (fresh handles, %d SIMPLE iterations from rest)" % (world, NCOEF)}
+        except Exception as ex:  # the check must not take the measurement down with it
+            parity = {"result": "error", "error": repr(ex)[:300]}
+        barrier()
+
     # ---- cpu_baseline: the oracle on a bounded sample of the same workload (rank 0, N=1) -------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and n_global ** 3 + 6 * n_global ** 2 < 2 ** 26:
@@ -523,14 +609,18 @@ def main():
         line = {"metric": "cell-iterations/s (SIMPLE)", "value": value, "unit": "cell-iterations/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args.mesh, n_global, ne), "solver": args.solver, "ncolors": ncol, "options": args.opt, "mesh_source": "structured per-rank generator" if structured else "reference-format arrays", "fused_two_colour_passes": bool(fused), "timed_loop": loop, "programmatic_dependent_launch": bool(fused and not args.no_pdl),
+                "config": {"workload": workload_name(args.mesh, n_global, ne, nz_global), "solver": args.solver, "ncolors": ncol, "options": args.opt, "mesh_source": "structured per-rank generator" if structured else "reference-format arrays", "fused_two_colour_passes": bool(fused), "timed_loop": loop, "programmatic_dependent_launch": bool(fused and not args.no_pdl),
                            "cells_per_gpu": ne // world, "setup_seconds": round(setup_s, 1), "l2": "working set (>1 GB per GPU) exceeds the 126 MB L2; no flush needed" if ne // world > 1000000 else
                            "working set may fit L2",
                            "parallelism": "1 GPU" if world == 1 else
-                           "%d GPUs, one RCB block of the global mesh per GPU; ghost-cell exchange: %s" % (world, exchange),
+                           "%d GPUs, one %s of the global mesh per GPU; ghost-cell exchange: %s" % (world, "z-slab" if partition == "slabs" else "RCB block", exchange),
+                           "pc_solve": ("one persistent launch per rank, chunks synchronise with neighbouring chunks only (across NVLink too), residual history combined once per launch"
+                                        if rbq_dist == 1 else ("one persistent launch, neighbour-only synchronisation" if (world == 1 and fused and int(s.get_info("rbq_active")) == 1) else "one launch per pass")),
+                           "passes_per_step": passes_per_step,
                            "solver_iterations_last_step(u,v,w,pc)": [int(x) for x in hist_last[:, 0]] if hist_last is not None else None,
                            "last_step_history(it,res_i,res_f,res_max)": hist_last.tolist() if hist_last is not None else None},
                 "roofline": roof, "roofline_other": extra_roof, "phase_ms_per_step": phase_ms, "cpu_baseline": cpu, "e2e": e2e,
+                "parity_check": parity,
                 "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     s.close()

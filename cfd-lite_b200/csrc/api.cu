@@ -351,6 +351,7 @@ int cfdl_get_info(cfdl_handle h, const char* key, double* value) {
   else if (!std::strcmp(key, "color_dist")) *value = h->prep.color_dist;
   else if (!std::strcmp(key, "rbq_active")) *value = (h->rbq && !h->rbq_refused && h->rbq_occ > 0) ? 1 : 0;
   else if (!std::strcmp(key, "rbq_refused")) *value = h->rbq_refused;
+  else if (!std::strcmp(key, "rbq_dist")) *value = h->rbq_dist_state;  // partitioned: 1 = persistent pc solve with chunk-to-chunk synchronisation over NVLink in use, -1 = refused (lists too long / not two colours), 0 = not decided yet
   else if (!std::strcmp(key, "rbq_occ")) *value = h->rbq_occ;
   else if (!std::strcmp(key, "rb_idx16")) *value = (h->rb_idx16 && h->ell_nb16) ? 1 : 0;
   else if (!std::strcmp(key, "rbq_extra_passes")) *value = (double)h->prof_extra_passes;
@@ -387,7 +388,7 @@ int cfdl_get_cell_order(cfdl_handle h, int32_t* c2o, int32_t* color_ptr) {
   do {                                                                 \
     CFDL_CUDA(cudaStreamSynchronize((h)->stream));                     \
     CFDL_CUDA(cudaGetLastError());                                     \
-    return CFDL_OK;                                                    \
+    return p2p_check(h); /* partitioned: CFDL_ERR_COMM if a wait on another rank timed out */ \
   } while (0)
 
 int cfdl_upload_field(cfdl_handle h, int field, const double* host) {

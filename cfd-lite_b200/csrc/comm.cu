@@ -159,6 +159,7 @@ struct PushArgs {
   unsigned long long* peer_red_seq[64];
   const double* my_red_val;
   const unsigned long long* my_red_seq;
+  int* err;
 };
 
 __global__ void __launch_bounds__(256) p2p_push_kernel(const __grid_constant__ PushArgs A) {
@@ -194,9 +195,7 @@ __global__ void __launch_bounds__(256) p2p_push_kernel(const __grid_constant__ P
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0, m = 0.0;
-    for (int r = 0; r < A.nranks; ++r) {
-      while (*((volatile const unsigned long long*)&A.my_red_seq[slot + r]) < A.seq) {}
-    }
+    for (int r = 0; r < A.nranks; ++r) spin_until_ge(&A.my_red_seq[slot + r], A.seq, A.err);
     __threadfence_system();
     for (int r = 0; r < A.nranks; ++r) {
       s += *((volatile const double*)&A.my_red_val[(slot + r) * 2]);
@@ -241,8 +240,25 @@ int p2p_alloc_slab(Handle* h) {
   hd.off_xflag = off; off += align256(64 * 8);
   hd.off_mail_val = off; off += align256(2 * 64 * 2 * 8);
   hd.off_mail_seq = off; off += align256(2 * 64 * 8);
+  const size_t off_err = off; off += 256;
   for (int b = 0; b < 2; ++b) { hd.off_stage[b] = (long long)off; off += align256(sizeof(double) * 3 * ((size_t)h->G + 32)); }
   for (int a = 0; a < 7; ++a) { hd.off_field[a] = (long long)off; off += arr; }
+  hd.off_mailv_val = (long long)off; off += align256(sizeof(double) * 2 * 64 * MAILV_LEN);
+  hd.off_mailv_seq = (long long)off; off += align256(2 * 64 * 8);
+  // the persistent pc solve on a partitioned two-colour mesh (kernels_rbq.inc): its value arrays and progress words are
+  // written by the neighbours, so they live in the exported slab; the launch geometry is fixed here so that peers can read it
+  hd.rbq_ok = 0;
+  if (p.ncolors == 2) {
+    const int nred = p.color_ptr[1], nblack = h->N - nred;
+    int L = 0, Gc = 0, Ls = 0, ifc = 0;
+    if (nred > 0 && nblack > 0 && rbq_plan(h, nred, h->N, h->K, true, p.color_if[0], p.color_if[1], &L, &Gc, &Ls, &ifc) == CFDL_OK && Gc <= RBQ_PROG_STRIDE) {
+      hd.rbq_ok = 1; hd.nred = nred; hd.color_if[0] = p.color_if[0]; hd.color_if[1] = p.color_if[1];
+      hd.rbq_L = L; hd.rbq_Gc = Gc; hd.rbq_Ls = Ls; hd.rbq_ifc = ifc;
+      hd.off_rbq_r2 = (long long)off; off += align256(sizeof(double) * 2 * ((size_t)nred + 2 + h->G + 2));
+      for (int b = 0; b < 2; ++b) { hd.off_rbq_b[b] = (long long)off; off += align256(sizeof(double) * ((size_t)nblack + 2 + h->G + 2)); }
+      hd.off_rbq_prog = (long long)off; off += align256(sizeof(unsigned long long) * RBQ_PROG_STRIDE * 9);
+    }
+  }
   for (int i = 0; i < hd.nnbr; ++i) hd.nbr_rank[i] = p.nbr_rank[i];
   for (size_t i = 0; i < p.recv_ptr.size(); ++i) hd.recv_ptr[i] = p.recv_ptr[i];
   CFDL_CUDA(cudaMalloc(&q.slab, off));
@@ -259,6 +275,7 @@ int p2p_alloc_slab(Handle* h) {
   h->rb3_work[1] = (double*)(q.slab + hd.off_field[P2P_WORK_W]);
   q.ticket = (unsigned int*)(q.slab + off_ticket);
   q.xticket = q.ticket + 8;
+  q.err = (int*)(q.slab + off_err);
   return CFDL_OK;
 }
 
@@ -268,6 +285,7 @@ P2PWait p2p_wait_args(Handle* h, unsigned long long expect) {
   w.expect = expect;
   w.n = h->nnbr;
   for (int i = 0; i < 8; ++i) w.r[i] = i < h->nnbr ? h->prep.nbr_rank[i] : 0;
+  w.err = h->p2p.err;
   return w;
 }
 
@@ -310,6 +328,7 @@ int p2p_reduce_args(Handle* h, int parity, unsigned long long seq, P2PReduce* ou
   }
   out->my_val = (const double*)(q.slab + q.hdr.off_red_val);
   out->my_seq = (const unsigned long long*)(q.slab + q.hdr.off_red_seq);
+  out->err = q.err;
   return CFDL_OK;
 }
 
@@ -363,6 +382,7 @@ int p2p_push(Handle* h, int color, const double* a, const double* b, unsigned lo
   }
   A.my_red_val = (const double*)(q.slab + q.hdr.off_red_val);
   A.my_red_seq = (const unsigned long long*)(q.slab + q.hdr.off_red_seq);
+  A.err = q.err;
   const int ctas = std::max(1, std::min(32, (total + 255) / 256));
   p2p_push_kernel<<<ctas, 256, 0, S(h)>>>(A);
   CFDL_CUDA(cudaGetLastError());
@@ -393,6 +413,7 @@ struct StageArgs {
   int nbr_rank[8];
   unsigned long long seq;
   unsigned int* ticket;
+  int* err;
 };
 
 __global__ void __launch_bounds__(256) stage_exchange_kernel(const __grid_constant__ StageArgs A) {
@@ -417,8 +438,7 @@ __global__ void __launch_bounds__(256) stage_exchange_kernel(const __grid_consta
     if (threadIdx.x == 0) *A.ticket = 0;
   }
   if ((int)threadIdx.x < A.nnbr) {
-    const volatile unsigned long long* f = (const volatile unsigned long long*)A.my_flags + A.nbr_rank[threadIdx.x];
-    while (*f < A.seq) {}
+    spin_until_ge(A.my_flags + A.nbr_rank[threadIdx.x], A.seq, A.err);
     __threadfence_system();
   }
   __syncthreads();
@@ -444,6 +464,7 @@ struct MailArgs {
   unsigned long long* peer_seq[64];
   const double* my_val;
   const unsigned long long* my_seq;
+  int* err;
 };
 
 __global__ void __launch_bounds__(64) mail_kernel(const __grid_constant__ MailArgs A) {
@@ -455,7 +476,7 @@ __global__ void __launch_bounds__(64) mail_kernel(const __grid_constant__ MailAr
     A.peer_val[r][(slot + A.rank) * 2 + 1] = v1;
     __threadfence_system();
     *((volatile unsigned long long*)&A.peer_seq[r][slot + A.rank]) = A.seq;
-    while (*((volatile const unsigned long long*)&A.my_seq[slot + r]) < A.seq) {}
+    spin_until_ge(&A.my_seq[slot + r], A.seq, A.err);
     __threadfence_system();
   }
   __syncthreads();
@@ -505,7 +526,7 @@ static int p2p_exchange(Handle* h, double* field, int ncomp, int color) {
   }
   A.my_stage = (const double*)(q.slab + q.hdr.off_stage[buf]);
   A.my_flags = (const unsigned long long*)(q.slab + q.hdr.off_xflag);
-  A.seq = seq; A.ticket = q.xticket; A.whole = color < 0 ? 1 : 0;
+  A.seq = seq; A.ticket = q.xticket; A.whole = color < 0 ? 1 : 0; A.err = q.err;
   const int ctas = std::max(1, std::min(64, (std::max(total, h->G) * ncomp + 255) / 256));
   stage_exchange_kernel<<<ctas, 256, 0, S(h)>>>(A);
   CFDL_CUDA(cudaGetLastError());
@@ -525,8 +546,77 @@ static int p2p_mail(Handle* h, double* dev, int mode, int root) {
   }
   A.my_val = (const double*)(q.slab + q.hdr.off_mail_val);
   A.my_seq = (const unsigned long long*)(q.slab + q.hdr.off_mail_seq);
+  A.err = q.err;
   mail_kernel<<<1, 64, 0, S(h)>>>(A);
   CFDL_CUDA(cudaGetLastError());
+  return CFDL_OK;
+}
+
+// vector form of the mailbox: every rank posts npairs (sum, max) pairs to every rank, waits for all and combines
+// element by element in rank order — one launch and one rendezvous for a whole block of solver iterations
+namespace {
+struct MailVArgs {
+  int nranks, rank, parity, n;  // n doubles = 2 * npairs
+  unsigned long long seq;
+  double* dev;
+  double* peer_val[64];
+  unsigned long long* peer_seq[64];
+  const double* my_val;
+  const unsigned long long* my_seq;
+  int* err;
+};
+__global__ void __launch_bounds__(256) mailv_kernel(const __grid_constant__ MailVArgs A) {
+  const int slot = A.parity * 64;
+  for (int r = 0; r < A.nranks; ++r)
+    for (int i = threadIdx.x; i < A.n; i += blockDim.x) A.peer_val[r][(size_t)(slot + A.rank) * MAILV_LEN + i] = A.dev[i];
+  __syncthreads();  // the CTA's remote stores are ordered before the publishing threads' system-scope fences
+  if ((int)threadIdx.x < A.nranks) {
+    const int r = threadIdx.x;
+    __threadfence_system();
+    *((volatile unsigned long long*)&A.peer_seq[r][slot + A.rank]) = A.seq;
+    spin_until_ge(&A.my_seq[slot + r], A.seq, A.err);
+    __threadfence_system();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < A.n; i += blockDim.x) {
+    double v = 0.0;
+    for (int r = 0; r < A.nranks; ++r) {
+      const double x = *((volatile const double*)&A.my_val[(size_t)(slot + r) * MAILV_LEN + i]);
+      v = (i & 1) ? fmax(v, x) : v + x;
+    }
+    A.dev[i] = v;
+  }
+}
+}  // namespace
+
+int comm_allreduce_pairs(Handle* h, double* dev, int npairs) {
+  if (h->prep.nranks == 1) return CFDL_OK;
+  P2P& q = h->p2p;
+  const Prep& p = h->prep;
+  if (!(q.connected && h->use_p2p)) return fail(CFDL_ERR_INTERNAL, "comm_allreduce_pairs needs the peer-to-peer slabs");
+  if (2 * npairs > MAILV_LEN) return fail(CFDL_ERR_INTERNAL, "comm_allreduce_pairs: %d pairs exceed the mailbox", npairs);
+  MailVArgs A;
+  std::memset(&A, 0, sizeof A);
+  A.nranks = p.nranks; A.rank = p.rank; A.n = 2 * npairs;
+  A.seq = ++q.vseq; A.parity = (int)(A.seq & 1); A.dev = dev;
+  for (int r = 0; r < p.nranks; ++r) {
+    A.peer_val[r] = (double*)(q.peer_base[r] + q.peer_hdr[r].off_mailv_val);
+    A.peer_seq[r] = (unsigned long long*)(q.peer_base[r] + q.peer_hdr[r].off_mailv_seq);
+  }
+  A.my_val = (const double*)(q.slab + q.hdr.off_mailv_val);
+  A.my_seq = (const unsigned long long*)(q.slab + q.hdr.off_mailv_seq);
+  A.err = q.err;
+  mailv_kernel<<<1, 256, 0, S(h)>>>(A);
+  CFDL_CUDA(cudaGetLastError());
+  return CFDL_OK;
+}
+
+int p2p_check(Handle* h) {
+  if (h->prep.nranks == 1 || !h->p2p.err) return CFDL_OK;
+  CFDL_CUDA(cudaMemcpyAsync(h->scal_host + 500, h->p2p.err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CFDL_CUDA(cudaStreamSynchronize(h->stream));
+  if (*reinterpret_cast<const int*>(h->scal_host + 500))
+    return fail(CFDL_ERR_COMM, "rank %d: a wait on another rank's flag word ran into its time limit (did a rank die or never launch?)", h->prep.rank);
   return CFDL_OK;
 }
 

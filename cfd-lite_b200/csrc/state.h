@@ -52,7 +52,20 @@ struct P2PHeader {
   long long off_mail_seq;  // unsigned long long mail_seq[2][64]
   int nbr_rank[64];
   int recv_ptr[64 * 4 + 1];
+  // the pc solve as one persistent launch per rank with chunk-to-chunk synchronisation over NVLink (kernels_rbq.inc, two colours)
+  int rbq_ok;              // 1: this rank can take part (two colours, launch geometry fits)
+  int nred;                // cells of the first colour
+  int color_if[2];         // leading interface cells per colour
+  int rbq_L, rbq_Gc;       // rows per interior chunk, chunks (= CTAs of the launch)
+  int rbq_ifc;             // chunks 0..rbq_ifc-1 hold the interface rows: they publish their progress to every neighbour
+  int rbq_Ls;              // rows per interface chunk (shorter, so that their pushes and flags travel while the interior chunks still work)
+  long long off_rbq_r2;    // double2 r2[nred + 2 + G]: red {newest, mid}; ghost g at nred + 2 + g
+  long long off_rbq_b[2];  // double b[N - nred + 2 + G] x 2: the two black buffers; ghost g at (N - nred) + 2 + g
+  long long off_rbq_prog;  // unsigned long long prog[RBQ_PROG_STRIDE * 9]: own chunks, then one block per neighbour (written by it)
+  long long off_mailv_val; // double mailv_val[2][64][MAILV_LEN]: vector all-reduce mailbox, alternating sets
+  long long off_mailv_seq; // unsigned long long mailv_seq[2][64]
 };
+enum { RBQ_PROG_STRIDE = 1024, MAILV_LEN = 2056 };
 struct P2P {
   bool connected = false;
   char* slab = nullptr;
@@ -65,6 +78,8 @@ struct P2P {
   unsigned long long xseq = 0, mseq = 0;  // staged exchanges / mailbox rounds done (every rank performs the same sequence)
   unsigned int* ticket = nullptr;
   unsigned int* xticket = nullptr;
+  unsigned long long vseq = 0;          // vector mailbox rounds done
+  int* err = nullptr;                   // device word: a peer-to-peer wait ran into its time limit (checked at the host syncs)
 };
 enum { P2P_U = 0, P2P_V = 1, P2P_W = 2, P2P_PC = 3, P2P_WORK = 4, P2P_WORK_V = 5, P2P_WORK_W = 6 };
 
@@ -115,6 +130,13 @@ struct Handle {
   int rbq_ctas_per_sm = 0;        // > 0: use fewer CTAs per SM than that
   double* rbq_mem = nullptr;      // red pairs, black buffers, per-pass partials, progress words
   size_t rbq_len = 0;
+  // partitioned meshes (peer-to-peer mode): value arrays and progress words live in the exported slab; per chunk the progress
+  // words to wait for (own chunks and the neighbours' interface chunks), the interface rows to push after a pass
+  int rbq_dist_state = 0;         // 0: not set up yet, 1: ready, -1: refused (on every rank alike)
+  int32_t* rbq_nbq = nullptr;     // K x Np: neighbour position in the other colour's value array (ghosts appended)
+  int32_t *rbq_wait_ptr = nullptr, *rbq_wait_idx = nullptr;
+  int32_t *rbq_push_ptr[2] = {nullptr, nullptr}, *rbq_push_src[2] = {nullptr, nullptr}, *rbq_push_nbr[2] = {nullptr, nullptr}, *rbq_push_dst[2] = {nullptr, nullptr};
+  unsigned long long rbq_epoch = 0;  // launches done (every rank performs the same sequence): progress words only ever grow
   int64_t prof_extra_passes = 0;  // passes executed a second time because the stopping rule fired inside a block
   int rb_idx16 = 1;               // pc passes read 16-bit neighbour offsets instead of 32-bit ids where prep.nb16 exists
   int pc_sumap = 1;               // fused pc passes rebuild ap as the slot-order sum of anb instead of reading it
@@ -235,7 +257,7 @@ int comm_allreduce_sum_max(Handle* h, double* dev2);  // dev2[0] summed, dev2[1]
 // over all ranks through the peers' reduction slots and advance ctl like finalize_residual_kernel
 int p2p_alloc_slab(Handle* h);  // carves u,v,w,pc and rb_work out of one exportable allocation
 int p2p_push(Handle* h, int color, const double* a, const double* b, unsigned long long seq, int reduce_parity, const double* local_sm);
-struct P2PWait { const unsigned long long* flags; unsigned long long expect; int n; int r[8]; };
+struct P2PWait { const unsigned long long* flags; unsigned long long expect; int n; int r[8]; int* err; };
 P2PWait p2p_wait_args(Handle* h, unsigned long long expect);
 // remote-store description of one launch (kernel parameter; tptr == nullptr: no remote stores):
 // cell c mirrors into ghost slot d0[i] + tpos[e] of neighbour i = tnbr[e], e in [tptr[c], tptr[c+1])
@@ -258,7 +280,34 @@ struct P2PReduce {
   unsigned long long* peer_seq[64];
   const double* my_val;
   const unsigned long long* my_seq;
+  int* err;
 };
+// Every wait on a word another GPU writes is time-limited (~10 s of SM clock, far beyond any legitimate wait): the
+// waiter that gives up raises the handle's error word, every later wait returns at once, the kernels run to their end
+// and the next API call that synchronises reports CFDL_ERR_COMM (p2p_check) — a dead rank is an error code, not a hang.
+#define CFDL_SPIN_LIMIT 20000000000ll
+#ifdef CUEMU
+#define CFDL_SPIN_PAUSE CUEMU_SPIN  // host emulation (tests/emul): a waiting CTA yields its core
+#else
+#define CFDL_SPIN_PAUSE
+#endif
+#if defined(__CUDACC__) || defined(CUEMU)
+__device__ __forceinline__ bool spin_until_ge(const volatile unsigned long long* w, unsigned long long need, int* err) {
+  const long long t0 = clock64();
+  while (*w < need) {
+    CFDL_SPIN_PAUSE;
+    if (err && *((volatile const int*)err)) return false;
+    if (clock64() - t0 > CFDL_SPIN_LIMIT) { if (err) *((volatile int*)err) = 1; return false; }
+  }
+  return true;
+}
+#endif
+int p2p_check(Handle* h);  // after a stream sync point: CFDL_ERR_COMM when a peer-to-peer wait has timed out on this handle
+// element-wise all-reduce of npairs (sum, max) pairs in device memory over the ranks, summed in rank order (peer-to-peer mailbox)
+int comm_allreduce_pairs(Handle* h, double* dev, int npairs);
+// launch geometry of the persistent pc solve for a rank with nred first-colour cells of N: rows per chunk, chunks
+// (partitioned: if0 / if1 leading interface rows per colour -> Ls rows per interface chunk, ifc such chunks in front)
+int rbq_plan(const Handle* h, int nred, int N, int K, bool dist, int if0, int if1, int* L, int* Gc, int* Ls, int* ifc);
 int p2p_store_args(Handle* h, int color, const double* a, const double* b, unsigned long long seq, P2PStore* out);
 int p2p_reduce_args(Handle* h, int parity, unsigned long long seq, P2PReduce* out);
 int p2p_reduce3_args(Handle* h, int parity, unsigned long long seq, P2PReduce* out);  // slots of 6 doubles (u, v, w)

@@ -19,17 +19,25 @@
 namespace cfdl {
 namespace {
 
+// n x n x nz cells of edge 1/n: the unit cube for nz = n (the cavity of BASELINE.json), a cavity of depth nz/n otherwise
+// (the weak-scaling series of bench.py stacks one 128^3 block per GPU along z)
 struct Hex {
-  int32_t n;
-  int64_t n2, n3, Fx, Fy;
-  explicit Hex(int32_t n_) : n(n_), n2((int64_t)n_ * n_), n3((int64_t)n_ * n_ * n_), Fx((int64_t)(n_ + 1) * n_ * n_), Fy(Fx) {}
-  double vx(int i) const { return i == n ? 1.0 : i * (1.0 / n); }
+  int32_t n, nz;
+  int64_t n2, n3, Fx, Fy, Fz, nB;
+  int64_t hoff[7];  // first halo of the sections bottom, top, west, east, south, north
+  explicit Hex(int32_t n_, int32_t nz_ = 0) : n(n_), nz(nz_ > 0 ? nz_ : n_) {
+    n2 = (int64_t)n * n; n3 = n2 * nz; Fx = (int64_t)(n + 1) * n * nz; Fy = Fx; Fz = n2 * (nz + 1);
+    const int64_t side = (int64_t)n * nz;
+    hoff[0] = 0; hoff[1] = n2; hoff[2] = 2 * n2; hoff[3] = hoff[2] + side; hoff[4] = hoff[3] + side; hoff[5] = hoff[4] + side; hoff[6] = hoff[5] + side;
+    nB = hoff[6];
+  }
+  double vx(int i) const { return i == n ? 1.0 : i * (1.0 / n); }  // x, y and (for i <= n) z vertex planes: the cube's bits
   // 0-based global face ids; i (resp. j, k) runs over n+1 planes
   int32_t fx(int i, int j, int k) const { return (int32_t)(i + (int64_t)(n + 1) * (j + (int64_t)n * k)); }
   int32_t fy(int i, int j, int k) const { return (int32_t)(Fx + i + (int64_t)n * (j + (int64_t)(n + 1) * k)); }
   int32_t fz(int i, int j, int k) const { return (int32_t)(Fx + Fy + i + (int64_t)n * (j + (int64_t)n * k)); }
   // halo offsets (0-based from gN): section s, in-plane (p, q)
-  int32_t halo(int s, int p, int q) const { return (int32_t)(s * n2 + (int64_t)q * n + p); }
+  int32_t halo(int s, int p, int q) const { return (int32_t)(hoff[s] + (int64_t)q * n + p); }
 
   // vertices of local face lf (0..5) of cell (i,j,k), CGNS order of the reference's faces_hexa8
   void face_vertices(int i, int j, int k, int lf, double (*r)[3]) const {
@@ -69,7 +77,7 @@ struct Hex {
     nb[2] = i < n - 1 ? e + 1 : gN + halo(3, j, k);           fg[2] = fx(i + 1, j, k) + 1;
     nb[3] = j < n - 1 ? e + n : gN + halo(5, i, k);           fg[3] = fy(i, j + 1, k) + 1;
     nb[4] = i > 0 ? e - 1 : gN + halo(2, j, k);               fg[4] = i > 0 ? -(fx(i, j, k) + 1) : fx(i, j, k) + 1;
-    nb[5] = k < n - 1 ? e + (int32_t)n2 : gN + halo(1, i, j); fg[5] = fz(i, j, k + 1) + 1;
+    nb[5] = k < nz - 1 ? e + (int32_t)n2 : gN + halo(1, i, j); fg[5] = fz(i, j, k + 1) + 1;
   }
   // centroid and volume of cell e with the reference's pyramid sums over its six faces
   void cell_geom(int32_t e, double* ctr, double* vol) const {
@@ -92,10 +100,13 @@ struct Hex {
   }
   // boundary face of halo h (0-based offset): the face of its interior cell
   void halo_owner(int32_t h, int* i, int* j, int* k, int* lf) const {
-    const int s = (int)(h / n2), p = (int)((h % n2) % n), q = (int)((h % n2) / n);
+    int s = 0;
+    while (h >= hoff[s + 1]) ++s;
+    const int64_t l = h - hoff[s];
+    const int p = (int)(l % n), q = (int)(l / n);
     switch (s) {
-      case 0: *i = p; *j = q; *k = 0;     *lf = 0; break;
-      case 1: *i = p; *j = q; *k = n - 1; *lf = 5; break;
+      case 0: *i = p; *j = q; *k = 0;      *lf = 0; break;
+      case 1: *i = p; *j = q; *k = nz - 1; *lf = 5; break;
       case 2: *i = 0;     *j = p; *k = q; *lf = 4; break;
       case 3: *i = n - 1; *j = p; *k = q; *lf = 2; break;
       case 4: *i = p; *j = 0;     *k = q; *lf = 1; break;
@@ -126,31 +137,35 @@ void bisect(std::vector<int32_t>& c2r, const Hex& hx, int lo[3], int hi[3], int 
 
 using namespace cfdl;
 
-extern "C" int cfdl_create_structured_hex(cfdl_handle* out, int32_t n, double rho, double mu, int32_t rank, int32_t nranks,
-                                          int32_t device) {
+// slabs: 0 = recursive bisection (x, y, z in turn), 1 = nranks slabs along z, the slowest index of the numbering:
+// every rank's interface cells are then the first and last planes of its own range — contiguous in the natural order
+static int create_structured(cfdl_handle* out, int32_t n, int32_t nz, double rho, double mu, int32_t rank, int32_t nranks, int32_t device, int slabs) {
   if (!out) return fail(CFDL_ERR_ARG, "cfdl_create_structured_hex: out is NULL");
   *out = nullptr;
   if (n < 2 || n > 700) return fail(CFDL_ERR_RANGE, "cfdl_create_structured_hex: n=%d outside 2..700 (int32 slot index)", n);
-  if (nranks < 1 || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks)
+  if (nz <= 0) nz = n;
+  if (nz < 2 || (int64_t)n * n * nz > 343000000ll) return fail(CFDL_ERR_RANGE, "cfdl_create_structured_hex: %d x %d x %d cells exceed the int32 slot index", n, n, nz);
+  if (nz != n && !slabs) return fail(CFDL_ERR_ARG, "cfdl_create_structured_hex: a depth other than n needs the slab partition");
+  if (nranks < 1 || (!slabs && (nranks & (nranks - 1))) || rank < 0 || rank >= nranks)
     return fail(CFDL_ERR_ARG, "cfdl_create_structured_hex: rank %d of %d (power-of-two rank counts only)", rank, nranks);
   int ndev = cfdl_device_count();
   if (ndev < 1) return fail(CFDL_ERR_CUDA, "cfdl_create_structured_hex: no CUDA device is usable (this library has no CPU path)");
   if (device < 0 || device >= ndev) return fail(CFDL_ERR_ARG, "cfdl_create_structured_hex: device %d of %d", device, ndev);
-  if (n < nranks) return fail(CFDL_ERR_ARG, "cfdl_create_structured_hex: %d ranks for n=%d", nranks, n);
-  const Hex hx(n);
+  if ((slabs ? nz : n) < nranks) return fail(CFDL_ERR_ARG, "cfdl_create_structured_hex: %d ranks for n=%d", nranks, n);
+  const Hex hx(n, nz);
   cfdl_handle_s* h = new (std::nothrow) cfdl_handle_s;
   if (!h) return fail(CFDL_ERR_INTERNAL, "out of host memory");
   h->device = device;
   Prep& p = h->prep;
   const int32_t gN = (int32_t)hx.n3;
-  p.gN = gN; p.gF = (int32_t)(3 * hx.Fx); p.gB = (int32_t)(6 * hx.n2); p.gZ = (int32_t)(6 * hx.n3);
+  p.gN = gN; p.gF = (int32_t)(hx.Fx + hx.Fy + hx.Fz); p.gB = (int32_t)hx.nB; p.gZ = (int32_t)(6 * hx.n3);
   p.K = 6; p.rank = rank; p.nranks = nranks; p.n_subdomains = 1;
   p.row_ptr.resize((size_t)gN + 1);
   for (int64_t e = 0; e <= gN; ++e) p.row_ptr[(size_t)e] = (int32_t)(6 * e);
   std::vector<int32_t> o_nb((size_t)p.gZ), o_fg((size_t)p.gZ), halo_e((size_t)p.gB), halo_lf((size_t)p.gB), c2r;
   {
     int64_t e = 0;
-    for (int k = 0; k < n; ++k)
+    for (int k = 0; k < nz; ++k)
       for (int j = 0; j < n; ++j)
         for (int i = 0; i < n; ++i, ++e) hx.slots(i, j, k, &o_nb[(size_t)(6 * e)], &o_fg[(size_t)(6 * e)]);
   }
@@ -163,14 +178,21 @@ extern "C" int cfdl_create_structured_hex(cfdl_handle* out, int32_t n, double rh
   if (nranks > 1) {
     c2r.resize((size_t)gN);
     int lo[3] = {0, 0, 0}, hi[3] = {n, n, n};
-    bisect(c2r, hx, lo, hi, 0, 0, nranks);
+    if (slabs) {
+      for (int r = 0; r < nranks; ++r) {
+        const int k0 = (int)((int64_t)nz * r / nranks), k1 = (int)((int64_t)nz * (r + 1) / nranks);
+        std::fill(c2r.begin() + (size_t)k0 * hx.n2, c2r.begin() + (size_t)k1 * hx.n2, r + 1);
+      }
+    } else {
+      bisect(c2r, hx, lo, hi, 0, 0, nranks);
+    }
   }
   // the cavity's boundary conditions: six wall sections, the top one moving with (1,0,0)
   int32_t bc_esec[12], bc_kind[6];
   double bc_uvw[18] = {0};
   for (int s = 0; s < 6; ++s) {
-    bc_esec[2 * s] = gN + 1 + (int32_t)(s * hx.n2);
-    bc_esec[2 * s + 1] = gN + (int32_t)((s + 1) * hx.n2);
+    bc_esec[2 * s] = gN + 1 + (int32_t)hx.hoff[s];
+    bc_esec[2 * s + 1] = gN + (int32_t)hx.hoff[s + 1];
     bc_kind[s] = (s == 1) ? CFDL_BC_LID : CFDL_BC_WALL;
   }
   bc_uvw[3] = 1.0;
@@ -192,6 +214,14 @@ extern "C" int cfdl_create_structured_hex(cfdl_handle* out, int32_t n, double rh
   G.mu = [mu](int32_t) { return mu; };
   G.face = [hx](int32_t f, double* a, double* r) { hx.face_geom(f, a, r); };
   return create_from_prep(h, G, out);
+}
+
+extern "C" int cfdl_create_structured_hex(cfdl_handle* out, int32_t n, double rho, double mu, int32_t rank, int32_t nranks, int32_t device) {
+  return create_structured(out, n, n, rho, mu, rank, nranks, device, 0);
+}
+extern "C" int cfdl_create_structured_hex_slabs(cfdl_handle* out, int32_t n, int32_t nz, double rho, double mu, int32_t rank, int32_t nranks,
+                                                int32_t device) {
+  return create_structured(out, n, nz, rho, mu, rank, nranks, device, 1);
 }
 
 // The arrays cfdl_create_structured_hex works from, for inspection and tests (no GPU needed).

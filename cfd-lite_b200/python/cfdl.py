@@ -264,21 +264,25 @@ class Solver:
         self.n_subdomains = n_subdomains
 
     @classmethod
-    def structured_hex(cls, n, rho=5.0, mu=0.01, device=0, rank=0, nranks=1):
+    def structured_hex(cls, n, rho=5.0, mu=0.01, device=0, rank=0, nranks=1, slabs=False, nz=None):
         """The n^3 lid-driven cavity generated per rank without the packed int32 arrays
         (cfdl_create_structured_hex): the way to the 512^3 target, identical to
         Solver(mesh_build(meshgen("hex", n)), default_bcs(...)) in everything but the host-side
         numbering of face fields."""
         self = cls.__new__(cls)
         self.rank, self.nranks = rank, nranks
-        self.ne, self.nbf = n ** 3, 6 * n * n
-        self.nf = 3 * n * n * (n + 1)
+        nz = nz or n  # nz != n (slabs only): n x n x nz cells of edge 1/n
+        self.ne, self.nbf = n * n * nz, 2 * n * n + 4 * n * nz
+        self.nf = 2 * (n + 1) * n * nz + n * n * (nz + 1)
         self.H = self.ne + self.nbf
         self.Z = 6 * self.ne
         self.n_subdomains = 1
         h = C.c_void_p()
-        _chk(lib().cfdl_create_structured_hex(C.byref(h), C.c_int32(n), C.c_double(rho), C.c_double(mu), C.c_int32(rank),
-                                              C.c_int32(nranks), C.c_int32(device)))
+        if slabs:  # nranks z-slabs instead of bisection
+            _chk(lib().cfdl_create_structured_hex_slabs(C.byref(h), C.c_int32(n), C.c_int32(nz), C.c_double(rho), C.c_double(mu), C.c_int32(rank),
+                                                        C.c_int32(nranks), C.c_int32(device)))
+        else:
+            _chk(lib().cfdl_create_structured_hex(C.byref(h), C.c_int32(n), C.c_double(rho), C.c_double(mu), C.c_int32(rank), C.c_int32(nranks), C.c_int32(device)))
         self.h = h
         return self
 

@@ -31,7 +31,8 @@ enum {
   CFDL_ERR_NCCL = 4,     /* NCCL error / library not loadable */
   CFDL_ERR_MESH = 5,     /* inconsistent connectivity (reference: `stop` in find_element_nb) */
   CFDL_ERR_INTERNAL = 6,
-  CFDL_ERR_UNSUPPORTED = 7
+  CFDL_ERR_UNSUPPORTED = 7,
+  CFDL_ERR_COMM = 8      /* a wait on another rank's flag word ran into its time limit (a rank died or never launched) */
 };
 
 /* boundary-condition kinds == the reference's BC callbacks (mod_uvwp.f90:493-570) */
@@ -263,6 +264,15 @@ int cfdl_create_distributed(cfdl_handle* out, int32_t ne, int32_t nf, int32_t nb
  * reference's face order; everything else, including comm_init / ipc_connect, is the same. */
 int cfdl_create_structured_hex(cfdl_handle* out, int32_t n, double rho, double mu,
                                int32_t rank, int32_t nranks, int32_t device);
+/* The same cavity cut into nranks slabs along z (any nranks <= nz), the slowest index of the cell numbering: every
+ * rank's interface cells are whole planes at the two ends of its own range.  nz = n (or 0) is the unit cube; any other
+ * nz gives n x n x nz cells of the same edge 1/n, i.e. a cavity of depth nz/n with the lid on its top (z) face —
+ * bench.py's weak-scaling series stacks one 128^3 block per GPU that way, so every GPU keeps the same work.  With such a partition the pc solve
+ * runs as one persistent launch per rank whose chunks synchronise with the neighbouring chunks only, across
+ * NVLink too (kernels_rbq.inc); with partitions that scatter the interface through the numbering (x slabs, octants)
+ * the library falls back to one launch per pass.  Same results either way. */
+int cfdl_create_structured_hex_slabs(cfdl_handle* out, int32_t n, int32_t nz, double rho, double mu,
+                                     int32_t rank, int32_t nranks, int32_t device);
 /* The arrays cfdl_create_structured_hex works from, for inspection and CPU tests (any output may
  * be NULL): nb/fg 6 n^3 slots (0-based neighbour cell, or n^3 + halo offset; signed 1-based face
  * id in the numbering described above), xc/yc/zc n^3 + 6 n^2, vol n^3, aip/rip 3 per face,

@@ -3,8 +3,9 @@
 ctypes view of oracle/_build/liboracle.so, the CPU restatement of the reference hot path
 (src/equations/mod_uvwp.f90, src/modules/mod_solver.f90, src/modules/mod_subdomains.f90) and
 of the mesh set-up that feeds it.  Only tests/, __graft_entry__.smoke() and bench.py's
-cpu_baseline / --impl reference legs may import this module.  PARITY UNPINNED: the reference
-has no golden vectors for this path and cannot be built here (no Fortran compiler).
+cpu_baseline / --impl reference legs may import this module.  Parity is pinned to the reference's SOURCE TEXT
+executed by oracle/f90run/f90py.py (tests/test_oracle_vs_reference_source.py, bit for bit) — the reference has no golden
+vectors for this path and cannot be compiled here (no Fortran compiler in the image or on the GPU box).
 """
 import ctypes as C
 import os

@@ -1,6 +1,6 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  C entry points for tests/, __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs (loaded with ctypes from oracle/oracle.py).
-// PARITY UNPINNED (see oracle_setup.hpp).
+// Parity: pinned to the reference's source text, see oracle_setup.hpp.
 #include "oracle_solver.hpp"
 #include <chrono>
 #include <cstring>

@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_setup.hpp).  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_setup.hpp).  Parity pinned to the reference's source text (tests/test_oracle_vs_reference_source.py).
 // Restates the reference's serial mesh set-up; each function cites the lines it follows.
 #include "oracle_setup.hpp"
 #include <cstring>

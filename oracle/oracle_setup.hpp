@@ -10,9 +10,12 @@
 //   RCB seed generator         src/setup/mod_agglomeration.f90:331-561
 //   g2gf block ordering        src/setup/mod_mg_lvl_uns.f90:873-903, src/modules/mod_util.f90:1683-1730
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or runnable case for this path
-// (bundled test/box.cgns.tar.gz is missing; no Fortran compiler here), so this restatement is
-// pinned only by the analytic known-answer tests in tests/test_oracle_kat.py.
+// PARITY PINNED TO THE REFERENCE'S SOURCE TEXT (not to a compiled binary): the reference ships no tests, golden
+// vectors or runnable case for this path (bundled test/box.cgns.tar.gz is missing) and no Fortran compiler exists here
+// or on the GPU box, so find_element_nb, calc_aip_xyzip_uns, calc_vol_cv_centers_uns and add_transformation_bt are
+// executed from the reference's unmodified files by oracle/f90run/f90py.py and this restatement must give the same
+// arrays bit for bit (tests/test_oracle_vs_reference_source.py).  Not executed from the reference: generate_seeds
+// (which subdomain a cell belongs to) — pinned by the RCB known-answer tests of tests/test_oracle_kat.py only.
 #pragma once
 #include <cstdint>
 #include <cstdio>

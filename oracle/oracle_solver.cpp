@@ -1,4 +1,4 @@
-// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_solver.hpp).  PARITY UNPINNED.
+// ORACLE — TEST INFRASTRUCTURE ONLY (see oracle_solver.hpp).  Parity pinned to the reference's source text (tests/test_oracle_vs_reference_source.py).
 // Operation order inside every expression follows the Fortran source left to right; build
 // with -ffp-contract=off so no FMA is formed.
 #include "oracle_solver.hpp"

@@ -1,8 +1,10 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Never linked into, loaded by, or called from the product.
 // CPU restatement (FP64, one thread, -ffp-contract=off) of the reference's per-iteration hot
 // path: src/equations/mod_uvwp.f90, src/modules/mod_solver.f90, src/modules/mod_subdomains.f90,
-// src/modules/mod_physics.f90:38-112.  PARITY UNPINNED (no reference goldens exist; see
-// oracle_setup.hpp) — pinned by the analytic KATs of tests/test_oracle_kat.py only.
+// src/modules/mod_physics.f90:38-112.  PARITY PINNED TO THE REFERENCE'S SOURCE TEXT: the reference has no goldens and
+// no Fortran compiler exists here, so its unmodified files are executed by oracle/f90run/f90py.py and this restatement
+// must reproduce every field, matrix and residual record of those runs bit for bit
+// (tests/test_oracle_vs_reference_source.py, fixtures tests/golden/ref_*.npz); plus the analytic KATs of tests/test_oracle_kat.py.
 #pragma once
 #include "oracle_setup.hpp"
 

@@ -4,7 +4,8 @@ every rank owns a handle of the emulated library, and the "IPC handle" of a slab
 so the peer-to-peer path of comm.cu / kernels_rb.inc (interface CTAs storing into the neighbours'
 ghost cells, flag words, mailbox all-reduce) runs for real, concurrently, on the host.  The merged
 result must equal the single-rank run like in tests/test_gpu_multi.py.  TEST INFRASTRUCTURE ONLY.
-usage: multirank_check.py <world> <n> [structured|pcg|tet|nccl|nccl-tet|nccl-pcg]
+usage: multirank_check.py <world> <n> [structured|slabs|structured-slabs|pcg|tet|nccl|nccl-tet|nccl-pcg]
+(slabs: z-slab partition — the persistent pc solve with chunk-to-chunk synchronisation across ranks must be in use)
 (nccl*: the library's NCCL exchange mode against tests/emul/fake_nccl.cpp instead of the peer-to-peer slabs)
 """
 import os
@@ -22,7 +23,9 @@ import conftest  # noqa: E402
 
 def main():
     world, n = int(sys.argv[1]), int(sys.argv[2])
-    structured = len(sys.argv) > 3 and sys.argv[3] == "structured"
+    structured = len(sys.argv) > 3 and sys.argv[3] in ("structured", "structured-slabs", "tall-slabs")
+    slabs = len(sys.argv) > 3 and sys.argv[3] in ("slabs", "structured-slabs", "tall-slabs")
+    nz = (n * world) // 2 + 1 if (len(sys.argv) > 3 and sys.argv[3] == "tall-slabs") else None  # n x n x nz cells (cfdl_create_structured_hex_slabs)
     pcg = len(sys.argv) > 3 and sys.argv[3] in ("pcg", "nccl-pcg")
     nccl = len(sys.argv) > 3 and sys.argv[3].startswith("nccl")
     tet = len(sys.argv) > 3 and sys.argv[3] in ("nccl-tet", "tet")  # "tet": peer-to-peer, one staged exchange per colour
@@ -39,6 +42,11 @@ def main():
     geom = cfdl.mesh_build(raw)
     bcs = cfdl.default_bcs(raw)
     c2r, _, _ = cfdl.partition_rcb(geom, world)
+    if slabs:  # z-slabs like cfdl_create_structured_hex_slabs: cell id = i + n (j + n k)
+        k = np.arange(n ** 3) // (n * n)
+        c2r = np.zeros(n ** 3, np.int32)
+        for r in range(world):
+            c2r[(k >= n * r // world) & (k < n * (r + 1) // world)] = r + 1
     bar = threading.Barrier(world)
     handles = [None] * world
     out = [None] * world
@@ -48,7 +56,7 @@ def main():
     def rank_main(rank):
         try:
             if structured:
-                s = cfdl.Solver.structured_hex(n, device=0, rank=rank, nranks=world)
+                s = cfdl.Solver.structured_hex(n, device=0, rank=rank, nranks=world, slabs=slabs, nz=nz)
             else:
                 s = cfdl.Solver(geom, bcs, device=0, cell2rank=c2r, rank=rank, nranks=world)
             s.set_option("solver", mode)
@@ -71,6 +79,8 @@ def main():
                 s.download_into(f, a)
                 fields[f] = a
             out[rank] = (hist, fields)
+            if slabs:
+                assert int(s.get_info("rbq_dist")) == 1, ("persistent partitioned pc solve not in use", rank, s.get_info("rbq_dist"))
             bar.wait()
             # cfdl_step_host with partition-local arrays (bench.py's e2e path on several GPUs) against the
             # separate local upload / solve / download calls, from the same state: same bits on every rank
@@ -98,7 +108,7 @@ def main():
     for t in th:
         t.join()
     assert not errs, errs
-    one = cfdl.Solver(geom, bcs, device=0)
+    one = cfdl.Solver(geom, bcs, device=0) if nz is None else cfdl.Solver.structured_hex(n, device=0, slabs=True, nz=nz)
     one.set_option("solver", mode)
     want_hist = one.run(dt=dt, nit=100, ntstep=2, ncoef=2)
     for r in range(world):

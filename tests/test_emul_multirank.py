@@ -12,7 +12,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("world,n,structured", [(4, 10, False), (8, 12, False), (4, 12, True), (4, 10, "pcg"), (3, 4, "tet")])
+@pytest.mark.parametrize("world,n,structured", [(4, 10, False), (8, 12, False), (4, 12, True), (4, 10, "pcg"), (3, 4, "tet"),
+                                                (4, 12, "slabs"), (3, 10, "slabs"), (4, 12, "structured-slabs")])
 def test_partitioned_p2p_run_equals_single_rank_under_emulation(world, n, structured):
     extra = [structured] if isinstance(structured, str) else (["structured"] if structured else [])
     cmd = [sys.executable, os.path.join(ROOT, "tests", "emul", "multirank_check.py"), str(world), str(n)] + extra

@@ -16,6 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 STRUCTURED = 2  # "kind" of the cases built with cfdl_create_structured_hex
+SLABS = 3       # hex mesh cut into z-slabs (general builder): the persistent pc solve with chunk-to-chunk synchronisation over NVLink
+STRUCTURED_SLABS = 4  # cfdl_create_structured_hex_slabs
 
 
 def _free_port():
@@ -34,16 +36,22 @@ def _worker(rank, world, port, kind, n, p2p, out_q):
     try:
         torch.cuda.set_device(rank)
         dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
-        structured = kind == STRUCTURED
-        if structured:  # per-rank analytic generator; the reference run below uses the general builder
+        structured = kind in (STRUCTURED, STRUCTURED_SLABS)
+        slabs = kind in (SLABS, STRUCTURED_SLABS)
+        if structured or slabs:  # per-rank analytic generator; the reference run below uses the general builder
             kind = 0
         raw = cfdl.meshgen(kind, n, jitter=0.2 if kind else 0.0, shuffle=bool(kind))
         geom = cfdl.mesh_build(raw)
         bcs = cfdl.default_bcs(raw)
         if structured:
-            s = cfdl.Solver.structured_hex(n, device=rank, rank=rank, nranks=world)
+            s = cfdl.Solver.structured_hex(n, device=rank, rank=rank, nranks=world, slabs=slabs)
         else:
             c2r, _, _ = cfdl.partition_rcb(geom, world)
+            if slabs:
+                k = np.arange(n ** 3) // (n * n)
+                c2r = np.zeros(n ** 3, np.int32)
+                for r in range(world):
+                    c2r[(k >= n * r // world) & (k < n * (r + 1) // world)] = r + 1
             s = cfdl.Solver(geom, bcs, device=rank, cell2rank=c2r, rank=rank, nranks=world)
         ids = [cfdl.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -54,6 +62,8 @@ def _worker(rank, world, port, kind, n, p2p, out_q):
             dist.all_gather_object(handles, s.ipc_handle())
             s.ipc_connect(handles)
         hist = s.run(dt=0.01, nit=100, ntstep=2, ncoef=3)
+        if slabs and p2p:
+            assert int(s.get_info("rbq_dist")) == 1, "the persistent partitioned pc solve is not in use"
         fields = {}
         for f in ("u", "v", "w", "p", "gp") + (() if structured else ("mip",)):  # structured: own face numbering
             a = np.full(s.field_size(f), np.nan)
@@ -90,7 +100,8 @@ def _worker(rank, world, port, kind, n, p2p, out_q):
         out_q.put((rank, "FAIL: " + "".join(traceback.format_exception(type(ex), ex, ex.__traceback__))))
 
 
-@pytest.mark.parametrize("kind,n,p2p", [(0, 10, False), (1, 5, False), (0, 10, True), (0, 24, True), (STRUCTURED, 12, False), (STRUCTURED, 16, True), (1, 5, True)])
+@pytest.mark.parametrize("kind,n,p2p", [(0, 10, False), (1, 5, False), (0, 10, True), (0, 24, True), (STRUCTURED, 12, False), (STRUCTURED, 16, True), (1, 5, True),
+                                          (SLABS, 24, True), (SLABS, 48, True), (STRUCTURED_SLABS, 32, True), (SLABS, 12, False)])
 def test_partitioned_run_equals_single_gpu(cfdl, kind, n, p2p):
     world = min(cfdl.device_count(), 4)
     if world < 2:

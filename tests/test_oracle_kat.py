@@ -1,8 +1,8 @@
 """Known-answer tests that pin the CPU oracle (oracle/*.cpp).
 
 The reference ships no tests, golden vectors or runnable case for this path
-and cannot be compiled here (no Fortran compiler), so the oracle's parity is UNPINNED by the
-reference itself.  These are the analytic properties the reference code satisfies by
+and cannot be compiled here (no Fortran compiler); since round 2 the oracle is pinned to the reference's source text
+executed by an interpreter (tests/test_oracle_vs_reference_source.py).  These are, in addition, the analytic properties the reference code satisfies by
 construction; each test names the reference lines it follows.
 """
 import numpy as np
