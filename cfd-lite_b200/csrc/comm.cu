@@ -256,7 +256,9 @@ int p2p_alloc_slab(Handle* h) {
       hd.rbq_L = L; hd.rbq_Gc = Gc; hd.rbq_Ls = Ls; hd.rbq_ifc = ifc;
       hd.off_rbq_r2 = (long long)off; off += align256(sizeof(double) * 2 * ((size_t)nred + 2 + h->G + 2));
       for (int b = 0; b < 2; ++b) { hd.off_rbq_b[b] = (long long)off; off += align256(sizeof(double) * ((size_t)nblack + 2 + h->G + 2)); }
-      hd.off_rbq_prog = (long long)off; off += align256(sizeof(unsigned long long) * RBQ_PROG_STRIDE * 9);
+      hd.off_rbq_prog = (long long)off; off += align256(sizeof(unsigned long long) * RBQ_PROG_STRIDE);
+      hd.off_rbq_llr = (long long)off; off += align256(32 * ((size_t)h->G + 2));
+      for (int b = 0; b < 2; ++b) { hd.off_rbq_llb[b] = (long long)off; off += align256(16 * ((size_t)h->G + 2)); }
     }
   }
   for (int i = 0; i < hd.nnbr; ++i) hd.nbr_rank[i] = p.nbr_rank[i];

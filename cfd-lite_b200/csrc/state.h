@@ -61,7 +61,9 @@ struct P2PHeader {
   int rbq_Ls;              // rows per interface chunk (shorter, so that their pushes and flags travel while the interior chunks still work)
   long long off_rbq_r2;    // double2 r2[nred + 2 + G]: red {newest, mid}; ghost g at nred + 2 + g
   long long off_rbq_b[2];  // double b[N - nred + 2 + G] x 2: the two black buffers; ghost g at (N - nred) + 2 + g
-  long long off_rbq_prog;  // unsigned long long prog[RBQ_PROG_STRIDE * 9]: own chunks, then one block per neighbour (written by it)
+  long long off_rbq_prog;  // unsigned long long prog[RBQ_PROG_STRIDE]: progress words of the own chunks
+  long long off_rbq_llr;   // {double value, u64 tag} x 2 per ghost: newest and mid value of a red ghost, each tagged with the pass that wrote it
+  long long off_rbq_llb[2];// {double value, u64 tag} per ghost and black buffer
   long long off_mailv_val; // double mailv_val[2][64][MAILV_LEN]: vector all-reduce mailbox, alternating sets
   long long off_mailv_seq; // unsigned long long mailv_seq[2][64]
 };
@@ -135,6 +137,7 @@ struct Handle {
   int rbq_dist_state = 0;         // 0: not set up yet, 1: ready, -1: refused (on every rank alike)
   int32_t* rbq_nbq = nullptr;     // K x Np: neighbour position in the other colour's value array (ghosts appended)
   int32_t *rbq_wait_ptr = nullptr, *rbq_wait_idx = nullptr;
+  int32_t *rbq_land_ptr[2] = {nullptr, nullptr}, *rbq_land_g[2] = {nullptr, nullptr};
   int32_t *rbq_push_ptr[2] = {nullptr, nullptr}, *rbq_push_src[2] = {nullptr, nullptr}, *rbq_push_nbr[2] = {nullptr, nullptr}, *rbq_push_dst[2] = {nullptr, nullptr};
   unsigned long long rbq_epoch = 0;  // launches done (every rank performs the same sequence): progress words only ever grow
   int64_t prof_extra_passes = 0;  // passes executed a second time because the stopping rule fired inside a block
@@ -159,6 +162,7 @@ struct Handle {
   int grad_variant = 1;        // calc_grad: 1 = on the LSQ statics (inverse matrix and weights precomputed), 0 = the reference's form
   double *fs_n[3] = {nullptr, nullptr, nullptr}, *fs_dr[3] = {nullptr, nullptr, nullptr}, *fs_drp[3] = {nullptr, nullptr, nullptr};
   int use_statics = 1;         // 0: recompute face geometry in every kernel (the reference's way)
+  int mip_hoist = 1;           // calc_mip: connectivity of all slots loaded up front (two CTAs per SM) / per face (three)
   int tune_ctas = 8;           // CTAs per SM for the solver passes (grid = min(need, num_sms * tune_ctas))
   // cfdl_step_host: transfer streams that run beside the compute stream, and a staging area of
   // its own (reference-numbered copies of the late input and the early outputs)

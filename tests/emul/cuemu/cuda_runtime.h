@@ -40,6 +40,7 @@ using std::min;
 struct uint3 { unsigned x, y, z; };
 struct alignas(16) double2 { double x, y; };
 struct alignas(8) int2 { int x, y; };
+struct alignas(16) ulonglong2 { unsigned long long x, y; };
 struct dim3 {
   unsigned x, y, z;
   constexpr dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
@@ -173,6 +174,7 @@ template <class T> inline T __shfl_sync(unsigned, T v, int src) {
 inline void __syncwarp(unsigned = 0xffffffffu) { char c = 0, all[32]; cuemu::warp_exchange(&c, all, 1); }
 long long clock64();
 inline long long __double_as_longlong(double v) { long long r; std::memcpy(&r, &v, sizeof r); return r; }
+inline double __longlong_as_double(long long v) { double r; std::memcpy(&r, &v, sizeof r); return r; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
