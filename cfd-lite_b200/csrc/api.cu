@@ -31,10 +31,14 @@ int dev_zero(Handle* h, T*& dst, size_t n) {
   return CFDL_OK;
 }
 
+// the fields of the energy / scalar equations (appended to the enum) fall into the same two categories
+inline bool is_cell_scalar(int f) { return f <= CFDL_F_PC || (f >= CFDL_F_T && f <= CFDL_F_S0); }
+inline bool is_cell_vector(int f) { return (f >= CFDL_F_GU && f <= CFDL_F_GPC) || (f >= CFDL_F_GT && f <= CFDL_F_GS); }
+
 // device-side length of a field (device numbering)
 size_t field_len(const Handle* h, int f) {
-  if (f <= CFDL_F_PC) return (size_t)h->H;
-  if (f <= CFDL_F_GPC) return 3 * (size_t)h->H;
+  if (is_cell_scalar(f)) return (size_t)h->H;
+  if (is_cell_vector(f)) return 3 * (size_t)h->H;
   if (f <= CFDL_F_MIP0) return (size_t)h->F;
   if (f == CFDL_F_ANB) return (size_t)h->K * h->Np;  // device ELL storage
   if (f == CFDL_F_D || f == CFDL_F_DC) return (size_t)h->Nc;  // gathered at neighbours: ghost copies needed
@@ -43,8 +47,8 @@ size_t field_len(const Handle* h, int f) {
 // host-side length (reference numbering of the global mesh)
 size_t host_len(const Handle* h, int f) {
   const Prep& p = h->prep;
-  if (f <= CFDL_F_PC) return (size_t)p.gN + p.gB;
-  if (f <= CFDL_F_GPC) return 3 * ((size_t)p.gN + p.gB);
+  if (is_cell_scalar(f)) return (size_t)p.gN + p.gB;
+  if (is_cell_vector(f)) return 3 * ((size_t)p.gN + p.gB);
   if (f <= CFDL_F_MIP0) return (size_t)p.gF;
   if (f == CFDL_F_ANB) return (size_t)p.gZ;
   return (size_t)p.gN;
@@ -62,8 +66,8 @@ int upload_field(Handle* h, int f, const double* host) {
   if (f == CFDL_F_AP || f == CFDL_F_ANB) h->pc_sumap_ok = false;  // caller-supplied matrix: the diagonal must be read
   CFDL_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * host_len(h, f), cudaMemcpyHostToDevice, h->stream));
   if (f == CFDL_F_ANB) return k_csr_to_ell(h, h->fld[f], h->stage);
-  if (f <= CFDL_F_PC) return k_gather(h, h->fld[f], h->stage, h->cellmap, h->H, 1);
-  if (f <= CFDL_F_GPC) return k_gather(h, h->fld[f], h->stage, h->cellmap, h->H, 3);
+  if (is_cell_scalar(f)) return k_gather(h, h->fld[f], h->stage, h->cellmap, h->H, 1);
+  if (is_cell_vector(f)) return k_gather(h, h->fld[f], h->stage, h->cellmap, h->H, 3);
   if (f <= CFDL_F_MIP0) return k_gather(h, h->fld[f], h->stage, h->f2o, h->F, 1);
   return k_gather(h, h->fld[f], h->stage, h->c2o, h->N, 1);
 }
@@ -75,8 +79,8 @@ int download_field(Handle* h, int f, double* host) {
   const Prep& p = h->prep;
   if (p.nranks == 1) {
     if (f == CFDL_F_ANB) rc = k_ell_to_csr(h, h->stage, h->fld[f]);
-    else if (f <= CFDL_F_PC) rc = k_scatter(h, h->stage, h->fld[f], h->cellmap, h->H, 1);
-    else if (f <= CFDL_F_GPC) rc = k_scatter(h, h->stage, h->fld[f], h->cellmap, h->H, 3);
+    else if (is_cell_scalar(f)) rc = k_scatter(h, h->stage, h->fld[f], h->cellmap, h->H, 1);
+    else if (is_cell_vector(f)) rc = k_scatter(h, h->stage, h->fld[f], h->cellmap, h->H, 3);
     else if (f <= CFDL_F_MIP0) rc = k_scatter(h, h->stage, h->fld[f], h->f2o, h->F, 1);
     else rc = k_scatter(h, h->stage, h->fld[f], h->c2o, h->N, 1);
     if (rc) return rc;
@@ -97,8 +101,8 @@ int download_field(Handle* h, int f, double* host) {
   t.resize(field_len(h, f));
   CFDL_CUDA(cudaMemcpyAsync(t.data(), h->fld[f], sizeof(double) * t.size(), cudaMemcpyDeviceToHost, h->stream));
   CFDL_CUDA(cudaStreamSynchronize(h->stream));
-  if (f <= CFDL_F_GPC) {
-    const int nc = (f <= CFDL_F_PC) ? 1 : 3;
+  if (is_cell_scalar(f) || is_cell_vector(f)) {
+    const int nc = is_cell_scalar(f) ? 1 : 3;
     for (int32_t c = 0; c < p.N; ++c) for (int q = 0; q < nc; ++q) host[(size_t)p.c2o[c] * nc + q] = t[(size_t)c * nc + q];
     for (int32_t j = 0; j < p.B; ++j) for (int q = 0; q < nc; ++q) host[((size_t)p.gN + p.h2o[j]) * nc + q] = t[((size_t)p.Nc + j) * nc + q];
   } else if (f <= CFDL_F_MIP0) {
@@ -225,7 +229,7 @@ int create_from_prep(cfdl_handle_s* h, const GeomSource& G, cfdl_handle* out) {
   // several GPUs: u, v, w, pc and the second solver array live in one IPC-exportable slab so
   // that neighbours can write their ghost cells directly (cfdl_comm_ipc_connect)
   if (nranks > 1 && (rc = p2p_alloc_slab(h))) return bail(rc);
-  for (int f = 0; f < CFDL_F_COUNT; ++f)
+  for (int f = 0; f <= CFDL_F_ANB; ++f)  // (the fields of the energy / scalar equations are allocated by their init calls)
     if (!h->fld[f] && (rc = dev_zero(h, h->fld[f], field_len(h, f) + 4))) return bail(rc);
   h->stage_len = std::max(std::max(3 * ((size_t)p.gN + p.gB), (size_t)p.gZ), (size_t)p.gF) + 4;
   if ((rc = dev_zero(h, h->stage, h->stage_len))) return bail(rc);
@@ -395,6 +399,7 @@ int cfdl_get_cell_order(cfdl_handle h, int32_t* c2o, int32_t* color_ptr) {
 int cfdl_upload_field(cfdl_handle h, int field, const double* host) {
   ENTER(h);
   if (field < 0 || field >= CFDL_F_COUNT || !host) return fail(CFDL_ERR_ARG, "cfdl_upload_field: bad field/pointer");
+  if (!h->fld[field]) return fail(CFDL_ERR_ARG, "cfdl_upload_field: field %d belongs to the energy / scalar equation: call cfdl_energy_init / cfdl_scalar_init first", field);
   int rc = upload_field(h, field, host);
   if (rc) return rc;
   FINISH(h);
@@ -402,6 +407,7 @@ int cfdl_upload_field(cfdl_handle h, int field, const double* host) {
 int cfdl_download_field(cfdl_handle h, int field, double* host) {
   ENTER(h);
   if (field < 0 || field >= CFDL_F_COUNT || !host) return fail(CFDL_ERR_ARG, "cfdl_download_field: bad field/pointer");
+  if (!h->fld[field]) return fail(CFDL_ERR_ARG, "cfdl_download_field: field %d belongs to the energy / scalar equation: call cfdl_energy_init / cfdl_scalar_init first", field);
   return download_field(h, field, host);
 }
 int cfdl_field_local_size(cfdl_handle h, int field, int64_t* n) {
@@ -412,6 +418,7 @@ int cfdl_field_local_size(cfdl_handle h, int field, int64_t* n) {
 int cfdl_upload_field_local(cfdl_handle h, int field, const double* host) {
   ENTER(h);
   if (field < 0 || field >= CFDL_F_COUNT || !host) return fail(CFDL_ERR_ARG, "cfdl_upload_field_local: bad field/pointer");
+  if (!h->fld[field]) return fail(CFDL_ERR_ARG, "cfdl_upload_field_local: field %d belongs to the energy / scalar equation: call cfdl_energy_init / cfdl_scalar_init first", field);
   if (field == CFDL_F_AP || field == CFDL_F_ANB) h->pc_sumap_ok = false;
   CFDL_CUDA(cudaMemcpyAsync(h->fld[field], host, sizeof(double) * field_len(h, field), cudaMemcpyHostToDevice, h->stream));
   FINISH(h);
@@ -419,6 +426,7 @@ int cfdl_upload_field_local(cfdl_handle h, int field, const double* host) {
 int cfdl_download_field_local(cfdl_handle h, int field, double* host) {
   ENTER(h);
   if (field < 0 || field >= CFDL_F_COUNT || !host) return fail(CFDL_ERR_ARG, "cfdl_download_field_local: bad field/pointer");
+  if (!h->fld[field]) return fail(CFDL_ERR_ARG, "cfdl_download_field_local: field %d belongs to the energy / scalar equation: call cfdl_energy_init / cfdl_scalar_init first", field);
   CFDL_CUDA(cudaMemcpyAsync(host, h->fld[field], sizeof(double) * field_len(h, field), cudaMemcpyDeviceToHost, h->stream));
   FINISH(h);
 }
@@ -443,6 +451,18 @@ int cfdl_run(cfdl_handle h, double dt, int32_t nit, int32_t ntstep, int32_t ncoe
   }
   FINISH(h);
 }
+
+// energy and scalar equations (kernels_transport.cu)
+int cfdl_energy_init(cfdl_handle h, const double* tc, const double* cp) { ENTER(h); int rc = k_energy_init(h, tc, cp); if (rc) return rc; FINISH(h); }
+int cfdl_solve_energy(cfdl_handle h, double dt, int32_t nit, double* out4) { ENTER(h); int rc = k_solve_energy(h, dt, nit, out4); if (rc) return rc; FINISH(h); }
+int cfdl_scalar_init(cfdl_handle h, double dcoef, const double* vel, const double* bc_value) {
+  ENTER(h);
+  if (!vel) return fail(CFDL_ERR_ARG, "cfdl_scalar_init: vel is NULL");
+  int rc = k_scalar_init(h, dcoef, vel, bc_value);
+  if (rc) return rc;
+  FINISH(h);
+}
+int cfdl_solve_scalar(cfdl_handle h, double dt, int32_t nit, double* out4) { ENTER(h); int rc = k_solve_scalar(h, dt, nit, out4); if (rc) return rc; FINISH(h); }
 
 int cfdl_calc_coef_uvw(cfdl_handle h, double dt) {
   ENTER(h);
@@ -588,8 +608,8 @@ namespace {
 // own; `map`/`ncomp`/`n` describe the permutation (device index i <-> host index map[i])
 struct FieldMap { const int32_t* map; int64_t n; int ncomp; };
 FieldMap field_map(const Handle* h, int f) {
-  if (f <= CFDL_F_PC) return {h->cellmap, h->H, 1};
-  if (f <= CFDL_F_GPC) return {h->cellmap, h->H, 3};
+  if (is_cell_scalar(f)) return {h->cellmap, h->H, 1};
+  if (is_cell_vector(f)) return {h->cellmap, h->H, 3};
   if (f <= CFDL_F_MIP0) return {h->f2o, h->F, 1};
   return {h->c2o, h->N, 1};
 }

@@ -45,6 +45,7 @@ int k_update_boundaries(Handle* h) {
                                                             h->bc_uvw, h->aip, h->fld[CFDL_F_U], h->fld[CFDL_F_V],
                                                             h->fld[CFDL_F_W], h->fld[CFDL_F_P], h->fld[CFDL_F_MIP]);
   CFDL_CUDA(cudaGetLastError());
+  if (h->has_energy || h->has_scalar) return k_transport_boundaries(h);  // mod_physics.f90:45,47
   return CFDL_OK;
 }
 
@@ -645,6 +646,7 @@ int k_update_time(Handle* h) {
   CFDL_CUDA(cudaMemcpyAsync(h->fld[CFDL_F_V0], h->fld[CFDL_F_V], hb, cudaMemcpyDeviceToDevice, h->stream));
   CFDL_CUDA(cudaMemcpyAsync(h->fld[CFDL_F_W0], h->fld[CFDL_F_W], hb, cudaMemcpyDeviceToDevice, h->stream));
   CFDL_CUDA(cudaMemcpyAsync(h->fld[CFDL_F_MIP0], h->fld[CFDL_F_MIP], sizeof(double) * (size_t)h->F, cudaMemcpyDeviceToDevice, h->stream));
+  if (h->has_energy || h->has_scalar) return k_transport_update_time(h);
   return CFDL_OK;
 }
 

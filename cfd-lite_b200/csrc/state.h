@@ -104,6 +104,11 @@ struct Handle {
   double *vol = nullptr, *rho = nullptr, *mu = nullptr;
   // fields, indexed by CFDL_F_*
   double* fld[CFDL_F_COUNT] = {nullptr};
+  // energy and scalar equations (kernels_transport.cu; fields allocated by cfdl_energy_init / cfdl_scalar_init)
+  bool has_energy = false, has_scalar = false;
+  double *tc = nullptr, *cp = nullptr;  // thermal conductivity, heat capacity per cell (Nc)
+  double* s_bc = nullptr;               // scalar: Dirichlet value per boundary section
+  double s_dcoef = 1.0, s_vel[3] = {0.0, 0.0, -100.0};
   // staging + solver work
   double* stage = nullptr;      // max(3H, Z, F) doubles for permuted host transfers
   size_t stage_len = 0;
@@ -132,6 +137,7 @@ struct Handle {
   int rbq_ctas_per_sm = 0;        // > 0: use fewer CTAs per SM than that
   double* rbq_mem = nullptr;      // red pairs, black buffers, per-pass partials, progress words
   size_t rbq_len = 0;
+  unsigned long long* rbq_prog = nullptr;  // one GPU: progress words of the chunks + error word (fixed place, never reset)
   // partitioned meshes (peer-to-peer mode): value arrays and progress words live in the exported slab; per chunk the progress
   // words to wait for (own chunks and the neighbours' interface chunks), the interface rows to push after a pass
   int rbq_dist_state = 0;         // 0: not set up yet, 1: ready, -1: refused (on every rank alike)
@@ -145,7 +151,7 @@ struct Handle {
   int pc_sumap = 1;               // fused pc passes rebuild ap as the slot-order sum of anb instead of reading it
   bool pc_sumap_ok = false;       // true while ap/anb on the device are what calc_coef_p wrote (cleared by any other writer)
   int uvw_fused = 1;              // 1: u, v, w side by side, 0: one after the other as the reference does (same bits)
-  int last_passes[4] = {1, 1, 1, 1};  // per equation: passes the previous solve needed (first-batch size estimate)
+  int last_passes[8] = {1, 1, 1, 1, 1, 1, 1, 1};  // per equation: passes the previous solve needed (first-batch size estimate)
   int fused_rb = 1;            // 0: always use one launch per colour + residual pass
   int use_p2p = 1;             // 0: NCCL send/recv even when peer slabs are connected
   int occ_grids = 1;           // assembly kernels: grid = resident CTAs (occupancy API) instead of 8 per SM
@@ -162,7 +168,7 @@ struct Handle {
   int grad_variant = 1;        // calc_grad: 1 = on the LSQ statics (inverse matrix and weights precomputed), 0 = the reference's form
   double *fs_n[3] = {nullptr, nullptr, nullptr}, *fs_dr[3] = {nullptr, nullptr, nullptr}, *fs_drp[3] = {nullptr, nullptr, nullptr};
   int use_statics = 1;         // 0: recompute face geometry in every kernel (the reference's way)
-  int mip_hoist = 1;           // calc_mip: connectivity of all slots loaded up front (two CTAs per SM) / per face (three)
+  int mip_hoist = 0;           // calc_mip: connectivity of all slots loaded up front (two CTAs per SM) / per face (three)
   int tune_ctas = 8;           // CTAs per SM for the solver passes (grid = min(need, num_sms * tune_ctas))
   // cfdl_step_host: transfer streams that run beside the compute stream, and a staging area of
   // its own (reference-numbered copies of the late input and the early outputs)
@@ -238,6 +244,13 @@ int k_update_uvwp(Handle* h);
 int k_calc_grad(Handle* h, const double* phi, double* grad);
 int k_calc_grad3(Handle* h);  // gu,gv,gw from u,v,w in one pass
 int k_update_time(Handle* h);
+// kernels_transport.cu: energy (mod_energy.f90) and scalar (mod_scalar.f90) equations
+int k_energy_init(Handle* h, const double* tc_host, const double* cp_host);
+int k_scalar_init(Handle* h, double dcoef, const double vel[3], const double* bc_value_host);
+int k_transport_boundaries(Handle* h);
+int k_transport_update_time(Handle* h);
+int k_solve_energy(Handle* h, double dt, int nit, double* out4);
+int k_solve_scalar(Handle* h, double dt, int nit, double* out4);
 int k_gather(Handle* h, double* dst, const double* src, const int32_t* map, int64_t n, int ncomp);
 int k_scatter(Handle* h, double* dst, const double* src, const int32_t* map, int64_t n, int ncomp);
 int k_csr_to_ell(Handle* h, double* ell, const double* csr);

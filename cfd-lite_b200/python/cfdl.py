@@ -20,7 +20,7 @@ MESH_HEX, MESH_TET = 0, 1
 BC_WALL, BC_LID, BC_SYMMETRY = 0, 1, 2
 SOLVER_PARITY, SOLVER_MCSGS, SOLVER_PCG = 0, 1, 2
 EQ_U, EQ_V, EQ_W, EQ_PC = 0, 1, 2, 3
-FIELDS = ("u v w p u0 v0 w0 pc gu gv gw gp gpc mip mip0 bu bv bw d dc ap b anb").split()
+FIELDS = ("u v w p u0 v0 w0 pc gu gv gw gp gpc mip mip0 bu bv bw d dc ap b anb t h h0 s s0 gt gh gs").split()
 FIELD_ID = {n: i for i, n in enumerate(FIELDS)}
 
 
@@ -298,9 +298,9 @@ class Solver:
             pass
 
     def field_size(self, name):
-        if name in ("u", "v", "w", "p", "u0", "v0", "w0", "pc"):
+        if name in ("u", "v", "w", "p", "u0", "v0", "w0", "pc", "t", "h", "h0", "s", "s0"):
             return self.H
-        if name in ("gu", "gv", "gw", "gp", "gpc"):
+        if name in ("gu", "gv", "gw", "gp", "gpc", "gt", "gh", "gs"):
             return 3 * self.H
         if name in ("mip", "mip0"):
             return self.nf
@@ -383,6 +383,28 @@ class Solver:
 
     def update_time(self):
         _chk(lib().cfdl_update_time(self.h))
+
+    def energy_init(self, tc=None, cp=None):
+        """construct_energy (mod_energy.f90:14-48); tc / cp per cell (reference numbering) or None for 5 / 1000"""
+        tc = _f64(tc) if tc is not None else None
+        cp = _f64(cp) if cp is not None else None
+        _chk(lib().cfdl_energy_init(self.h, _d(tc) if tc is not None else None, _d(cp) if cp is not None else None))
+
+    def solve_energy(self, dt=0.01, nit=100):
+        out = np.zeros(4)
+        _chk(lib().cfdl_solve_energy(self.h, C.c_double(dt), C.c_int32(nit), _d(out)))
+        return out
+
+    def scalar_init(self, dcoef=1.0, vel=(0.0, 0.0, -100.0), bc_value=None):
+        """construct_scalar (mod_scalar.f90:16-46) with a Dirichlet value per boundary section of this mesh"""
+        vel = _f64(vel)
+        bcv = _f64(bc_value) if bc_value is not None else None
+        _chk(lib().cfdl_scalar_init(self.h, C.c_double(dcoef), _d(vel), _d(bcv) if bcv is not None else None))
+
+    def solve_scalar(self, dt=0.01, nit=100):
+        out = np.zeros(4)
+        _chk(lib().cfdl_solve_scalar(self.h, C.c_double(dt), C.c_int32(nit), _d(out)))
+        return out
 
     def solve_uvwp(self, dt=0.01, nit=100):
         hist = np.zeros(16)

@@ -69,11 +69,15 @@ enum {
   CFDL_F_BU, CFDL_F_BV, CFDL_F_BW, CFDL_F_D, CFDL_F_DC, /* (ne) */
   CFDL_F_AP, CFDL_F_B,                                /* (ne)  shared ap / b of phys_t */
   CFDL_F_ANB,                                         /* (2nf-nbf) CSR order of ef2nb */
+  /* energy_t (mod_energy.f90:5-10: t, phi = enthalpy cp t, phi0) and scalar_t (mod_scalar.f90:5-12: phi, phi0);
+     allocated by cfdl_energy_init / cfdl_scalar_init */
+  CFDL_F_T, CFDL_F_H, CFDL_F_H0, CFDL_F_S, CFDL_F_S0, /* (ne+nbf) */
+  CFDL_F_GT, CFDL_F_GH, CFDL_F_GS,                    /* 3*(ne+nbf), AoS: gt, grad of the energy equation, grad of the scalar */
   CFDL_F_COUNT
 };
 
 /* equation selector replacing the Fortran `cname` string (mod_solver.f90:268-269) */
-enum { CFDL_EQ_U = 0, CFDL_EQ_V = 1, CFDL_EQ_W = 2, CFDL_EQ_PC = 3 };
+enum { CFDL_EQ_U = 0, CFDL_EQ_V = 1, CFDL_EQ_W = 2, CFDL_EQ_PC = 3, CFDL_EQ_E = 4 /* energy */, CFDL_EQ_S = 5 /* scalar */ };
 
 typedef struct cfdl_handle_s* cfdl_handle;
 
@@ -153,6 +157,24 @@ int cfdl_update_boundaries(cfdl_handle h);
 int cfdl_solve_uvwp(cfdl_handle h, double dt, int32_t nit, double* hist);
 /* update_time, mod_physics.f90:101-112 */
 int cfdl_update_time(cfdl_handle h);
+/* The energy (enthalpy) and passive-scalar equations of the reference (single-GPU handles).
+ *   cfdl_energy_init   construct_energy, mod_energy.f90:14-48: t = 273, phi = cp t, phi0 = phi, gradients 0; tc / cp are
+ *                      per-cell arrays (ne, reference numbering) or NULL for init_properties' 5 and 1000
+ *                      (mod_properties.f90:88-89).  From then on cfdl_update_boundaries also runs the energy callbacks
+ *                      (lid: 373 K on the CFDL_BC_LID section, dirichlet0: 273 K elsewhere, mod_energy.f90:173-212) and
+ *                      cfdl_update_time copies phi0 = phi (mod_physics.f90:110).
+ *   cfdl_solve_energy  solve_energy, mod_energy.f90:59-80 (the call main.f90:59 has commented out): gradients of t and
+ *                      phi, calc_coef_energy, solve_gs('e'), calc_temperature; out4 = (it, res_i, res_f, res_max).
+ *   cfdl_scalar_init   construct_scalar, mod_scalar.f90:16-46, with this mesh's boundary sections: bc_value[i] is the
+ *                      Dirichlet value on section i (dirichlet0 / dirichlet1; NULL: all 0); dcoef and vel are the
+ *                      type's components (reference defaults 1 and (0,0,-100)).
+ *   cfdl_solve_scalar  solve_scalar, mod_scalar.f90:56-72.
+ * Fields: CFDL_F_T, CFDL_F_H (phi), CFDL_F_H0, CFDL_F_GT, CFDL_F_GH; CFDL_F_S, CFDL_F_S0, CFDL_F_GS.  The shared
+ * ap / anb / b arrays hold the last assembled equation, as in the reference. */
+int cfdl_energy_init(cfdl_handle h, const double* tc, const double* cp);
+int cfdl_solve_energy(cfdl_handle h, double dt, int32_t nit, double* out4);
+int cfdl_scalar_init(cfdl_handle h, double dcoef, const double* vel, const double* bc_value);
+int cfdl_solve_scalar(cfdl_handle h, double dt, int32_t nit, double* out4);
 /* the main.f90:50-63 loop: ntstep x (ncoef x (update_boundaries; solve_uvwp); update_time).
  * hist (ntstep*ncoef*16 doubles) may be NULL. */
 int cfdl_run(cfdl_handle h, double dt, int32_t nit, int32_t ntstep, int32_t ncoef, double* hist);

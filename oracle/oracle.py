@@ -61,7 +61,7 @@ class OracleCase:
     """One reference run: mesh set-up (cell_input) + construct_physics, then the hot path."""
 
     REAL = ("xc yc zc aip rip vol rho mu ap anb b phic u v w p gu gv gw gp gpc mip mip0 "
-            "u0 v0 w0 bu bv bw d dc").split()
+            "u0 v0 w0 bu bv bw d dc tc cp t gt h h0 gh s s0 gs").split()
     INT = "ef2nb_idx ef2nb_nb ef2nb_fg s2g bs gf2g g2gf_p g2gf_idx".split()
 
     def __init__(self, raw, n_subdomains=1, geom=None):
@@ -153,6 +153,26 @@ class OracleCase:
         sec = C.c_double()
         self._chk(lib().orc_run(self.h, C.c_int(ntstep), C.c_int(ncoef), _d(hist), C.byref(sec)))
         return hist.reshape(ntstep * ncoef, 4, 4), sec.value
+
+    def construct_energy(self):
+        """construct_energy (mod_energy.f90:14-48): t = 273, phi = cp t, tc = 5, cp = 1000"""
+        self._chk(lib().orc_construct_energy(self.h))
+
+    def solve_energy(self):
+        out = np.zeros(4)
+        self._chk(lib().orc_solve_energy(self.h, _d(out)))
+        return out
+
+    def construct_scalar(self, dcoef=1.0, vel=(0.0, 0.0, -100.0), bc_value=None):
+        """construct_scalar (mod_scalar.f90:16-46) with a Dirichlet value per boundary section"""
+        vel = _f64(vel)
+        bcv = _f64(bc_value) if bc_value is not None else None
+        self._chk(lib().orc_construct_scalar(self.h, C.c_double(dcoef), _d(vel), _d(bcv) if bcv is not None else None))
+
+    def solve_scalar(self):
+        out = np.zeros(4)
+        self._chk(lib().orc_solve_scalar(self.h, _d(out)))
+        return out
 
     def calc_coef_uvw(self):
         self._chk(lib().orc_calc_coef_uvw(self.h))

@@ -93,7 +93,9 @@ double* orc_real(void* h, const char* name, long* n) {
              {"b", &c->b}, {"phic", &c->phic}, {"u", &c->u}, {"v", &c->v}, {"w", &c->w}, {"p", &c->p},
              {"gu", &c->gu}, {"gv", &c->gv}, {"gw", &c->gw}, {"gp", &c->gp}, {"gpc", &c->gpc},
              {"mip", &c->mip}, {"mip0", &c->mip0}, {"u0", &c->u0}, {"v0", &c->v0}, {"w0", &c->w0},
-             {"bu", &c->bu}, {"bv", &c->bv}, {"bw", &c->bw}, {"d", &c->d}, {"dc", &c->dc}};
+             {"bu", &c->bu}, {"bv", &c->bv}, {"bw", &c->bw}, {"d", &c->d}, {"dc", &c->dc},
+             {"tc", &c->tc}, {"cp", &c->cp}, {"t", &c->t}, {"gt", &c->gt}, {"h", &c->h}, {"h0", &c->h0}, {"gh", &c->gh},
+             {"s", &c->s}, {"s0", &c->s0}, {"gs", &c->gs}};
   for (auto& e : tab)
     if (!std::strcmp(e.k, name)) { *n = e.a->size(); return e.a->data(); }
   *n = -1;
@@ -150,6 +152,12 @@ static void put_stats(const SolveStat* st, int n, double* out) {
 
 int orc_update_boundaries(void* h) { ORC_TRY update_boundaries(*(Case*)h); return 0; ORC_CATCH(1) }
 int orc_update_time(void* h) { ORC_TRY update_time(*(Case*)h); return 0; ORC_CATCH(1) }
+int orc_construct_energy(void* h) { ORC_TRY construct_energy(*(Case*)h); return 0; ORC_CATCH(1) }
+int orc_solve_energy(void* h, double* out4) { ORC_TRY SolveStat st = solve_energy(*(Case*)h); if (out4) put_stats(&st, 1, out4); return 0; ORC_CATCH(1) }
+int orc_construct_scalar(void* h, double dcoef, const double* vel, const double* bc_value) {
+  ORC_TRY construct_scalar(*(Case*)h, dcoef, vel, bc_value); return 0; ORC_CATCH(1)
+}
+int orc_solve_scalar(void* h, double* out4) { ORC_TRY SolveStat st = solve_scalar(*(Case*)h); if (out4) put_stats(&st, 1, out4); return 0; ORC_CATCH(1) }
 int orc_solve_uvwp(void* h, double* hist16) {
   ORC_TRY
   SolveStat st[4];

@@ -556,6 +556,8 @@ void update_uvwp(Case& c) {  // :370-436 (cell-velocity correction is if(.false.
 }
 
 // BC callbacks dirichlet0 / lid / symmetry, mod_uvwp.f90:493-570
+static void energy_boundaries(Case& c);
+static void scalar_boundaries(Case& c);
 void update_boundaries(Case& c) {  // mod_physics.f90:38-50
   Mesh& g = c.m;
   for (size_t i = 0; i < c.bcs.size(); ++i) {
@@ -584,10 +586,165 @@ void update_boundaries(Case& c) {  // mod_physics.f90:38-50
       c.mip(fg) = 0.0;
     }
   }
+  if (c.has_energy) energy_boundaries(c);  // :47
+  if (c.has_scalar) scalar_boundaries(c);  // :45 (commented out in the reference)
 }
 
 void update_time(Case& c) {  // mod_physics.f90:101-112
   c.u0.d = c.u.d; c.v0.d = c.v.d; c.w0.d = c.w.d; c.mip0.d = c.mip.d;
+  if (c.has_energy) c.h0.d = c.h.d;  // :110
+  if (c.has_scalar) c.s0.d = c.s.d;  // :104 (commented out in the reference, whose scalar equation is never constructed)
+}
+
+// ---- energy equation (enthalpy phi = cp*T), src/equations/mod_energy.f90 ---------------------------------------------
+void construct_energy(Case& c) {  // :14-48; init_properties: tc = 5, cp = 1000 (mod_properties.f90:88-89)
+  Mesh& g = c.m;
+  const long H = g.ne + g.nbf;
+  c.tc.alloc(g.ne, 5.0); c.cp.alloc(g.ne, 1000.0);
+  c.t.alloc(H, 273.0); c.gt.alloc(3 * H, 0.0); c.h.alloc(H, 0.0); c.h0.alloc(H, 0.0); c.gh.alloc(3 * H, 0.0);
+  // :33 eqn%phi = eqn%t*prop%cp with arrays of ne+nbf and ne entries (non-conforming in the reference): the halo entries are
+  // overwritten by the boundary callbacks before they are read, the cell entries are t*cp
+  for (long e = 1; e <= H; ++e) c.h(e) = c.t(e) * c.cp(e <= g.ne ? e : 1);
+  c.h0.d = c.h.d;
+  c.has_energy = true;
+}
+
+static void energy_boundaries(Case& c) {  // lid / dirichlet0 of mod_energy.f90:173-212 ('top' -> 373 K, the others 273 K)
+  Mesh& g = c.m;
+  for (BC& bc : c.bcs)
+    for (int e = bc.esec[0]; e <= bc.esec[1]; ++e) {
+      int enb, lfnb;
+      get_idx(std::abs(g.bs(e)), enb, lfnb);
+      c.t(e) = bc.kind == BC_LID ? 373.0 : 273.0;
+      c.h(e) = c.cp(enb) * c.t(e);
+    }
+}
+
+void calc_coef_energy(Case& c) {  // :82-169
+  Mesh& g = c.m;
+  const double dt = c.dt;
+  for (int e = 1; e <= g.ne; ++e) {
+    c.ap(e) = 0.0;
+    double sumf = 0.0, sumdefc = 0.0;
+    double rp[3] = {g.xc(e), g.yc(e), g.zc(e)};
+    for (int idx = g.ef2nb_idx(e); idx <= g.ef2nb_idx(e + 1) - 1; ++idx) {
+      c.anb(idx) = 0.0;
+      int enb, lfnb;
+      get_idx(g.ef2nb1(idx), enb, lfnb);
+      if (lfnb == 0) continue;
+      int fg = g.ef2nb2(idx);
+      int fg_sgn = sgn(fg);
+      fg = std::abs(fg);
+      long i = 3 * (long)fg - 2;
+      double area = std::sqrt(g.aip(i) * g.aip(i) + g.aip(i + 1) * g.aip(i + 1) + g.aip(i + 2) * g.aip(i + 2));
+      double norm[3] = {fg_sgn * g.aip(i) / area, fg_sgn * g.aip(i + 1) / area, fg_sgn * g.aip(i + 2) / area};
+      double rip[3] = {g.rip(i), g.rip(i + 1), g.rip(i + 2)};
+      double rpnb[3] = {g.xc(enb), g.yc(enb), g.zc(enb)};
+      double dr[3] = {rpnb[0] - rp[0], rpnb[1] - rp[1], rpnb[2] - rp[2]};
+      double wt;
+      vec_weight(wt, rip, rp, rpnb);
+      double f = -fg_sgn * c.mip(fg);
+      double fnb = std::max(f, 0.0);
+      sumf = sumf + f;
+      double tci = (1.0 - wt) * c.tc(e) + wt * c.tc(enb);
+      double cpi = (1.0 - wt) * c.cp(e) + wt * c.cp(enb);
+      double d = tci / cpi / dot3(dr, norm) * area;
+      double ghi[3], gti[3];
+      for (int k = 0; k < 3; ++k) {
+        ghi[k] = (1.0 - wt) * c.gh(3 * (long)e - 2 + k) + wt * c.gh(3 * (long)enb - 2 + k);
+        gti[k] = (1.0 - wt) * c.gt(3 * (long)e - 2 + k) + wt * c.gt(3 * (long)enb - 2 + k);
+      }
+      sumdefc = sumdefc + tci * area * (dot3(gti, norm) - dot3(ghi, norm) / cpi);
+      c.anb(idx) = d + fnb;
+      c.ap(e) = c.ap(e) + d + fnb;
+    }
+    double ap0 = c.rho(e) * g.vol(e) / dt;
+    c.ap(e) = c.ap(e) + ap0;
+    c.b(e) = ap0 * c.h0(e) + sumf * c.h(e) + sumdefc;
+  }
+  double d = 0.0, f = 0.0;  // locals of the routine: a 'zero_flux' section would reuse the last values (never the case: both callbacks are 'dirichlet')
+  for (size_t ibc = 0; ibc < c.bcs.size(); ++ibc)
+    for (int enb = c.bcs[ibc].esec[0]; enb <= c.bcs[ibc].esec[1]; ++enb) {
+      int e, lf;
+      get_idx(std::abs(g.bs(enb)), e, lf);
+      int idx = g.ef2nb_idx(e) + lf - 1;
+      int fg = g.ef2nb2(idx);
+      long i = 3 * (long)fg - 2;
+      double area = std::sqrt(g.aip(i) * g.aip(i) + g.aip(i + 1) * g.aip(i + 1) + g.aip(i + 2) * g.aip(i + 2));
+      double norm[3] = {g.aip(i) / area, g.aip(i + 1) / area, g.aip(i + 2) / area};
+      double dr[3] = {g.xc(enb) - g.xc(e), g.yc(enb) - g.yc(e), g.zc(enb) - g.zc(e)};
+      double ds = dot3(dr, norm);
+      f = 0.0;
+      d = c.tc(e) * area / ds / c.cp(e);
+      c.ap(e) = c.ap(e) + d + f;
+      c.anb(idx) = c.anb(idx) + d + f;
+    }
+}
+
+SolveStat solve_energy(Case& c) {  // :59-80
+  Mesh& g = c.m;
+  calc_grad(c.t.data(), c.gt.data(), g.xc.data(), g.yc.data(), g.zc.data(), g.ef2nb_idx.data(), g.ef2nb1.data(), g.ne);
+  calc_grad(c.h.data(), c.gh.data(), g.xc.data(), g.yc.data(), g.zc.data(), g.ef2nb_idx.data(), g.ef2nb1.data(), g.ne);
+  calc_coef_energy(c);
+  SolveStat st = solve_gs(false, c.h.data(), c.ap.data(), c.anb.data(), c.b.data(), g.ef2nb_idx.data(), g.ef2nb1.data(), g.ne, c.nit);
+  for (int e = 1; e <= g.ne; ++e) c.t(e) = c.h(e) / c.cp(e);  // calc_temperature, mod_properties.f90:214-222
+  return st;
+}
+
+// ---- passive scalar, src/equations/mod_scalar.f90 ---------------------------------------------------------------------
+void construct_scalar(Case& c, double dcoef, const double vel[3], const double* bc_value) {  // :16-46
+  Mesh& g = c.m;
+  const long H = g.ne + g.nbf;
+  c.s.alloc(H, 0.0); c.s0.alloc(H, 0.0); c.gs.alloc(3 * H, 0.0);
+  c.s_dcoef = dcoef;
+  for (int k = 0; k < 3; ++k) c.s_vel[k] = vel[k];
+  c.s_bc.assign(c.bcs.size(), 0.0);
+  if (bc_value) for (size_t i = 0; i < c.bcs.size(); ++i) c.s_bc[i] = bc_value[i];
+  c.has_scalar = true;
+}
+
+static void scalar_boundaries(Case& c) {  // dirichlet0 / dirichlet1, :129-155
+  for (size_t i = 0; i < c.bcs.size(); ++i)
+    for (int e = c.bcs[i].esec[0]; e <= c.bcs[i].esec[1]; ++e) c.s(e) = c.s_bc[i];
+}
+
+void calc_coef_scalar(Case& c) {  // :74-126
+  Mesh& g = c.m;
+  const double dt = c.dt;
+  for (int e = 1; e <= g.ne; ++e) {
+    c.ap(e) = 0.0;
+    double sumf = 0.0;
+    for (int idx = g.ef2nb_idx(e); idx <= g.ef2nb_idx(e + 1) - 1; ++idx) {
+      int fg = g.ef2nb2(idx);
+      int fg_sgn = sgn(fg);
+      fg = std::abs(fg);
+      long i = 3 * (long)fg - 2;
+      double area = std::sqrt(g.aip(i) * g.aip(i) + g.aip(i + 1) * g.aip(i + 1) + g.aip(i + 2) * g.aip(i + 2));
+      double norm[3] = {fg_sgn * g.aip(i) / area, fg_sgn * g.aip(i + 1) / area, fg_sgn * g.aip(i + 2) / area};
+      int enb, lfnb;
+      get_idx(g.ef2nb1(idx), enb, lfnb);
+      double dr[3] = {g.xc(enb) - g.xc(e), g.yc(enb) - g.yc(e), g.zc(enb) - g.zc(e)};
+      double mnorm[3] = {-norm[0], -norm[1], -norm[2]};
+      double f = dot3(c.s_vel, mnorm) * area;
+      double wnb = 0.0;
+      if (f > 0.0) wnb = 1.0;
+      double fnb = wnb * f;
+      sumf = sumf + f;
+      double d = c.s_dcoef / dot3(dr, dr) * dot3(dr, norm) * area;
+      c.anb(idx) = d + fnb;
+      c.ap(e) = c.ap(e) + d + fnb;
+    }
+    double ap0 = g.vol(e) / dt;
+    c.ap(e) = c.ap(e) + ap0;
+    c.b(e) = ap0 * c.s0(e) + sumf * c.s(e);
+  }
+}
+
+SolveStat solve_scalar(Case& c) {  // :56-72 (eqn%name = 'scalar': sor = 1)
+  Mesh& g = c.m;
+  calc_coef_scalar(c);
+  calc_grad(c.s.data(), c.gs.data(), g.xc.data(), g.yc.data(), g.zc.data(), g.ef2nb_idx.data(), g.ef2nb1.data(), g.ne);
+  return solve_gs(false, c.s.data(), c.ap.data(), c.anb.data(), c.b.data(), g.ef2nb_idx.data(), g.ef2nb1.data(), g.ne, c.nit);
 }
 
 void solve_uvwp(Case& c, SolveStat st[4]) {  // :95-134

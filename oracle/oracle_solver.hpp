@@ -47,6 +47,13 @@ struct Case {
   // uvwp_t, mod_uvwp.f90:6-16
   A1<double> u, v, w, p, gu, gv, gw, gp, gpc, mip, mip0, u0, v0, w0, bu, bv, bw, d, dc;
   std::vector<BC> bcs;
+  // energy_t (mod_energy.f90:5-10; phi = enthalpy cp*T) and scalar_t (mod_scalar.f90:5-12), constructed on request
+  bool has_energy = false, has_scalar = false;
+  A1<double> tc, cp;               // properties_t (mod_properties.f90:88-89)
+  A1<double> t, gt, h, h0, gh;     // energy: t, gt, phi, phi0, grad
+  A1<double> s, s0, gs;            // scalar: phi, phi0, grad
+  double s_dcoef = 1.0, s_vel[3] = {0.0, 0.0, -100.0};
+  std::vector<double> s_bc;        // scalar: Dirichlet value per boundary section (dirichlet0 / dirichlet1)
   Intf& I(int c, int cnb) { return intf[(size_t)(c - 1) * n_subdomains + (cnb - 1)]; }
 };
 
@@ -61,6 +68,13 @@ void calc_coef_p(Case& c);                                // mod_uvwp.f90:289-36
 void calc_mip(Case& c, bool lRhieChow);                   // mod_uvwp.f90:438-490
 void adjust_pc(Case& c, double pref);                     // mod_uvwp.f90:136-158
 void update_uvwp(Case& c);                                // mod_uvwp.f90:370-436
+
+void construct_energy(Case& c);                           // mod_energy.f90:14-48 (after construct_physics)
+SolveStat solve_energy(Case& c);                          // mod_energy.f90:59-80
+void calc_coef_energy(Case& c);                           // mod_energy.f90:82-169
+void construct_scalar(Case& c, double dcoef, const double vel[3], const double* bc_value);  // mod_scalar.f90:16-46
+SolveStat solve_scalar(Case& c);                          // mod_scalar.f90:56-72
+void calc_coef_scalar(Case& c);                           // mod_scalar.f90:74-126
 
 // flat-signature routines of mod_solver.f90 (arrays 1-based through the raw pointers: p[i-1])
 void calc_grad(const double* phi, double* grad, const double* xc, const double* yc, const double* zc,

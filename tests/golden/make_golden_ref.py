@@ -58,7 +58,13 @@ CASES = {
     "tet3_sub4": (1, 3, 0.2, True, 4, 1, 2, {}, 0.01),
     "hex5_sym_sub1": (0, 5, 0.0, False, 1, 1, 2, {"east": "symmetry", "west": "symmetry"}, 0.01),
     "hex5_symjit_sub4": (0, 5, 0.15, False, 4, 1, 2, {"south": "symmetry", "bottom": "symmetry"}, 0.01),
+    # the energy (enthalpy) and scalar equations next to uvwp: solve_energy is the call main.f90:59 has commented out,
+    # solve_scalar the one at :56; the scalar's boundary values are 1 on 'top' and 'east', 0 elsewhere (dirichlet1 / dirichlet0)
+    "hex6_energy_scalar_sub1": (0, 6, 0.1, False, 1, 1, 3, {}, 0.01),
+    "tet3_energy_scalar_sub2": (1, 3, 0.2, True, 2, 1, 2, {}, 0.01),
 }
+EXTRA_EQUATIONS = ("hex6_energy_scalar_sub1", "tet3_energy_scalar_sub2")
+SCALAR_ONES = ("top", "east")
 
 
 def world():
@@ -192,12 +198,36 @@ def run_case(name, w=None, verbose=True):
                 bc.coef = w.get(routine, "mod_uvwp")
     del ns["_records"][:]
     update_boundaries, solve_uvwp, update_time = w.get("update_boundaries"), w.get("solve_uvwp"), w.get("update_time")
+    extra = name in EXTRA_EQUATIONS
+    if extra:
+        solve_energy, solve_scalar = w.get("solve_energy"), w.get("solve_scalar")
+        # construct_scalar (mod_scalar.f90:16-46) statement by statement, with this mesh's section names instead of the
+        # hard-wired ones of another mesh ('fp-connect', 'out_wall', 'outlet')
+        sc = ns["T_scalar_t"]()
+        length = geom.ne + geom.nbf
+        sc.name = "scalar"
+        sc.phi, sc.phi0, sc.grad = np.zeros(length), np.zeros(length), np.zeros(3 * length)
+        sc.bcs = f90py._newarr((geom.mg.nintf_c2b,), "type", ns["T_bc_t"])
+        make_bc = w.get("make_bc")
+        for sname in [x.strip() for x in geom.mg.sectionname[1:]]:
+            bcp = make_bc(sc, geom, sname)
+            bcp.coef = w.get("dirichlet1" if sname in SCALAR_ONES else "dirichlet0", "mod_scalar")
+        phys.scalar = sc
     for tstep in range(ntstep):  # src/main.f90:50-63
         for icoef in range(ncoef):
             update_boundaries(phys, geom)
+            if extra:  # mod_physics.f90:45, commented out there
+                for bc in phys.scalar.bcs:
+                    bc.coef(bc, geom, phys.scalar, phys.prop)
+                solve_scalar(phys.scalar, phys.prop, geom, phys.dt, phys.nit, phys.ap, phys.anb, phys.b, phys.phic)  # main.f90:56
             solve_uvwp(phys.uvwp, phys.prop, geom, phys.dt, phys.nit, phys.ap, phys.anb, phys.b, phys.phic, phys.subdomain, phys.intf, phys.n_subdomains)
+            if extra:
+                solve_energy(phys.energy, phys.prop, geom, phys.dt, phys.nit, phys.ap, phys.anb, phys.b, phys.phic)  # main.f90:59
         update_time(phys)
-    rec = [r for r in ns["_records"] if len(r) == 5]
+        if extra:
+            phys.scalar.phi0[...] = phys.scalar.phi  # mod_physics.f90:104, commented out there
+    rec_all = [r for r in ns["_records"] if len(r) == 5]
+    rec = [r for r in rec_all if r[0].strip() in ("u", "v", "w", "pc")]
     hist = np.array([[float(r[1]), float(r[2]), float(r[3]), float(r[4])] for r in rec]).reshape(ntstep * ncoef, 4, 4)
     names = [r[0].strip() for r in rec[:4]]
     assert names == ["u", "v", "w", "pc"], names
@@ -207,6 +237,12 @@ def run_case(name, w=None, verbose=True):
                case=np.array([kind, n, nsub, ntstep, ncoef]), dt=np.array(dt), jitter=np.array(jitter), shuffle=np.array(shuffle),
                bc_sections=np.array(list(bcs.keys()), dtype="U16"), bc_routines=np.array(list(bcs.values()), dtype="U16"))
     out.update({"setup_" + k: v for k, v in setup.items()})
+    if extra:
+        en = phys.energy
+        out.update(hist_e=np.array([[float(x) for x in r[1:]] for r in rec_all if r[0].strip() == "e"]),
+                   hist_s=np.array([[float(x) for x in r[1:]] for r in rec_all if r[0].strip() == "scalar"]),
+                   t=en.t, gt=en.gt, h=en.phi, h0=en.phi0, gh=en.grad, s=sc.phi, s0=sc.phi0, gs=sc.grad,
+                   scalar_ones=np.array(SCALAR_ONES, dtype="U16"))
     if verbose:
         print("%-14s ne=%d nf=%d: %d SIMPLE iterations of the reference source in %.1f s; iterations %s" %
               (name, oc.ne, oc.nf, ntstep * ncoef, time.time() - t0, hist[:, :, 0].astype(int).tolist()))

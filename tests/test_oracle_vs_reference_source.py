@@ -38,6 +38,13 @@ def section_index(raw, section):
     return secs.index(section) - 1  # boundary sections follow the volume section
 
 
+def scalar_bc_values(raw, g):
+    names = raw["names"].decode()
+    secs = [names[32 * i:32 * (i + 1)].strip() for i in range(1, int(raw["nsec"]))]
+    ones = set(str(x) for x in g["scalar_ones"])
+    return np.array([1.0 if s in ones else 0.0 for s in secs])
+
+
 def test_fixtures_present():
     assert len(FIXTURES) >= 10, FIXTURES
 
@@ -54,7 +61,25 @@ def test_oracle_equals_reference_source_bit_for_bit(cfdl, oracle, name):
         assert np.array_equal(oc[k], g["setup_" + k]), "set-up array %s differs from the reference source" % k
     if kw["nsub"] > 1:
         assert np.array_equal(oc["g2gf_p"], g["setup_g2gf_p"]) and np.array_equal(oc["g2gf_idx"], g["setup_g2gf_idx"])
-    hist, _ = oc.run(kw["ntstep"], kw["ncoef"])
+    extra = "hist_e" in g.files  # energy (mod_energy.f90) and scalar (mod_scalar.f90) equations next to uvwp
+    if extra:
+        oc.construct_energy()
+        oc.construct_scalar(bc_value=scalar_bc_values(raw, g))
+        hist, he, hs = [], [], []
+        for ts in range(kw["ntstep"]):
+            for ic in range(kw["ncoef"]):
+                oc.update_boundaries()
+                hs.append(oc.solve_scalar())
+                hist.append(oc.solve_uvwp())
+                he.append(oc.solve_energy())
+            oc.update_time()
+        hist = np.array(hist)
+        assert np.array_equal(np.array(he), g["hist_e"]), "energy: residual records differ from the reference source"
+        assert np.array_equal(np.array(hs), g["hist_s"]), "scalar: residual records differ from the reference source"
+        for f in ("t", "gt", "h", "h0", "gh", "s", "s0", "gs"):
+            assert np.array_equal(oc[f], g[f]), "%s differs from the reference source: max rel %.3e" % (f, rel_err(oc[f], g[f]))
+    else:
+        hist, _ = oc.run(kw["ntstep"], kw["ncoef"])
     assert np.array_equal(hist[:, :, 0], g["hist"][:, :, 0]), "iteration counts differ from the reference source"
     assert np.array_equal(hist, g["hist"]), "residual history differs from the reference source: max rel %.3e" % rel_err(hist, g["hist"])
     for f in FIELDS:
@@ -94,7 +119,24 @@ def test_cuda_equals_reference_source(cfdl, name):
         s = cfdl.Solver(geom, bcs)
     try:
         s.set_option("solver", cfdl.SOLVER_PARITY)
-        hist = s.run(dt=kw["dt"], nit=100, ntstep=kw["ntstep"], ncoef=kw["ncoef"])
+        if "hist_e" in g.files:  # energy and scalar equations next to uvwp, in the order of the fixture's loop
+            s.energy_init()
+            s.scalar_init(bc_value=scalar_bc_values(raw, g))
+            hist, he, hs = [], [], []
+            for ts in range(kw["ntstep"]):
+                for ic in range(kw["ncoef"]):
+                    s.update_boundaries()
+                    hs.append(s.solve_scalar(kw["dt"], 100))
+                    hist.append(s.solve_uvwp(kw["dt"], 100))
+                    he.append(s.solve_energy(kw["dt"], 100))
+                s.update_time()
+            hist, he, hs = np.array(hist), np.array(he), np.array(hs)
+            assert np.array_equal(he[:, 0], g["hist_e"][:, 0]) and np.array_equal(hs[:, 0], g["hist_s"][:, 0])
+            assert rel_err(he[:, 1:3], g["hist_e"][:, 1:3]) < 1e-10 and rel_err(hs[:, 1:3], g["hist_s"][:, 1:3]) < 1e-10
+            for f in ("t", "gt", "h", "h0", "gh", "s", "s0", "gs"):
+                assert rel_err(s.download(f), g[f]) < 1e-10, f
+        else:
+            hist = s.run(dt=kw["dt"], nit=100, ntstep=kw["ntstep"], ncoef=kw["ncoef"])
         assert np.array_equal(hist[:, :, 0], g["hist"][:, :, 0])
         # residual norms: summation order of the device reduction; everything else is the reference's arithmetic
         assert rel_err(hist[:, :, 1:3], g["hist"][:, :, 1:3]) < 1e-10
