@@ -125,6 +125,8 @@ struct Handle {
   int coop_ctas = 0;
   double* rb_work = nullptr;   // second value array of the fused two-colour solver (H doubles)
   double *pcg_r = nullptr, *pcg_q = nullptr, *pcg_p = nullptr;  // conjugate-gradient work vectors (first use)
+  double* pcg_z = nullptr;     // preconditioned residual (multicolour SSOR preconditioner)
+  int pcg_precond = 1;         // 1: multicolour SSOR on two-colour single-GPU meshes, 0: Jacobi
   // the three momentum solves side by side (kernels_rb3.inc): second value arrays of v and w (u uses rb_work),
   // one control block per equation
   double* rb3_work[2] = {nullptr, nullptr};

@@ -384,6 +384,13 @@ class Solver:
     def update_time(self):
         _chk(lib().cfdl_update_time(self.h))
 
+    def write_vtu(self, path, raw, equation=0):
+        """write_vtubin (mod_vtu_output.f90:6-326) from the device fields; raw = the mesh file content (meshgen / rawmesh)"""
+        x, y, z = _f64(raw["x"]), _f64(raw["y"]), _f64(raw["z"])
+        esec, etype, e2vx = _i32(raw["esec"]), _i32(raw["etype"]), _i32(raw["e2vx"])
+        _chk(lib().cfdl_write_vtu(self.h, path.encode(), C.c_int32(equation), C.c_int32(len(x)), _d(x), _d(y), _d(z), C.c_int32(len(etype)),
+                                  _i(esec), _i(etype), C.c_int32(int(raw["ne2vx_max"])), _i(e2vx)))
+
     def energy_init(self, tc=None, cp=None):
         """construct_energy (mod_energy.f90:14-48); tc / cp per cell (reference numbering) or None for 5 / 1000"""
         tc = _f64(tc) if tc is not None else None

@@ -175,6 +175,15 @@ int cfdl_energy_init(cfdl_handle h, const double* tc, const double* cp);
 int cfdl_solve_energy(cfdl_handle h, double dt, int32_t nit, double* out4);
 int cfdl_scalar_init(cfdl_handle h, double dcoef, const double* vel, const double* bc_value);
 int cfdl_solve_scalar(cfdl_handle h, double dt, int32_t nit, double* out4);
+/* write_vtubin + vtu_data, src/modules/mod_vtu_output.f90:6-326: the reference's binary .vtu file of one equation
+ * (equation 0 = uvwp: u, v, w, p, gpc, 'mip'; 1 = energy: enthalpy, grad_enthalpy, temperature, grad_temperature; 2 = scalar:
+ * phi, grad), byte for byte what the reference writes to <projPath>VTK/output-<iout>/<name>.vtu — `path` is that file
+ * (its directory must exist).  The vertex coordinates and the element table are the arrays cell_input read from the mesh file
+ * (geom%x,y,z; mg%esec(2,nsec), mg%etype(nsec), mg%e2vx(ne2vx_max, nelem), 1-based vertex ids).  For uvwp the reference's side
+ * effect is kept: CFDL_F_DC is overwritten with the per-cell sum of the signed face mass fluxes (:114-123), which is what the
+ * 'mip' array of the file holds.  Single-GPU handles. */
+int cfdl_write_vtu(cfdl_handle h, const char* path, int32_t equation, int32_t nvx, const double* x, const double* y, const double* z,
+                   int32_t nsec, const int32_t* esec, const int32_t* etype, int32_t ne2vx_max, const int32_t* e2vx);
 /* the main.f90:50-63 loop: ntstep x (ncoef x (update_boundaries; solve_uvwp); update_time).
  * hist (ntstep*ncoef*16 doubles) may be NULL. */
 int cfdl_run(cfdl_handle h, double dt, int32_t nit, int32_t ntstep, int32_t ncoef, double* hist);

@@ -60,6 +60,8 @@ def main():
             else:
                 s = cfdl.Solver(geom, bcs, device=0, cell2rank=c2r, rank=rank, nranks=world)
             s.set_option("solver", mode)
+            if pcg:
+                s.set_option("pcg_precond", 0)  # partitioned handles run the Jacobi form
             if fused is not None:
                 s.set_option("uvw_fused", int(fused))
             if nccl:
@@ -110,6 +112,8 @@ def main():
     assert not errs, errs
     one = cfdl.Solver(geom, bcs, device=0) if nz is None else cfdl.Solver.structured_hex(n, device=0, slabs=True, nz=nz)
     one.set_option("solver", mode)
+    if pcg:
+        one.set_option("pcg_precond", 0)
     want_hist = one.run(dt=dt, nit=100, ntstep=2, ncoef=2)
     for r in range(world):
         hist = out[r][0]

@@ -446,9 +446,10 @@ def test_calc_coef_p_overwrites_stale_values(case):
         s.set_option("statics", 1)
 
 
-def _numpy_pcg(ne, idx, nb_packed, ap, anb, b, phi0, nit):
-    """Jacobi-preconditioned CG with the reference's residual definition and stopping rule, in plain
-    numpy on the reference-format (CSR, packed neighbour ids) system: the model of solver=pcg."""
+def _numpy_pcg(ne, idx, nb_packed, ap, anb, b, phi0, nit, red=None):
+    """Preconditioned CG with the reference's residual definition and stopping rule, in plain numpy on the
+    reference-format (CSR, packed neighbour ids) system: the model of solver=pcg.  red = None: Jacobi; red = boolean
+    mask of the first colour: two-colour symmetric Gauss-Seidel, z = (D - U)^-1 D (D - L)^-1 r with red before black."""
     rows = np.repeat(np.arange(ne), np.diff(idx))
     cols = (nb_packed >> 5) - 1  # cells and halos share the id space of phi
     x = phi0.copy()
@@ -456,12 +457,24 @@ def _numpy_pcg(ne, idx, nb_packed, ap, anb, b, phi0, nit):
     def nbsum(v):
         return np.bincount(rows, weights=anb * v[cols], minlength=ne)
 
+    def precond(r):
+        if red is None:
+            return r / ap
+        z = np.zeros_like(x)
+        z[:ne][red] = (r / ap)[red]                       # y_r
+        zb = (r + nbsum(z)) / ap                           # black rows gather the red y
+        z[:ne][~red] = zb[~red]
+        zr = z[:ne] + nbsum(z) / ap                        # red rows gather the black z
+        z[:ne][red] = zr[red]
+        return z[:ne].copy()
+
     r = b + nbsum(x) - ap * x[:ne]
     res_i = np.sqrt(np.sum(r * r) / ne)
     res_f, res_max, it = res_i, 0.0, 0
     p = np.zeros_like(x)
-    p[:ne] = r / ap
-    rz = np.sum(r * r / ap)
+    z = precond(r)
+    p[:ne] = z
+    rz = np.sum(r * z)
     while it < nit and res_f > res_i / 10.0:
         q = ap * p[:ne] - nbsum(p)
         pq = np.sum(p[:ne] * q)
@@ -472,8 +485,9 @@ def _numpy_pcg(ne, idx, nb_packed, ap, anb, b, phi0, nit):
         r = r - alpha * q
         it += 1
         res_f, res_max = np.sqrt(np.sum(r * r) / ne), np.abs(r).max()
-        rz_new = np.sum(r * r / ap)
-        p[:ne] = r / ap + (rz_new / rz) * p[:ne]
+        z = precond(r)
+        rz_new = np.sum(r * z)
+        p[:ne] = z + (rz_new / rz) * p[:ne]
         rz = rz_new
     return x, (it, res_i, res_f, res_max)
 
@@ -494,17 +508,40 @@ def test_pcg_solves_the_pc_system_like_its_numpy_model(case, cfdl):
     idx = geom["ef2nb_idx"].astype(np.int64) - 1
     nbp = geom["ef2nb_nb"].astype(np.int64)
     s.set_option("solver", cfdl.SOLVER_PCG)
+    # the library's first colour on a two-colour mesh: the cells at even graph distance from cell 1 (greedy colouring in natural order)
+    red = None
+    if int(s.get_info("ncolors")) == 2:
+        rows = np.repeat(np.arange(oc.ne), np.diff(idx))
+        cols = (nbp >> 5) - 1
+        dist = np.full(oc.ne, -1)
+        dist[0], frontier = 0, [0]
+        while frontier:
+            nxt = []
+            for c in frontier:
+                for j in cols[idx[c]:idx[c + 1]]:
+                    if j < oc.ne and dist[j] < 0:
+                        dist[j] = dist[c] + 1
+                        nxt.append(j)
+            frontier = nxt
+        red = dist % 2 == 0
     try:
-        for nit in (1, 3, 12, 400):
-            want_phi, want = _numpy_pcg(oc.ne, idx, nbp, ap, anb, b, phi0, nit)
-            got_phi, got = s.host_solve(3, phi0, ap, anb, b, nit=nit)
-            assert got[0] == want[0], (nit, got, want)
-            scale = max(np.abs(want_phi[:oc.ne]).max(), 1e-300)
-            assert np.abs(got_phi[:oc.ne] - want_phi[:oc.ne]).max() / scale < 1e-9, nit
-            for k in (1, 2, 3):
-                if want[k] != 0.0:
-                    assert abs(got[k] - want[k]) <= 1e-9 * abs(want[k]), (nit, k, got, want)
-        assert got[2] <= got[1] / 10.0 and got[0] < 400  # converged by the reference's criterion, not by the cap
+        iters = {}
+        for precond in ((1, 0) if red is not None else (0,)):
+            s.set_option("pcg_precond", precond)
+            for nit in (1, 3, 12, 400):
+                want_phi, want = _numpy_pcg(oc.ne, idx, nbp, ap, anb, b, phi0, nit, red if precond else None)
+                got_phi, got = s.host_solve(3, phi0, ap, anb, b, nit=nit)
+                assert got[0] == want[0], (precond, nit, got, want)
+                scale = max(np.abs(want_phi[:oc.ne]).max(), 1e-300)
+                assert np.abs(got_phi[:oc.ne] - want_phi[:oc.ne]).max() / scale < 1e-9, (precond, nit)
+                for k in (1, 2, 3):
+                    if want[k] != 0.0:
+                        assert abs(got[k] - want[k]) <= 1e-9 * abs(want[k]), (precond, nit, k, got, want)
+            assert got[2] <= got[1] / 10.0 and got[0] < 400  # converged by the reference's criterion, not by the cap
+            iters[precond] = got[0]
+        if red is not None:
+            assert iters[1] <= iters[0], iters  # the Gauss-Seidel preconditioner never needs more iterations than Jacobi
+        s.set_option("pcg_precond", 1)
         # momentum equations are not symmetric: solver=pcg keeps them on MCSGS
         s.set_option("solver", cfdl.SOLVER_MCSGS)
         ap_u, anb_u, b_u, phi_u = assembled_system(oc)
