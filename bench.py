@@ -313,18 +313,21 @@ def main():
         step(i)
         dbg("warmup step", i)
     hist_last = None
+    hist_all = []
     barrier()
     s.set_option("reset_counters", 1)
     s.timer_record(0)
     if args.warmup % NCOEF == 0 and args.steps % NCOEF == 0:
         # the reference's loop (main.f90:50-63: ntstep x (ncoef x (update_boundaries; solve_uvwp); update_time)) as ONE C-ABI
         # call, cfdl_run: the same steps as the per-step calls below without a host round trip between them
-        hist_last = s.run(dt=DT, nit=NIT, ntstep=args.steps // NCOEF, ncoef=NCOEF)[-1]
+        hist_all = s.run(dt=DT, nit=NIT, ntstep=args.steps // NCOEF, ncoef=NCOEF)
+        hist_last = hist_all[-1]
         loop = "cfdl_run (one call for all timed steps)"
     else:
         for i in range(args.steps):
             s.update_boundaries()
             hist_last = s.solve_uvwp(DT, NIT)
+            hist_all.append(hist_last)
             if (args.warmup + i + 1) % NCOEF == 0:
                 s.update_time()
         loop = "cfdl_update_boundaries + cfdl_solve_uvwp (+ cfdl_update_time) per step"
@@ -618,6 +621,8 @@ def main():
                                         if rbq_dist == 1 else ("one persistent launch, neighbour-only synchronisation" if (world == 1 and fused and int(s.get_info("rbq_active")) == 1) else "one launch per pass")),
                            "passes_per_step": passes_per_step,
                            "solver_iterations_last_step(u,v,w,pc)": [int(x) for x in hist_last[:, 0]] if hist_last is not None else None,
+                           "solver_iterations_mean_over_timed_steps(u,v,w,pc)": [round(float(x), 2) for x in np.asarray(hist_all)[:, :, 0].mean(axis=0)] if len(hist_all) else None,
+                           "pc_residual_reduction_mean(res_f/res_i)": round(float(np.mean([h[3, 2] / h[3, 1] for h in np.asarray(hist_all) if h[3, 1] > 0])), 4) if len(hist_all) else None,
                            "last_step_history(it,res_i,res_f,res_max)": hist_last.tolist() if hist_last is not None else None},
                 "roofline": roof, "roofline_other": extra_roof, "phase_ms_per_step": phase_ms, "cpu_baseline": cpu, "e2e": e2e,
                 "parity_check": parity,

@@ -129,12 +129,17 @@ int solve_uvwp_impl(Handle* h, double dt, int nit, double* hist, StepHook* hook 
   int rc;
   double st[16] = {0};
   if ((rc = k_calc_coef_uvw(h, dt))) return rc;                                              // :111
-  if ((rc = comm_exchange(h, h->fld[CFDL_F_D], 1, -1)) || (rc = comm_exchange(h, h->fld[CFDL_F_DC], 1, -1))) return rc;
+  {
+    double* ddc[2] = {h->fld[CFDL_F_D], h->fld[CFDL_F_DC]};
+    if ((rc = comm_exchange_multi(h, ddc, 2, 1))) return rc;
+  }
   if ((rc = solve_momentum(h, nit, st))) return rc;                                          // :114-116
   if (hook && (rc = hook->at(STEP_MOMENTUM_DONE))) return rc;
   if ((rc = k_calc_grad3(h))) return rc;                                                     // :118-120
-  for (int f = CFDL_F_GU; f <= CFDL_F_GW; ++f)
-    if ((rc = comm_exchange(h, h->fld[f], 3, -1))) return rc;
+  {
+    double* g3[3] = {h->fld[CFDL_F_GU], h->fld[CFDL_F_GV], h->fld[CFDL_F_GW]};
+    if ((rc = comm_exchange_multi(h, g3, 3, 3))) return rc;
+  }
   if (hook && ((rc = hook->at(STEP_GRAD_DONE)) || (rc = hook->at(STEP_BEFORE_MIP)))) return rc;
   if ((rc = k_calc_mip(h, true, dt))) return rc;                                             // :122
   if ((rc = k_calc_coef_p(h))) return rc;                                                    // :124

@@ -77,12 +77,12 @@ __global__ void __launch_bounds__(256) pack_kernel(double* __restrict__ buf, con
 
 }  // namespace
 
-static int p2p_exchange(Handle* h, double* field, int ncomp, int color = -1);
+static int p2p_exchange(Handle* h, double* const* fields, int nf, int ncomp, int color = -1);
 static int p2p_mail(Handle* h, double* dev, int mode, int root);
 
 int comm_exchange(Handle* h, double* field, int ncomp, int color) {
   if (h->prep.nranks == 1 || h->nnbr == 0) return CFDL_OK;
-  if (ncomp <= 3 && h->p2p.connected && h->use_p2p) return p2p_exchange(h, field, ncomp, color);  // all colours (-1) or one
+  if (ncomp <= 3 && h->p2p.connected && h->use_p2p) return p2p_exchange(h, &field, 1, ncomp, color);  // all colours (-1) or one
   if (!h->comm) return fail(CFDL_ERR_NCCL, "this handle is one partition of %d: call cfdl_comm_init before computing", h->prep.nranks);
   if (ncomp < 1 || ncomp > 9) return fail(CFDL_ERR_ARG, "comm_exchange: ncomp %d", ncomp);
   const Prep& p = h->prep;
@@ -241,7 +241,7 @@ int p2p_alloc_slab(Handle* h) {
   hd.off_mail_val = off; off += align256(2 * 64 * 2 * 8);
   hd.off_mail_seq = off; off += align256(2 * 64 * 8);
   const size_t off_err = off; off += 256;
-  for (int b = 0; b < 2; ++b) { hd.off_stage[b] = (long long)off; off += align256(sizeof(double) * 3 * ((size_t)h->G + 32)); }
+  for (int b = 0; b < 2; ++b) { hd.off_stage[b] = (long long)off; off += align256(sizeof(double) * 9 * ((size_t)h->G + 32)); }
   for (int a = 0; a < 7; ++a) { hd.off_field[a] = (long long)off; off += arr; }
   hd.off_mailv_val = (long long)off; off += align256(sizeof(double) * 2 * 64 * MAILV_LEN);
   hd.off_mailv_seq = (long long)off; off += align256(2 * 64 * 8);
@@ -402,9 +402,9 @@ namespace {
 
 struct StageArgs {
   int nnbr, ncomp, N, G;
+  int nf;                     // fields exchanged by this launch (1..3), ncomp components each: one rendezvous for all of them
   const int32_t* send_cells;
-  const double* src;          // field (device numbering, ncomp interleaved)
-  double* field;
+  double* field[3];           // fields (device numbering, ncomp interleaved)
   int s0[8], cnt[8], d0[8];   // per neighbour: first send cell, count, first ghost slot at the neighbour
   int g0[8], gcnt[8];         // per neighbour: the ghost range that receives (one colour: a sub-range of the neighbour's ghosts)
   int whole;                  // 1: all colours — the landing zone is copied as one block
@@ -425,7 +425,9 @@ __global__ void __launch_bounds__(256) stage_exchange_kernel(const __grid_consta
     int i = 0, k = t;
     while (k >= A.cnt[i]) { k -= A.cnt[i]; ++i; }
     const int cell = A.send_cells[A.s0[i] + k];
-    for (int q = 0; q < A.ncomp; ++q) A.peer_stage[i][(size_t)(A.d0[i] + k) * A.ncomp + q] = A.src[(size_t)cell * A.ncomp + q];
+    const int nct = A.nf * A.ncomp;
+    for (int fi = 0; fi < A.nf; ++fi)
+      for (int q = 0; q < A.ncomp; ++q) A.peer_stage[i][(size_t)(A.d0[i] + k) * nct + fi * A.ncomp + q] = A.field[fi][(size_t)cell * A.ncomp + q];
   }
   __syncthreads();
   __shared__ bool last;
@@ -444,15 +446,20 @@ __global__ void __launch_bounds__(256) stage_exchange_kernel(const __grid_consta
     __threadfence_system();
   }
   __syncthreads();
-  double* ghosts = A.field + (size_t)A.N * A.ncomp;
+  const int nct = A.nf * A.ncomp;
+  auto land = [&](size_t t) {  // t indexes the landing zone: ghost g, field fi, component q
+    const size_t g = t / nct;
+    const int r = (int)(t % nct), fi = r / A.ncomp, q = r % A.ncomp;
+    A.field[fi][((size_t)A.N + g) * A.ncomp + q] = __ldcg(&A.my_stage[t]);
+  };
   if (A.whole) {
-    const size_t n = (size_t)A.G * A.ncomp;
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) ghosts[t] = __ldcg(&A.my_stage[t]);
+    const size_t n = (size_t)A.G * nct;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) land(t);
     return;
   }
   for (int i = 0; i < A.nnbr; ++i) {  // one colour: only the ghost sub-ranges that received
-    const size_t b = (size_t)A.g0[i] * A.ncomp, n = (size_t)A.gcnt[i] * A.ncomp;
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) ghosts[b + t] = __ldcg(&A.my_stage[b + t]);
+    const size_t b = (size_t)A.g0[i] * nct, n = (size_t)A.gcnt[i] * nct;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) land(b + t);
   }
 }
 
@@ -498,7 +505,18 @@ __global__ void __launch_bounds__(64) mail_kernel(const __grid_constant__ MailAr
 
 }  // namespace
 
-static int p2p_exchange(Handle* h, double* field, int ncomp, int color) {
+// several fields of equal width in one exchange (peer-to-peer: one launch and one rendezvous for all of them)
+int comm_exchange_multi(Handle* h, double* const* fields, int nf, int ncomp) {
+  if (h->prep.nranks == 1 || h->nnbr == 0) return CFDL_OK;
+  if (nf >= 1 && nf <= 3 && ncomp <= 3 && h->p2p.connected && h->use_p2p) return p2p_exchange(h, fields, nf, ncomp, -1);
+  for (int i = 0; i < nf; ++i) {
+    int rc = comm_exchange(h, fields[i], ncomp, -1);
+    if (rc) return rc;
+  }
+  return CFDL_OK;
+}
+
+static int p2p_exchange(Handle* h, double* const* fields, int nf, int ncomp, int color) {
   P2P& q = h->p2p;
   const Prep& p = h->prep;
   StageArgs A;
@@ -506,7 +524,8 @@ static int p2p_exchange(Handle* h, double* field, int ncomp, int color) {
   const int nc = p.ncolors;
   const unsigned long long seq = ++q.xseq;
   const int buf = (int)(seq & 1);
-  A.nnbr = h->nnbr; A.ncomp = ncomp; A.N = h->N; A.G = h->G; A.send_cells = h->send_cells; A.src = field; A.field = field;
+  A.nnbr = h->nnbr; A.ncomp = ncomp; A.N = h->N; A.G = h->G; A.send_cells = h->send_cells; A.nf = nf;
+  for (int i = 0; i < nf; ++i) A.field[i] = fields[i];
   int total = 0;
   for (int i = 0; i < h->nnbr; ++i) {
     const int r = p.nbr_rank[i];
@@ -529,7 +548,14 @@ static int p2p_exchange(Handle* h, double* field, int ncomp, int color) {
   A.my_stage = (const double*)(q.slab + q.hdr.off_stage[buf]);
   A.my_flags = (const unsigned long long*)(q.slab + q.hdr.off_xflag);
   A.seq = seq; A.ticket = q.xticket; A.whole = color < 0 ? 1 : 0; A.err = q.err;
-  const int ctas = std::max(1, std::min(64, (std::max(total, h->G) * ncomp + 255) / 256));
+  // (all CTAs of this launch must be co-resident: they wait for flags that the last CTA to finish its stores raises.  64 CTAs
+  // always are on a GPU; the host emulation of tests/emul runs a grid on as many workers as it has cores, hence the cap there)
+#ifdef CUEMU
+  constexpr int kMaxCtas = 4;
+#else
+  constexpr int kMaxCtas = 64;
+#endif
+  const int ctas = std::max(1, std::min(kMaxCtas, (std::max(total, h->G) * ncomp * nf + 255) / 256));
   stage_exchange_kernel<<<ctas, 256, 0, S(h)>>>(A);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;

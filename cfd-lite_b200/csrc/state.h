@@ -269,6 +269,7 @@ int residual_plain(Handle* h, const double* phi, const double* rhs, bool signed_
 // refresh the ghost-cell entries of a device field from their owner ranks; ncomp doubles per
 // cell (AoS); color >= 0 restricts the exchange to ghosts/sends of that colour
 int comm_exchange(Handle* h, double* field, int ncomp, int color);
+int comm_exchange_multi(Handle* h, double* const* fields, int nf, int ncomp);  // all colours, up to three fields of equal width at once
 int comm_allreduce_sum_max(Handle* h, double* dev2);  // dev2[0] summed, dev2[1] maxed over ranks
 // peer-to-peer path (after cfdl_comm_ipc_connect): write the colour-`color` interface values of
 // up to two arrays straight into the neighbours' ghost cells, then publish sequence number
@@ -304,7 +305,11 @@ struct P2PReduce {
 // Every wait on a word another GPU writes is time-limited (~10 s of SM clock, far beyond any legitimate wait): the
 // waiter that gives up raises the handle's error word, every later wait returns at once, the kernels run to their end
 // and the next API call that synchronises reports CFDL_ERR_COMM (p2p_check) — a dead rank is an error code, not a hang.
+#ifdef CUEMU
+#define CFDL_SPIN_LIMIT 4000000ll      // host emulation: 4 s (its clock64 counts microseconds) so that the dead-rank test stays short
+#else
 #define CFDL_SPIN_LIMIT 20000000000ll
+#endif
 #ifdef CUEMU
 #define CFDL_SPIN_PAUSE CUEMU_SPIN  // host emulation (tests/emul): a waiting CTA yields its core
 #else

@@ -42,3 +42,14 @@ def test_partitioned_momentum_solves_side_by_side_and_one_by_one(fused):
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "multirank emulation ok" in r.stdout
+
+
+@pytest.mark.parametrize("mode", ["rcb", "slabs"])
+def test_silent_rank_is_an_error_code_not_a_hang(mode):
+    """Every wait on a word another rank writes is time-limited: a rank that connects and then never launches surfaces on
+    its neighbour as CFDL_ERR_COMM after the limit (tests/emul/silent_rank_check.py), with the pass-by-pass and the persistent
+    form of the pc solve alike."""
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "emul", "silent_rank_check.py")] + (["slabs"] if mode == "slabs" else [])
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "silent rank ok" in r.stdout
