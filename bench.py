@@ -307,8 +307,10 @@ def main():
     dbg("setup %.1f s;" % setup_s, "solver ready; owned", int(s.get_info("owned_cells")), "ghost", int(s.get_info("ghost_cells")))
     # the clock sampler (nvidia-smi takes a few 100 ms to come up) starts before the warm-up and
     # covers the timed region; it samples the GPU under the same load throughout
+    # (rank 0 only: one nvidia-smi polling loop per rank perturbs the launches of all of them — the driver lock is shared)
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         step(i)
         dbg("warmup step", i)

@@ -97,6 +97,8 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b);
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p);
 cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned flags);
 cudaError_t cudaIpcCloseMemHandle(void* p);
+enum { cudaFuncAttributePreferredSharedMemoryCarveout = 9, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class Kern> inline cudaError_t cudaFuncSetAttribute(Kern, int, int) { return cudaSuccess; }
 template <class Kern> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, Kern, int, size_t) { *n = 2; return cudaSuccess; }
 
 // ---- launches -----------------------------------------------------------------------------------
