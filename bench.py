@@ -107,10 +107,11 @@ def ncu_traffic(kernel_key, args, world):
         return None
 
 
-def build_mesh(cfdl, kind, n):
+def build_mesh(cfdl, kind, n, device=None):
+    """device: connectivity + geometry on that GPU (cfdl_mesh_build_gpu); None: the host builder (the CPU reference arm)"""
     raw = cfdl.meshgen(cfdl.MESH_HEX if kind == "hex" else cfdl.MESH_TET, n, jitter=0.0 if kind == "hex" else 0.2,
                        shuffle=(kind == "tet"), seed=12345)
-    geom = cfdl.mesh_build(raw)
+    geom = cfdl.mesh_build(raw) if device is None else cfdl.mesh_build(raw, gpu=True, device=device)
     return raw, geom
 
 
@@ -252,7 +253,7 @@ def main():
         if use_structured:  # same mesh, same numbering, generated analytically on every rank (cfdl_create_structured_hex[_slabs])
             sv = cfdl.Solver.structured_hex(n, device=local_rank, rank=rk, nranks=nranks, slabs=(partition == "slabs"), nz=nz)
         else:
-            r, g = build_mesh(cfdl, args.mesh, n)
+            r, g = build_mesh(cfdl, args.mesh, n, device=local_rank)
             if nranks == 1:
                 sv = cfdl.Solver(g, cfdl.default_bcs(r), device=local_rank)
             else:

@@ -326,7 +326,6 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "pdl")) { h->use_pdl = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "rb_idx16")) { h->rb_idx16 = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "mip_hoist")) { h->mip_hoist = value != 0.0; return CFDL_OK; }
-  if (!std::strcmp(key, "uvw_async")) { h->uvw_async = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "pcg_precond")) { h->pcg_precond = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "rbq")) { h->rbq = value != 0.0; if (value == 2.0) h->rbq_refused = 0; return CFDL_OK; }
   if (!std::strcmp(key, "rbq_ctas")) { h->rbq_ctas_per_sm = std::max(0, (int)value); return CFDL_OK; }

@@ -98,7 +98,10 @@ struct UvwArgsS {
 // register variants 0.48-0.56, forced occupancy 0.53-0.59, locality order 0.46); the winner is what is left.
 // A slot-parallel form on the statics (one thread per (cell, face slot), terms handed over in shared memory, one
 // thread per cell summing in slot order; 56-80 registers, 37-56 % occupancy) was measured too: 0.91-1.16 ms — more
-// than half of its stall cycles sit at the hand-over barrier (profiles/r02_ncu_assembly.md) — and was dropped.
+// than half of its stall cycles sit at the hand-over barrier — and was dropped.  So was a form that staged the ~23 operands
+// of a face through per-thread shared-memory slots with cp.async, two faces in flight and no barrier (138 LDGSTS, 118
+// registers, four CTAs of 128 threads per SM): 0.626 ms against 0.444 — the long-scoreboard stalls fell from 12.6 to 8.2
+// cycles per issue, but the 8-byte asynchronous copies saturate the LSU / shared-memory path (profiles/r02_summary.md).
 template <int K>
 __device__ __forceinline__ void coef_uvw_statics_cell(const UvwArgsS& A, const int c) {
   const int Nc = A.Nc, Np = A.Np;
@@ -210,173 +213,6 @@ __device__ __forceinline__ void coef_uvw_statics_cell(const UvwArgsS& A, const i
   A.dc[c] = vol / dcv;
 }
 
-// ---- the same routine with the face data staged through shared memory by asynchronous copies ------------------------------
-// calc_coef_uvw is latency bound (ncu, round 2: 77 % of the stall samples are long-scoreboard waits; 120 registers, 23 %
-// occupancy): a thread loads the ~23 operands of a face, waits a DRAM latency, computes ~350 instructions, and only then
-// asks for the next face.  Here every thread owns two slots of 23 doubles in shared memory and fills them with
-// cp.async (LDGSTS: no destination registers, no scoreboard wait at issue): while face k is being evaluated the operands
-// of face k+1 are already in flight.  A thread only ever reads the slots it filled itself, so cp.async.wait_group is all the
-// synchronisation there is — no barrier (the slot-parallel form died on its barriers).  Same expressions on the same
-// operands in the same order: same bits as coef_uvw_statics_cell (test: array_equal against the oracle).
-#define UVA_TPB 128   // 2 stages x 23 values x 128 threads x 8 B = 47 104 B of static shared memory, four CTAs per SM
-#define UVA_NV 23
-enum { UA_AREA = 0, UA_DS, UA_DSP, UA_RDS, UA_RDSP, UA_WT, UA_DR, UA_DRP = UA_DR + 3, UA_MIP = UA_DRP + 3, UA_MU, UA_GU, UA_GV = UA_GU + 3, UA_GW = UA_GV + 3 };
-
-__device__ __forceinline__ void cp_async8(double* smem, const double* g) {
-#if defined(__CUDA_ARCH__)
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(g) : "memory");
-#else
-  *smem = *g;  // (host emulation: synchronous)
-#endif
-}
-__device__ __forceinline__ void cp_async_commit() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-#if defined(__CUDA_ARCH__)
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-#endif
-}
-
-template <int K>
-__global__ void __launch_bounds__(UVA_TPB, 4) coef_uvw_async_kernel(const UvwArgsS A) {
-  __shared__ double sm[2][UVA_NV][UVA_TPB];
-  const int t = threadIdx.x;
-  const int Nc = A.Nc, Np = A.Np;
-  for (int i = blockIdx.x * blockDim.x + t; i < A.N; i += gridDim.x * blockDim.x) {
-    const int c = A.order ? A.order[i] : i;
-    const int n = A.nfc[c];
-    int nbk[K], fsk[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      nbk[k] = __ldg(&A.ell_nb[(size_t)k * Np + c]);
-      fsk[k] = __ldg(&A.ell_fs[(size_t)k * Np + c]);
-    }
-    // operands of face k -> slot k % 2 (interior faces only; boundary faces are handled after the loop as in the synchronous form)
-    auto issue = [&](int k) {
-      if (k < K && k < n && nbk[k] < Nc) {
-        const int nb = nbk[k], f = abs(fsk[k]) - 1;
-        const bool own = fsk[k] > 0;
-        double(*s)[UVA_TPB] = sm[k & 1];
-        cp_async8(&s[UA_AREA][t], A.S.area + f); cp_async8(&s[UA_DS][t], A.S.ds + f); cp_async8(&s[UA_DSP][t], A.S.dsp + f);
-        cp_async8(&s[UA_RDS][t], A.S.rds + f); cp_async8(&s[UA_RDSP][t], A.S.rdsp + f);
-        cp_async8(&s[UA_WT][t], (own ? A.S.wto : A.S.wtn) + f);
-#pragma unroll
-        for (int m = 0; m < 3; ++m) { cp_async8(&s[UA_DR + m][t], A.S.dr[m] + f); cp_async8(&s[UA_DRP + m][t], A.S.drp[m] + f); }
-        cp_async8(&s[UA_MIP][t], A.mip + f); cp_async8(&s[UA_MU][t], A.mu + nb);
-#pragma unroll
-        for (int m = 0; m < 3; ++m) {
-          cp_async8(&s[UA_GU + m][t], A.gu + 3 * (size_t)nb + m); cp_async8(&s[UA_GV + m][t], A.gv + 3 * (size_t)nb + m);
-          cp_async8(&s[UA_GW + m][t], A.gw + 3 * (size_t)nb + m);
-        }
-      }
-      cp_async_commit();  // (an empty group when the slot has no interior face: the group count stays uniform)
-    };
-    issue(0);
-    const double mu_e = A.mu[c];
-    double gue[3], gve[3], gwe[3];
-    load3(A.gu, c, gue); load3(A.gv, c, gve); load3(A.gw, c, gwe);
-    double ap = 0.0, sumf = 0.0, sumss[3] = {0, 0, 0}, sumdefc[3] = {0, 0, 0};
-    double anbk[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      issue(k + 1);
-      cp_async_wait<1>();  // everything but the newest group has landed: face k's operands are in its slot
-      anbk[k] = 0.0;
-      if (k >= n) nbk[k] = -1;
-      if (k < n) {
-        double d = 0.0, fnb = 0.0;
-        if (nbk[k] < Nc) {
-          const double(*s)[UVA_TPB] = sm[k & 1];
-          const double sg = fsk[k] > 0 ? 1.0 : -1.0;
-          const double area = s[UA_AREA][t], ds = s[UA_DS][t], ds_p = s[UA_DSP][t];
-          const double wt = s[UA_WT][t];
-          const double dr[3] = {sg * s[UA_DR][t], sg * s[UA_DR + 1][t], sg * s[UA_DR + 2][t]};
-          const double dr_p[3] = {sg * s[UA_DRP][t], sg * s[UA_DRP + 1][t], sg * s[UA_DRP + 2][t]};
-          const double f_in = -sg * s[UA_MIP][t];
-          fnb = fmax(f_in, 0.0);
-          sumf = sumf + f_in;
-          const double muip = (1.0 - wt) * mu_e + wt * s[UA_MU][t];
-          const double rds = s[UA_RDS][t], rdsp = s[UA_RDSP][t];
-          d = quot<true>(muip * area, ds, rds);
-          const double gun[3] = {s[UA_GU][t], s[UA_GU + 1][t], s[UA_GU + 2][t]};
-          const double gvn[3] = {s[UA_GV][t], s[UA_GV + 1][t], s[UA_GV + 2][t]};
-          const double gwn[3] = {s[UA_GW][t], s[UA_GW + 1][t], s[UA_GW + 2][t]};
-          const double w1 = 1.0 - wt;
-#pragma unroll
-          for (int m = 0; m < 3; ++m) {
-            const double gip[3] = {w1 * gue[m] + wt * gun[m], w1 * gve[m] + wt * gvn[m], w1 * gwe[m] + wt * gwn[m]};
-            sumss[m] = sumss[m] + quot<true>(muip * area * dot3(gip, dr), ds, rds);
-          }
-          {
-            double gip[3] = {w1 * gue[0] + wt * gun[0], w1 * gue[1] + wt * gun[1], w1 * gue[2] + wt * gun[2]};
-            sumdefc[0] = sumdefc[0] + muip * area * (quot<true>(dot3(gip, dr_p), ds_p, rdsp) - quot<true>(dot3(gip, dr), ds, rds));
-            gip[0] = w1 * gve[0] + wt * gvn[0]; gip[1] = w1 * gve[1] + wt * gvn[1]; gip[2] = w1 * gve[2] + wt * gvn[2];
-            sumdefc[1] = sumdefc[1] + muip * area * (quot<true>(dot3(gip, dr_p), ds_p, rdsp) - quot<true>(dot3(gip, dr), ds, rds));
-            gip[0] = w1 * gwe[0] + wt * gwn[0]; gip[1] = w1 * gwe[1] + wt * gwn[1]; gip[2] = w1 * gwe[2] + wt * gwn[2];
-            sumdefc[2] = sumdefc[2] + muip * area * (quot<true>(dot3(gip, dr_p), ds_p, rdsp) - quot<true>(dot3(gip, dr), ds, rds));
-          }
-        }
-        anbk[k] = d + fnb;
-        ap = ap + d + fnb;
-      }
-    }
-    cp_async_wait<0>();
-    const double vol = A.vol[c];
-    const double ap0 = A.rho[c] * vol / A.dt;
-    ap = ap + ap0;
-    const double ue = A.u[c], ve = A.v[c], we = A.w[c];
-    double bu = ap0 * A.u0[c] + sumf * ue - vol * A.gp[3 * (size_t)c] + sumss[0] + sumdefc[0];
-    double bv = ap0 * A.v0[c] + sumf * ve - vol * A.gp[3 * (size_t)c + 1] + sumss[1] + sumdefc[1];
-    double bw = ap0 * A.w0[c] + sumf * we - vol * A.gp[3 * (size_t)c + 2] + sumss[2] + sumdefc[2];
-    int last = -1;  // boundary faces in halo order (rare: geometry evaluated on the fly as in the reference)
-    for (int tt = 0; tt < K; ++tt) {
-      int best = 0x7fffffff, bk = -1;
-#pragma unroll
-      for (int k = 0; k < K; ++k)
-        if (nbk[k] >= Nc && nbk[k] > last && nbk[k] < best) { best = nbk[k]; bk = k; }
-      if (bk < 0) break;
-      last = best;
-      const int bc = A.halo_bc[best - Nc];
-      if (bc < 0) continue;
-      const int f = A.ell_fs[(size_t)bk * Np + c] - 1;
-      double a[3];
-      load3(A.aip, f, a);
-      const double area = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-      const double norm[3] = {a[0] / area, a[1] / area, a[2] / area};
-      const double dr[3] = {A.xc[best] - A.xc[c], A.yc[best] - A.yc[c], A.zc[best] - A.zc[c]};
-      const double ds = sqrt(dot3(dr, dr));
-      const double d = mu_e * area / ds;
-      if (A.bc_kind[bc] != CFDL_BC_SYMMETRY) {
-        const double vbnc[3] = {A.u[best], A.v[best], A.w[best]};
-        double vrel[3] = {ue, ve, we};
-        const double vn = dot3(vrel, norm);
-        vrel[0] = vrel[0] - vn * norm[0]; vrel[1] = vrel[1] - vn * norm[1]; vrel[2] = vrel[2] - vn * norm[2];
-        vrel[0] = vbnc[0] - vrel[0]; vrel[1] = vbnc[1] - vrel[1]; vrel[2] = vbnc[2] - vrel[2];
-        bu = bu + d * vrel[0] - d * ue;
-        bv = bv + d * vrel[1] - d * ve;
-        bw = bw + d * vrel[2] - d * we;
-      }
-      ap = ap + d;
-#pragma unroll
-      for (int k = 0; k < K; ++k)
-        if (k == bk) anbk[k] = anbk[k] + d;
-    }
-    double dcv = ap;
-#pragma unroll
-    for (int k = 0; k < K; ++k)
-      if (k < n) { dcv = dcv - anbk[k]; A.anb[(size_t)k * Np + c] = anbk[k]; }
-    A.ap[c] = ap;
-    A.bu[c] = bu; A.bv[c] = bv; A.bw[c] = bw;
-    A.d[c] = vol / ap;
-    A.dc[c] = vol / dcv;
-  }
-}
-
 // Locality order (any number of colours): thread i takes the i-th cell of the base (natural | Morton) order,
 // so the lanes of a warp hold cells of all colours that are neighbours in space — the two cells of a face read
 // its statics in the same instruction or a few instructions apart (L1), where a colour-major sweep reads them
@@ -401,17 +237,7 @@ int k_calc_coef_uvw_statics(Handle* h, double dt) {
   A.S = statics_of(h);
   A.ncol0 = h->prep.ncolors == 2 ? h->prep.color_ptr[1] : h->N;
   A.order = h->loc_order;
-  if (h->uvw_async) {
-    static bool carve = false;
-    if (!carve) {  // four CTAs of 46 KB per SM: ask for the large shared-memory carve-out once
-      cudaFuncSetAttribute(coef_uvw_async_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      cudaFuncSetAttribute(coef_uvw_async_kernel<6>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-      cudaGetLastError();
-      carve = true;
-    }
-    if (h->K <= 4) coef_uvw_async_kernel<4><<<occ_grid<coef_uvw_async_kernel<4>>(h, h->N, UVA_TPB), UVA_TPB, 0, S(h)>>>(A);
-    else coef_uvw_async_kernel<6><<<occ_grid<coef_uvw_async_kernel<6>>(h, h->N, UVA_TPB), UVA_TPB, 0, S(h)>>>(A);
-  } else if (h->K <= 4) coef_uvw_statics_kernel<4><<<occ_grid<coef_uvw_statics_kernel<4>>(h, h->N, TPB), TPB, 0, S(h)>>>(A);
+  if (h->K <= 4) coef_uvw_statics_kernel<4><<<occ_grid<coef_uvw_statics_kernel<4>>(h, h->N, TPB), TPB, 0, S(h)>>>(A);
   else coef_uvw_statics_kernel<6><<<occ_grid<coef_uvw_statics_kernel<6>>(h, h->N, TPB), TPB, 0, S(h)>>>(A);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;

@@ -170,7 +170,6 @@ struct Handle {
   int grad_variant = 1;        // calc_grad: 1 = on the LSQ statics (inverse matrix and weights precomputed), 0 = the reference's form
   double *fs_n[3] = {nullptr, nullptr, nullptr}, *fs_dr[3] = {nullptr, nullptr, nullptr}, *fs_drp[3] = {nullptr, nullptr, nullptr};
   int use_statics = 1;         // 0: recompute face geometry in every kernel (the reference's way)
-  int uvw_async = 1;           // calc_coef_uvw: face operands staged through shared memory with cp.async, two faces in flight (0: plain loads)
   int mip_hoist = 0;           // calc_mip: connectivity of all slots loaded up front (two CTAs per SM) / per face (three)
   int tune_ctas = 8;           // CTAs per SM for the solver passes (grid = min(need, num_sms * tune_ctas))
   // cfdl_step_host: transfer streams that run beside the compute stream, and a staging area of

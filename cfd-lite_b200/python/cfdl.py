@@ -107,8 +107,8 @@ def rawmesh_read(path):
                 x=x, y=y, z=z, e2vx=e2vx, etype=etype, esec=esec, names=names.raw)
 
 
-def mesh_build(raw):
-    """Connectivity + geometry (find_element_nb, calc_aip_xyzip_uns, calc_vol_cv_centers_uns)."""
+def mesh_build(raw, gpu=False, device=0):
+    """Connectivity + geometry (find_element_nb, calc_aip_xyzip_uns, calc_vol_cv_centers_uns); gpu=True: cfdl_mesh_build_gpu."""
     L = lib()
     ne, nbf = int(raw["ne"]), int(raw["nbf"])
     nface_per = {17: 6, 10: 4, 12: 5, 14: 5}
@@ -127,10 +127,14 @@ def mesh_build(raw):
              xc=np.zeros(H), yc=np.zeros(H), zc=np.zeros(H), aip=np.zeros(3 * nf), rip=np.zeros(3 * nf), vol=np.zeros(ne))
     x, y, z = _f64(raw["x"]), _f64(raw["y"]), _f64(raw["z"])
     et, es, e2vx = _i32(raw["etype"]), _i32(raw["esec"]), _i32(raw["e2vx"])
-    _chk(L.cfdl_mesh_build(C.c_int64(len(x)), _d(x), _d(y), _d(z), C.c_int(len(et)), _i(et), _i(es),
-                           C.c_int(int(raw["ne2vx_max"])), _i(e2vx), C.c_int32(ne), C.c_int32(nf), C.c_int32(nbf),
-                           _i(g["ef2nb_idx"]), _i(g["ef2nb_nb"]), _i(g["ef2nb_fg"]), _i(g["s2g"]), _i(g["bs"]),
-                           _d(g["xc"]), _d(g["yc"]), _d(g["zc"]), _d(g["aip"]), _d(g["rip"]), _d(g["vol"])))
+    args = (C.c_int64(len(x)), _d(x), _d(y), _d(z), C.c_int(len(et)), _i(et), _i(es),
+            C.c_int(int(raw["ne2vx_max"])), _i(e2vx), C.c_int32(ne), C.c_int32(nf), C.c_int32(nbf),
+            _i(g["ef2nb_idx"]), _i(g["ef2nb_nb"]), _i(g["ef2nb_fg"]), _i(g["s2g"]), _i(g["bs"]),
+            _d(g["xc"]), _d(g["yc"]), _d(g["zc"]), _d(g["aip"]), _d(g["rip"]), _d(g["vol"]))
+    if gpu:
+        _chk(L.cfdl_mesh_build_gpu(C.c_int32(device), *args))
+    else:
+        _chk(L.cfdl_mesh_build(*args))
     return g
 
 

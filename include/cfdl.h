@@ -367,6 +367,16 @@ int cfdl_mesh_build(int64_t nvx, const double* x, const double* y, const double*
                     int32_t* ef2nb_idx, int32_t* ef2nb_nb, int32_t* ef2nb_fg, int32_t* s2g,
                     int32_t* bs, double* xc, double* yc, double* zc, double* aip, double* rip,
                     double* vol);
+/* The same arrays computed on the GPU: face records bucketed by the smallest vertex of their face (atomics +
+ * scan), one thread per vertex pairs the records of its bucket in (element, face) order — which is the reference's face
+ * numbering order, so no sort is needed — then the geometry kernels with the reference's formulas.  Bit for bit the output of
+ * cfdl_mesh_build; inputs and outputs are host arrays.  Fails with CFDL_ERR_CUDA without a device (no CPU path). */
+int cfdl_mesh_build_gpu(int32_t device, int64_t nvx, const double* x, const double* y, const double* z,
+                    int nsec, const int32_t* etype, const int32_t* esec, int ne2vx_max,
+                    const int32_t* e2vx, int32_t ne, int32_t nf, int32_t nbf,
+                    int32_t* ef2nb_idx, int32_t* ef2nb_nb, int32_t* ef2nb_fg, int32_t* s2g,
+                    int32_t* bs, double* xc, double* yc, double* zc, double* aip, double* rip,
+                    double* vol);
 
 /* the reference's recursive-coordinate-bisection block decomposition (generate_seeds/grow/
  * split_leaf, mod_agglomeration.f90:380-561) and its block-local cell order (the unstable

@@ -32,6 +32,7 @@
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __shared__ static thread_local
+#define __constant__ static const
 #define __CUDACC_VER_MAJOR__ 12
 
 using std::max;
