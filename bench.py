@@ -107,11 +107,18 @@ def ncu_traffic(kernel_key, args, world):
         return None
 
 
+SETUP_S = {}  # seconds per set-up stage of the product arm (reported in config.setup_breakdown_seconds)
+
+
 def build_mesh(cfdl, kind, n, device=None):
     """device: connectivity + geometry on that GPU (cfdl_mesh_build_gpu); None: the host builder (the CPU reference arm)"""
+    t0 = time.perf_counter()
     raw = cfdl.meshgen(cfdl.MESH_HEX if kind == "hex" else cfdl.MESH_TET, n, jitter=0.0 if kind == "hex" else 0.2,
                        shuffle=(kind == "tet"), seed=12345)
+    t1 = time.perf_counter()
     geom = cfdl.mesh_build(raw) if device is None else cfdl.mesh_build(raw, gpu=True, device=device)
+    SETUP_S["meshgen (vertices + element lists, host)"] = round(t1 - t0, 2)
+    SETUP_S["mesh_build (connectivity + geometry, %s; the first CUDA call of the process creates the context)" % ("host" if device is None else "GPU")] = round(time.perf_counter() - t1, 2)
     return raw, geom
 
 
@@ -255,7 +262,9 @@ def main():
         else:
             r, g = build_mesh(cfdl, args.mesh, n, device=local_rank)
             if nranks == 1:
+                t0 = time.perf_counter()
                 sv = cfdl.Solver(g, cfdl.default_bcs(r), device=local_rank)
+                SETUP_S["cfdl_create (colouring, renumbering, ELL + statics on the host, upload)"] = round(time.perf_counter() - t0, 2)
             else:
                 if partition == "slabs" and args.mesh == "hex":  # cell id = i + n (j + n k)
                     kk = np.arange(n ** 3) // (n * n)
@@ -616,12 +625,15 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args.mesh, n_global, ne, nz_global), "solver": args.solver, "ncolors": ncol, "options": args.opt, "mesh_source": "structured per-rank generator" if structured else "reference-format arrays", "fused_two_colour_passes": bool(fused), "timed_loop": loop, "programmatic_dependent_launch": bool(fused and not args.no_pdl),
-                           "cells_per_gpu": ne // world, "setup_seconds": round(setup_s, 1), "l2": "working set (>1 GB per GPU) exceeds the 126 MB L2; no flush needed" if ne // world > 1000000 else
+                           "cells_per_gpu": ne // world, "setup_seconds": round(setup_s, 1), "setup_breakdown_seconds": dict(SETUP_S), "l2": "working set (>1 GB per GPU) exceeds the 126 MB L2; no flush needed" if ne // world > 1000000 else
                            "working set may fit L2",
                            "parallelism": "1 GPU" if world == 1 else
                            "%d GPUs, one %s of the global mesh per GPU; ghost-cell exchange: %s" % (world, "z-slab" if partition == "slabs" else "RCB block", exchange),
                            "pc_solve": ("one persistent launch per rank, chunks synchronise with neighbouring chunks only (across NVLink too), residual history combined once per launch"
                                         if rbq_dist == 1 else ("one persistent launch, neighbour-only synchronisation" if (world == 1 and fused and int(s.get_info("rbq_active")) == 1) else "one launch per pass")),
+                           "pc_solve_chunks": ({"chunks_per_colour": int(s.get_info("rbq_chunks")), "ctas": int(s.get_info("rbq_grid")), "rows_per_chunk": int(s.get_info("rbq_chunk_rows")),
+                                                "assignment": "round-robin" if int(s.get_info("rbq_chunks")) > int(s.get_info("rbq_grid")) else "one chunk per CTA"}
+                                               if int(s.get_info("rbq_chunks")) > 0 else None),
                            "passes_per_step": passes_per_step,
                            "solver_iterations_last_step(u,v,w,pc)": [int(x) for x in hist_last[:, 0]] if hist_last is not None else None,
                            "solver_iterations_mean_over_timed_steps(u,v,w,pc)": [round(float(x), 2) for x in np.asarray(hist_all)[:, :, 0].mean(axis=0)] if len(hist_all) else None,

@@ -328,6 +328,10 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "mip_hoist")) { h->mip_hoist = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "pcg_precond")) { h->pcg_precond = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "rbq")) { h->rbq = value != 0.0; if (value == 2.0) h->rbq_refused = 0; return CFDL_OK; }
+  if (!std::strcmp(key, "rbq_rounds")) { h->rbq_rounds = value != 0.0; if (h->rbq_rounds) h->rbq_refused = 0; return CFDL_OK; }  // (partitioned handles: before cfdl_comm_ipc_handle, which fixes the chunks)
+  if (!std::strcmp(key, "rbq_lmax")) { h->rbq_lmax = std::max(0, (int)value); h->rbq_refused = 0; return CFDL_OK; }
+  if (!std::strcmp(key, "rbq_lbig")) { h->rbq_lbig = std::max(0, (int)value); return CFDL_OK; }
+  if (!std::strcmp(key, "rbq_cap")) { h->rbq_cap = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "rbq_ctas")) { h->rbq_ctas_per_sm = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "pc_sumap")) { h->pc_sumap = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "uvw_fused")) { h->uvw_fused = value != 0.0; return CFDL_OK; }
@@ -362,6 +366,9 @@ int cfdl_get_info(cfdl_handle h, const char* key, double* value) {
   else if (!std::strcmp(key, "color_dist")) *value = h->prep.color_dist;
   else if (!std::strcmp(key, "rbq_active")) *value = (h->rbq && !h->rbq_refused && h->rbq_occ > 0) ? 1 : 0;
   else if (!std::strcmp(key, "rbq_refused")) *value = h->rbq_refused;
+  else if (!std::strcmp(key, "rbq_chunks")) *value = h->rbq_last_chunks;  // chunks per colour / CTAs / rows per chunk of the last persistent pc solve
+  else if (!std::strcmp(key, "rbq_grid")) *value = h->rbq_last_grid;      // (rbq_grid < rbq_chunks: chunks dealt round-robin to the CTAs)
+  else if (!std::strcmp(key, "rbq_chunk_rows")) *value = h->rbq_last_L;
   else if (!std::strcmp(key, "rbq_dist")) *value = h->rbq_dist_state;  // partitioned: 1 = persistent pc solve with chunk-to-chunk synchronisation over NVLink in use, -1 = refused (lists too long / not two colours), 0 = not decided yet
   else if (!std::strcmp(key, "rbq_occ")) *value = h->rbq_occ;
   else if (!std::strcmp(key, "rb_idx16")) *value = (h->rb_idx16 && h->ell_nb16) ? 1 : 0;
@@ -749,10 +756,22 @@ extern "C" int cfdl_step_host(cfdl_handle h, double dt, int32_t nit, int32_t app
 // rank, same partition on restart).  Continuing from a checkpoint reproduces the uninterrupted run bit
 // for bit (test).
 namespace {
-const char kCkpMagic[8] = {'C', 'F', 'D', 'L', 'C', 'K', 'P', '1'};
+const char kCkpMagic[8] = {'C', 'F', 'D', 'L', 'C', 'K', 'P', '2'};
 const int kCkpFields[13] = {CFDL_F_U, CFDL_F_V, CFDL_F_W, CFDL_F_P, CFDL_F_U0, CFDL_F_V0, CFDL_F_W0,
                             CFDL_F_GU, CFDL_F_GV, CFDL_F_GW, CFDL_F_GP, CFDL_F_MIP, CFDL_F_MIP0};
-struct CkpHeader { char magic[8]; int64_t ne, nbf, nf; int32_t rank, nranks, nfields, pad; };
+struct CkpHeader { char magic[8]; int64_t ne, nbf, nf; int32_t rank, nranks, nfields, pad; uint64_t mesh; };
+// Identifies the mesh (and, on a partitioned handle, this rank's part of it) beyond its counts: every face
+// contributes a hash of (reference face id, reference ids of its two sides); the sum does not depend on the
+// device numbering, so a file written with one reordering mode is accepted by a handle created with another.
+uint64_t mesh_fingerprint(const Handle* h) {
+  const Prep& P = h->prep;
+  auto orig = [&](int32_t d) -> uint64_t { return d < P.Nc ? (uint64_t)P.c2o[d] : (uint64_t)P.gN + (uint64_t)P.h2o[d - P.Nc]; };
+  auto mix = [](uint64_t x) { x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33; return x; };
+  uint64_t s = mix((uint64_t)P.gN * 31u + (uint64_t)P.rank) ^ mix((uint64_t)P.nranks);
+  for (int32_t f = 0; f < P.F; ++f)
+    s += mix(mix((uint64_t)P.f2o[f] + 1) ^ (mix(orig(P.face_a[f]) + 0x9e3779b97f4a7c15ULL) + 3 * mix(orig(P.face_b[f]) + 0x7f4a7c15ULL)));
+  return s;
+}
 std::string ckp_path(const Handle* h, const char* path) {
   std::string p(path);
   if (h->prep.nranks > 1) p += ".r" + std::to_string(h->prep.rank) + "of" + std::to_string(h->prep.nranks);
@@ -770,7 +789,7 @@ extern "C" int cfdl_checkpoint_write(cfdl_handle h, const char* path) {
   CkpHeader hd;
   std::memset(&hd, 0, sizeof hd);
   std::memcpy(hd.magic, kCkpMagic, 8);
-  hd.ne = h->prep.gN; hd.nbf = h->prep.gB; hd.nf = h->prep.gF; hd.rank = h->prep.rank; hd.nranks = h->prep.nranks; hd.nfields = 13;
+  hd.ne = h->prep.gN; hd.nbf = h->prep.gB; hd.nf = h->prep.gF; hd.rank = h->prep.rank; hd.nranks = h->prep.nranks; hd.nfields = 13; hd.mesh = mesh_fingerprint(h);
   bool ok = std::fwrite(&hd, sizeof hd, 1, f) == 1;
   std::vector<double> buf;
   int rc = CFDL_OK;
@@ -804,28 +823,36 @@ extern "C" int cfdl_checkpoint_read(cfdl_handle h, const char* path) {
   CkpHeader hd;
   int rc = CFDL_OK;
   if (std::fread(&hd, sizeof hd, 1, f) != 1 || std::memcmp(hd.magic, kCkpMagic, 8) != 0) rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: %s is not a checkpoint", p.c_str());
-  else if (hd.ne != h->prep.gN || hd.nbf != h->prep.gB || hd.nf != h->prep.gF || hd.rank != h->prep.rank || hd.nranks != h->prep.nranks)
-    rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: %s belongs to another mesh or partition (ne %lld nbf %lld nf %lld, rank %d of %d)", p.c_str(),
-              (long long)hd.ne, (long long)hd.nbf, (long long)hd.nf, hd.rank, hd.nranks);
-  std::vector<double> buf;
-  for (int i = 0; i < hd.nfields && !rc; ++i) {
+  else if (hd.ne != h->prep.gN || hd.nbf != h->prep.gB || hd.nf != h->prep.gF || hd.rank != h->prep.rank || hd.nranks != h->prep.nranks ||
+           hd.mesh != mesh_fingerprint(h))
+    rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: %s belongs to another mesh or partition (ne %lld nbf %lld nf %lld, rank %d of %d, mesh id %016llx)", p.c_str(),
+              (long long)hd.ne, (long long)hd.nbf, (long long)hd.nf, hd.rank, hd.nranks, (unsigned long long)hd.mesh);
+  else if (hd.nfields != 13)
+    rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: %s holds %d fields, a checkpoint has 13", p.c_str(), hd.nfields);
+  // the whole file is read and checked before the first upload: a short or damaged file leaves the handle as it was
+  std::vector<std::vector<double>> buf(13);
+  for (int i = 0; i < 13 && !rc; ++i) {
     int32_t id = -1;
     int64_t n = -1;
-    if (std::fread(&id, 4, 1, f) != 1 || std::fread(&n, 8, 1, f) != 1 || id < 0 || id >= CFDL_F_COUNT) { rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: damaged record %d", i); break; }
+    if (std::fread(&id, 4, 1, f) != 1 || std::fread(&n, 8, 1, f) != 1) { rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: file ends before record %d", i); break; }
+    if (id != kCkpFields[i]) { rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: record %d holds field %d, expected %d", i, id, kCkpFields[i]); break; }
     const int64_t want = (int64_t)(local ? field_len(h, id) : host_len(h, id));
     if (n != want) { rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: field %d has %lld entries, expected %lld", id, (long long)n, (long long)want); break; }
-    buf.resize((size_t)n);
-    if (std::fread(buf.data(), 8, (size_t)n, f) != (size_t)n) { rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: file ends inside field %d", id); break; }
+    buf[i].resize((size_t)n);
+    if (std::fread(buf[i].data(), 8, (size_t)n, f) != (size_t)n) { rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: file ends inside field %d", id); break; }
+  }
+  if (!rc && std::fgetc(f) != EOF) rc = fail(CFDL_ERR_ARG, "cfdl_checkpoint_read: %s has data after the last field", p.c_str());
+  std::fclose(f);
+  for (int i = 0; i < 13 && !rc; ++i) {
+    const int id = kCkpFields[i];
     if (local) {
-      if (cudaMemcpyAsync(h->fld[id], buf.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
-          cudaStreamSynchronize(h->stream) != cudaSuccess)
+      if (cudaMemcpyAsync(h->fld[id], buf[i].data(), sizeof(double) * buf[i].size(), cudaMemcpyHostToDevice, h->stream) != cudaSuccess)
         rc = fail(CFDL_ERR_CUDA, "cfdl_checkpoint_read: upload failed");
     } else {
-      rc = upload_field(h, id, buf.data());
-      if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(CFDL_ERR_CUDA, "cfdl_checkpoint_read: upload failed");
+      rc = upload_field(h, id, buf[i].data());
     }
   }
-  std::fclose(f);
+  if (cudaStreamSynchronize(h->stream) != cudaSuccess && !rc) rc = fail(CFDL_ERR_CUDA, "cfdl_checkpoint_read: upload failed");
   return rc;
 }
 

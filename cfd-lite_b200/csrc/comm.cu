@@ -250,13 +250,13 @@ int p2p_alloc_slab(Handle* h) {
   hd.rbq_ok = 0;
   if (p.ncolors == 2) {
     const int nred = p.color_ptr[1], nblack = h->N - nred;
-    int L = 0, Gc = 0, Ls = 0, ifc = 0;
-    if (nred > 0 && nblack > 0 && rbq_plan(h, nred, h->N, h->K, true, p.color_if[0], p.color_if[1], &L, &Gc, &Ls, &ifc) == CFDL_OK && Gc <= RBQ_PROG_STRIDE) {
+    int L = 0, Gc = 0, Ls = 0, ifc = 0, grid = 0;
+    if (nred > 0 && nblack > 0 && rbq_plan(h, nred, h->N, h->K, true, p.color_if[0], p.color_if[1], &L, &Gc, &Ls, &ifc, &grid) == CFDL_OK) {
       hd.rbq_ok = 1; hd.nred = nred; hd.color_if[0] = p.color_if[0]; hd.color_if[1] = p.color_if[1];
-      hd.rbq_L = L; hd.rbq_Gc = Gc; hd.rbq_Ls = Ls; hd.rbq_ifc = ifc;
+      hd.rbq_L = L; hd.rbq_Gc = Gc; hd.rbq_Ls = Ls; hd.rbq_ifc = ifc; hd.rbq_grid = grid;
       hd.off_rbq_r2 = (long long)off; off += align256(sizeof(double) * 2 * ((size_t)nred + 2 + h->G + 2));
       for (int b = 0; b < 2; ++b) { hd.off_rbq_b[b] = (long long)off; off += align256(sizeof(double) * ((size_t)nblack + 2 + h->G + 2)); }
-      hd.off_rbq_prog = (long long)off; off += align256(sizeof(unsigned long long) * RBQ_PROG_STRIDE);
+      hd.off_rbq_prog = (long long)off; off += align256(sizeof(unsigned long long) * std::max((size_t)RBQ_PROG_STRIDE, (size_t)Gc));
       hd.off_rbq_llr = (long long)off; off += align256(32 * ((size_t)h->G + 2));
       for (int b = 0; b < 2; ++b) { hd.off_rbq_llb[b] = (long long)off; off += align256(16 * ((size_t)h->G + 2)); }
     }

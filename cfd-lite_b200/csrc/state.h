@@ -56,12 +56,13 @@ struct P2PHeader {
   int rbq_ok;              // 1: this rank can take part (two colours, launch geometry fits)
   int nred;                // cells of the first colour
   int color_if[2];         // leading interface cells per colour
-  int rbq_L, rbq_Gc;       // rows per interior chunk, chunks (= CTAs of the launch)
+  int rbq_L, rbq_Gc;       // rows per interior chunk, chunks per colour
+  int rbq_grid, rbq_pad;   // CTAs of the launch (= chunks on small meshes; fewer: chunks dealt round-robin)
   int rbq_ifc;             // chunks 0..rbq_ifc-1 hold the interface rows: they publish their progress to every neighbour
   int rbq_Ls;              // rows per interface chunk (shorter, so that their pushes and flags travel while the interior chunks still work)
   long long off_rbq_r2;    // double2 r2[nred + 2 + G]: red {newest, mid}; ghost g at nred + 2 + g
   long long off_rbq_b[2];  // double b[N - nred + 2 + G] x 2: the two black buffers; ghost g at (N - nred) + 2 + g
-  long long off_rbq_prog;  // unsigned long long prog[RBQ_PROG_STRIDE]: progress words of the own chunks
+  long long off_rbq_prog;  // unsigned long long prog[max(RBQ_PROG_STRIDE, rbq_Gc)]: progress words of the own chunks
   long long off_rbq_llr;   // {double value, u64 tag} x 2 per ghost: newest and mid value of a red ghost, each tagged with the pass that wrote it
   long long off_rbq_llb[2];// {double value, u64 tag} per ghost and black buffer
   long long off_mailv_val; // double mailv_val[2][64][MAILV_LEN]: vector all-reduce mailbox, alternating sets
@@ -140,6 +141,10 @@ struct Handle {
   double* rbq_mem = nullptr;      // red pairs, black buffers, per-pass partials, progress words
   size_t rbq_len = 0;
   unsigned long long* rbq_prog = nullptr;  // one GPU: progress words of the chunks + error word (fixed place, never reset)
+  size_t rbq_prog_len = 0;                 // words allocated (the error word sits behind them)
+  int rbq_lmax = 0, rbq_lbig = 0, rbq_cap = 0;  // options (0: defaults / environment): largest one-chunk-per-CTA size, chunk size of the round-robin form, CTA limit
+  int rbq_last_chunks = 0, rbq_last_grid = 0, rbq_last_L = 0;  // geometry of the last persistent pc solve (info)
+  int rbq_rounds = 1;                      // option: large meshes run the persistent pc solve with chunks dealt round-robin (0: pass by pass)
   // partitioned meshes (peer-to-peer mode): value arrays and progress words live in the exported slab; per chunk the progress
   // words to wait for (own chunks and the neighbours' interface chunks), the interface rows to push after a pass
   int rbq_dist_state = 0;         // 0: not set up yet, 1: ready, -1: refused (on every rank alike)
@@ -331,7 +336,7 @@ int p2p_check(Handle* h);  // after a stream sync point: CFDL_ERR_COMM when a pe
 int comm_allreduce_pairs(Handle* h, double* dev, int npairs);
 // launch geometry of the persistent pc solve for a rank with nred first-colour cells of N: rows per chunk, chunks
 // (partitioned: if0 / if1 leading interface rows per colour -> Ls rows per interface chunk, ifc such chunks in front)
-int rbq_plan(const Handle* h, int nred, int N, int K, bool dist, int if0, int if1, int* L, int* Gc, int* Ls, int* ifc);
+int rbq_plan(const Handle* h, int nred, int N, int K, bool dist, int if0, int if1, int* L, int* Gc, int* Ls, int* ifc, int* grid);
 int p2p_store_args(Handle* h, int color, const double* a, const double* b, unsigned long long seq, P2PStore* out);
 int p2p_reduce_args(Handle* h, int parity, unsigned long long seq, P2PReduce* out);
 int p2p_reduce3_args(Handle* h, int parity, unsigned long long seq, P2PReduce* out);  // slots of 6 doubles (u, v, w)

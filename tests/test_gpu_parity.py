@@ -633,10 +633,14 @@ def test_persistent_pc_solve_keeps_the_bits(case, cfdl):
     s.set_option("solver", cfdl.SOLVER_MCSGS)
     try:
         res = {}
-        combos = [(0, 1), (1, 1), (1, 0), (0, 0)]
+        # third entry: the large-mesh form (chunks of 64 rows dealt round-robin to at most 2 CTAs)
+        combos = [(0, 1, 0), (1, 1, 0), (1, 0, 0), (0, 0, 0), (1, 1, 1), (1, 0, 1)]
         for combo in combos:
             s.set_option("rbq", combo[0])
             s.set_option("rb_idx16", combo[1])
+            s.set_option("rbq_lmax", 64 if combo[2] else 0)
+            s.set_option("rbq_lbig", 64 if combo[2] else 0)
+            s.set_option("rbq_cap", 2 if combo[2] else 0)
             randomize(oc, s, seed=61)
             hs = []
             for nit in (1, 2, 7, 40, 100, 3):
@@ -645,6 +649,8 @@ def test_persistent_pc_solve_keeps_the_bits(case, cfdl):
             res[combo] = (np.array(hs), {f: s.download(f) for f in ("u", "v", "w", "p", "pc", "mip")})
             if combo[0]:
                 assert int(s.get_info("rbq_active")) == 1 and int(s.get_info("rbq_refused")) == 0
+                if combo[2] and s.ne >= 512:
+                    assert int(s.get_info("rbq_grid")) == 2 and int(s.get_info("rbq_chunks")) > 2 and int(s.get_info("rbq_chunk_rows")) == 64
         ref_hist, ref_fields = res[combos[0]]
         for combo, (hist, fields) in res.items():
             assert same_history(hist, ref_hist), (combo, hist, ref_hist)
@@ -653,6 +659,8 @@ def test_persistent_pc_solve_keeps_the_bits(case, cfdl):
     finally:
         s.set_option("rbq", 1)
         s.set_option("rb_idx16", 1)
+        for k in ("rbq_lmax", "rbq_lbig", "rbq_cap"):
+            s.set_option(k, 0)
         s.set_option("solver", cfdl.SOLVER_PARITY)
 
 
@@ -674,10 +682,17 @@ def test_restart_from_checkpoint_reproduces_the_run(case, cfdl, tmp_path, solver
         assert same_history(ha, hb)
         for f in ("u", "v", "w", "p", "gp", "mip", "mip0", "u0"):
             assert np.array_equal(a.download(f), b.download(f)), f
-        # a checkpoint of another mesh is refused
-        with open(path, "r+b") as fh:
-            fh.seek(8); fh.write((12345).to_bytes(8, "little"))
-        with pytest.raises(cfdl.CfdlError):
-            b.checkpoint_read(path)
+        # a truncated file, a file with a foreign mesh id and a file of another mesh size are refused,
+        # and a refused file leaves the handle's state as it was
+        good = open(path, "rb").read()
+        before = {f: b.download(f) for f in ("u", "p", "mip", "mip0")}
+        for bad in (good[: len(good) - 4096], good[:48] + bytes(8) + good[56:], good[:8] + (12345).to_bytes(8, "little") + good[16:],
+                    good + b"x"):
+            with open(path, "wb") as fh:
+                fh.write(bad)
+            with pytest.raises(cfdl.CfdlError):
+                b.checkpoint_read(path)
+            for f, v in before.items():
+                assert np.array_equal(b.download(f), v), f
     finally:
         a.close(); b.close()
