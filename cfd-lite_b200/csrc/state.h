@@ -141,6 +141,7 @@ struct Handle {
   double* rbq_mem = nullptr;      // red pairs, black buffers, per-pass partials, progress words
   size_t rbq_len = 0;
   unsigned long long* rbq_prog = nullptr;  // one GPU: progress words of the chunks + error word (fixed place, never reset)
+  unsigned int* rbq_ticket = nullptr;  // large meshes: the counter the CTAs draw their next (pass, chunk) from
   size_t rbq_prog_len = 0;                 // words allocated (the error word sits behind them)
   int rbq_lmax = 0, rbq_lbig = 0, rbq_cap = 0;  // options (0: defaults / environment): largest one-chunk-per-CTA size, chunk size of the round-robin form, CTA limit
   int rbq_last_chunks = 0, rbq_last_grid = 0, rbq_last_L = 0;  // geometry of the last persistent pc solve (info)
