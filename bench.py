@@ -632,7 +632,7 @@ def main():
                            "pc_solve": ("one persistent launch per rank, chunks synchronise with neighbouring chunks only (across NVLink too), residual history combined once per launch"
                                         if rbq_dist == 1 else ("one persistent launch, neighbour-only synchronisation" if (world == 1 and fused and int(s.get_info("rbq_active")) == 1) else "one launch per pass")),
                            "pc_solve_chunks": ({"chunks_per_colour": int(s.get_info("rbq_chunks")), "ctas": int(s.get_info("rbq_grid")), "rows_per_chunk": int(s.get_info("rbq_chunk_rows")),
-                                                "assignment": "round-robin" if int(s.get_info("rbq_chunks")) > int(s.get_info("rbq_grid")) else "one chunk per CTA"}
+                                                "assignment": "handed out in order from a counter" if int(s.get_info("rbq_chunks")) > int(s.get_info("rbq_grid")) else "one chunk per CTA"}
                                                if int(s.get_info("rbq_chunks")) > 0 else None),
                            "passes_per_step": passes_per_step,
                            "solver_iterations_last_step(u,v,w,pc)": [int(x) for x in hist_last[:, 0]] if hist_last is not None else None,

@@ -198,6 +198,7 @@ int create_from_prep(cfdl_handle_s* h, const GeomSource& G, cfdl_handle* out) {
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(CFDL_ERR_CUDA, "cudaGetDeviceProperties failed"));
   if (prop.major < 10) return bail(fail(CFDL_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor));
   h->num_sms = prop.multiProcessorCount;
+  h->l2_bytes = (size_t)std::max(0, prop.l2CacheSize);
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(CFDL_ERR_CUDA, "cudaStreamCreate failed"));
   const Prep& p = h->prep;
   h->N = p.N; h->G = p.G; h->Nc = p.Nc; h->F = p.F; h->B = p.B; h->H = p.H; h->Z = p.Z; h->K = p.K; h->Np = p.Np; h->Fi = p.Fi;
@@ -328,7 +329,11 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   if (!std::strcmp(key, "mip_hoist")) { h->mip_hoist = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "pcg_precond")) { h->pcg_precond = value != 0.0; return CFDL_OK; }
   if (!std::strcmp(key, "rbq")) { h->rbq = value != 0.0; if (value == 2.0) h->rbq_refused = 0; return CFDL_OK; }
-  if (!std::strcmp(key, "rbq_rounds")) { h->rbq_rounds = value != 0.0; if (h->rbq_rounds) h->rbq_refused = 0; return CFDL_OK; }  // (partitioned handles: before cfdl_comm_ipc_handle, which fixes the chunks)
+  // rbq_counter: the persistent pc solve hands its chunks out from a counter: -1 = only where one chunk per CTA would be too long (default), 0 = never
+  // (such meshes run pass by pass), 1 = always.  rbq_l2_fraction: largest share of the L2 the value arrays may take for the persistent form.
+  // (partitioned handles: set both before cfdl_comm_ipc_handle, which fixes the chunks)
+  if (!std::strcmp(key, "rbq_counter")) { h->rbq_counter = value < 0 ? -1 : (value != 0.0); h->rbq_refused = 0; return CFDL_OK; }
+  if (!std::strcmp(key, "rbq_l2_fraction")) { h->rbq_l2_fraction = value; h->rbq_refused = 0; return CFDL_OK; }
   if (!std::strcmp(key, "rbq_lmax")) { h->rbq_lmax = std::max(0, (int)value); h->rbq_refused = 0; return CFDL_OK; }
   if (!std::strcmp(key, "rbq_lbig")) { h->rbq_lbig = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "rbq_cap")) { h->rbq_cap = std::max(0, (int)value); return CFDL_OK; }

@@ -145,7 +145,9 @@ struct Handle {
   size_t rbq_prog_len = 0;                 // words allocated (the error word sits behind them)
   int rbq_lmax = 0, rbq_lbig = 0, rbq_cap = 0;  // options (0: defaults / environment): largest one-chunk-per-CTA size, chunk size of the round-robin form, CTA limit
   int rbq_last_chunks = 0, rbq_last_grid = 0, rbq_last_L = 0;  // geometry of the last persistent pc solve (info)
-  int rbq_rounds = 1;                      // option: large meshes run the persistent pc solve with chunks dealt round-robin (0: pass by pass)
+  int rbq_counter = -1;                    // option: chunks handed out from a counter: -1 where one chunk per CTA would be too long, 0 never, 1 always
+  double rbq_l2_fraction = 0.0;            // option: share of the L2 the value arrays may take for the persistent pc solve (0: default / environment)
+  size_t l2_bytes = 0;
   // partitioned meshes (peer-to-peer mode): value arrays and progress words live in the exported slab; per chunk the progress
   // words to wait for (own chunks and the neighbours' interface chunks), the interface rows to push after a pass
   int rbq_dist_state = 0;         // 0: not set up yet, 1: ready, -1: refused (on every rank alike)

@@ -58,7 +58,7 @@ enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cuda
 enum { cudaStreamNonBlocking = 1, cudaIpcMemLazyEnablePeerAccess = 1 };
 struct cudaDeviceProp {
   char name[256];
-  int major, minor, multiProcessorCount, cooperativeLaunch;
+  int major, minor, multiProcessorCount, cooperativeLaunch, l2CacheSize;
   size_t totalGlobalMem;
 };
 struct cudaIpcMemHandle_t { char reserved[64]; };

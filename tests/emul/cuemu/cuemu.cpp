@@ -332,6 +332,7 @@ cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
   const char* e = std::getenv("CUEMU_SMS");
   p->multiProcessorCount = e ? std::atoi(e) : 3;
   p->totalGlobalMem = (size_t)8 << 30;
+  p->l2CacheSize = 126 << 20;
   return cudaSuccess;
 }
 cudaError_t cudaGetLastError() { return cudaSuccess; }

@@ -83,7 +83,7 @@ def main():
             out[rank] = (hist, fields)
             if slabs:
                 assert int(s.get_info("rbq_dist")) == 1, ("persistent partitioned pc solve not in use", rank, s.get_info("rbq_dist"))
-                if os.environ.get("CFDL_TEST_RBQ_ROUNDS"):  # the large-mesh form: more chunks than CTAs, dealt round-robin
+                if os.environ.get("CFDL_TEST_RBQ_ROUNDS"):  # more chunks than CTAs, handed out from a counter
                     assert int(s.get_info("rbq_chunks")) > int(s.get_info("rbq_grid")), (rank, s.get_info("rbq_chunks"), s.get_info("rbq_grid"))
             bar.wait()
             # cfdl_step_host with partition-local arrays (bench.py's e2e path on several GPUs) against the

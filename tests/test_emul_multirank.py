@@ -45,9 +45,9 @@ def test_partitioned_momentum_solves_side_by_side_and_one_by_one(fused):
 
 
 @pytest.mark.parametrize("world,n", [(2, 16), (4, 16)])
-def test_partitioned_persistent_pc_solve_with_round_robin_chunks(world, n):
-    """The large-mesh form of the partitioned persistent pc solve (more chunks than co-resident CTAs: chunks of 64 rows dealt
-    round-robin, interface chunks first, tagged 128-bit stores across the ranks) forced on small slabs: same fields as one rank."""
+def test_partitioned_persistent_pc_solve_with_chunks_from_a_counter(world, n):
+    """The partitioned persistent pc solve with more chunks than co-resident CTAs (chunks of 64 rows handed out in order from a
+    counter, interface chunks first, tagged 128-bit stores across the ranks), forced on small slabs: same fields as one rank."""
     env = dict(os.environ, CFDL_RBQ_LMAX="64", CFDL_RBQ_LBIG="64", CFDL_RBQ_LS_MIN="64", CFDL_TEST_RBQ_ROUNDS="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "multirank_check.py"), str(world), str(n), "slabs"], cwd=ROOT, env=env,
                        capture_output=True, text=True, timeout=900)

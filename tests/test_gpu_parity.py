@@ -633,7 +633,7 @@ def test_persistent_pc_solve_keeps_the_bits(case, cfdl):
     s.set_option("solver", cfdl.SOLVER_MCSGS)
     try:
         res = {}
-        # third entry: the large-mesh form (chunks of 64 rows dealt round-robin to at most 2 CTAs)
+        # third entry: more chunks than CTAs (chunks of 64 rows handed out in order from a counter to at most 2 CTAs)
         combos = [(0, 1, 0), (1, 1, 0), (1, 0, 0), (0, 0, 0), (1, 1, 1), (1, 0, 1)]
         for combo in combos:
             s.set_option("rbq", combo[0])

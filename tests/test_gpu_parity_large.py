@@ -93,33 +93,33 @@ def test_hex128_fast_mode_vs_oracle_on_colour_ordered_mesh(cfdl, oracle):
         assert hist[:, 3, 0].max() == 100  # the pc solve runs into the reference's iteration cap at this size
 
 
-def test_persistent_pc_solve_with_round_robin_chunks_keeps_the_bits(cfdl):
-    """The form of the persistent pc solve that large meshes take (kernels_rbq.inc: chunks of a fixed size dealt round-robin to
-    the co-resident CTAs, one progress word per chunk), forced on a 64^3 mesh by small chunks: 1 024 chunks of 128 rows per colour
+def test_persistent_pc_solve_with_chunks_from_a_counter_keeps_the_bits(cfdl):
+    """The persistent pc solve with more chunks than co-resident CTAs (kernels_rbq.inc: chunks of a fixed size handed out in order
+    from a counter, one progress word per chunk), forced on a 64^3 mesh by small chunks: 1 024 chunks of 128 rows per colour
     on at most 444 CTAs, 17 chunks of look-back per side.  Against the pass-by-pass kernels: same iteration counts, same fields
     bit for bit, residual norms to rounding (they are summed per chunk)."""
     n = 12 if conftest.EMULATED else 64
     raw = cfdl.meshgen(cfdl.MESH_HEX, n)
     geom = cfdl.mesh_build(raw)
     res = {}
-    for form in ("pass by pass", "one chunk per CTA", "round robin"):
+    for form in ("pass by pass", "one chunk per CTA", "chunks from a counter"):
         s = cfdl.Solver(geom, cfdl.default_bcs(raw))
         try:
             s.set_option("solver", cfdl.SOLVER_MCSGS)
             s.set_option("rbq", 0 if form == "pass by pass" else 1)
-            if form == "round robin":
+            if form == "chunks from a counter":
                 s.set_option("rbq_lmax", 64 if conftest.EMULATED else 128)
                 s.set_option("rbq_lbig", 64 if conftest.EMULATED else 128)
             hist = s.run(dt=0.01, nit=100, ntstep=1, ncoef=3)
             if form != "pass by pass":
                 assert int(s.get_info("rbq_active")) == 1 and int(s.get_info("rbq_refused")) == 0
                 chunks, grid = int(s.get_info("rbq_chunks")), int(s.get_info("rbq_grid"))
-                assert (chunks > grid) == (form == "round robin"), (form, chunks, grid)
+                assert (chunks > grid) == (form == "chunks from a counter"), (form, chunks, grid)
             res[form] = (hist, {f: s.download(f) for f in ("u", "v", "w", "p", "pc", "mip")})
         finally:
             s.close()
     want_hist, want = res["pass by pass"]
-    for form in ("one chunk per CTA", "round robin"):
+    for form in ("one chunk per CTA", "chunks from a counter"):
         hist, got = res[form]
         assert conftest.same_history(hist, want_hist), form
         for f in got:
