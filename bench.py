@@ -201,6 +201,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="cfdl_set_option(KEY, VALUE) after creation (tuning experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--bind-cores", action="store_true", help="several ranks: pin each rank's host threads to its own 1/local-world share of the cores this process may use")
     ap.add_argument("--e2e-separate", action="store_true", help="e2e through separate upload/solve/download calls instead of cfdl_step_host")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -220,6 +221,18 @@ def main():
         args.warmup = 3
     args.warmup = max(args.warmup, 3)
 
+    bound = None
+    if args.bind_cores and world > 1:
+        try:
+            lw = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+            cores = sorted(os.sched_getaffinity(0))
+            share = len(cores) // lw
+            if share >= 2:
+                mine = cores[local_rank * share:(local_rank + 1) * share]
+                os.sched_setaffinity(0, mine)
+                bound = "%d cores from %d" % (len(mine), mine[0])
+        except Exception as ex:
+            dbg("core binding failed:", ex)
     import cfdl
     if cfdl.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
@@ -409,7 +422,7 @@ def main():
             kname = "rb_red_kernel / rb_black_kernel (fused two-colour SGS pass incl. residual; average of the two)"
             kkey = "rb_pass_i16" if i16 else "rb_pass_i32"
             if rbq:
-                kkey = "rbq_i16" if i16 else "rbq_i32"
+                kkey = ("rbq_i16" if i16 else "rbq_i32") + ("_counter" if int(s.get_info("rbq_chunks")) > int(s.get_info("rbq_grid")) else "")
                 kname = ("rbq_kernel (all red/black passes of a pc solve in one persistent launch, neighbour-only synchronisation; "
                          "launch time / passes; the 'isolated' figure is the pass-by-pass kernels rb_red_kernel / rb_black_kernel, one event pair per launch)")
         else:
@@ -625,7 +638,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args.mesh, n_global, ne, nz_global), "solver": args.solver, "ncolors": ncol, "options": args.opt, "mesh_source": "structured per-rank generator" if structured else "reference-format arrays", "fused_two_colour_passes": bool(fused), "timed_loop": loop, "programmatic_dependent_launch": bool(fused and not args.no_pdl),
-                           "cells_per_gpu": ne // world, "setup_seconds": round(setup_s, 1), "setup_breakdown_seconds": dict(SETUP_S), "l2": "working set (>1 GB per GPU) exceeds the 126 MB L2; no flush needed" if ne // world > 1000000 else
+                           "cells_per_gpu": ne // world, "host_cores": bound or "not pinned", "host_cpus": os.cpu_count(), "setup_seconds": round(setup_s, 1), "setup_breakdown_seconds": dict(SETUP_S), "l2": "working set (>1 GB per GPU) exceeds the 126 MB L2; no flush needed" if ne // world > 1000000 else
                            "working set may fit L2",
                            "parallelism": "1 GPU" if world == 1 else
                            "%d GPUs, one %s of the global mesh per GPU; ghost-cell exchange: %s" % (world, "z-slab" if partition == "slabs" else "RCB block", exchange),
