@@ -50,14 +50,34 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons of one GPU sampled during the timed region: NVML inside this process (nvidia_ml_py; initialised
+    before the warm-up, then one cheap query every 50 ms from a thread), or — without NVML bindings — an `nvidia-smi -lms 50` child.
+    Measured (8 GPUs, round 2): the nvidia-smi child, whose start-up enumerates every GPU of the box while the ranks are launching,
+    is visible in short timed regions; the in-process queries are not."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
-        self.device, self.proc, self.lines = device, None, []
+    def __init__(self, device, how="nvml"):
+        self.device, self.proc, self.lines, self.how = device, None, [], how
+        self.nvml, self.handle, self.t, self.samples, self.stop_flag = None, None, None, [], threading.Event()
 
     def start(self):
+        if self.how == "off":
+            return
+        if self.how == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+                self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+                pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+                self.nvml = pynvml
+                self.t = threading.Thread(target=self._poll, daemon=True)
+                self.t.start()
+                return
+            except Exception as ex:
+                dbg("NVML sampler unavailable (%s): nvidia-smi child instead" % ex)
+                self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -66,11 +86,37 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", n.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksThrottleReasonSwPowerCap))
+        while not self.stop_flag.is_set():
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((mhz, [name for name, b in bits if mask & b]))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.05)
+
     def _read(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if self.how == "off":
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled (--clock-sampler off)"]}
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.t.join(timeout=2)
+            sm = [m for m, _ in self.samples]
+            reasons = sorted({r for _, rs in self.samples for r in rs})
+            try:
+                self.nvml.nvmlShutdown()
+            except Exception:
+                pass
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
+                    "source": "NVML in-process, every 50 ms"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()  # exact PID of the sampler we started
@@ -91,7 +137,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 50 (child process)"}
 
 
 def ncu_traffic(kernel_key, args, world):
@@ -201,6 +247,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="cfdl_set_option(KEY, VALUE) after creation (tuning experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi", "off"], help="how clocks / throttle reasons are sampled during the timed region")
     ap.add_argument("--bind-cores", action="store_true", help="several ranks: pin each rank's host threads to its own 1/local-world share of the cores this process may use")
     ap.add_argument("--e2e-separate", action="store_true", help="e2e through separate upload/solve/download calls instead of cfdl_step_host")
     args = ap.parse_args()
@@ -331,7 +378,7 @@ def main():
     # the clock sampler (nvidia-smi takes a few 100 ms to come up) starts before the warm-up and
     # covers the timed region; it samples the GPU under the same load throughout
     # (rank 0 only: one nvidia-smi polling loop per rank perturbs the launches of all of them — the driver lock is shared)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_sampler)
     if rank == 0:
         sampler.start()
     for i in range(args.warmup):
@@ -362,9 +409,13 @@ def main():
     barrier()
     clocks = sampler.stop()
     launches = int(s.get_info("launches"))
+    ms_by_rank = None
     if dist is not None:
         import torch
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        ms_by_rank = [round(float(x.item()) / args.steps, 4) for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = ne * args.steps / (ms * 1e-3)  # ne = cells of the whole (global) mesh over all ranks
@@ -638,7 +689,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args.mesh, n_global, ne, nz_global), "solver": args.solver, "ncolors": ncol, "options": args.opt, "mesh_source": "structured per-rank generator" if structured else "reference-format arrays", "fused_two_colour_passes": bool(fused), "timed_loop": loop, "programmatic_dependent_launch": bool(fused and not args.no_pdl),
-                           "cells_per_gpu": ne // world, "host_cores": bound or "not pinned", "host_cpus": os.cpu_count(), "setup_seconds": round(setup_s, 1), "setup_breakdown_seconds": dict(SETUP_S), "l2": "working set (>1 GB per GPU) exceeds the 126 MB L2; no flush needed" if ne // world > 1000000 else
+                           "cells_per_gpu": ne // world, "ms_per_step_by_rank": ms_by_rank, "host_cores": bound or "not pinned", "host_cpus": os.cpu_count(), "setup_seconds": round(setup_s, 1), "setup_breakdown_seconds": dict(SETUP_S), "l2": "working set (>1 GB per GPU) exceeds the 126 MB L2; no flush needed" if ne // world > 1000000 else
                            "working set may fit L2",
                            "parallelism": "1 GPU" if world == 1 else
                            "%d GPUs, one %s of the global mesh per GPU; ghost-cell exchange: %s" % (world, "z-slab" if partition == "slabs" else "RCB block", exchange),

@@ -334,6 +334,7 @@ int cfdl_set_option(cfdl_handle h, const char* key, double value) {
   // (partitioned handles: set both before cfdl_comm_ipc_handle, which fixes the chunks)
   if (!std::strcmp(key, "rbq_counter")) { h->rbq_counter = value < 0 ? -1 : (value != 0.0); h->rbq_refused = 0; return CFDL_OK; }
   if (!std::strcmp(key, "rbq_l2_fraction")) { h->rbq_l2_fraction = value; h->rbq_refused = 0; return CFDL_OK; }
+  if (!std::strcmp(key, "rbq_prefetch")) { h->rbq_prefetch = std::max(-1, std::min(4, (int)value)); return CFDL_OK; }
   if (!std::strcmp(key, "rbq_lmax")) { h->rbq_lmax = std::max(0, (int)value); h->rbq_refused = 0; return CFDL_OK; }
   if (!std::strcmp(key, "rbq_lbig")) { h->rbq_lbig = std::max(0, (int)value); return CFDL_OK; }
   if (!std::strcmp(key, "rbq_cap")) { h->rbq_cap = std::max(0, (int)value); return CFDL_OK; }

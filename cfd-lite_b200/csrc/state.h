@@ -145,6 +145,7 @@ struct Handle {
   size_t rbq_prog_len = 0;                 // words allocated (the error word sits behind them)
   int rbq_lmax = 0, rbq_lbig = 0, rbq_cap = 0;  // options (0: defaults / environment): largest one-chunk-per-CTA size, chunk size of the round-robin form, CTA limit
   int rbq_last_chunks = 0, rbq_last_grid = 0, rbq_last_L = 0;  // geometry of the last persistent pc solve (info)
+  int rbq_prefetch = -1;                   // option: L2 prefetch of the next trips' constants in the persistent pc solve (trips ahead; 0 = off, -1 = by size)
   int rbq_counter = -1;                    // option: chunks handed out from a counter: -1 where one chunk per CTA would be too long, 0 never, 1 always
   double rbq_l2_fraction = 0.0;            // option: share of the L2 the value arrays may take for the persistent pc solve (0: default / environment)
   size_t l2_bytes = 0;
