@@ -52,8 +52,9 @@ def peaks():
 class ClockSampler:
     """SM clock and throttle reasons of one GPU sampled during the timed region: NVML inside this process (nvidia_ml_py; initialised
     before the warm-up, then one cheap query every 50 ms from a thread), or — without NVML bindings — an `nvidia-smi -lms 50` child.
-    Measured (8 GPUs, round 2): the nvidia-smi child, whose start-up enumerates every GPU of the box while the ranks are launching,
-    is visible in short timed regions; the in-process queries are not."""
+    Measured (8 GPUs, 30 timed steps, round 2, profiles/r02_exp_8gpu_stack_sampler_*.json): 5.90 ms per step without a sampler, 5.85 with
+    the in-process queries, 5.88 with the nvidia-smi child — neither disturbs the run; the in-process form needs no child process
+    and no start-up time."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -375,9 +376,8 @@ def main():
     # ---- value: device-resident steps, CUDA events on the library's stream -------------------
     setup_s = time.perf_counter() - t_setup
     dbg("setup %.1f s;" % setup_s, "solver ready; owned", int(s.get_info("owned_cells")), "ghost", int(s.get_info("ghost_cells")))
-    # the clock sampler (nvidia-smi takes a few 100 ms to come up) starts before the warm-up and
-    # covers the timed region; it samples the GPU under the same load throughout
-    # (rank 0 only: one nvidia-smi polling loop per rank perturbs the launches of all of them — the driver lock is shared)
+    # the clock sampler starts before the warm-up and covers the timed region; it samples the GPU under the same load
+    # throughout (rank 0 only: one sample stream describes the box)
     sampler = ClockSampler(local_rank, args.clock_sampler)
     if rank == 0:
         sampler.start()
@@ -493,6 +493,13 @@ def main():
                 "bytes_per_launch": per_launch, "avg_launch_ms": avg_ms, "launches_timed": timed, "timing": how,
                 "isolated": {"achieved": iso, "frac": iso / peak, "avg_launch_ms": iso_ms, "launches_timed": prof["sgs"][1],
                              "timing": "one CUDA-event pair per launch (launches serialised, no overlap)"}}
+        if roof["traffic"]:
+            # `achieved` counts ALGORITHMIC bytes; the persistent pc solve keeps its value arrays in the L2, so the DRAM moves fewer
+            # (the ncu figure): frac can approach or pass 1 while the DRAM itself is at dram_frac of its measured copy rate
+            roof["dram_achieved"] = roof["traffic"] / (avg_ms * 1e-3) / 1e9
+            roof["dram_frac"] = roof["dram_achieved"] / peak
+            roof["note"] = ("achieved/frac relate the algorithmic bytes of a pass to the measured HBM copy rate; traffic is the DRAM traffic ncu measured "
+                            "for the same pass (the L2 serves the rest), dram_achieved/dram_frac relate that to the same peak")
     if prof["residual"][1] > 0:
         # residual_kernel only (one right-hand side: 20N + 12Z + 8H); the three-RHS residual3_kernel of the
         # side-by-side momentum solves and its cross-rank reduction are timed under their own kind (residual3)
