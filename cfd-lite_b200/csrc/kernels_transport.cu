@@ -9,8 +9,11 @@
 // The reference constructs the energy equation and never solves it (main.f90:59 is commented out) and never constructs
 // the scalar one; both reuse everything the uvwp path has — gather-type cell kernels over the ELL slots in the reference's
 // face order (bit-identical sums), the face statics, calc_grad, and the solvers (solve_equation: exact natural-order
-// SGS in parity mode, multicolour SGS otherwise).  One GPU only for now: their fields live outside the exported slab.
+// SGS in parity mode, multicolour SGS otherwise).  Partitioned handles: tc / cp carry the ghost cells, the gradients' and the
+// solved fields' ghosts are exchanged like those of uvwp; the fields live outside the peer-to-peer slab, so the solve itself
+// runs on a slab-resident work array (the side-by-side momentum solve's, idle here) and the result is copied back.
 #include "state.h"
+#include <vector>
 #include "device_math.cuh"
 
 namespace cfdl {
@@ -178,9 +181,9 @@ __global__ void __launch_bounds__(TPB) coef_scalar_kernel(const ScalarArgs A) {
 __global__ void __launch_bounds__(TPB) fill_kernel(double* a, double v, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] = v;
 }
-__global__ void __launch_bounds__(TPB) mul_cp_kernel(int N, int H, const double* __restrict__ t, const double* __restrict__ cp, double* hh) {
+__global__ void __launch_bounds__(TPB) mul_cp_kernel(int Nc, int H, const double* __restrict__ t, const double* __restrict__ cp, double* hh) {
   // construct_energy :33 phi = t*cp (cp has one entry per cell; the halo entries are set by the boundary callbacks before use)
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < H; c += gridDim.x * blockDim.x) hh[c] = t[c] * cp[c < N ? c : 0];
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < H; c += gridDim.x * blockDim.x) hh[c] = t[c] * cp[c < Nc ? c : 0];
 }
 
 static int ensure(Handle* h, double*& p, size_t n) {
@@ -191,15 +194,28 @@ static int ensure(Handle* h, double*& p, size_t n) {
   return CFDL_OK;
 }
 
-static int single_rank_only(const Handle* h, const char* what) {
-  if (h->prep.nranks > 1) return fail(CFDL_ERR_UNSUPPORTED, "%s: the energy and scalar equations run on single-GPU handles only", what);
-  if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "cells with more than 6 faces are not supported");
+static int transport_supported(const Handle* h, const char* what) {
+  if (h->K > 6) return fail(CFDL_ERR_UNSUPPORTED, "%s: cells with more than 6 faces are not supported", what);
+  return CFDL_OK;
+}
+
+// solve_equation for a field that lives outside the peer-to-peer slab: the two-colour passes store interface values straight
+// into the neighbours' copies of the array they sweep, so that array must be one every rank exports
+static int solve_transport(Handle* h, int eq, double* phi, int nit, double* out4) {
+  const bool scratch = h->prep.nranks > 1 && h->p2p.connected && h->use_p2p;
+  if (!scratch) return solve_equation(h, eq, phi, h->fld[CFDL_F_B], nit, out4, false);
+  double* w = h->rb3_work[0];
+  const size_t bytes = sizeof(double) * (size_t)h->H;
+  CFDL_CUDA(cudaMemcpyAsync(w, phi, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  int rc = solve_equation(h, eq, w, h->fld[CFDL_F_B], nit, out4, false);
+  if (rc) return rc;
+  CFDL_CUDA(cudaMemcpyAsync(phi, w, bytes, cudaMemcpyDeviceToDevice, h->stream));
   return CFDL_OK;
 }
 
 // construct_energy (mod_energy.f90:14-48) + the tc, cp of init_properties (mod_properties.f90:88-89; NULL: 5 and 1000)
 int k_energy_init(Handle* h, const double* tc_host, const double* cp_host) {
-  int rc = single_rank_only(h, "cfdl_energy_init");
+  int rc = transport_supported(h, "cfdl_energy_init");
   if (rc) return rc;
   const size_t H = (size_t)h->H;
   if ((rc = ensure(h, h->tc, (size_t)h->Nc)) || (rc = ensure(h, h->cp, (size_t)h->Nc)) || (rc = ensure(h, h->fld[CFDL_F_T], H)) ||
@@ -207,15 +223,22 @@ int k_energy_init(Handle* h, const double* tc_host, const double* cp_host) {
       (rc = ensure(h, h->fld[CFDL_F_GH], 3 * H)))
     return rc;
   const int g = grid_for(h, h->H, TPB);
-  // per-cell arrays in the reference's numbering -> device numbering (one rank: every cell is owned)
+  // per-cell arrays in the reference's numbering -> device numbering (owned cells, then the ghosts of a partition)
   auto put = [&](double* dst, const double* host, double dflt) -> int {
     if (!host) { fill_kernel<<<g, TPB, 0, S(h)>>>(dst, dflt, h->Nc); return CFDL_OK; }
+    if (h->prep.nranks > 1) {
+      std::vector<double> t((size_t)h->Nc);
+      for (int32_t c = 0; c < h->Nc; ++c) t[(size_t)c] = host[h->prep.c2o[(size_t)c]];
+      CFDL_CUDA(cudaMemcpyAsync(dst, t.data(), sizeof(double) * t.size(), cudaMemcpyHostToDevice, h->stream));
+      CFDL_CUDA(cudaStreamSynchronize(h->stream));  // (t goes out of scope)
+      return CFDL_OK;
+    }
     CFDL_CUDA(cudaMemcpyAsync(h->stage, host, sizeof(double) * (size_t)h->prep.gN, cudaMemcpyHostToDevice, h->stream));
     return k_gather(h, dst, h->stage, h->c2o, h->Nc, 1);
   };
   if ((rc = put(h->tc, tc_host, 5.0)) || (rc = put(h->cp, cp_host, 1000.0))) return rc;
   fill_kernel<<<g, TPB, 0, S(h)>>>(h->fld[CFDL_F_T], 273.0, h->H);
-  mul_cp_kernel<<<g, TPB, 0, S(h)>>>(h->N, h->H, h->fld[CFDL_F_T], h->cp, h->fld[CFDL_F_H]);
+  mul_cp_kernel<<<g, TPB, 0, S(h)>>>(h->Nc, h->H, h->fld[CFDL_F_T], h->cp, h->fld[CFDL_F_H]);
   CFDL_CUDA(cudaMemcpyAsync(h->fld[CFDL_F_H0], h->fld[CFDL_F_H], sizeof(double) * H, cudaMemcpyDeviceToDevice, h->stream));
   CFDL_CUDA(cudaMemsetAsync(h->fld[CFDL_F_GT], 0, sizeof(double) * 3 * H, h->stream));
   CFDL_CUDA(cudaMemsetAsync(h->fld[CFDL_F_GH], 0, sizeof(double) * 3 * H, h->stream));
@@ -225,7 +248,7 @@ int k_energy_init(Handle* h, const double* tc_host, const double* cp_host) {
 }
 
 int k_scalar_init(Handle* h, double dcoef, const double vel[3], const double* bc_value_host) {
-  int rc = single_rank_only(h, "cfdl_scalar_init");
+  int rc = transport_supported(h, "cfdl_scalar_init");
   if (rc) return rc;
   const size_t H = (size_t)h->H, nbc = h->prep.bc_kind.size();
   if ((rc = ensure(h, h->fld[CFDL_F_S], H)) || (rc = ensure(h, h->fld[CFDL_F_S0], H)) || (rc = ensure(h, h->fld[CFDL_F_GS], 3 * H)) ||
@@ -262,11 +285,20 @@ int k_transport_update_time(Handle* h) {  // mod_physics.f90:104 (scalar, commen
 }
 
 int k_solve_energy(Handle* h, double dt, int nit, double* out4) {  // mod_energy.f90:59-80
-  int rc = single_rank_only(h, "cfdl_solve_energy");
+  int rc = transport_supported(h, "cfdl_solve_energy");
   if (rc) return rc;
   if (!h->has_energy) return fail(CFDL_ERR_ARG, "cfdl_solve_energy: call cfdl_energy_init first");
   if (!h->use_statics) return fail(CFDL_ERR_UNSUPPORTED, "cfdl_solve_energy needs the face statics (option statics = 1)");
+  const bool dist = h->prep.nranks > 1;
+  if (dist) {  // ghosts of t and phi (uploads and callbacks touch owned cells and halos only), then of the two gradients
+    double* th[2] = {h->fld[CFDL_F_T], h->fld[CFDL_F_H]};
+    if ((rc = comm_exchange_multi(h, th, 2, 1))) return rc;
+  }
   if ((rc = k_calc_grad(h, h->fld[CFDL_F_T], h->fld[CFDL_F_GT])) || (rc = k_calc_grad(h, h->fld[CFDL_F_H], h->fld[CFDL_F_GH]))) return rc;
+  if (dist) {
+    double* gg[2] = {h->fld[CFDL_F_GT], h->fld[CFDL_F_GH]};
+    if ((rc = comm_exchange_multi(h, gg, 2, 3))) return rc;
+  }
   EnergyArgs A;
   A.N = h->N; A.Nc = h->Nc; A.Np = h->Np; A.ell_nb = h->ell_nb; A.ell_fs = h->ell_fs; A.halo_bc = h->halo_bc; A.nfc = h->nfc;
   A.xc = h->xc; A.yc = h->yc; A.zc = h->zc; A.aip = h->aip; A.vol = h->vol; A.rho = h->rho; A.tc = h->tc; A.cp = h->cp;
@@ -278,16 +310,18 @@ int k_solve_energy(Handle* h, double dt, int nit, double* out4) {  // mod_energy
   if (h->K <= 4) coef_energy_kernel<4><<<grid_for(h, h->N, TPB, 4), TPB, 0, S(h)>>>(A);
   else coef_energy_kernel<6><<<grid_for(h, h->N, TPB, 4), TPB, 0, S(h)>>>(A);
   CFDL_CUDA(cudaGetLastError());
-  if ((rc = solve_equation(h, CFDL_EQ_E, h->fld[CFDL_F_H], h->fld[CFDL_F_B], nit, out4, false))) return rc;
-  temperature_kernel<<<grid_for(h, h->N, TPB), TPB, 0, S(h)>>>(h->N, h->fld[CFDL_F_H], h->cp, h->fld[CFDL_F_T]);
+  if ((rc = solve_transport(h, CFDL_EQ_E, h->fld[CFDL_F_H], nit, out4))) return rc;
+  // (owned cells and ghosts: the solve leaves the ghosts of phi current, cp carries them)
+  temperature_kernel<<<grid_for(h, h->Nc, TPB), TPB, 0, S(h)>>>(h->Nc, h->fld[CFDL_F_H], h->cp, h->fld[CFDL_F_T]);
   CFDL_CUDA(cudaGetLastError());
   return CFDL_OK;
 }
 
 int k_solve_scalar(Handle* h, double dt, int nit, double* out4) {  // mod_scalar.f90:56-72
-  int rc = single_rank_only(h, "cfdl_solve_scalar");
+  int rc = transport_supported(h, "cfdl_solve_scalar");
   if (rc) return rc;
   if (!h->has_scalar) return fail(CFDL_ERR_ARG, "cfdl_solve_scalar: call cfdl_scalar_init first");
+  if (h->prep.nranks > 1 && (rc = comm_exchange(h, h->fld[CFDL_F_S], 1, -1))) return rc;  // ghosts of phi for the gradient
   ScalarArgs A;
   A.N = h->N; A.Np = h->Np; A.ell_nb = h->ell_nb; A.ell_fs = h->ell_fs; A.nfc = h->nfc;
   A.xc = h->xc; A.yc = h->yc; A.zc = h->zc; A.aip = h->aip; A.vol = h->vol; A.s = h->fld[CFDL_F_S]; A.s0 = h->fld[CFDL_F_S0];
@@ -298,7 +332,8 @@ int k_solve_scalar(Handle* h, double dt, int nit, double* out4) {  // mod_scalar
   else coef_scalar_kernel<6><<<grid_for(h, h->N, TPB, 4), TPB, 0, S(h)>>>(A);
   CFDL_CUDA(cudaGetLastError());
   if ((rc = k_calc_grad(h, h->fld[CFDL_F_S], h->fld[CFDL_F_GS]))) return rc;
-  return solve_equation(h, CFDL_EQ_S, h->fld[CFDL_F_S], h->fld[CFDL_F_B], nit, out4, false);
+  if (h->prep.nranks > 1 && (rc = comm_exchange(h, h->fld[CFDL_F_GS], 3, -1))) return rc;
+  return solve_transport(h, CFDL_EQ_S, h->fld[CFDL_F_S], nit, out4);
 }
 
 }  // namespace cfdl

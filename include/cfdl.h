@@ -157,7 +157,8 @@ int cfdl_update_boundaries(cfdl_handle h);
 int cfdl_solve_uvwp(cfdl_handle h, double dt, int32_t nit, double* hist);
 /* update_time, mod_physics.f90:101-112 */
 int cfdl_update_time(cfdl_handle h);
-/* The energy (enthalpy) and passive-scalar equations of the reference (single-GPU handles).
+/* The energy (enthalpy) and passive-scalar equations of the reference (single-GPU and partitioned handles:
+ * tc / cp are given for every cell of the global mesh in the reference numbering, on every rank).
  *   cfdl_energy_init   construct_energy, mod_energy.f90:14-48: t = 273, phi = cp t, phi0 = phi, gradients 0; tc / cp are
  *                      per-cell arrays (ne, reference numbering) or NULL for init_properties' 5 and 1000
  *                      (mod_properties.f90:88-89).  From then on cfdl_update_boundaries also runs the energy callbacks

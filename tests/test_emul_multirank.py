@@ -55,6 +55,17 @@ def test_partitioned_persistent_pc_solve_with_chunks_from_a_counter(world, n):
     assert "multirank emulation ok" in r.stdout
 
 
+@pytest.mark.parametrize("world,n,how", [(4, 10, "p2p"), (3, 8, "nccl"), (4, 12, "slabs")])
+def test_partitioned_energy_and_scalar_equations_equal_single_rank(world, n, how):
+    """cfdl_solve_energy / cfdl_solve_scalar on partitioned handles (tc / cp with ghost cells, ghost exchange of t, phi and the
+    gradients, the solve on a slab-resident work array in peer-to-peer mode): fields equal to the single-rank run, same
+    iteration counts (tests/emul/multirank_transport_check.py)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emul", "multirank_transport_check.py"), str(world), str(n), how], cwd=ROOT,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert "multirank transport ok" in r.stdout
+
+
 @pytest.mark.parametrize("mode", ["rcb", "slabs"])
 def test_silent_rank_is_an_error_code_not_a_hang(mode):
     """Every wait on a word another rank writes is time-limited: a rank that connects and then never launches surfaces on

@@ -28,7 +28,22 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, kind, n, p2p, out_q):
+def _transport_steps(s, tc, cp, bcv):
+    """energy + scalar equations next to uvwp: three time steps; returns the (scalar, energy) solve records"""
+    s.energy_init(tc=tc, cp=cp)
+    s.scalar_init(dcoef=0.7, vel=(3.0, -2.0, 5.0), bc_value=bcv)
+    recs = []
+    for _ in range(3):
+        s.update_boundaries()
+        s.solve_uvwp(0.01, 30)
+        hs = s.solve_scalar(0.01, 100)
+        he = s.solve_energy(50.0, 100)  # (a long time step: several iterations)
+        s.update_time()
+        recs.append((hs, he))
+    return recs
+
+
+def _worker(rank, world, port, kind, n, p2p, out_q, transport=False):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, os.path.join(ROOT, "cfd-lite_b200", "python"))
@@ -64,8 +79,16 @@ def _worker(rank, world, port, kind, n, p2p, out_q):
         hist = s.run(dt=0.01, nit=100, ntstep=2, ncoef=3)
         if slabs and p2p:
             assert int(s.get_info("rbq_dist")) == 1, "the persistent partitioned pc solve is not in use"
+        recs = None
+        if transport:  # per-cell properties in the reference numbering, the same on every rank
+            rng = np.random.default_rng(5)
+            ne = int(raw["ne"])
+            tc = 5.0 * (1.0 + 0.3 * rng.random(ne))
+            cp = 1000.0 * (1.0 + 0.2 * rng.random(ne))
+            bcv = rng.integers(0, 2, len(bcs[1])).astype(np.float64)
+            recs = _transport_steps(s, tc, cp, bcv)
         fields = {}
-        for f in ("u", "v", "w", "p", "gp") + (() if structured else ("mip",)):  # structured: own face numbering
+        for f in ("u", "v", "w", "p", "gp") + (() if structured else ("mip",)) + (("t", "h", "s", "gt", "gh", "gs") if transport else ()):  # structured: own face numbering
             a = np.full(s.field_size(f), np.nan)
             s.download_into(f, a)  # writes only the entries this rank owns
             fields[f] = a
@@ -86,6 +109,10 @@ def _worker(rank, world, port, kind, n, p2p, out_q):
             assert np.array_equal(hist[:, :, 0], want_hist[:, :, 0]), (hist[:, :, 0], want_hist[:, :, 0])
             err_h = np.abs(hist[:, :, 1:3] - want_hist[:, :, 1:3]).max() / np.abs(want_hist[:, :, 1:3]).max()
             assert err_h < 1e-10, err_h
+            if transport:
+                want = _transport_steps(one, tc, cp, bcv)
+                for (hs, he), (ws, we) in zip(recs, want):
+                    assert hs[0] == ws[0] and he[0] == we[0], (hs, ws, he, we)
             for f in merged:
                 w = one.download(f)
                 err = np.abs(merged[f] - w).max() / max(np.abs(w).max(), 1e-300)
@@ -103,6 +130,17 @@ def _worker(rank, world, port, kind, n, p2p, out_q):
 @pytest.mark.parametrize("kind,n,p2p", [(0, 10, False), (1, 5, False), (0, 10, True), (0, 24, True), (STRUCTURED, 12, False), (STRUCTURED, 16, True), (1, 5, True),
                                           (SLABS, 24, True), (SLABS, 48, True), (STRUCTURED_SLABS, 32, True), (SLABS, 12, False)])
 def test_partitioned_run_equals_single_gpu(cfdl, kind, n, p2p):
+    _run_ranks(cfdl, kind, n, p2p, False)
+
+
+@pytest.mark.parametrize("kind,n,p2p", [(0, 10, True), (0, 10, False), (SLABS, 16, True)])
+def test_partitioned_energy_and_scalar_equations_equal_single_gpu(cfdl, kind, n, p2p):
+    """cfdl_solve_energy / cfdl_solve_scalar on partitioned handles (kernels_transport.cu): t, phi, s and their gradients equal the
+    single-GPU fields, same iteration counts — peer-to-peer (the solve runs on a slab-resident work array) and NCCL exchange."""
+    _run_ranks(cfdl, kind, n, p2p, True)
+
+
+def _run_ranks(cfdl, kind, n, p2p, transport):
     world = min(cfdl.device_count(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -112,7 +150,7 @@ def test_partitioned_run_equals_single_gpu(cfdl, kind, n, p2p):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, n, p2p, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, n, p2p, q, transport)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=600) for _ in range(world)]
