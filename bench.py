@@ -62,14 +62,23 @@ class ClockSampler:
         self.device, self.proc, self.lines, self.how = device, None, [], how
         self.nvml, self.handle, self.t, self.samples, self.stop_flag = None, None, None, [], threading.Event()
 
+    def _nvml_id(self):
+        """the GPU this process computes on, as NVML / nvidia-smi name it: CUDA device i is entry i of CUDA_VISIBLE_DEVICES
+        (an index or a UUID) when that is set, else index i"""
+        vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+        if self.device < len(vis):
+            return vis[self.device]
+        return str(self.device)
+
     def start(self):
         if self.how == "off":
             return
+        ident = self._nvml_id()
         if self.how == "nvml":
             try:
                 import pynvml
                 pynvml.nvmlInit()
-                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(int(ident)) if ident.isdigit() else pynvml.nvmlDeviceGetHandleByUUID(ident.encode())
                 self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
                 pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
                 self.nvml = pynvml
@@ -80,7 +89,7 @@ class ClockSampler:
                 dbg("NVML sampler unavailable (%s): nvidia-smi child instead" % ex)
                 self.nvml = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ident, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
