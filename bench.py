@@ -51,7 +51,7 @@ def peaks():
 
 class ClockSampler:
     """SM clock and throttle reasons of one GPU sampled during the timed region: NVML inside this process (nvidia_ml_py; initialised
-    before the warm-up, then one cheap query every 50 ms from a thread), or — without NVML bindings — an `nvidia-smi -lms 50` child.
+    before the warm-up, then one cheap query every 20 ms from a thread; only the samples of the timed region count), or — without NVML bindings — an `nvidia-smi -lms 50` child.
     Measured (8 GPUs, 30 timed steps, round 2, profiles/r02_exp_8gpu_stack_sampler_*.json): 5.90 ms per step without a sampler, 5.85 with
     the in-process queries, 5.88 with the nvidia-smi child — neither disturbs the run; the in-process form needs no child process
     and no start-up time."""
@@ -61,6 +61,7 @@ class ClockSampler:
     def __init__(self, device, how="nvml"):
         self.device, self.proc, self.lines, self.how = device, None, [], how
         self.nvml, self.handle, self.t, self.samples, self.stop_flag = None, None, None, [], threading.Event()
+        self.samples_before = self.lines_before = 0
 
     def _nvml_id(self):
         """the GPU this process computes on, as NVML / nvidia-smi name it: CUDA device i is entry i of CUDA_VISIBLE_DEVICES
@@ -96,6 +97,11 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """the timed region starts here: earlier samples (warm-up, clocks still ramping up from idle) are dropped"""
+        self.samples_before = len(self.samples)
+        self.lines_before = len(self.lines)
+
     def _poll(self):
         n = self.nvml
         bits = (("hw_slowdown", n.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksThrottleReasonHwThermalSlowdown),
@@ -107,7 +113,7 @@ class ClockSampler:
                 self.samples.append((mhz, [name for name, b in bits if mask & b]))
             except Exception:
                 pass
-            self.stop_flag.wait(0.05)
+            self.stop_flag.wait(0.02)
 
     def _read(self):
         for ln in self.proc.stdout:
@@ -119,14 +125,15 @@ class ClockSampler:
         if self.nvml is not None:
             self.stop_flag.set()
             self.t.join(timeout=2)
-            sm = [m for m, _ in self.samples]
-            reasons = sorted({r for _, rs in self.samples for r in rs})
+            timed = self.samples[self.samples_before:] or self.samples
+            sm = [m for m, _ in timed]
+            reasons = sorted({r for _, rs in timed for r in rs})
             try:
                 self.nvml.nvmlShutdown()
             except Exception:
                 pass
             return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm),
-                    "source": "NVML in-process, every 50 ms"}
+                    "source": "NVML in-process, every 20 ms, samples of the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()  # exact PID of the sampler we started
@@ -135,7 +142,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in (self.lines[self.lines_before:] or self.lines):
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -396,6 +403,7 @@ def main():
     hist_last = None
     hist_all = []
     barrier()
+    sampler.mark()
     s.set_option("reset_counters", 1)
     s.timer_record(0)
     if args.warmup % NCOEF == 0 and args.steps % NCOEF == 0:
