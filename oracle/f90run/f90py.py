@@ -527,6 +527,8 @@ class World:
                     s = stmts[i]
                     if gname and s[:2] == [('name', 'module'), ('name', 'procedure')]:
                         self.generics.setdefault(gname, []).extend(x[1] for x in s[2:] if x[0] == 'name')
+                    elif gname and s[0] == ('name', 'procedure') and len(s) > 1:
+                        self.generics.setdefault(gname, []).extend(x[1] for x in s[1:] if x[0] == 'name')
                     i += 1
                 i += 1
                 continue
@@ -663,6 +665,15 @@ class World:
     @staticmethod
     def attr(n):
         return n + '_' if keyword.iskeyword(n) else n
+
+    def extends(self, tname, ancestor):
+        """is type `tname` the type `ancestor` or an extension of it"""
+        while tname is not None:
+            if tname == ancestor:
+                return True
+            td = self.types.get(tname)
+            tname = td.parent if td else None
+        return False
 
     def comp(self, tname, cname):
         td = self.types.get(tname)
@@ -1071,9 +1082,11 @@ class CodeGen:
                     raise F90Unsupported('type %s has no component %s' % (T[1], cname))
                 self.deps.add(bp)
                 p = self.w.analyse(bp)
-                cargs = ', '.join([code] + [self.gen(a)[0] for a in (args or [])])
                 rT = p.vars[p.result or p.name].T() if p.kind == 'function' else ('unknown', None, 0)
-                code, T = '%s(%s)' % (bp, cargs), rT
+                if p.kind == 'function':
+                    code, T = self.fn_call(bp, p, [code] + [self.gen(a)[0] for a in (args or [])], [None] + list(args or [])), rT
+                else:
+                    code, T = '%s(%s)' % (bp, ', '.join([code] + [self.gen(a)[0] for a in (args or [])])), rT
                 continue
             if T[2] > 0:
                 raise F90Unsupported('component of an array section: %s%%%s' % (code, cname))
@@ -1097,6 +1110,53 @@ class CodeGen:
                     raise F90Unsupported('subscript on scalar component %s' % cname)
         return code, T
 
+    def fn_call(self, key, p, codes, args):
+        """a reference to function `key` whose actual arguments have the codes `codes` (nodes `args`, None for the passed
+        object of a type-bound call): plain call, or -- when the function writes by-reference dummies -- an expression
+        that calls it, stores the returned dummies into the actual arguments and yields the result"""
+        callc = '%s(%s)' % (key, ', '.join(codes))
+        if not p.outs:
+            return callc
+        t = self.newtmp()
+        parts = ['(%s := %s)' % (t, callc)]
+        for i, o in enumerate(p.outs):
+            pos = p.args.index(o)
+            a = None
+            if pos < len(args) and (args[pos] is None or args[pos][0] != 'kw'):
+                a = args[pos]
+            else:
+                for x in args:
+                    if x is not None and x[0] == 'kw' and x[1] == o:
+                        a = x[2]
+            if a is None or a[0] != 'des':
+                continue
+            try:
+                v0, _ = self.lookup(a[1][0][0])
+                if v0 is None:
+                    continue
+                tgt = self.gen_des(a[1], target=True)[0]
+            except F90Unsupported:
+                continue
+            val = '%s[%d]' % (t, i + 1)
+            if tgt.isidentifier():
+                parts.append('(%s := %s)' % (tgt, val))
+            elif tgt.endswith(']'):
+                depth, k = 0, len(tgt) - 1
+                while k >= 0:
+                    if tgt[k] == ']':
+                        depth += 1
+                    elif tgt[k] == '[':
+                        depth -= 1
+                        if depth == 0:
+                            break
+                    k -= 1
+                parts.append('%s.__setitem__(%s, %s)' % (tgt[:k], tgt[k + 1:-1], val))
+            else:
+                obj, attr = tgt.rsplit('.', 1)
+                parts.append('setattr(%s, %r, %s)' % (obj, attr, val))
+        parts.append('%s[0]' % t)
+        return '(' + ', '.join(parts) + ')[-1]'
+
     def gen_call_expr(self, name, args):
         if name in _INTRINSICS and name not in self.w.byname:
             return _INTRINSICS[name](self, args)
@@ -1110,9 +1170,8 @@ class CodeGen:
             raise F90Unsupported('unknown function %s' % name)
         p = self.w.analyse(target)
         self.deps.add(target)
-        cargs = ', '.join(self.gen(a)[0] for a in args)
         rv = p.vars[p.result or p.name]
-        return '%s(%s)' % (target, cargs), rv.T()
+        return self.fn_call(target, p, [self.gen(a)[0] for a in args], list(args)), rv.T()
 
     # ---- statements
     def procedure(self):
@@ -1147,6 +1206,14 @@ class CodeGen:
                             l = pre.gen(Parser(list(lo)).expr())[0] if lo else '1'
                             ext.append('(%s) - (%s) + 1' % (h, l))
                     head.append('    %s = _reshape(%s, (%s,))' % (py, py, ', '.join(ext)))
+                elif v.rank == 1 and v.dims and v.dims[0][1] is not None and not v.alloc and not v.pointer:
+                    # explicit-shape dummy of rank 1: the dummy IS its declared extent (whole-array operations such as
+                    # minval(x) or x = 0 must not see the rest of a longer actual argument)
+                    lo, hi = v.dims[0]
+                    if not (len(hi) == 1 and hi[0] == ('op', '*')):
+                        h = pre.gen(Parser(list(hi)).expr())[0]
+                        l = pre.gen(Parser(list(lo)).expr())[0] if lo else '1'
+                        head.append('    %s = _view1(%s, (%s) - (%s) + 1)' % (py, py, h, l))
                 continue
             if v.param:
                 head.append('    %s = %s' % (py, pre.gen(Parser(list(v.init)).expr())[0]))
@@ -1178,6 +1245,8 @@ class CodeGen:
     def ret(self):
         p = self.p
         if p.kind == 'function':
+            if p.outs:  # a function that also writes by-reference dummies: (result, dummies...)
+                return 'return (' + ', '.join([self.w.pyname(p.result or p.name)] + [self.w.pyname(a) for a in p.outs]) + ',)'
             return 'return ' + self.w.pyname(p.result or p.name)
         if not p.outs:
             return 'return None'
@@ -1411,6 +1480,18 @@ class CodeGen:
         rc, Tr = self.gen(Parser(list(rhs)).expr())
         if kind == '=>':
             return self.emit('%s = %s' % (tgt, rc))
+        if Tl[0] == 'type' and Tr[0] == 'type' and Tl[2] == 0 and Tr[2] == 0 and Tl[1] != Tr[1]:
+            # defined assignment (interface assignment(=)): the specific whose dummies have these two types
+            for cand in self.w.generics.get('assignment', []):
+                key = self.rproc(cand)
+                if key is None:
+                    continue
+                pc = self.w.analyse(key)
+                if len(pc.args) != 2:
+                    continue
+                a0, a1 = pc.vars[pc.args[0]], pc.vars[pc.args[1]]
+                if a0.base == 'type' and a1.base == 'type' and a1.tname == Tr[1] and (a0.tname == Tl[1] or self.w.extends(Tl[1], a0.tname)):
+                    return self.call_proc(cand, [node, Parser(list(rhs)).expr()])
         last_args = node[1][-1][1]
         if Tl[2] > 0:
             if tgt.endswith(']'):
@@ -1580,7 +1661,7 @@ _INTRINSICS = {
     'nint': _simple('_nint({0})', _intT), 'floor': _simple('math.floor({0})', _intT), 'ceiling': _simple('math.ceil({0})', _intT),
     'tiny': _tiny, 'huge': _huge, 'epsilon': lambda cg, a: ('2.220446049250313e-16', ('real', None, 0)),
     'maxval': _simple('_maxval({0})', _elem), 'minval': _simple('_minval({0})', _elem),
-    'associated': lambda cg, a: ('(%s is not None)' % cg.gen(a[0])[0], ('logical', None, 0)) if len(a) == 1 else ('(%s is %s)' % (cg.gen(a[0])[0], cg.gen(a[1])[0]), ('logical', None, 0)),
+    'associated': lambda cg, a: ('(%s is not None)' % cg.gen(a[0])[0], ('logical', None, 0)) if len(a) == 1 else ('(%s is %s)' % (cg.gen(a[0])[0], cg.gen(a[1][2] if a[1][0] == 'kw' else a[1])[0]), ('logical', None, 0)),
     'allocated': _simple('({0} is not None)', _scalar('logical')), 'present': _simple('({0} is not None)', _scalar('logical')),
     'exp': _simple('math.exp({0})', _realT), 'log': _simple('math.log({0})', _realT), 'log10': _simple('math.log10({0})', _realT),
     'sin': _simple('math.sin({0})', _realT), 'cos': _simple('math.cos({0})', _realT), 'tan': _simple('math.tan({0})', _realT),
@@ -1609,6 +1690,13 @@ def _newarr(shape, base, tcls=None):
             a[idx] = tcls()
     elif base == 'char':
         a[...] = ''
+    return a
+
+
+def _view1(a, n):
+    """a rank-1 explicit-shape dummy: the first n elements of the actual argument (a view: writes reach the caller)"""
+    if isinstance(a, np.ndarray) and a.ndim == 1 and a.shape[0] > n >= 0:
+        return a[:n]
     return a
 
 

@@ -12,10 +12,10 @@
 //
 // PARITY PINNED TO THE REFERENCE'S SOURCE TEXT (not to a compiled binary): the reference ships no tests, golden
 // vectors or runnable case for this path (bundled test/box.cgns.tar.gz is missing) and no Fortran compiler exists here
-// or on the GPU box, so find_element_nb, calc_aip_xyzip_uns, calc_vol_cv_centers_uns and add_transformation_bt are
-// executed from the reference's unmodified files by oracle/f90run/f90py.py and this restatement must give the same
-// arrays bit for bit (tests/test_oracle_vs_reference_source.py).  Not executed from the reference: generate_seeds
-// (which subdomain a cell belongs to) — pinned by the RCB known-answer tests of tests/test_oracle_kat.py only.
+// or on the GPU box, so find_element_nb, calc_aip_xyzip_uns, calc_vol_cv_centers_uns, generate_seeds (which subdomain a
+// cell belongs to) and add_transformation_bt are executed from the reference's unmodified files by
+// oracle/f90run/f90py.py and this restatement must give the same arrays bit for bit
+// (tests/test_oracle_vs_reference_source.py).
 #pragma once
 #include <cstdint>
 #include <cstdio>

@@ -14,9 +14,10 @@ The mesh set-up is the reference's too: cell_input (src/setup/cell_input.f90) is
 only its CGNS library calls (:36-93, cgnslib is not available) replaced by the arrays of the synthetic mesh file --
 add_meshds / find_element_nb (connectivity), calc_aip_xyzip_uns, calc_vol_cv_centers_uns (geometry) and
 add_transformation_bt (order of the cells inside the subdomains, incl. the unstable qsort_key_nRec) run from the reference's
-source.  One input is not the reference's: which subdomain a cell belongs to (generate_seeds, a threaded-tree bisection
-outside the interpreter's subset) comes from this repository's RCB (tests/test_oracle_kat.py checks its boxes).  The
-fixtures therefore also hold the reference's connectivity, geometry and subdomain order.
+source, and so does generate_seeds (mod_mg_lvl_uns.f90:95-117: which subdomain a cell belongs to -- the threaded binary tree
+of mod_agglomeration.f90 over the doubly linked lists of mod_dll, with their defined assignments, structure-constructor
+generics and functions that rebind their pointer dummies).  The fixtures therefore hold the reference's connectivity,
+geometry, subdomain membership (setup_gf2g) and subdomain order.
 
 Each fixture tests/golden/ref_<case>.npz holds the per-solve records the reference prints (name, it, res_i, res_f, res_max
 -- taken from the argument list of its `write(*,oformat)` statements at full precision) and the final u, v, w, p, gp, mip,
@@ -109,12 +110,16 @@ def reference_cell_input(w, raw, n_subdomains, gf2g=None):
     w.get("calc_vol_cv_centers_uns")(g.xc, g.yc, g.zc, g.vol, g.x, g.y, g.z, mg.e2vx, mg.fine_lvl.gs2nb, mg.fine_lvl.gs2nb_idx, mg.etype,
                                      nvx, nelem, nbf, nf, m, nsec, mg.esec, g.rip, g.aip)
     if n_subdomains > 1:
-        # :131-153 ('Oct-Tree Isotropic', nl = (n_subdomains, 1)).  generate_seeds (the threaded-tree bisection of
-        # mod_agglomeration.f90: defined assignment, polymorphic list nodes) is beyond the interpreter's subset, so the
-        # MEMBERSHIP cell -> subdomain (gf2g) is taken from this repository's RCB; the ORDER of the cells inside the
-        # subdomains -- add_transformation_bt with the reference's unstable qsort_key_nRec -- is the reference's own.
-        # (The second add_meshds builds the coarse level's connectivity, which the hot path never reads.)
-        mg.gf2g[0].p = np.array(gf2g, dtype=np.int64)
+        # :131-153 ('Oct-Tree Isotropic', nl = (n_subdomains, 1)): generate_seeds -- the threaded-tree bisection of
+        # mod_agglomeration.f90 over the doubly linked lists of mod_dll (mod_util.f90:2064-2290) -- decides which subdomain a
+        # cell belongs to, add_transformation_bt (with the reference's unstable qsort_key_nRec) the order inside the
+        # subdomains; both are executed from the reference's source.  (The second add_meshds builds the coarse level's
+        # connectivity, which the hot path never reads.)
+        nl = np.zeros(10, dtype=np.int64)
+        nl[0], nl[1] = n_subdomains, 1
+        w.get("generate_seeds")(mg, nl, 2, nelem - nbf, g.vol, g.xc, g.yc, g.zc)
+        if gf2g is not None:  # (what the oracle's restatement says, for the caller's information only)
+            g.gf2g_matches_oracle = bool(np.array_equal(np.asarray(mg.gf2g[0].p)[:nelem - nbf], np.asarray(gf2g)))
         w.get("add_transformation_bt")(mg)
     g.ef2nb, g.ef2nb_idx = mg.fine_lvl.gs2nb, mg.fine_lvl.gs2nb_idx
     g.ne, g.nf, g.nbf, g.nvx = int(mg.fine_lvl.ng), int(mg.fine_lvl.ns), int(mg.fine_lvl.nbs), nvx
@@ -170,7 +175,7 @@ def run_case(name, w=None, verbose=True):
     setup = dict(ef2nb_nb=geom.ef2nb[:, 0], ef2nb_fg=geom.ef2nb[:, 1], ef2nb_idx=geom.ef2nb_idx, s2g=geom.mg.fine_lvl.s2g[:geom.nf],
                  bs=geom.mg.fine_lvl.bs[geom.ne:geom.ne + geom.nbf], xc=geom.xc, yc=geom.yc, zc=geom.zc, aip=geom.aip, rip=geom.rip, vol=geom.vol)
     if nsub > 1:
-        setup.update(g2gf_p=geom.mg.g2gf[0].p, g2gf_idx=geom.mg.g2gf[0].idx)
+        setup.update(g2gf_p=geom.mg.g2gf[0].p, g2gf_idx=geom.mg.g2gf[0].idx, gf2g=np.asarray(geom.mg.gf2g[0].p)[:geom.ne])
     phys = ns["T_phys_t"]()
     phys.n_subdomains = nsub
     phys.ntstep, phys.ncoef, phys.dt = ntstep, ncoef, dt

@@ -3,7 +3,8 @@ the unmodified files under /root/reference/src executed statement by statement b
 (tests/golden/make_golden_ref.py; no Fortran compiler exists here or on the GPU box, profiles/r02_fortran_probe_*.log).
 
 CPU: the C++ oracle must reproduce those fixtures BIT FOR BIT — the set-up arrays of cell_input (connectivity of
-find_element_nb, geometry of calc_aip_xyzip_uns / calc_vol_cv_centers_uns, subdomain order of add_transformation_bt), the
+find_element_nb, geometry of calc_aip_xyzip_uns / calc_vol_cv_centers_uns, subdomain membership of generate_seeds (the
+threaded-tree bisection of mod_agglomeration.f90), subdomain order of add_transformation_bt), the
 per-solve records (it, res_i, res_f, res_max) of solve_gs / multi_subdomain_solver and every field and matrix of solve_uvwp
 (src/equations/mod_uvwp.f90:95-134) — on hex and tet meshes, orthogonal and jittered, 1 / 2 / 4 subdomains, wall / lid /
 symmetry boundaries, small and large time steps.  The product's host-side set-up (cfdl_mesh_build, cfdl_partition_rcb) is
@@ -60,6 +61,7 @@ def test_oracle_equals_reference_source_bit_for_bit(cfdl, oracle, name):
     for k in SETUP:
         assert np.array_equal(oc[k], g["setup_" + k]), "set-up array %s differs from the reference source" % k
     if kw["nsub"] > 1:
+        assert np.array_equal(oc["gf2g"], g["setup_gf2g"]), "subdomain membership differs from the reference's generate_seeds"
         assert np.array_equal(oc["g2gf_p"], g["setup_g2gf_p"]) and np.array_equal(oc["g2gf_idx"], g["setup_g2gf_idx"])
     extra = "hist_e" in g.files  # energy (mod_energy.f90) and scalar (mod_scalar.f90) equations next to uvwp
     if extra:
@@ -96,7 +98,8 @@ def test_product_mesh_build_equals_reference_source(cfdl, name):
     for k in SETUP:
         assert np.array_equal(np.asarray(geom[k]), g["setup_" + k]), "cfdl_mesh_build: %s differs from the reference source" % k
     if kw["nsub"] > 1:
-        _, p, idx = cfdl.partition_rcb(geom, kw["nsub"])
+        c2r, p, idx = cfdl.partition_rcb(geom, kw["nsub"])
+        assert np.array_equal(c2r, g["setup_gf2g"]), "cfdl_partition_rcb: membership differs from the reference's generate_seeds"
         assert np.array_equal(p, g["setup_g2gf_p"]) and np.array_equal(idx, g["setup_g2gf_idx"])
 
 
