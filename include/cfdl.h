@@ -110,7 +110,22 @@ int cfdl_create(cfdl_handle* out, int32_t ne, int32_t nf, int32_t nbf,
                 int32_t device);
 int cfdl_destroy(cfdl_handle h);
 
-/* options: "solver" (CFDL_SOLVER_*), "reorder" (0/1, set before first use) ... */
+/* Options (key, value); unknown keys return CFDL_ERR_ARG.  What a caller may want to set:
+ *   "solver"          CFDL_SOLVER_PARITY (the reference's sweep order, one GPU) | CFDL_SOLVER_MCSGS (multicolour order) |
+ *                     CFDL_SOLVER_PCG (conjugate gradients for pc)
+ *   "pcg_precond"     1 multicolour-SSOR preconditioner on two-colour meshes (default), 0 Jacobi
+ *   "uvw_fused"       1 the three momentum solves side by side (default), 0 one after the other (same bits)
+ *   "p2p"             1 peer-to-peer ghost exchange once cfdl_comm_ipc_connect has run (default), 0 NCCL send/recv
+ *   "rbq"             1 the pc solve as one persistent launch where it pays (default), 0 one launch per colour pass
+ *   "rbq_counter"     -1 chunks handed out from a counter where one chunk per CTA would be too long (default), 0 never, 1 always
+ *   "rbq_l2_fraction" largest share of the L2 the value arrays may take for the persistent form (default 0.55)
+ *   "rbq_prefetch"    trips ahead the constants are prefetched into the L2 in the persistent form (-1 by mesh size, 0 off)
+ *   "statics"         1 face statics precomputed at creation (default; needed by cfdl_solve_energy), 0 geometry re-evaluated
+ *   "profile"         0 off, 1 one CUDA-event pair per launch, 2 one per batch of passes (bench.py's phase times)
+ * The remaining keys ("fused", "pdl", "pdl_rows", "rb_idx16", "pc_sumap", "grad_variant", "mip_hoist", "occ_grids",
+ * "ctas_per_sm", "rbq_lmax", "rbq_lbig", "rbq_cap", "rbq_ctas", "reset_counters") select measured alternatives of single
+ * kernels for tests and tuning experiments; every setting gives the same results (tests/test_gpu_parity.py).
+ * On partitioned handles the rbq_* options must be set before cfdl_comm_ipc_handle, which fixes the chunk geometry. */
 int cfdl_set_option(cfdl_handle h, const char* key, double value);
 int cfdl_get_info(cfdl_handle h, const char* key, double* value);
 /* device cell numbering (colour-major, optionally Morton inside a colour): c2o[i] = 1-based
