@@ -26,7 +26,8 @@ def main():
     structured = len(sys.argv) > 3 and sys.argv[3] in ("structured", "structured-slabs", "tall-slabs")
     slabs = len(sys.argv) > 3 and sys.argv[3] in ("slabs", "structured-slabs", "tall-slabs")
     nz = (n * world) // 2 + 1 if (len(sys.argv) > 3 and sys.argv[3] == "tall-slabs") else None  # n x n x nz cells (cfdl_create_structured_hex_slabs)
-    pcg = len(sys.argv) > 3 and sys.argv[3] in ("pcg", "nccl-pcg")
+    pcg = len(sys.argv) > 3 and sys.argv[3] in ("pcg", "nccl-pcg", "pcg-ssor", "nccl-pcg-ssor")
+    precond = 1 if (pcg and sys.argv[3].endswith("ssor")) else 0  # multicolour-SSOR (colour-wise ghost exchanges inside the preconditioner) / Jacobi
     nccl = len(sys.argv) > 3 and sys.argv[3].startswith("nccl")
     tet = len(sys.argv) > 3 and sys.argv[3] in ("nccl-tet", "tet")  # "tet": peer-to-peer, one staged exchange per colour
     if nccl:
@@ -61,7 +62,7 @@ def main():
                 s = cfdl.Solver(geom, bcs, device=0, cell2rank=c2r, rank=rank, nranks=world)
             s.set_option("solver", mode)
             if pcg:
-                s.set_option("pcg_precond", 0)  # partitioned handles run the Jacobi form
+                s.set_option("pcg_precond", precond)
             if fused is not None:
                 s.set_option("uvw_fused", int(fused))
             if nccl:
@@ -115,7 +116,7 @@ def main():
     one = cfdl.Solver(geom, bcs, device=0) if nz is None else cfdl.Solver.structured_hex(n, device=0, slabs=True, nz=nz)
     one.set_option("solver", mode)
     if pcg:
-        one.set_option("pcg_precond", 0)
+        one.set_option("pcg_precond", precond)
     want_hist = one.run(dt=dt, nit=100, ntstep=2, ncoef=2)
     for r in range(world):
         hist = out[r][0]

@@ -12,7 +12,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("world,n,structured", [(4, 10, False), (8, 12, False), (4, 12, True), (4, 10, "pcg"), (3, 4, "tet"),
+@pytest.mark.parametrize("world,n,structured", [(4, 10, False), (8, 12, False), (4, 12, True), (4, 10, "pcg"), (4, 10, "pcg-ssor"), (3, 4, "tet"),
                                                 (4, 12, "slabs"), (3, 10, "slabs"), (4, 12, "structured-slabs")])
 def test_partitioned_p2p_run_equals_single_rank_under_emulation(world, n, structured):
     extra = [structured] if isinstance(structured, str) else (["structured"] if structured else [])
@@ -22,7 +22,7 @@ def test_partitioned_p2p_run_equals_single_rank_under_emulation(world, n, struct
     assert "multirank emulation ok" in r.stdout
 
 
-@pytest.mark.parametrize("world,n,mode", [(4, 10, "nccl"), (3, 4, "nccl-tet"), (4, 10, "nccl-pcg")])
+@pytest.mark.parametrize("world,n,mode", [(4, 10, "nccl"), (3, 4, "nccl-tet"), (4, 10, "nccl-pcg"), (3, 8, "nccl-pcg-ssor")])
 def test_partitioned_nccl_mode_equals_single_rank_under_emulation(world, n, mode):
     """The library's NCCL exchange mode (grouped send/recv of ghost values per colour, all-reduced residual norms and
     dot products, broadcast of pc(1)) against an in-process stand-in for NCCL (tests/emul/fake_nccl.cpp): hex mesh,
