@@ -57,6 +57,9 @@ CASES = {
     "tet2_sub1": (1, 2, 0.2, True, 1, 1, 2, {}, 0.01),
     "tet3_sub2": (1, 3, 0.2, True, 2, 1, 3, {}, 0.01),
     "tet3_sub4": (1, 3, 0.2, True, 4, 1, 2, {}, 0.01),
+    "tet4_sub4": (1, 4, 0.2, True, 4, 1, 2, {}, 0.01),        # 384 tets: uneven subdomains out of the bisection (threshold relaxation)
+    "hex7_jit_dt5_sub4": (0, 7, 0.15, False, 4, 1, 3, {}, 5.0),  # block solver + iterating momentum solves on a non-orthogonal mesh
+    "hex6_sub3": (0, 6, 0.0, False, 3, 1, 2, {}, 0.01),       # a subdomain count that is not a power of two
     "hex5_sym_sub1": (0, 5, 0.0, False, 1, 1, 2, {"east": "symmetry", "west": "symmetry"}, 0.01),
     "hex5_symjit_sub4": (0, 5, 0.15, False, 4, 1, 2, {"south": "symmetry", "bottom": "symmetry"}, 0.01),
     # the energy (enthalpy) and scalar equations next to uvwp: solve_energy is the call main.f90:59 has commented out,
